@@ -1,0 +1,125 @@
+"""Import pieces of the REFERENCE (read-only /root/reference) in the authoring container.
+
+Used only by tests/golden/make_golden.py to generate golden vectors; never at test/bench time
+(the GPU box has no /root/reference).  mmcv / mmdet cannot be imported as packages here
+(mmcv-full 1.3.16 is not installable offline), so the handful of reference *files* on the hot
+path are loaded individually with tiny stand-ins for the mmcv symbols they import
+(Registry / build_from_cfg / Hook / is_module_wrapper).  No reference source is copied: the
+files are exec'd from where they lie.
+"""
+import importlib.util
+import sys
+import types
+
+REF = "/root/reference"
+MMDET = REF + "/thirdparty/mmdetection/mmdet"
+
+
+class _Registry:
+    def __init__(self, name):
+        self.name = name
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def deco(cls):
+            self.module_dict[name or cls.__name__] = cls
+            return cls
+        if module is not None:
+            return deco(module)
+        return deco
+
+    def get(self, key):
+        return self.module_dict[key]
+
+
+def _build_from_cfg(cfg, registry, default_args=None):
+    cfg = dict(cfg)
+    if default_args:
+        for k, v in default_args.items():
+            cfg.setdefault(k, v)
+    return registry.get(cfg.pop("type"))(**cfg)
+
+
+def _pkg(name):
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+        if "." in name:
+            parent, child = name.rsplit(".", 1)
+            setattr(_pkg(parent), child, m)
+    return sys.modules[name]
+
+
+def _load(name, path):
+    if name in sys.modules and getattr(sys.modules[name], "__file__", None) == path:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    parent, child = name.rsplit(".", 1)
+    setattr(_pkg(parent), child, mod)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _install_mmcv_stub():
+    mmcv = _pkg("mmcv")
+    utils = _pkg("mmcv.utils")
+    utils.Registry = _Registry
+    utils.build_from_cfg = _build_from_cfg
+    par = _pkg("mmcv.parallel")
+    par.is_module_wrapper = lambda m: False
+    _pkg("mmcv.runner")
+    hooks = _pkg("mmcv.runner.hooks")
+
+    class Hook:
+        pass
+    hooks.Hook = Hook
+    hooks.HOOKS = _Registry("hook")
+    return mmcv
+
+
+def load_msda_python():
+    """functions/ms_deform_attn_func.py with a stub for the CUDA extension it imports at :18."""
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    return _load("ref_ops.ms_deform_attn_func",
+                 REF + "/detr_od/models/utils/ops/functions/ms_deform_attn_func.py")
+
+
+def load_hungarian():
+    """The real mmdet HungarianAssigner + match costs (hungarian_assigner.py, match_cost.py,
+    iou2d_calculator.py, transforms.py) on stubbed registries."""
+    _install_mmcv_stub()
+    for p in ("mmdet", "mmdet.core", "mmdet.core.bbox", "mmdet.core.bbox.iou_calculators",
+              "mmdet.core.bbox.match_costs", "mmdet.core.bbox.assigners", "mmdet.utils"):
+        _pkg(p)
+    _load("mmdet.utils.util_mixins", MMDET + "/utils/util_mixins.py")
+    b = MMDET + "/core/bbox"
+    _load("mmdet.core.bbox.iou_calculators.builder", b + "/iou_calculators/builder.py")
+    iou = _load("mmdet.core.bbox.iou_calculators.iou2d_calculator", b + "/iou_calculators/iou2d_calculator.py")
+    sys.modules["mmdet.core.bbox.iou_calculators"].bbox_overlaps = iou.bbox_overlaps
+    _load("mmdet.core.bbox.transforms", b + "/transforms.py")
+    mcb = _load("mmdet.core.bbox.match_costs.builder", b + "/match_costs/builder.py")
+    mc = _load("mmdet.core.bbox.match_costs.match_cost", b + "/match_costs/match_cost.py")
+    sys.modules["mmdet.core.bbox.match_costs"].build_match_cost = mcb.build_match_cost
+    _load("mmdet.core.bbox.builder", b + "/builder.py")
+    _load("mmdet.core.bbox.assigners.assign_result", b + "/assigners/assign_result.py")
+    _load("mmdet.core.bbox.assigners.base_assigner", b + "/assigners/base_assigner.py")
+    lg = types.ModuleType("mmdet.core.bbox.assigners.logger")
+    lg.log_image_with_boxes = lambda *a, **k: None
+    sys.modules["mmdet.core.bbox.assigners.logger"] = lg
+    ha = _load("mmdet.core.bbox.assigners.hungarian_assigner", b + "/assigners/hungarian_assigner.py")
+    return ha, mc, iou
+
+
+def load_mean_teacher():
+    """detr_ssod/utils/hooks/mean_teacher.py on a stubbed mmcv Hook."""
+    _install_mmcv_stub()
+    for p in ("detr_ssod_ref", "detr_ssod_ref.utils", "detr_ssod_ref.utils.hooks"):
+        _pkg(p)
+    lg = types.ModuleType("detr_ssod_ref.utils.logger")
+    lg.log_every_n = lambda *a, **k: None
+    sys.modules["detr_ssod_ref.utils.logger"] = lg
+    sys.modules["detr_ssod_ref.utils"].logger = lg
+    return _load("detr_ssod_ref.utils.hooks.mean_teacher", REF + "/detr_ssod/utils/hooks/mean_teacher.py")

@@ -1,0 +1,214 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE's own python code.
+
+Run in the authoring container only (needs read access to /root/reference):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed, small):
+  msda_golden.npz       inputs + outputs + gradients of the reference's
+                        ms_deform_attn_core_pytorch (functions/ms_deform_attn_func.py:41-61),
+                        fp64, incl. the ops/test.py case (seed 3; test.py:21-36)
+  hungarian_golden.npz  inputs + (gt_inds, labels) of the real mmdet HungarianAssigner.assign
+                        (hungarian_assigner.py:55-188) with the DINO config's costs, and its cost matrix
+  lsap_golden.npz       float32 cost matrices + scipy.optimize.linear_sum_assignment answers
+                        (scipy 1.18.1), incl. tie KATs
+  ema_golden.npz        MeanTeacher.momentum_update / before_train_iter results
+                        (detr_ssod/utils/hooks/mean_teacher.py:37-64)
+"""
+import os
+import sys
+
+import numpy as np
+import scipy
+import scipy.optimize
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_import as R  # noqa: E402
+
+
+def _msda_case(rng_seed, N, M, D, Lq, L, P, shapes, value_scale=1.0, loc_mode="uniform", test_py=False):
+    g = torch.Generator().manual_seed(rng_seed)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    S = int((shapes_t[:, 0] * shapes_t[:, 1]).sum())
+    start = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    if test_py:
+        # ops/test.py:21-36 draws with the global RNG after torch.manual_seed(3)
+        torch.manual_seed(3)
+        value = torch.rand(N, S, M, D) * 0.01
+        loc = torch.rand(N, Lq, M, L, P, 2)
+        attn = torch.rand(N, Lq, M, L, P) + 1e-5
+        attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    else:
+        value = torch.randn(N, S, M, D, generator=g) * value_scale
+        if loc_mode == "uniform":
+            loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+        elif loc_mode == "wide":        # exercises the out-of-range branch and all border cases
+            loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.6 - 0.3
+        else:
+            raise ValueError(loc_mode)
+        attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    gout = torch.randn(N, Lq, M * D, generator=g)
+    return dict(value=value, shapes=shapes_t, start=start, loc=loc, attn=attn, gout=gout)
+
+
+def make_msda():
+    ref = R.load_msda_python()
+    cases = {
+        "testpy": _msda_case(3, 1, 2, 2, 2, 2, 2, [(6, 4), (3, 2)], test_py=True),
+        "small_d32": _msda_case(11, 2, 8, 32, 19, 4, 4, [(7, 9), (4, 5), (2, 3), (1, 2)]),
+        "wide_d32": _msda_case(12, 1, 8, 32, 23, 4, 4, [(6, 7), (3, 4), (2, 2), (1, 1)], loc_mode="wide"),
+        "odd_d30": _msda_case(13, 1, 2, 30, 9, 2, 3, [(5, 4), (3, 2)], loc_mode="wide"),
+        "d64_l5": _msda_case(14, 1, 2, 64, 7, 5, 4, [(4, 5), (3, 3), (2, 3), (1, 2), (1, 1)], loc_mode="wide"),
+        "one_point": _msda_case(15, 3, 1, 4, 5, 1, 1, [(4, 6)], loc_mode="wide"),
+    }
+    out = {}
+    for name, c in cases.items():
+        v = c["value"].double().requires_grad_(True)
+        l = c["loc"].double().requires_grad_(True)
+        a = c["attn"].double().requires_grad_(True)
+        y = ref.ms_deform_attn_core_pytorch(v, c["shapes"], l, a)
+        y.backward(c["gout"].double())
+        for k in ("value", "loc", "attn", "gout"):
+            out[f"{name}/{k}"] = c[k].numpy()
+        out[f"{name}/shapes"] = c["shapes"].numpy()
+        out[f"{name}/start"] = c["start"].numpy()
+        out[f"{name}/out"] = y.detach().numpy()
+        out[f"{name}/grad_value"] = v.grad.numpy()
+        out[f"{name}/grad_loc"] = l.grad.numpy()
+        out[f"{name}/grad_attn"] = a.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "msda_golden.npz"), **out)
+    print("msda_golden.npz:", list(cases))
+
+
+def _gt(g, G, img_h, img_w):
+    cx = torch.rand(G, generator=g) * 0.8 + 0.1
+    cy = torch.rand(G, generator=g) * 0.8 + 0.1
+    w = torch.rand(G, generator=g) * 0.45 + 0.05
+    h = torch.rand(G, generator=g) * 0.45 + 0.05
+    x1 = (cx - w / 2).clamp(0, 1) * img_w
+    x2 = (cx + w / 2).clamp(0, 1) * img_w
+    y1 = (cy - h / 2).clamp(0, 1) * img_h
+    y2 = (cy + h / 2).clamp(0, 1) * img_h
+    return torch.stack([x1, y1, x2, y2], -1), torch.randint(0, 80, (G,), generator=g)
+
+
+def make_hungarian():
+    ha, mc, iou = R.load_hungarian()
+    assigner = ha.HungarianAssigner(
+        cls_cost=dict(type="FocalLossCost", weight=2.0),
+        reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+        iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0))
+    out = {}
+    specs = [("q900_g7", 900, 7, 800, 1333), ("q300_g1", 300, 1, 800, 1333), ("q400_g30", 400, 30, 750, 1333),
+             ("q900_g100", 900, 100, 800, 1201), ("q100_g0", 100, 0, 800, 1333), ("q50_g60", 50, 60, 600, 800),
+             ("q300_g13", 300, 13, 512, 640)]
+    for i, (name, Q, G, ih, iw) in enumerate(specs):
+        g = torch.Generator().manual_seed(100 + i)
+        bbox_pred = torch.rand(Q, 4, generator=g) * torch.tensor([1.0, 1.0, 0.5, 0.5]) + torch.tensor([0, 0, 0.01, 0.01])
+        cls_pred = torch.randn(Q, 80, generator=g) * 2 - 3
+        gt_b, gt_l = _gt(g, G, ih, iw)
+        meta = dict(img_shape=(ih, iw, 3))
+        res = assigner.assign(bbox_pred, cls_pred, gt_b, gt_l, meta)
+        out[f"{name}/bbox_pred"] = bbox_pred.numpy()
+        out[f"{name}/cls_pred"] = cls_pred.numpy()
+        out[f"{name}/gt_bboxes"] = gt_b.numpy()
+        out[f"{name}/gt_labels"] = gt_l.numpy()
+        out[f"{name}/img_hw"] = np.array([ih, iw])
+        out[f"{name}/gt_inds"] = res.gt_inds.numpy()
+        out[f"{name}/labels"] = res.labels.numpy()
+        if G > 0:
+            factor = gt_b.new_tensor([iw, ih, iw, ih]).unsqueeze(0)
+            from mmdet.core.bbox.transforms import bbox_cxcywh_to_xyxy
+            cost = (assigner.cls_cost(cls_pred, gt_l) + assigner.reg_cost(bbox_pred, gt_b / factor)
+                    + assigner.iou_cost(bbox_cxcywh_to_xyxy(bbox_pred) * factor, gt_b))
+            out[f"{name}/cost"] = cost.numpy()
+    # the reference's only KAT on this path: IoUCost doctest, match_cost.py:155-162
+    b = torch.FloatTensor([[1, 1, 2, 2], [2, 2, 3, 4]])
+    gtb = torch.FloatTensor([[0, 0, 2, 4], [1, 2, 3, 4]])
+    out["ioucost_doctest/out"] = mc.IoUCost()(b, gtb).numpy()
+    np.savez_compressed(os.path.join(HERE, "hungarian_golden.npz"), **out)
+    print("hungarian_golden.npz:", [s[0] for s in specs])
+
+
+def make_lsap():
+    rng = np.random.default_rng(7)
+    out = {}
+    mats = {
+        "zeros_4x2": np.zeros((4, 2), np.float32),
+        "tie_3x2": np.array([[1, 1], [1, 1], [0, 0]], np.float32),
+        "n_900x7": rng.standard_normal((900, 7)).astype(np.float32),
+        "n_900x30": rng.standard_normal((900, 30)).astype(np.float32),
+        "n_900x100": rng.standard_normal((900, 100)).astype(np.float32),
+        "n_40x70": rng.standard_normal((40, 70)).astype(np.float32),
+        "int_60x25": rng.integers(0, 3, (60, 25)).astype(np.float32),
+        "int_25x60": rng.integers(0, 2, (25, 60)).astype(np.float32),
+        "sq_33": np.round(rng.standard_normal((33, 33)) * 2).astype(np.float32),
+        "inf_some": np.where(rng.random((30, 9)) < 0.3, np.inf, rng.standard_normal((30, 9))).astype(np.float32),
+        "one_1x1": np.array([[3.5]], np.float32),
+    }
+    for k, c in mats.items():
+        r, cc = scipy.optimize.linear_sum_assignment(c)
+        out[f"{k}/cost"] = c
+        out[f"{k}/rows"] = r.astype(np.int64)
+        out[f"{k}/cols"] = cc.astype(np.int64)
+    out["scipy_version"] = np.array(scipy.__version__)
+    np.savez_compressed(os.path.join(HERE, "lsap_golden.npz"), **out)
+    print("lsap_golden.npz:", list(mats))
+
+
+def make_ema():
+    mt = R.load_mean_teacher()
+    g = torch.Generator().manual_seed(5)
+    shapes = [(16, 3, 7, 7), (64,), (48, 40), (1, 1), (300, 4), (17,), (1025,), (3, 5, 7)]
+
+    class Net(torch.nn.Module):
+        def __init__(self, scale):
+            super().__init__()
+            self.ps = torch.nn.ParameterList(
+                [torch.nn.Parameter(torch.randn(*s, generator=g) * scale) for s in shapes])
+            self.register_buffer("buf", torch.randn(9, generator=g))     # buffers are NOT blended
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.teacher = Net(1.0)
+            self.student = Net(0.5)
+
+    class LogBuf:
+        output = {}
+
+    class Runner:
+        pass
+
+    model = Model()
+    hook = mt.MeanTeacher(momentum=0.999, interval=1, warm_up=0)
+    runner = Runner()
+    runner.model = model
+    runner.log_buffer = LogBuf()
+    out = {}
+    for i, p in enumerate(model.student.ps):
+        out[f"student/{i}"] = p.detach().numpy().copy()
+    for i, p in enumerate(model.teacher.ps):
+        out[f"teacher0/{i}"] = p.detach().numpy().copy()
+    moms = []
+    for it in (1, 2, 7, 999, 5000):           # iter 0 is a plain copy (momentum 0)
+        runner.iter = it
+        hook.before_train_iter(runner)
+        moms.append(runner.log_buffer.output["ema_momentum"])
+        for i, p in enumerate(model.teacher.ps):
+            out[f"teacher_after_{it}/{i}"] = p.detach().numpy().copy()
+    out["iters"] = np.array([1, 2, 7, 999, 5000])
+    out["momenta"] = np.array(moms, dtype=np.float64)
+    out["buf_teacher"] = model.teacher.buf.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "ema_golden.npz"), **out)
+    print("ema_golden.npz: momenta", moms)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    make_msda()
+    make_hungarian()
+    make_lsap()
+    make_ema()
