@@ -1,0 +1,178 @@
+/* semidetr_b200 -- C ABI of the B200-native (sm_100a) Semi-DETR hot path.
+ *
+ * This is the drop-in boundary: a plain C interface (pointers + sizes, no torch / ATen types)
+ * exported by semi_detr_b200/lib/libsemidetr_b200.so.  Every entry point replaces one native
+ * (or host-side Python/scipy) step of the reference, cited as file:line relative to
+ * /root/reference.  The reference-side bindings a maintainer would add are shown in
+ * INTEGRATION.md; the Python host code in semi_detr_b200/ binds these symbols with ctypes.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers unless the parameter is documented as "host".
+ *  - `stream` is a cudaStream_t (pass NULL / 0 for the legacy default stream).  Calls only
+ *    enqueue work; nothing synchronises the host (the reference's per-call D2H syncs are gone).
+ *  - Return value: SDB_OK (0) or an SDB_ERR_* code; sdb_last_error() then returns a
+ *    thread-local, human-readable message (the Python layer raises RuntimeError with it,
+ *    matching the reference's AT_ASSERTM -> RuntimeError behaviour,
+ *    detr_od/models/utils/ops/src/cuda/ms_deform_attn_cuda.cu:28-52).
+ *    Unlike the reference (which only printf's launch failures, ms_deform_im2col_cuda.cuh:948-952),
+ *    kernel-launch errors are returned.
+ *  - Inputs are never modified; outputs must not alias inputs.
+ *  - There is NO CPU implementation behind this ABI.
+ */
+#ifndef SEMIDETR_B200_H_
+#define SEMIDETR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_ABI_VERSION 1
+
+enum {
+  SDB_OK = 0,
+  SDB_ERR_INVALID_ARG = 1, /* bad sizes / null pointers / unsupported combination */
+  SDB_ERR_CUDA = 2,        /* a CUDA runtime call or kernel launch failed */
+  SDB_ERR_UNSUPPORTED = 3  /* shape outside what the kernels were built for */
+};
+
+typedef void* sdb_stream_t; /* cudaStream_t */
+
+int sdb_abi_version(void);
+const char* sdb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention (MSDA).
+ *
+ * Replaces the launchers ms_deformable_im2col_cuda / ms_deformable_col2im_cuda
+ * (detr_od/models/utils/ops/src/cuda/ms_deform_im2col_cuda.cuh:923-954 and :956-1327) that
+ * ms_deform_attn_cuda_forward / _backward (ms_deform_attn_cuda.cu:20-80, 83-153) call, with the
+ * same argument meaning:
+ *   value              (batch, spatial_size, num_heads, channels)       channels-last, head-major
+ *   spatial_shapes     (num_levels, 2) int64 on device, rows (H_l, W_l)
+ *   level_start_index  (num_levels,)   int64 on device
+ *   sampling_loc       (batch, num_query, num_heads, num_levels, num_point, 2)   (x, y) in [0,1]
+ *   attn_weight        (batch, num_query, num_heads, num_levels, num_point)
+ *   out / grad_out     (batch, num_query, num_heads * channels)
+ * Semantics (zero padding, pixel = loc * size - 0.5, sample kept iff -1 < pixel < size) follow
+ * ms_deform_im2col_cuda.cuh:33-84, 237-299 (forward) and :87-159, 301-403 (backward).
+ *
+ * Differences from the reference launchers, all in the caller's favour:
+ *  - `out` need not be zero-filled (every element is written);
+ *  - `grad_value` is zero-filled by the call (stream-ordered), `grad_sampling_loc` and
+ *    `grad_attn_weight` are fully overwritten -- the three at::zeros_like of
+ *    ms_deform_attn_cuda.cu:121-123 are not needed;
+ *  - im2col_step chunking is unnecessary: one launch covers the whole batch.
+ * The f32 entry points take the tuned sm_100a path when channels == 32 and
+ * num_levels * num_point <= 32 (every shipped config) and a generic kernel otherwise; the f64
+ * entry points exist for the reference's gradcheck (ops/test.py:63-86).
+ * ------------------------------------------------------------------------------------------ */
+int sdb_msda_forward_f32(sdb_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                         const int64_t* level_start_index, const float* sampling_loc,
+                         const float* attn_weight, int batch, int spatial_size, int num_heads,
+                         int channels, int num_levels, int num_query, int num_point, float* out);
+
+int sdb_msda_forward_f64(sdb_stream_t stream, const double* value, const int64_t* spatial_shapes,
+                         const int64_t* level_start_index, const double* sampling_loc,
+                         const double* attn_weight, int batch, int spatial_size, int num_heads,
+                         int channels, int num_levels, int num_query, int num_point, double* out);
+
+int sdb_msda_backward_f32(sdb_stream_t stream, const float* grad_out, const float* value,
+                          const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const float* sampling_loc, const float* attn_weight, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels,
+                          int num_query, int num_point, float* grad_value,
+                          float* grad_sampling_loc, float* grad_attn_weight);
+
+int sdb_msda_backward_f64(sdb_stream_t stream, const double* grad_out, const double* value,
+                          const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const double* sampling_loc, const double* attn_weight, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels,
+                          int num_query, int num_point, double* grad_value,
+                          double* grad_sampling_loc, double* grad_attn_weight);
+
+/* Tuning knob for benchmarking kernel variants (0 = default heuristic).  Not part of the
+ * reference surface; see DESIGN.md "MSDA forward variants". */
+int sdb_msda_set_variant(int forward_variant, int backward_variant);
+
+/* ------------------------------------------------------------------------------------------
+ * Hungarian matching, batched over P independent problems (decoder layer x image).
+ *
+ * Replaces, per problem, HungarianAssigner.assign
+ * (thirdparty/mmdetection/mmdet/core/bbox/assigners/hungarian_assigner.py:96-148):
+ *   cost = FocalLossCost(w_cls, alpha .25, gamma 2, eps 1e-12)          match_cost.py:83-99
+ *        + BBoxL1Cost(w_l1, box_format='xywh')                           match_cost.py:33-50
+ *        + IoUCost('giou', w_iou)  (bbox_overlaps eps 1e-6)              match_cost.py:169-185
+ *   cost.cpu(); scipy.optimize.linear_sum_assignment(cost)               hungarian_assigner.py:131-140
+ *   gt_inds[row] = col + 1; labels[row] = gt_labels[col]                 hungarian_assigner.py:142-148
+ * with no device->host copy and no host synchronisation.
+ *
+ * Layout.  Problem p uses predictions cls_pred[p] (Q, C) / bbox_pred[p] (Q, 4: cx,cy,w,h in [0,1])
+ * and ground-truth segment s = prob_seg[p]: boxes gt_bboxes[seg_offsets[s] .. seg_offsets[s+1])
+ * (x1,y1,x2,y2 in pixels), labels gt_labels[...], image size seg_img_wh[s] = (w, h) of
+ * img_meta['img_shape'].  prob_seg / seg_offsets are int32 on device, gt_labels int64.
+ * cost_offsets (P+1, int64, device): element offset of each problem's matrix in `cost`
+ * (Q*G_p elements each).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Builds the fp32 cost matrices.  cost_qg (optional, may be NULL): reference layout (Q, G_p)
+ * row-major.  cost_solver (required): the layout sdb_lsap_solve_f32 consumes -- row-major with
+ * the SMALLER dimension as rows, i.e. (G_p, Q) when Q > G_p (scipy solves the transpose of a tall
+ * matrix), else (Q, G_p). */
+int sdb_match_cost_f32(sdb_stream_t stream, const float* cls_pred, const float* bbox_pred,
+                       const float* gt_bboxes, const int64_t* gt_labels, const int32_t* prob_seg,
+                       const int32_t* seg_offsets, const float* seg_img_wh,
+                       const int64_t* cost_offsets, int num_problems, int num_query,
+                       int num_classes, float w_cls, float w_l1, float w_iou, float* cost_qg,
+                       float* cost_solver);
+
+/* Exact rectangular linear-sum-assignment, one CTA per problem, float64 duals, reproducing
+ * scipy.optimize.linear_sum_assignment's result including its tie-breaking (see oracle/lsap.c
+ * for the step-for-step CPU twin).  For problem p with G_p = seg size of prob_seg[p]:
+ *   gt_inds[p, q]  = 0 (background) or k+1 (matched to GT k)           int64 (P, Q)
+ *   labels[p, q]   = -1 or gt_labels[k]  (gt_labels may be NULL -> labels not written)
+ *   status[p]      = 0 ok, 1 invalid entry (NaN / -inf), 2 infeasible   int32 (P,)
+ *                    (scipy raises ValueError in those cases; the host wrapper checks status
+ *                     lazily so the hot path stays sync-free)
+ * `max_gt` (host int) is an upper bound on every G_p; it sizes the kernel's shared memory.
+ * max(Q, max_gt) is limited by shared memory to SDB_LSAP_MAX_DIM. */
+#define SDB_LSAP_MAX_DIM 4096
+int sdb_lsap_solve_f32(sdb_stream_t stream, const float* cost_solver, const int64_t* cost_offsets,
+                       const int32_t* prob_seg, const int32_t* seg_offsets,
+                       const int64_t* gt_labels, int num_problems, int num_query, int max_gt,
+                       int64_t* gt_inds, int64_t* labels, int32_t* status);
+
+/* Convenience: sdb_match_cost_f32 followed by sdb_lsap_solve_f32 on the same stream.
+ * `workspace` must hold cost_offsets[P] floats. */
+int sdb_hungarian_assign_f32(sdb_stream_t stream, const float* cls_pred, const float* bbox_pred,
+                             const float* gt_bboxes, const int64_t* gt_labels,
+                             const int32_t* prob_seg, const int32_t* seg_offsets,
+                             const float* seg_img_wh, const int64_t* cost_offsets,
+                             int num_problems, int num_query, int num_classes, int max_gt,
+                             float w_cls, float w_l1, float w_iou, float* workspace, float* cost_qg,
+                             int64_t* gt_inds, int64_t* labels, int32_t* status);
+
+/* ------------------------------------------------------------------------------------------
+ * Mean-teacher EMA, all parameters in ONE launch.
+ *
+ * Replaces MeanTeacher.momentum_update (detr_ssod/utils/hooks/mean_teacher.py:60-64), a Python
+ * loop of `teacher.mul_(m).add_(student, alpha=1-m)` over ~430 tensors (~860 launches):
+ *   teacher[i] = fma((float)(1-m), student[i], (float)m * teacher[i])
+ * `chunks` is a device table that tiles the parameter list; entry c covers
+ * count[c] floats starting at teacher_ptr[c] / student_ptr[c] (a flat parameter buffer is the
+ * special case of contiguous chunks).  momentum is the Python double of mean_teacher.py:45-47.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float* teacher;       /* in/out */
+  const float* student; /* in */
+  int64_t count;
+} sdb_ema_chunk;
+
+int sdb_ema_update_f32(sdb_stream_t stream, const sdb_ema_chunk* chunks, int num_chunks,
+                       double momentum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMIDETR_B200_H_ */

@@ -1,0 +1,72 @@
+"""ctypes binding of libsemidetr_b200.so (the C ABI declared in include/semidetr_b200.h).
+
+The product path has NO fallback: if the shared library is missing, or an op is called without a
+CUDA device, this module raises -- it never routes to a CPU / PyTorch implementation.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsemidetr_b200.so")
+
+c_void_p, c_int, c_float, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
+
+_MSDA_FWD = [c_void_p] * 6 + [c_int] * 7 + [c_void_p]
+_MSDA_BWD = [c_void_p] * 7 + [c_int] * 7 + [c_void_p] * 3
+
+# symbol -> argtypes; every function returns int.  Must list every symbol include/semidetr_b200.h declares
+# (tests/test_abi.py parses the header and checks this table and the .so against it).
+SIGNATURES = {
+    "sdb_abi_version": [],
+    "sdb_msda_forward_f32": _MSDA_FWD,
+    "sdb_msda_forward_f64": _MSDA_FWD,
+    "sdb_msda_backward_f32": _MSDA_BWD,
+    "sdb_msda_backward_f64": _MSDA_BWD,
+    "sdb_msda_set_variant": [c_int, c_int],
+    "sdb_match_cost_f32": [c_void_p] * 9 + [c_int] * 3 + [c_float] * 3 + [c_void_p] * 2,
+    "sdb_lsap_solve_f32": [c_void_p] * 6 + [c_int] * 3 + [c_void_p] * 3,
+    "sdb_hungarian_assign_f32": [c_void_p] * 9 + [c_int] * 4 + [c_float] * 3 + [c_void_p] * 5,
+    "sdb_ema_update_f32": [c_void_p, c_void_p, c_int, c_double],
+}
+
+_lib = None
+
+
+class EmaChunk(ctypes.Structure):
+    """sdb_ema_chunk"""
+    _fields_ = [("teacher", c_void_p), ("student", c_void_p), ("count", ctypes.c_int64)]
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m semi_detr_b200.build` "
+                "(semi_detr_b200 has no CPU or PyTorch fallback)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        l.sdb_last_error.restype = ctypes.c_char_p
+        l.sdb_last_error.argtypes = []
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    """Mirror of the reference's AT_ASSERTM / AT_ERROR -> RuntimeError behaviour."""
+    if rc != 0:
+        msg = lib().sdb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def current_stream(device):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

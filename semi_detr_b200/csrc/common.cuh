@@ -1,0 +1,67 @@
+// Shared helpers for the semidetr_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/semidetr_b200.h"
+
+namespace sdb {
+
+// thread-local last-error message (abi.cu)
+void set_error(const char* fmt, ...);
+int cuda_error(cudaError_t e, const char* what);
+int sm_count();
+
+}  // namespace sdb
+
+#define SDB_REQUIRE(cond, ...)       \
+  do {                               \
+    if (!(cond)) {                   \
+      sdb::set_error(__VA_ARGS__);   \
+      return SDB_ERR_INVALID_ARG;    \
+    }                                \
+  } while (0)
+
+#define SDB_CUDA(call)                                      \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return sdb::cuda_error(e__, #call); \
+  } while (0)
+
+#define SDB_LAUNCH_CHECK(name)                                  \
+  do {                                                          \
+    cudaError_t e__ = cudaGetLastError();                       \
+    if (e__ != cudaSuccess) return sdb::cuda_error(e__, name);  \
+  } while (0)
+
+namespace sdb {
+
+// streaming (read-once) loads: keep them out of L1 so the gathered value lines stay resident
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ld_stream_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream_f2(float2* p, const float2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+// 16-byte vector reduction into global memory (sm_90+): one L2 atomic transaction per 4 floats
+__device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+}  // namespace sdb

@@ -1,0 +1,102 @@
+// Bilinear-tap arithmetic shared by the MSDA forward / backward kernels.
+//
+// Semantics follow the reference op: pixel coordinate = loc * size - 0.5,
+// a sample participates iff -1 < h < H and -1 < w < W (ms_deform_im2col_cuda.cuh:285-288), corners
+// outside [0,H-1]x[0,W-1] read as zero (:55-78), weights (1-lh)(1-lw), (1-lh)lw, lh(1-lw), lh*lw (:80).
+#pragma once
+#include "common.cuh"
+
+namespace sdb {
+
+constexpr int kMaxLevels = 16;  // tuned kernels keep per-level geometry in shared memory
+
+template <typename T>
+struct Tap {
+  int h0, w0;   // top-left corner (may be -1)
+  T lh, lw;     // fractional offsets
+  bool ok;      // sample inside the (-1, size) window
+  bool c00, c01, c10, c11;  // corner validity: (h0,w0) (h0,w0+1) (h0+1,w0) (h0+1,w0+1)
+};
+
+template <typename T>
+__device__ __forceinline__ Tap<T> make_tap(T x, T y, int H, int W) {
+  Tap<T> t;
+  const T h_im = y * (T)H - (T)0.5;
+  const T w_im = x * (T)W - (T)0.5;
+  t.ok = (h_im > (T)-1) && (w_im > (T)-1) && (h_im < (T)H) && (w_im < (T)W);
+  const T hf = floor(h_im), wf = floor(w_im);
+  t.lh = h_im - hf;
+  t.lw = w_im - wf;
+  t.h0 = t.ok ? (int)hf : 0;
+  t.w0 = t.ok ? (int)wf : 0;
+  if (!t.ok) { t.lh = 0; t.lw = 0; }
+  const bool hlo = t.h0 >= 0, wlo = t.w0 >= 0, hhi = t.h0 + 1 <= H - 1, whi = t.w0 + 1 <= W - 1;
+  t.c00 = t.ok && hlo && wlo;
+  t.c01 = t.ok && hlo && whi;
+  t.c10 = t.ok && hhi && wlo;
+  t.c11 = t.ok && hhi && whi;
+  return t;
+}
+
+// Per-level geometry staged once per CTA.  In "tiled" mode (num_query == spatial_size, i.e. encoder
+// self-attention where query i sits on pixel i of the level pyramid) the work list is cut into
+// TH x TW pixel tiles per level so that the value lines a CTA gathers stay L1-resident; otherwise
+// tiles are TH*TW consecutive queries.
+struct LevelTable {
+  int H[kMaxLevels], W[kMaxLevels], start[kMaxLevels], tiles_x[kMaxLevels];
+  int tile_begin[kMaxLevels + 1];
+};
+
+template <int TH, int TW>
+__device__ __forceinline__ void load_levels(LevelTable& t, const int64_t* __restrict__ shapes,
+                                            const int64_t* __restrict__ lsi, int L) {
+  if (threadIdx.x < L) {
+    const int l = threadIdx.x;
+    t.H[l] = (int)shapes[2 * l];
+    t.W[l] = (int)shapes[2 * l + 1];
+    t.start[l] = (int)lsi[l];
+    t.tiles_x[l] = (t.W[l] + TW - 1) / TW;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < L; ++l) {
+      t.tile_begin[l] = acc;
+      acc += ((t.H[l] + TH - 1) / TH) * t.tiles_x[l];
+    }
+    t.tile_begin[L] = acc;
+  }
+  __syncthreads();
+}
+
+// query index of local slot i of a tile, or -1
+template <int TH, int TW>
+struct TileCursor {
+  int lvl, y0, x0, Hl, Wl, start, first_q;
+  bool tiled;
+  __device__ __forceinline__ void seek(const LevelTable& t, int L, int tile, bool tiled_, int) {
+    tiled = tiled_;
+    if (tiled) {
+      lvl = 0;
+      while (lvl + 1 < L && tile >= t.tile_begin[lvl + 1]) ++lvl;
+      const int tt = tile - t.tile_begin[lvl];
+      y0 = (tt / t.tiles_x[lvl]) * TH;
+      x0 = (tt % t.tiles_x[lvl]) * TW;
+      Hl = t.H[lvl];
+      Wl = t.W[lvl];
+      start = t.start[lvl];
+    } else {
+      first_q = tile * (TH * TW);
+    }
+  }
+  __device__ __forceinline__ int query(int i, int Lq) const {
+    if (tiled) {
+      const int y = y0 + i / TW, x = x0 + i % TW;
+      return (y < Hl && x < Wl) ? start + y * Wl + x : -1;
+    }
+    const int q = first_q + i;
+    return q < Lq ? q : -1;
+  }
+};
+
+}  // namespace sdb

@@ -1,0 +1,268 @@
+// Multi-scale deformable attention, forward.  sm_100a.
+//
+// Replaces ms_deformable_im2col_cuda / ms_deformable_im2col_gpu_kernel
+// (/root/reference/detr_od/models/utils/ops/src/cuda/ms_deform_im2col_cuda.cuh:923-954, 237-299).
+//
+// Tuned path (fp32, head dim 32 -- every shipped config):
+//  * 8 lanes own one (query, head) pair; lane j holds channels 4j..4j+3, so every bilinear corner is ONE
+//    128-byte line read as 8 x LDG.128 (the reference reads it as 32 scalar loads per corner and re-reads
+//    the sampling location / weight in all 32 lanes).  A warp works on 4 pairs at a time.
+//  * the 8 lanes of a pair load its sampling locations / weights cooperatively (one coalesced float4 +
+//    float2 per lane = 2 points), each lane turns its 2 points into (pixel offset, row stride, 4 corner
+//    weights pre-multiplied by the attention weight) and the group broadcasts them with width-8 shuffles;
+//  * work is a persistent loop over (image, head, query-tile) items.  When num_query == spatial_size
+//    (encoder self-attention) tiles are TH x TW pixel blocks of one level, so the value lines a CTA gathers
+//    for ONE head (128 B per pixel) stay L1-resident: 16x16 queries touch ~1200 distinct lines (154 KB) for
+//    16384 corner reads.  Streamed operands (loc, attn, out) bypass L1 (L1::no_allocate);
+//  * `out` is written exactly once with 16-byte stores -- no zero-fill pass.
+// Roofline: the gather moves N*Lq*M*L*P*4*128 B through L1 (36 TB/s aggregate) against 4*(value+loc+attn+out)
+// bytes of HBM traffic, so the kernel is L1-wavefront bound at ~30% of the HBM roofline.
+#include "msda_common.cuh"
+
+namespace sdb {
+
+static int g_fwd_variant = 0;
+int g_bwd_variant = 0;
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: any channel count, float or double.  One thread per output element.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_fwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                        const T* __restrict__ attn, long long total, int S, int M, int D, int L, int Lq,
+                        int P, T* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % D);
+    const long long pair = e / D;
+    const int m = (int)(pair % M);
+    const long long n = pair / ((long long)M * Lq);
+    const T* lp = loc + pair * L * P * 2;
+    const T* ap = attn + pair * L * P;
+    const T* vb = value + (n * S * M + m) * (long long)D + c;
+    const long long px = (long long)M * D;  // elements per pixel
+    T acc = 0;
+    for (int l = 0; l < L; ++l) {
+      const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+      const T* vl = vb + lsi[l] * px;
+      for (int p = 0; p < P; ++p) {
+        const Tap<T> t = make_tap<T>(lp[0], lp[1], H, W);
+        const T a = ap[0];
+        lp += 2;
+        ap += 1;
+        if (!t.ok) continue;
+        const T hh = 1 - t.lh, hw = 1 - t.lw;
+        const T* v00 = vl + ((long long)t.h0 * W + t.w0) * px;
+        T s = 0;
+        if (t.c00) s += hh * hw * v00[0];
+        if (t.c01) s += hh * t.lw * v00[px];
+        if (t.c10) s += t.lh * hw * v00[(long long)W * px];
+        if (t.c11) s += t.lh * t.lw * v00[(long long)(W + 1) * px];
+        acc += s * a;
+      }
+    }
+    out[e] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tuned kernel: fp32, D == 32, L*P even.
+// ------------------------------------------------------------------------------------------------
+struct PointPrep {
+  int off;    // float offset of corner (h0,w0), channel 0 of this head, relative to the image's value base
+  int wstr;   // float stride between rows (W * M * 32)
+  float w00, w01, w10, w11;  // corner weights * attention weight, 0 where the corner does not contribute
+};
+
+__device__ __forceinline__ PointPrep prep_point(const LevelTable& lt, int lvl, float x, float y, float a,
+                                                int px_stride, int head_off) {
+  const int H = lt.H[lvl], W = lt.W[lvl];
+  const Tap<float> t = make_tap<float>(x, y, H, W);
+  PointPrep r;
+  const float hh = 1.f - t.lh, hw = 1.f - t.lw;
+  r.w00 = t.c00 ? hh * hw * a : 0.f;
+  r.w01 = t.c01 ? hh * t.lw * a : 0.f;
+  r.w10 = t.c10 ? t.lh * hw * a : 0.f;
+  r.w11 = t.c11 ? t.lh * t.lw * a : 0.f;
+  r.off = (lt.start[lvl] + t.h0 * W + t.w0) * px_stride + head_off;
+  r.wstr = W * px_stride;
+  return r;
+}
+
+template <int kThreads, int TH, int TW, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                    const float* __restrict__ attn, int batch, int S, int M, int L, int Lq, int P,
+                    int tiled, float* __restrict__ out) {
+  __shared__ LevelTable lt;
+  load_levels<TH, TW>(lt, shapes, lsi, L);
+  constexpr int TQ = TH * TW;
+  constexpr int kGroups = kThreads / 8;
+  const int n_tiles = tiled ? lt.tile_begin[L] : (Lq + TQ - 1) / TQ;
+  const long long total = (long long)batch * n_tiles * M;
+  const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+  const int LP = L * P;
+  const int px_stride = M * 32;
+
+  for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+    const int m = (int)(item % M);
+    const long long t2 = item / M;
+    const int tile = (int)(t2 % n_tiles);
+    const int n = (int)(t2 / n_tiles);
+    TileCursor<TH, TW> cur;
+    cur.seek(lt, L, tile, tiled != 0, Lq);
+    const float* vimg = value + (long long)n * S * px_stride;
+    const int head_off = m * 32 + 4 * j;
+
+    for (int i = grp; i < TQ; i += kGroups) {
+      const int q = cur.query(i, Lq);
+      if (q < 0) continue;  // group-uniform
+      const long long pair = ((long long)n * Lq + q) * M + m;
+      const float* lp = loc + pair * LP * 2;
+      const float* ap = attn + pair * LP;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+      for (int c0 = 0; c0 < LP; c0 += 16) {
+        const int pt = c0 + 2 * j;
+        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 a2 = make_float2(0.f, 0.f);
+        if (pt < LP) {
+          l4 = ld_stream_f4(reinterpret_cast<const float4*>(lp + 2 * pt));
+          a2 = ld_stream_f2(reinterpret_cast<const float2*>(ap + pt));
+        }
+        const int lv0 = min(pt / P, L - 1), lv1 = min((pt + 1) / P, L - 1);
+        const PointPrep p0 = prep_point(lt, lv0, l4.x, l4.y, a2.x, px_stride, head_off - 4 * j);
+        const PointPrep p1 = prep_point(lt, lv1, l4.z, l4.w, a2.y, px_stride, head_off - 4 * j);
+        const int npt = min(16, LP - c0);
+#pragma unroll
+        for (int s = 0; s < 16; ++s) {
+          if (s >= npt) break;  // uniform
+          const PointPrep& src = (s & 1) ? p1 : p0;
+          const int sl = s >> 1;
+          const int off = __shfl_sync(gmask, src.off, sl, 8) + 4 * j;
+          const int wstr = __shfl_sync(gmask, src.wstr, sl, 8);
+          const float w00 = __shfl_sync(gmask, src.w00, sl, 8);
+          const float w01 = __shfl_sync(gmask, src.w01, sl, 8);
+          const float w10 = __shfl_sync(gmask, src.w10, sl, 8);
+          const float w11 = __shfl_sync(gmask, src.w11, sl, 8);
+          const float4* b = reinterpret_cast<const float4*>(vimg + off);
+          const int ps4 = px_stride >> 2, ws4 = wstr >> 2;
+          float4 v;
+          if (w00 != 0.f) {
+            v = __ldg(b);
+            acc.x = fmaf(w00, v.x, acc.x); acc.y = fmaf(w00, v.y, acc.y);
+            acc.z = fmaf(w00, v.z, acc.z); acc.w = fmaf(w00, v.w, acc.w);
+          }
+          if (w01 != 0.f) {
+            v = __ldg(b + ps4);
+            acc.x = fmaf(w01, v.x, acc.x); acc.y = fmaf(w01, v.y, acc.y);
+            acc.z = fmaf(w01, v.z, acc.z); acc.w = fmaf(w01, v.w, acc.w);
+          }
+          if (w10 != 0.f) {
+            v = __ldg(b + ws4);
+            acc.x = fmaf(w10, v.x, acc.x); acc.y = fmaf(w10, v.y, acc.y);
+            acc.z = fmaf(w10, v.z, acc.z); acc.w = fmaf(w10, v.w, acc.w);
+          }
+          if (w11 != 0.f) {
+            v = __ldg(b + ws4 + ps4);
+            acc.x = fmaf(w11, v.x, acc.x); acc.y = fmaf(w11, v.y, acc.y);
+            acc.z = fmaf(w11, v.z, acc.z); acc.w = fmaf(w11, v.w, acc.w);
+          }
+        }
+      }
+      st_stream_f4(reinterpret_cast<float4*>(out + pair * 32 + 4 * j), acc);
+    }
+  }
+}
+
+template <int kThreads, int TH, int TW, int kMinBlocks>
+static int launch_fwd_d32(cudaStream_t st, const float* value, const int64_t* shapes, const int64_t* lsi,
+                          const float* loc, const float* attn, int batch, int S, int M, int L, int Lq, int P,
+                          float* out) {
+  auto kern = msda_fwd_d32_kernel<kThreads, TH, TW, kMinBlocks>;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    // all of the unified L1/shared array as cache: the kernel's reuse lives in L1
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    int b = 0;
+    SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, 0));
+    blocks_per_sm = b > 0 ? b : 1;
+  }
+  const int tiled = (Lq == S) ? 1 : 0;
+  // upper bound on items so tiny problems do not launch idle CTAs
+  const long long approx_items = (long long)batch * M * ((Lq + TH * TW - 1) / (TH * TW) + (tiled ? 4 * L : 0));
+  long long grid = (long long)sm_count() * blocks_per_sm;
+  if (grid > approx_items) grid = approx_items;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, tiled, out);
+  SDB_LAUNCH_CHECK("msda_fwd_d32_kernel");
+  return SDB_OK;
+}
+
+template <typename T>
+static int msda_forward(cudaStream_t st, const T* value, const int64_t* shapes, const int64_t* lsi,
+                        const T* loc, const T* attn, int batch, int S, int M, int D, int L, int Lq, int P,
+                        T* out) {
+  SDB_REQUIRE(batch >= 0 && S >= 0 && M > 0 && D > 0 && L > 0 && Lq >= 0 && P > 0,
+              "msda_forward: bad sizes batch=%d spatial=%d heads=%d channels=%d levels=%d query=%d point=%d",
+              batch, S, M, D, L, Lq, P);
+  const long long total = (long long)batch * Lq * M * D;
+  if (total == 0) return SDB_OK;
+  SDB_REQUIRE(value && shapes && lsi && loc && attn && out, "msda_forward: null pointer");
+  if constexpr (sizeof(T) == 4) {
+    const bool fits32 = (long long)S * M * D < (1ll << 31);
+    const bool fast_ok = D == 32 && ((L * P) % 2 == 0) && L <= kMaxLevels && fits32 &&
+                         ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(loc) |
+                           reinterpret_cast<uintptr_t>(attn) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    int v = g_fwd_variant;
+    if (v != 9 && fast_ok) {
+      if (v == 0) v = (Lq == S) ? 1 : 4;
+      switch (v) {
+        case 1: return launch_fwd_d32<1024, 16, 16, 1>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+        case 2: return launch_fwd_d32<512, 8, 16, 2>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+        case 3: return launch_fwd_d32<256, 8, 8, 4>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+        case 5: return launch_fwd_d32<512, 16, 16, 2>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+        case 6: return launch_fwd_d32<256, 16, 16, 4>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+        case 7: return launch_fwd_d32<1024, 8, 32, 1>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+        default: return launch_fwd_d32<256, 4, 8, 4>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+      }
+    }
+  }
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  msda_fwd_generic_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(value, shapes, lsi, loc, attn, total, S, M, D, L,
+                                                               Lq, P, out);
+  SDB_LAUNCH_CHECK("msda_fwd_generic_kernel");
+  return SDB_OK;
+}
+
+}  // namespace sdb
+
+extern "C" int sdb_msda_forward_f32(sdb_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                                    const int64_t* level_start_index, const float* sampling_loc,
+                                    const float* attn_weight, int batch, int spatial_size, int num_heads,
+                                    int channels, int num_levels, int num_query, int num_point, float* out) {
+  return sdb::msda_forward<float>((cudaStream_t)stream, value, spatial_shapes, level_start_index, sampling_loc,
+                                  attn_weight, batch, spatial_size, num_heads, channels, num_levels, num_query,
+                                  num_point, out);
+}
+
+extern "C" int sdb_msda_forward_f64(sdb_stream_t stream, const double* value, const int64_t* spatial_shapes,
+                                    const int64_t* level_start_index, const double* sampling_loc,
+                                    const double* attn_weight, int batch, int spatial_size, int num_heads,
+                                    int channels, int num_levels, int num_query, int num_point, double* out) {
+  return sdb::msda_forward<double>((cudaStream_t)stream, value, spatial_shapes, level_start_index, sampling_loc,
+                                   attn_weight, batch, spatial_size, num_heads, channels, num_levels, num_query,
+                                   num_point, out);
+}
+
+extern "C" int sdb_msda_set_variant(int forward_variant, int backward_variant) {
+  sdb::g_fwd_variant = forward_variant;
+  sdb::g_bwd_variant = backward_variant;
+  return SDB_OK;
+}

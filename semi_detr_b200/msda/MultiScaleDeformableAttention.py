@@ -1,0 +1,89 @@
+"""Drop-in for the reference's compiled extension module ``MultiScaleDeformableAttention``.
+
+The reference builds a pybind11 module of that name exporting ``ms_deform_attn_forward`` and
+``ms_deform_attn_backward`` (detr_od/models/utils/ops/src/vision.cpp:13-16, signatures
+src/ms_deform_attn.h:20-61) and imports it as ``MSDA`` in functions/ms_deform_attn_func.py:18.
+This module has the same two functions with the same argument order, checks and error type, and
+forwards to the sm_100a kernels through the C ABI (include/semidetr_b200.h).  Installing it under
+that name (``sys.modules['MultiScaleDeformableAttention'] = this module``, see
+``semi_detr_b200.install_as_reference_extension``) lets the reference's own ``MSDeformAttnFunction``
+run on it unchanged.
+"""
+import torch
+
+from .. import _lib
+
+_FLOAT = (torch.float32, torch.float64)
+
+
+def _check_inputs(named):
+    # ms_deform_attn_cuda.cu:28-38 / :93-105 -- contiguity and device asserts, same messages
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+    for name, t in named:
+        if not t.is_cuda:
+            if name == "value":
+                raise RuntimeError("Not implemented on the CPU")      # src/ms_deform_attn.h:38,60
+            raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _dims(value, spatial_shapes, sampling_loc, im2col_step):
+    batch, spatial_size, num_heads, channels = value.shape
+    num_levels = spatial_shapes.shape[0]
+    num_query, num_point = sampling_loc.shape[1], sampling_loc.shape[4]
+    step = min(batch, im2col_step)
+    if batch > 0 and (step <= 0 or batch % step != 0):
+        # ms_deform_attn_cuda.cu:50-52
+        raise RuntimeError(f"batch({batch}) must divide im2col_step({step})")
+    return batch, spatial_size, num_heads, channels, num_levels, num_query, num_point
+
+
+def _index_tensors(spatial_shapes, level_start_index):
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64 (torch.long)")
+    return spatial_shapes, level_start_index
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    """-> output (batch, num_query, num_heads*channels).  ms_deform_attn_cuda.cu:20-80."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
+    _index_tensors(spatial_shapes, level_start_index)
+    if value.dtype not in _FLOAT:
+        raise RuntimeError(f'"ms_deform_attn_forward_cuda" not implemented for \'{value.dtype}\'')
+    if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("value, sampling_loc and attn_weight must share one floating dtype")
+    b, s, m, d, l, q, p = _dims(value, spatial_shapes, sampling_loc, im2col_step)
+    out = torch.empty((b, q, m * d), dtype=value.dtype, device=value.device)   # every element is written
+    fn = _lib.lib().sdb_msda_forward_f32 if value.dtype == torch.float32 else _lib.lib().sdb_msda_forward_f64
+    with torch.cuda.device(value.device):
+        rc = fn(_lib.current_stream(value.device), value.data_ptr(), spatial_shapes.data_ptr(),
+                level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                b, s, m, d, l, q, p, out.data_ptr())
+    _lib.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight].  ms_deform_attn_cuda.cu:83-153."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
+    _index_tensors(spatial_shapes, level_start_index)
+    if value.dtype not in _FLOAT:
+        raise RuntimeError(f'"ms_deform_attn_backward_cuda" not implemented for \'{value.dtype}\'')
+    if not (sampling_loc.dtype == attn_weight.dtype == grad_output.dtype == value.dtype):
+        raise RuntimeError("value, sampling_loc, attn_weight and grad_output must share one floating dtype")
+    b, s, m, d, l, q, p = _dims(value, spatial_shapes, sampling_loc, im2col_step)
+    grad_value = torch.empty_like(value)            # zero-filled by the call, stream-ordered
+    grad_loc = torch.empty_like(sampling_loc)       # fully overwritten
+    grad_attn = torch.empty_like(attn_weight)       # fully overwritten
+    fn = _lib.lib().sdb_msda_backward_f32 if value.dtype == torch.float32 else _lib.lib().sdb_msda_backward_f64
+    with torch.cuda.device(value.device):
+        rc = fn(_lib.current_stream(value.device), grad_output.data_ptr(), value.data_ptr(),
+                spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                attn_weight.data_ptr(), b, s, m, d, l, q, p, grad_value.data_ptr(), grad_loc.data_ptr(),
+                grad_attn.data_ptr())
+    _lib.check(rc, "ms_deform_attn_backward")
+    return [grad_value, grad_loc, grad_attn]

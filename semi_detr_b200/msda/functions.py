@@ -1,0 +1,35 @@
+"""``MSDeformAttnFunction`` -- same surface as the reference's autograd Function
+(detr_od/models/utils/ops/functions/ms_deform_attn_func.py:21-38):
+
+    MSDeformAttnFunction.apply(value, value_spatial_shapes, value_level_start_index,
+                               sampling_locations, attention_weights, im2col_step) -> (N, Lq, M*D)
+
+saves the same five tensors, is once-differentiable, and returns ``None`` gradients for the shapes,
+the level start index and ``im2col_step``.  There is deliberately no pure-PyTorch core here: the
+CPU restatement lives under ``oracle/`` and is test infrastructure only.
+"""
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import MultiScaleDeformableAttention as MSDA
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = MSDA.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                             sampling_locations, attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, sampling_locations, attention_weights = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = MSDA.ms_deform_attn_backward(
+            value, shapes, level_start, sampling_locations, attention_weights, grad_output.contiguous(),
+            ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None

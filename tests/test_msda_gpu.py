@@ -1,0 +1,224 @@
+"""MSDA CUDA kernels (through the C ABI) against the oracle, the committed golden vectors from the reference's
+python op, the reference's own CUDA op compiled for sm_100a, and size-independent properties at full size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["testpy", "small_d32", "wide_d32", "odd_d30", "d64_l5", "one_point"]
+FWD_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+BWD_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 9]
+RTOL = 1e-3          # north star: attention tensors within 1e-3 relative of the reference's op
+
+
+def _relerr(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _dev(c, k, dtype):
+    t = torch.from_numpy(c[k]).cuda()
+    return t.to(dtype) if t.is_floating_point() else t
+
+
+def _apply(c, dtype):
+    from semi_detr_b200.msda import MSDeformAttnFunction
+    v = _dev(c, "value", dtype).requires_grad_(True)
+    l = _dev(c, "loc", dtype).requires_grad_(True)
+    a = _dev(c, "attn", dtype).requires_grad_(True)
+    out = MSDeformAttnFunction.apply(v, _dev(c, "shapes", None), _dev(c, "start", None), l, a, 64)
+    out.backward(_dev(c, "gout", dtype))
+    return out.detach(), v.grad, l.grad, a.grad
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_fp64(msda_golden, name):
+    c = msda_golden[name]
+    out, gv, gl, ga = _apply(c, torch.float64)
+    np.testing.assert_allclose(out.cpu().numpy(), c["out"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gv.cpu().numpy(), c["grad_value"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gl.cpu().numpy(), c["grad_loc"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(ga.cpu().numpy(), c["grad_attn"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_fp32(msda_golden, name):
+    c = msda_golden[name]
+    out, gv, gl, ga = _apply(c, torch.float32)
+    if name == "testpy":   # the reference's own tolerance, ops/test.py:55
+        assert torch.allclose(out.cpu().double(), torch.from_numpy(c["out"]), rtol=1e-2, atol=1e-3)
+    for got, key in ((out, "out"), (gv, "grad_value"), (gl, "grad_loc"), (ga, "grad_attn")):
+        assert _relerr(got.cpu(), torch.from_numpy(c[key])) < 1e-5, key
+
+
+@pytest.mark.parametrize("fv", FWD_VARIANTS)
+@pytest.mark.parametrize("mode,Lq", [("encoder", None), ("wide", 300), ("uniform", 77)])
+def test_forward_variants_vs_oracle(fv, mode, Lq):
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import msda_inputs
+    levels = [(19, 27), (10, 14), (5, 7), (3, 4)]
+    x = msda_inputs(levels, N=2, Lq=Lq, mode=mode, seed=fv)
+    ref = O.msda_forward(x["value"].cpu().numpy(), levels, x["start"].cpu().numpy(), x["loc"].cpu().numpy(),
+                         x["attn"].cpu().numpy())
+    _lib.lib().sdb_msda_set_variant(fv, 0)
+    try:
+        out = MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
+    finally:
+        _lib.lib().sdb_msda_set_variant(0, 0)
+    assert _relerr(out.cpu(), torch.from_numpy(ref)) < 1e-5
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=1e-4)
+
+
+@pytest.mark.parametrize("bv", BWD_VARIANTS)
+@pytest.mark.parametrize("mode,Lq", [("encoder", None), ("wide", 300)])
+def test_backward_variants_vs_oracle(bv, mode, Lq):
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import msda_inputs
+    levels = [(19, 27), (10, 14), (5, 7), (3, 4)]
+    x = msda_inputs(levels, N=2, Lq=Lq, mode=mode, seed=10 + bv)
+    gv, gl, ga = O.msda_backward(x["value"].cpu().numpy(), levels, x["start"].cpu().numpy(),
+                                 x["loc"].cpu().numpy(), x["attn"].cpu().numpy(), x["gout"].cpu().numpy())
+    _lib.lib().sdb_msda_set_variant(0, bv)
+    try:
+        got = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["gout"], 64)
+    finally:
+        _lib.lib().sdb_msda_set_variant(0, 0)
+    for g, r, k in zip(got, (gv, gl, ga), ("grad_value", "grad_loc", "grad_attn")):
+        assert _relerr(g.cpu(), torch.from_numpy(r)) < 1e-5, k
+        np.testing.assert_allclose(g.cpu().numpy(), r, rtol=RTOL, atol=2e-3, err_msg=k)
+
+
+def test_five_levels_and_odd_points():
+    """5-scale (L*P = 20: one full + one partial point chunk) on the tuned path; L*P odd -> generic path."""
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import msda_inputs
+    for levels, P in (([(21, 30), (11, 15), (6, 8), (3, 4), (2, 2)], 4), ([(9, 8), (4, 5), (2, 3)], 3)):
+        x = msda_inputs(levels, N=1, P=P, Lq=123, mode="wide", seed=3)
+        a = [x[k].cpu().numpy() for k in ("value",)] + [levels] + [x[k].cpu().numpy() for k in ("start", "loc", "attn")]
+        ref = O.msda_forward(*a)
+        out = MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
+        assert _relerr(out.cpu(), torch.from_numpy(ref)) < 1e-5
+        gref = O.msda_backward(*a, x["gout"].cpu().numpy())
+        got = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["gout"], 64)
+        for g, r in zip(got, gref):
+            assert _relerr(g.cpu(), torch.from_numpy(r)) < 1e-5
+
+
+def test_empty_inputs():
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    shapes = torch.tensor([[3, 4]], device="cuda")
+    start = torch.tensor([0], device="cuda")
+    v = torch.randn(2, 12, 8, 32, device="cuda")
+    loc = torch.zeros(2, 0, 8, 1, 4, 2, device="cuda")
+    att = torch.zeros(2, 0, 8, 1, 4, device="cuda")
+    out = MSDA.ms_deform_attn_forward(v, shapes, start, loc, att, 64)
+    assert out.shape == (2, 0, 256)
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v, shapes, start, loc, att, out, 64)
+    assert gv.shape == v.shape and not gv.any() and gl.shape == loc.shape and ga.shape == att.shape
+
+
+def test_error_behaviour():
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    shapes = torch.tensor([[3, 4]], device="cuda")
+    start = torch.tensor([0], device="cuda")
+    v = torch.randn(3, 12, 8, 32, device="cuda")
+    loc = torch.rand(3, 5, 8, 1, 4, 2, device="cuda")
+    att = torch.rand(3, 5, 8, 1, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="contiguous"):
+        MSDA.ms_deform_attn_forward(v.transpose(2, 3), shapes, start, loc, att, 64)
+    with pytest.raises(RuntimeError, match="must divide"):      # ms_deform_attn_cuda.cu:52
+        MSDA.ms_deform_attn_forward(v, shapes, start, loc, att, 2)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        MSDA.ms_deform_attn_forward(v, shapes.cpu(), start, loc, att, 64)
+
+
+@pytest.mark.parametrize("D", [30, 32, 64, 71])
+def test_reference_gradcheck(D):
+    """ops/test.py:63-86 (same shapes and seed; the very wide heads 1025/2048/3096 run in test_wide_heads)."""
+    from semi_detr_b200.msda import MSDeformAttnFunction
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = 30
+    torch.manual_seed(3)
+    value = (torch.rand(N, S, M, D).cuda() * 0.01).double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).cuda().double().requires_grad_(True)
+    att = torch.rand(N, Lq, M, L, P).cuda() + 1e-5
+    att = (att / att.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, start, loc, att, 2))
+
+
+@pytest.mark.parametrize("D", [1025, 2048, 3096])
+def test_wide_heads(D):
+    """The head widths ops/test.py:85 uses to reach its >1024-channel kernels: here one generic kernel."""
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import msda_inputs
+    levels = [(6, 4), (3, 2)]
+    x = msda_inputs(levels, N=1, M=2, D=D, P=2, Lq=2, mode="wide", seed=D, dtype=torch.float64)
+    a = [x["value"].cpu().numpy(), levels, x["start"].cpu().numpy(), x["loc"].cpu().numpy(), x["attn"].cpu().numpy()]
+    out = MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 2)
+    np.testing.assert_allclose(out.cpu().numpy(), O.msda_forward(*a), rtol=1e-9, atol=1e-12)
+    got = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["gout"], 2)
+    for g, r in zip(got, O.msda_backward(*a, x["gout"].cpu().numpy())):
+        np.testing.assert_allclose(g.cpu().numpy(), r, rtol=1e-8, atol=1e-10)
+
+
+# ---- full-size checks (BASELINE.json config 5 / config 2 shapes) ------------------------------------
+
+@pytest.mark.parametrize("levels_name,mode", [("micro", "encoder"), ("micro", "uniform"), ("coco", "encoder")])
+def test_full_size_against_reference_cuda_op(levels_name, mode):
+    """Same inputs through the reference's own CUDA kernels (compiled for sm_100a) and ours: <= 1e-3 relative."""
+    import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libref_msda.so not built")
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import COCO_4SCALE_LEVELS, MICROBENCH_LEVELS, msda_inputs
+    levels = MICROBENCH_LEVELS if levels_name == "micro" else COCO_4SCALE_LEVELS
+    x = msda_inputs(levels, N=2, mode=mode, Lq=1100, seed=0)
+    args = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"])
+    out = MSDA.ms_deform_attn_forward(*args, 64)
+    ref = ref_cuda.forward(*args)
+    assert _relerr(out, ref) < 1e-5
+    assert torch.allclose(out, ref, rtol=RTOL, atol=1e-4)
+    got = MSDA.ms_deform_attn_backward(*args, x["gout"], 64)
+    want = ref_cuda.backward(*args, x["gout"])
+    for g, r, k in zip(got, want, ("grad_value", "grad_loc", "grad_attn")):
+        assert _relerr(g, r) < 1e-4, k
+        assert torch.allclose(g, r, rtol=RTOL, atol=1e-2 if k == "grad_loc" else 1e-3), k
+
+
+def test_full_size_properties():
+    """Size-independent properties at the microbench size: linearity in value, adjointness of backward
+    (<grad_value, dv> == <grad_out, fwd(dv)>), attention-weight gradient == per-point sampled dot product,
+    and uniform-field invariance (constant value + weights summing to 1 + in-range samples -> constant)."""
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import MICROBENCH_LEVELS, msda_inputs
+    x = msda_inputs(MICROBENCH_LEVELS, N=2, mode="encoder", seed=1)
+    sh, st, loc, att = x["shapes"], x["start"], x["loc"], x["attn"]
+    v1 = x["value"]
+    v2 = torch.randn_like(v1)
+    f = lambda v: MSDA.ms_deform_attn_forward(v, sh, st, loc, att, 64)
+    o1, o2, o12 = f(v1), f(v2), f(v1 + 2 * v2)
+    assert _relerr(o12, o1 + 2 * o2) < 1e-5
+    gv, gl, ga = MSDA.ms_deform_attn_backward(v1, sh, st, loc, att, x["gout"], 64)
+    lhs = (gv.double() * v2.double()).sum()
+    rhs = (x["gout"].double() * o2.double()).sum()
+    assert abs(lhs - rhs) / abs(rhs) < 1e-5
+    # d out / d attn is linear in attn: <ga, att> == <gout, out>
+    assert abs((ga.double() * att.double()).sum() - (x["gout"].double() * o1.double()).sum()) / \
+        abs((x["gout"].double() * o1.double()).sum()) < 1e-5
+    # constant field: interior samples reproduce the constant, so out <= c everywhere and == c in the interior
+    c = torch.full_like(v1, 3.0)
+    loc_in = loc.clamp(0.2, 0.8)
+    oc = MSDA.ms_deform_attn_forward(c, sh, st, loc_in, att, 64)
+    assert torch.allclose(oc, torch.full_like(oc, 3.0), rtol=1e-5)
+    gvc, glc, _ = MSDA.ms_deform_attn_backward(c, sh, st, loc_in, att, x["gout"], 64)
+    assert glc.abs().max() < 1e-3          # no spatial gradient on a constant field
+    # grad_value of an interior-sampled field sums to sum(grad_out * 1) per (n, head, channel)
+    N, S, M, D = v1.shape
+    assert _relerr(gvc.sum(1), x["gout"].view(N, -1, M, D).sum(1)) < 1e-4
