@@ -12,6 +12,14 @@ void set_error(const char* fmt, ...);
 int cuda_error(cudaError_t e, const char* what);
 int sm_count();
 
+// predicated form: no branch around the reduction
+__device__ __forceinline__ void red_add_f4_if(bool pred, float* p, float x, float y, float z, float w) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+      ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w), "r"((int)pred));  // no "memory" clobber: grad_value is
+  // write-only in the kernel, and a clobber would pin every corner load behind the previous point's reductions
+}
+
 }  // namespace sdb
 
 #define SDB_REQUIRE(cond, ...)       \

@@ -10,10 +10,10 @@
 //  * same 8-lanes-per-(query, head) ownership and persistent tiled work list as the forward kernel;
 //  * grad_value: one `red.global.add.v4.f32` per lane per corner -- a whole 128-byte line per 8 lanes and
 //    4x fewer L2 atomic transactions than scalar atomicAdd;
-//  * grad_sampling_loc / grad_attn_weight: the sum over the 32 channels is 4 in-register adds + a 3-step
-//    width-8 shuffle tree, no shared memory, no barrier; the lane that loaded a point keeps its result and the
-//    group writes them back as one coalesced float4 + float2 per lane, so these two tensors are written
-//    exactly once (no zero-fill pass; the reference memsets all three gradients);
+//  * grad_sampling_loc / grad_attn_weight: per point each lane reduces its 4 channels to four corner dot
+//    products; a width-8 reduce-scatter (4 shuffles per point, no shared memory, no barrier) sums them over the
+//    head and one lane pair finishes the point, so these two tensors are written exactly once (no zero-fill
+//    pass; the reference memsets all three gradients);
 //  * grad_value is zero-filled with one cudaMemsetAsync on the same stream.
 // Summation order differs from the reference's (fp32 atomics are unordered there too); parity is to 1e-3 rel.
 #include "msda_common.cuh"
@@ -88,25 +88,29 @@ msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ va
 }
 
 // ------------------------------------------------------------------------------------------------
-// tuned kernel: fp32, D == 32, L*P even.
+// tuned kernel: fp32, D == 32, num_heads == 8, num_point == 4 (every shipped config).
+//
+// Per point every lane needs only FOUR scalars from its 4 channels: d_k = <grad_out, value_corner_k>.  With
+// tgv = a * grad_out the reference's three sums over the 32 channels collapse to
+//   grad_attn = sum_k w_k d_k,  grad_x = W a (hh (d01-d00) + lh (d11-d10)),  grad_y = H a (hw (d10-d00) + lw (d11-d01))
+// so the cross-lane work is a reduce-scatter of 4 values per point (4 shuffles per point, in batches of 4
+// points) instead of the reference's shared-memory staging + serial sum.
 // ------------------------------------------------------------------------------------------------
 struct BwdPrep {
-  int off, wstr;     // as in the forward kernel
-  float lh, lw, a;   // fractional offsets and attention weight (0,0,0 when the sample is out of range)
-  int info;          // bits 0..3 corner validity, bits 4.. level index
+  int offm;        // float offset of pixel (h0,w0) in the image (multiple of 256) | corner-validity bits 0..3
+  float lh, lw, a; // fractional offsets, attention weight (all 0 when the sample is out of range / dead)
 };
 
 __device__ __forceinline__ BwdPrep bwd_prep(const LevelTable& lt, int lvl, float x, float y, float a,
-                                            int px_stride, int head_off) {
+                                            int px_stride) {
   const int H = lt.H[lvl], W = lt.W[lvl];
   const Tap<float> t = make_tap<float>(x, y, H, W);
   BwdPrep r;
   r.lh = t.lh;
   r.lw = t.lw;
   r.a = t.ok ? a : 0.f;
-  r.info = (t.c00 ? 1 : 0) | (t.c01 ? 2 : 0) | (t.c10 ? 4 : 0) | (t.c11 ? 8 : 0) | (lvl << 4);
-  r.off = (lt.start[lvl] + t.h0 * W + t.w0) * px_stride + head_off;
-  r.wstr = W * px_stride;
+  const int mask = (t.c00 ? 1 : 0) | (t.c01 ? 2 : 0) | (t.c10 ? 4 : 0) | (t.c11 ? 8 : 0);
+  r.offm = ((lt.start[lvl] + t.h0 * W + t.w0) * px_stride) | mask;
   return r;
 }
 
@@ -114,24 +118,27 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
+constexpr unsigned kFull = 0xffffffffu;
+
 template <int kThreads, int TH, int TW, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
-                    const float* __restrict__ loc, const float* __restrict__ attn, int batch, int S, int M,
-                    int L, int Lq, int P, int tiled, float* __restrict__ grad_value,
-                    float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+                    const float* __restrict__ loc, const float* __restrict__ attn, int batch, int S, int L,
+                    int Lq, int tiled, float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                    float* __restrict__ grad_attn) {
+  constexpr int M = 8, P = 4;
+  constexpr int px_stride = M * 32;
   __shared__ LevelTable lt;
-  load_levels<TH, TW>(lt, shapes, lsi, L);
+  load_levels<TH, TW>(lt, shapes, lsi, L, px_stride);
   constexpr int TQ = TH * TW;
   constexpr int kGroups = kThreads / 8;
+  static_assert(TQ % kGroups == 0 && kGroups % 4 == 0, "tile must be a whole number of CTA passes");
   const int n_tiles = tiled ? lt.tile_begin[L] : (Lq + TQ - 1) / TQ;
   const long long total = (long long)batch * n_tiles * M;
   const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
-  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+  const bool hi4 = (j & 4) != 0, hi2 = (j & 2) != 0;
   const int LP = L * P;
-  const int px_stride = M * 32;
-  const int ps4 = px_stride >> 2;
 
   for (long long item = blockIdx.x; item < total; item += gridDim.x) {
     const int m = (int)(item % M);
@@ -140,98 +147,101 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
     const int n = (int)(t2 / n_tiles);
     TileCursor<TH, TW> cur;
     cur.seek(lt, L, tile, tiled != 0, Lq);
-    const long long img = (long long)n * S * px_stride;
-    const float* vimg = value + img;
-    float* gvimg = grad_value + img;
-    const int head_off = m * 32;
+    const long long img = (long long)n * S * px_stride + m * 32 + 4 * j;
+    const float* vhead = value + img;
+    float* gvhead = grad_value + img;
 
-    for (int i = grp; i < TQ; i += kGroups) {
-      const int q = cur.query(i, Lq);
-      if (q < 0) continue;  // group-uniform
-      const long long pair = ((long long)n * Lq + q) * M + m;
+#pragma unroll 1
+    for (int it = 0; it < TQ / kGroups; ++it) {   // compile-time trip count: shuffles stay convergent
+      const int q = cur.query(grp + it * kGroups, Lq);
+      const bool live = q >= 0;
+      const long long pair = ((long long)n * Lq + (live ? q : 0)) * M + m;
       const float* lp = loc + pair * LP * 2;
       const float* ap = attn + pair * LP;
-      const float4 g = ld_stream_f4(reinterpret_cast<const float4*>(grad_out + pair * 32 + 4 * j));
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) g = ld_stream_f4(reinterpret_cast<const float4*>(grad_out + pair * 32 + 4 * j));
 
+#pragma unroll 1
       for (int c0 = 0; c0 < LP; c0 += 16) {
         const int pt = c0 + 2 * j;
         float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 a2 = make_float2(0.f, 0.f);
-        if (pt < LP) {
+        if (live && pt < LP) {
           l4 = ld_stream_f4(reinterpret_cast<const float4*>(lp + 2 * pt));
           a2 = ld_stream_f2(reinterpret_cast<const float2*>(ap + pt));
         }
-        const int lv0 = min(pt / P, L - 1), lv1 = min((pt + 1) / P, L - 1);
-        const BwdPrep p0 = bwd_prep(lt, lv0, l4.x, l4.y, a2.x, px_stride, head_off);
-        const BwdPrep p1 = bwd_prep(lt, lv1, l4.z, l4.w, a2.y, px_stride, head_off);
-        float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);  // (d/dx, d/dy) of this lane's two points
-        float2 gatt = make_float2(0.f, 0.f);
-        const int npt = min(16, LP - c0);
+        const int lvj = min(pt / P, L - 1);   // both of this lane's points sit on one level (P = 4)
+        const BwdPrep p0 = bwd_prep(lt, lvj, l4.x, l4.y, a2.x, px_stride);
+        const BwdPrep p1 = bwd_prep(lt, lvj, l4.z, l4.w, a2.y, px_stride);
+        const int nb = min(4, (LP - c0) / 4);
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-          if (s >= npt) break;  // uniform
-          const BwdPrep& src = (s & 1) ? p1 : p0;
-          const int sl = s >> 1;
-          const int off = __shfl_sync(gmask, src.off, sl, 8) + 4 * j;
-          const int ws4 = __shfl_sync(gmask, src.wstr, sl, 8) >> 2;
-          const float lh = __shfl_sync(gmask, src.lh, sl, 8);
-          const float lw = __shfl_sync(gmask, src.lw, sl, 8);
-          const float a = __shfl_sync(gmask, src.a, sl, 8);
-          const int info = __shfl_sync(gmask, src.info, sl, 8);
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          const float4 tg = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
-          const float4* b = reinterpret_cast<const float4*>(vimg + off);
-          float* gb = gvimg + off;
-          float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
-          if (info & 1) {
-            v00 = __ldg(b);
-            const float w = hh * hw;
-            red_add_f4(gb, make_float4(w * tg.x, w * tg.y, w * tg.z, w * tg.w));
-          }
-          if (info & 2) {
-            v01 = __ldg(b + ps4);
-            const float w = hh * lw;
-            red_add_f4(gb + px_stride, make_float4(w * tg.x, w * tg.y, w * tg.z, w * tg.w));
-          }
-          if (info & 4) {
-            v10 = __ldg(b + ws4);
-            const float w = lh * hw;
-            red_add_f4(gb + 4 * ws4, make_float4(w * tg.x, w * tg.y, w * tg.z, w * tg.w));
-          }
-          if (info & 8) {
-            v11 = __ldg(b + ws4 + ps4);
-            const float w = lh * lw;
-            red_add_f4(gb + 4 * ws4 + px_stride, make_float4(w * tg.x, w * tg.y, w * tg.z, w * tg.w));
-          }
-          // d(out)/d(attn) = g . bilinear(value);  d/dh, d/dw via the corner differences
-          const float4 top = make_float4(v01.x - v00.x, v01.y - v00.y, v01.z - v00.z, v01.w - v00.w);
-          const float4 bot = make_float4(v11.x - v10.x, v11.y - v10.y, v11.z - v10.z, v11.w - v10.w);
-          const float4 lef = make_float4(v10.x - v00.x, v10.y - v00.y, v10.z - v00.z, v10.w - v00.w);
-          const float4 rig = make_float4(v11.x - v01.x, v11.y - v01.y, v11.z - v01.z, v11.w - v01.w);
-          const float4 val = make_float4(
-              hh * (hw * v00.x + lw * v01.x) + lh * (hw * v10.x + lw * v11.x),
-              hh * (hw * v00.y + lw * v01.y) + lh * (hw * v10.y + lw * v11.y),
-              hh * (hw * v00.z + lw * v01.z) + lh * (hw * v10.z + lw * v11.z),
-              hh * (hw * v00.w + lw * v01.w) + lh * (hw * v10.w + lw * v11.w));
-          float ga = dot4(g, val);
-          float gw = hh * dot4(tg, top) + lh * dot4(tg, bot);
-          float gh = hw * dot4(tg, lef) + lw * dot4(tg, rig);
+        for (int b = 0; b < 4; ++b) {   // batch of 4 points = one level
+          if (b >= nb) break;           // warp-uniform
+          const int lvl = min((c0 + 4 * b) / P, L - 1);
+          const int ws = lt.wstr[lvl];
+          float d[4][4];
+          float klh = 0.f, klw = 0.f, ka = 0.f;   // the point this lane finalises: batch index j >> 1
 #pragma unroll
-          for (int o = 4; o > 0; o >>= 1) {
-            ga += __shfl_xor_sync(gmask, ga, o, 8);
-            gw += __shfl_xor_sync(gmask, gw, o, 8);
-            gh += __shfl_xor_sync(gmask, gh, o, 8);
+          for (int r = 0; r < 4; ++r) {
+            const int sl = 2 * b + (r >> 1);
+            const BwdPrep& src = (r & 1) ? p1 : p0;
+            const int offm = __shfl_sync(kFull, src.offm, sl, 8);
+            const float lh = __shfl_sync(kFull, src.lh, sl, 8);
+            const float lw = __shfl_sync(kFull, src.lw, sl, 8);
+            const float a = __shfl_sync(kFull, src.a, sl, 8);
+            if ((j >> 1) == r) { klh = lh; klw = lw; ka = a; }
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const float4 tg = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+            const int off = offm & ~15;
+            const float* pv = vhead + off;
+            float* pg = gvhead + off;
+            float4 v00, v01, v10, v11;
+            const bool q00 = offm & 1, q01 = offm & 2, q10 = offm & 4, q11 = offm & 8;
+            if (q00) v00 = __ldg(reinterpret_cast<const float4*>(pv));
+            if (q01) v01 = __ldg(reinterpret_cast<const float4*>(pv + px_stride));
+            if (q10) v10 = __ldg(reinterpret_cast<const float4*>(pv + ws));
+            if (q11) v11 = __ldg(reinterpret_cast<const float4*>(pv + ws + px_stride));
+            {
+              // the reductions need no loaded data: they fill the wait for the four corner loads
+              const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
+              red_add_f4_if(q00, pg, w00 * tg.x, w00 * tg.y, w00 * tg.z, w00 * tg.w);
+              red_add_f4_if(q01, pg + px_stride, w01 * tg.x, w01 * tg.y, w01 * tg.z, w01 * tg.w);
+              red_add_f4_if(q10, pg + ws, w10 * tg.x, w10 * tg.y, w10 * tg.z, w10 * tg.w);
+              red_add_f4_if(q11, pg + ws + px_stride, w11 * tg.x, w11 * tg.y, w11 * tg.z, w11 * tg.w);
+            }
+            d[r][0] = q00 ? dot4(g, v00) : 0.f;
+            d[r][1] = q01 ? dot4(g, v01) : 0.f;
+            d[r][2] = q10 ? dot4(g, v10) : 0.f;
+            d[r][3] = q11 ? dot4(g, v11) : 0.f;
           }
-          if (j == sl) {
-            const int lvl = info >> 4;
-            const float Wf = (float)lt.W[lvl], Hf = (float)lt.H[lvl];
-            if (s & 1) { gl.z = Wf * gw; gl.w = Hf * gh; gatt.y = ga; }
-            else       { gl.x = Wf * gw; gl.y = Hf * gh; gatt.x = ga; }
+          // reduce-scatter over the 8 lanes: afterwards lanes (j, j^1) hold the sums of point j >> 1
+          float e[2][4], f[4];
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float keep = hi4 ? d[r + 2][k] : d[r][k];
+              const float send = hi4 ? d[r][k] : d[r + 2][k];
+              e[r][k] = keep + __shfl_xor_sync(kFull, send, 4, 8);
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float keep = hi2 ? e[1][k] : e[0][k];
+            const float send = hi2 ? e[0][k] : e[1][k];
+            f[k] = keep + __shfl_xor_sync(kFull, send, 2, 8);
+            f[k] += __shfl_xor_sync(kFull, f[k], 1, 8);
           }
-        }
-        if (pt < LP) {
-          st_stream_f4(reinterpret_cast<float4*>(grad_loc + pair * LP * 2 + 2 * pt), gl);
-          st_stream_f2(reinterpret_cast<float2*>(grad_attn + pair * LP + pt), gatt);
+          const float hh = 1.f - klh, hw = 1.f - klw;
+          const int point = c0 + 4 * b + (j >> 1);
+          if (live) {
+            if ((j & 1) == 0) {
+              const float gx = (float)lt.W[lvl] * ka * (hh * (f[1] - f[0]) + klh * (f[3] - f[2]));
+              const float gy = (float)lt.H[lvl] * ka * (hw * (f[2] - f[0]) + klw * (f[3] - f[1]));
+              st_stream_f2(reinterpret_cast<float2*>(grad_loc + (pair * LP + point) * 2), make_float2(gx, gy));
+            } else {
+              grad_attn[pair * LP + point] = hh * (hw * f[0] + klw * f[1]) + klh * (hw * f[2] + klw * f[3]);
+            }
+          }
         }
       }
     }
@@ -255,11 +265,13 @@ static int launch_bwd_d32(cudaStream_t st, const float* grad_out, const float* v
   long long grid = (long long)sm_count() * blocks_per_sm;
   if (grid > approx_items) grid = approx_items;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, kThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P,
-                                           tiled, grad_value, grad_loc, grad_attn);
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, batch, S, L, Lq, tiled,
+                                           grad_value, grad_loc, grad_attn);
   SDB_LAUNCH_CHECK("msda_bwd_d32_kernel");
   return SDB_OK;
 }
+
+#define SDB_BWD_ARGS st, grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, grad_value, grad_loc, grad_attn
 
 template <typename T>
 static int msda_backward(cudaStream_t st, const T* grad_out, const T* value, const int64_t* shapes,
@@ -283,17 +295,17 @@ static int msda_backward(cudaStream_t st, const T* grad_out, const T* value, con
                          reinterpret_cast<uintptr_t>(attn) | reinterpret_cast<uintptr_t>(grad_out) |
                          reinterpret_cast<uintptr_t>(grad_value) | reinterpret_cast<uintptr_t>(grad_loc) |
                          reinterpret_cast<uintptr_t>(grad_attn);
-    const bool fast_ok = D == 32 && ((L * P) % 2 == 0) && L <= kMaxLevels && fits32 && (al & 15) == 0;
+    const bool fast_ok = D == 32 && M == 8 && P == 4 && L <= kMaxLevels && fits32 && (al & 15) == 0;
     int v = g_bwd_variant;
     if (v != 9 && fast_ok) {
-      if (v == 0) v = (Lq == S) ? 2 : 4;
+      if (v == 0) v = 1;  // measured best on B200 (profiles/)
       switch (v) {
-        case 1: return launch_bwd_d32<1024, 16, 16, 1>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, grad_value, grad_loc, grad_attn);
-        case 2: return launch_bwd_d32<512, 8, 16, 2>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, grad_value, grad_loc, grad_attn);
-        case 3: return launch_bwd_d32<256, 8, 8, 4>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, grad_value, grad_loc, grad_attn);
-        case 5: return launch_bwd_d32<512, 16, 16, 2>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, grad_value, grad_loc, grad_attn);
-        case 6: return launch_bwd_d32<256, 16, 16, 4>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, grad_value, grad_loc, grad_attn);
-        default: return launch_bwd_d32<256, 4, 8, 4>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, grad_value, grad_loc, grad_attn);
+        case 1: return launch_bwd_d32<128, 4, 8, 6>(SDB_BWD_ARGS);
+        case 2: return launch_bwd_d32<256, 4, 8, 3>(SDB_BWD_ARGS);
+        case 3: return launch_bwd_d32<256, 4, 8, 2>(SDB_BWD_ARGS);
+        case 4: return launch_bwd_d32<128, 4, 8, 8>(SDB_BWD_ARGS);
+        case 5: return launch_bwd_d32<128, 4, 8, 4>(SDB_BWD_ARGS);
+        default: return launch_bwd_d32<512, 8, 8, 1>(SDB_BWD_ARGS);
       }
     }
   }

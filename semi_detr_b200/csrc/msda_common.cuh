@@ -44,18 +44,20 @@ __device__ __forceinline__ Tap<T> make_tap(T x, T y, int H, int W) {
 // tiles are TH*TW consecutive queries.
 struct LevelTable {
   int H[kMaxLevels], W[kMaxLevels], start[kMaxLevels], tiles_x[kMaxLevels];
+  int wstr[kMaxLevels];  // floats between two rows of the level: W * num_heads * 32
   int tile_begin[kMaxLevels + 1];
 };
 
 template <int TH, int TW>
 __device__ __forceinline__ void load_levels(LevelTable& t, const int64_t* __restrict__ shapes,
-                                            const int64_t* __restrict__ lsi, int L) {
+                                            const int64_t* __restrict__ lsi, int L, int px_stride = 0) {
   if (threadIdx.x < L) {
     const int l = threadIdx.x;
     t.H[l] = (int)shapes[2 * l];
     t.W[l] = (int)shapes[2 * l + 1];
     t.start[l] = (int)lsi[l];
     t.tiles_x[l] = (t.W[l] + TW - 1) / TW;
+    t.wstr[l] = t.W[l] * px_stride;
   }
   __syncthreads();
   if (threadIdx.x == 0) {

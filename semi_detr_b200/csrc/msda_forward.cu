@@ -68,16 +68,17 @@ msda_fwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// tuned kernel: fp32, D == 32, L*P even.
+// tuned kernel: fp32, D == 32, L*P even.  kHeads / kPoints > 0 bake num_heads / num_point in (8 / 4 in every
+// shipped config) so corner strides are immediates and a point's level is a shift; 0 = runtime values.
 // ------------------------------------------------------------------------------------------------
 struct PointPrep {
-  int off;    // float offset of corner (h0,w0), channel 0 of this head, relative to the image's value base
-  int wstr;   // float stride between rows (W * M * 32)
+  int off;    // float offset of pixel (h0,w0) relative to the image's value base (head / channel offset excluded)
+  int wstr;   // float stride between rows of the point's level
   float w00, w01, w10, w11;  // corner weights * attention weight, 0 where the corner does not contribute
 };
 
 __device__ __forceinline__ PointPrep prep_point(const LevelTable& lt, int lvl, float x, float y, float a,
-                                                int px_stride, int head_off) {
+                                                int px_stride) {
   const int H = lt.H[lvl], W = lt.W[lvl];
   const Tap<float> t = make_tap<float>(x, y, H, W);
   PointPrep r;
@@ -86,27 +87,36 @@ __device__ __forceinline__ PointPrep prep_point(const LevelTable& lt, int lvl, f
   r.w01 = t.c01 ? hh * t.lw * a : 0.f;
   r.w10 = t.c10 ? t.lh * hw * a : 0.f;
   r.w11 = t.c11 ? t.lh * t.lw * a : 0.f;
-  r.off = (lt.start[lvl] + t.h0 * W + t.w0) * px_stride + head_off;
-  r.wstr = W * px_stride;
+  r.off = (lt.start[lvl] + t.h0 * W + t.w0) * px_stride;
+  r.wstr = lt.wstr[lvl];
   return r;
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks>
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  acc.x = fmaf(w, v.x, acc.x);
+  acc.y = fmaf(w, v.y, acc.y);
+  acc.z = fmaf(w, v.z, acc.z);
+  acc.w = fmaf(w, v.w, acc.w);
+}
+
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, int batch, int S, int M, int L, int Lq, int P,
                     int tiled, float* __restrict__ out) {
   __shared__ LevelTable lt;
-  load_levels<TH, TW>(lt, shapes, lsi, L);
+  const int px_stride = kHeads > 0 ? kHeads * 32 : M * 32;
+  load_levels<TH, TW>(lt, shapes, lsi, L, px_stride);
   constexpr int TQ = TH * TW;
   constexpr int kGroups = kThreads / 8;
+  static_assert(TQ % 4 == 0 && kGroups % 4 == 0, "warp-uniform trip counts need whole warps of groups");
   const int n_tiles = tiled ? lt.tile_begin[L] : (Lq + TQ - 1) / TQ;
   const long long total = (long long)batch * n_tiles * M;
   const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;
-  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
   const int LP = L * P;
-  const int px_stride = M * 32;
 
   for (long long item = blockIdx.x; item < total; item += gridDim.x) {
     const int m = (int)(item % M);
@@ -115,13 +125,16 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
     const int n = (int)(t2 / n_tiles);
     TileCursor<TH, TW> cur;
     cur.seek(lt, L, tile, tiled != 0, Lq);
-    const float* vimg = value + (long long)n * S * px_stride;
-    const int head_off = m * 32 + 4 * j;
+    const float* vhead = value + (long long)n * S * px_stride + m * 32 + 4 * j;
 
-    for (int i = grp; i < TQ; i += kGroups) {
+    // every group of the warp runs the same trip counts: shuffles stay full-mask and convergent
+    static_assert(TQ % kGroups == 0, "tile must be a whole number of CTA passes");
+#pragma unroll 1
+    for (int it = 0; it < TQ / kGroups; ++it) {   // compile-time trip count: provably convergent shuffles
+      const int i = grp + it * kGroups;
       const int q = cur.query(i, Lq);
-      if (q < 0) continue;  // group-uniform
-      const long long pair = ((long long)n * Lq + q) * M + m;
+      const bool live = q >= 0;
+      const long long pair = ((long long)n * Lq + (live ? q : 0)) * M + m;
       const float* lp = loc + pair * LP * 2;
       const float* ap = attn + pair * LP;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -129,61 +142,65 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
       for (int c0 = 0; c0 < LP; c0 += 16) {
         const int pt = c0 + 2 * j;
         float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 a2 = make_float2(0.f, 0.f);
-        if (pt < LP) {
+        float2 a2 = make_float2(0.f, 0.f);   // weight 0 -> a dead group / padded point gathers nothing
+        if (live && pt < LP) {
           l4 = ld_stream_f4(reinterpret_cast<const float4*>(lp + 2 * pt));
           a2 = ld_stream_f2(reinterpret_cast<const float2*>(ap + pt));
         }
-        const int lv0 = min(pt / P, L - 1), lv1 = min((pt + 1) / P, L - 1);
-        const PointPrep p0 = prep_point(lt, lv0, l4.x, l4.y, a2.x, px_stride, head_off - 4 * j);
-        const PointPrep p1 = prep_point(lt, lv1, l4.z, l4.w, a2.y, px_stride, head_off - 4 * j);
+        int lv0, lv1;
+        if (kPoints > 0) { lv0 = pt / kPoints; lv1 = (pt + 1) / kPoints; }
+        else             { lv0 = pt / P;       lv1 = (pt + 1) / P; }
+        lv0 = min(lv0, L - 1);
+        lv1 = min(lv1, L - 1);
+        const PointPrep p0 = prep_point(lt, lv0, l4.x, l4.y, a2.x, px_stride);
+        const PointPrep p1 = prep_point(lt, lv1, l4.z, l4.w, a2.y, px_stride);
         const int npt = min(16, LP - c0);
 #pragma unroll
-        for (int s = 0; s < 16; ++s) {
-          if (s >= npt) break;  // uniform
-          const PointPrep& src = (s & 1) ? p1 : p0;
-          const int sl = s >> 1;
-          const int off = __shfl_sync(gmask, src.off, sl, 8) + 4 * j;
-          const int wstr = __shfl_sync(gmask, src.wstr, sl, 8);
-          const float w00 = __shfl_sync(gmask, src.w00, sl, 8);
-          const float w01 = __shfl_sync(gmask, src.w01, sl, 8);
-          const float w10 = __shfl_sync(gmask, src.w10, sl, 8);
-          const float w11 = __shfl_sync(gmask, src.w11, sl, 8);
-          const float4* b = reinterpret_cast<const float4*>(vimg + off);
-          const int ps4 = px_stride >> 2, ws4 = wstr >> 2;
-          float4 v;
-          if (w00 != 0.f) {
-            v = __ldg(b);
-            acc.x = fmaf(w00, v.x, acc.x); acc.y = fmaf(w00, v.y, acc.y);
-            acc.z = fmaf(w00, v.z, acc.z); acc.w = fmaf(w00, v.w, acc.w);
+        for (int s = 0; s < 16; s += kStep) {
+          if (s >= npt) break;  // warp-uniform (L*P is a multiple of kStep on this path)
+          // kStep points per step: all their corner loads are issued before the first use
+          int off[kStep], ws[kStep];
+          float w[kStep][4];
+#pragma unroll
+          for (int u = 0; u < kStep; ++u) {
+            const int sl = (s + u) >> 1;  // lane of the group that prepared point s+u
+            const PointPrep& src = ((s + u) & 1) ? p1 : p0;
+            off[u] = __shfl_sync(kFull, src.off, sl, 8);
+            w[u][0] = __shfl_sync(kFull, src.w00, sl, 8);
+            w[u][1] = __shfl_sync(kFull, src.w01, sl, 8);
+            w[u][2] = __shfl_sync(kFull, src.w10, sl, 8);
+            w[u][3] = __shfl_sync(kFull, src.w11, sl, 8);
+            if (kPoints > 0 && kPoints % kStep == 0) ws[u] = lt.wstr[min((c0 + s) / kPoints, L - 1)];
+            else ws[u] = __shfl_sync(kFull, src.wstr, sl, 8);
           }
-          if (w01 != 0.f) {
-            v = __ldg(b + ps4);
-            acc.x = fmaf(w01, v.x, acc.x); acc.y = fmaf(w01, v.y, acc.y);
-            acc.z = fmaf(w01, v.z, acc.z); acc.w = fmaf(w01, v.w, acc.w);
+          float4 v[kStep][4];
+#pragma unroll
+          for (int u = 0; u < kStep; ++u) {
+            const float* pa = vhead + off[u];
+            const float* pa2 = pa + ws[u];
+            // a corner with zero weight (outside the map, or a dead / padded point) is neither loaded nor used
+            if (w[u][0] != 0.f) v[u][0] = __ldg(reinterpret_cast<const float4*>(pa));
+            if (w[u][1] != 0.f) v[u][1] = __ldg(reinterpret_cast<const float4*>(pa + px_stride));
+            if (w[u][2] != 0.f) v[u][2] = __ldg(reinterpret_cast<const float4*>(pa2));
+            if (w[u][3] != 0.f) v[u][3] = __ldg(reinterpret_cast<const float4*>(pa2 + px_stride));
           }
-          if (w10 != 0.f) {
-            v = __ldg(b + ws4);
-            acc.x = fmaf(w10, v.x, acc.x); acc.y = fmaf(w10, v.y, acc.y);
-            acc.z = fmaf(w10, v.z, acc.z); acc.w = fmaf(w10, v.w, acc.w);
-          }
-          if (w11 != 0.f) {
-            v = __ldg(b + ws4 + ps4);
-            acc.x = fmaf(w11, v.x, acc.x); acc.y = fmaf(w11, v.y, acc.y);
-            acc.z = fmaf(w11, v.z, acc.z); acc.w = fmaf(w11, v.w, acc.w);
-          }
+#pragma unroll
+          for (int u = 0; u < kStep; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (w[u][k] != 0.f) fma4(acc, w[u][k], v[u][k]);
         }
       }
-      st_stream_f4(reinterpret_cast<float4*>(out + pair * 32 + 4 * j), acc);
+      if (live) st_stream_f4(reinterpret_cast<float4*>(out + pair * 32 + 4 * j), acc);
     }
   }
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks>
+template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep>
 static int launch_fwd_d32(cudaStream_t st, const float* value, const int64_t* shapes, const int64_t* lsi,
                           const float* loc, const float* attn, int batch, int S, int M, int L, int Lq, int P,
                           float* out) {
-  auto kern = msda_fwd_d32_kernel<kThreads, TH, TW, kMinBlocks>;
+  auto kern = msda_fwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kHeads, kPoints, kStep>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     // all of the unified L1/shared array as cache: the kernel's reuse lives in L1
@@ -203,6 +220,8 @@ static int launch_fwd_d32(cudaStream_t st, const float* value, const int64_t* sh
   return SDB_OK;
 }
 
+#define SDB_FWD_ARGS st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out
+
 template <typename T>
 static int msda_forward(cudaStream_t st, const T* value, const int64_t* shapes, const int64_t* lsi,
                         const T* loc, const T* attn, int batch, int S, int M, int D, int L, int Lq, int P,
@@ -220,16 +239,22 @@ static int msda_forward(cudaStream_t st, const T* value, const int64_t* shapes, 
                            reinterpret_cast<uintptr_t>(attn) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     int v = g_fwd_variant;
     if (v != 9 && fast_ok) {
-      if (v == 0) v = (Lq == S) ? 1 : 4;
-      switch (v) {
-        case 1: return launch_fwd_d32<1024, 16, 16, 1>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
-        case 2: return launch_fwd_d32<512, 8, 16, 2>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
-        case 3: return launch_fwd_d32<256, 8, 8, 4>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
-        case 5: return launch_fwd_d32<512, 16, 16, 2>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
-        case 6: return launch_fwd_d32<256, 16, 16, 4>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
-        case 7: return launch_fwd_d32<1024, 8, 32, 1>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
-        default: return launch_fwd_d32<256, 4, 8, 4>(st, value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, out);
+      if (v == 0) v = 1;  // measured best on B200 (profiles/)
+      if (M == 8 && P == 4) {
+        switch (v) {
+          case 1:
+            if (Lq == S) return launch_fwd_d32<256, 8, 8, 3, 8, 4, 2>(SDB_FWD_ARGS);
+            return launch_fwd_d32<256, 4, 8, 3, 8, 4, 2>(SDB_FWD_ARGS);
+          case 2: return launch_fwd_d32<256, 4, 8, 4, 8, 4, 2>(SDB_FWD_ARGS);
+          case 3: return launch_fwd_d32<256, 4, 8, 2, 8, 4, 4>(SDB_FWD_ARGS);
+          case 4: return launch_fwd_d32<256, 4, 8, 3, 8, 4, 4>(SDB_FWD_ARGS);
+          case 5: return launch_fwd_d32<512, 8, 8, 1, 8, 4, 4>(SDB_FWD_ARGS);
+          case 6: return launch_fwd_d32<128, 4, 8, 4, 8, 4, 4>(SDB_FWD_ARGS);
+          case 7: return launch_fwd_d32<256, 16, 16, 3, 8, 4, 2>(SDB_FWD_ARGS);
+          default: return launch_fwd_d32<256, 4, 8, 3, 0, 0, 2>(SDB_FWD_ARGS);
+        }
       }
+      return launch_fwd_d32<256, 4, 8, 3, 0, 0, 2>(SDB_FWD_ARGS);
     }
   }
   long long blocks = (total + 255) / 256;

@@ -1,0 +1,339 @@
+"""DINO deformable transformer -- host-side mirror of detr_od/models/utils/transformer.py:435-1406.
+
+Same module tree and parameter names as the reference (``encoder.layers.N.self_attn.*``,
+``decoder.layers.N.cross_attn.*``, ``decoder.ref_point_head``, ``level_embed``, ``tgt_embed``, ``enc_output`` ...)
+so reference checkpoints load; every ``MSDeformAttn`` runs on the sm_100a kernels.  Only the configuration the
+shipped configs use is implemented (two_stage_type='standard', deformable encoder+decoder, 'sa'->'ca'->'ffn',
+learnable tgt, no query scale); anything else raises.
+
+Host-side differences that do not change numerics:
+ * encoder reference points / level geometry are built once per distinct (shapes, valid ratios) instead of
+   per-level python meshgrids each call;
+ * the decoder's sine embedding table (``dim_t``) is cached.
+"""
+import copy
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..msda import MSDeformAttn
+from ..registry import TRANSFORMER
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    """transformer.py:435-451"""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+class MLP(nn.Module):
+    """transformer.py:453-465"""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        dims = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.layers):
+            x = layer(x)
+            if i < self.num_layers - 1:
+                x = F.relu(x)
+        return x
+
+
+_DIM_T = {}
+
+
+def gen_sineembed_for_position(pos):
+    """(nq, bs, 2|4) in [0,1] -> (nq, bs, 256|512); 128 dims per coordinate, temperature 10000, order y,x,w,h
+    (transformer.py:467-493)."""
+    key = pos.device
+    if key not in _DIM_T:
+        i = torch.arange(128, dtype=torch.float32, device=pos.device)
+        _DIM_T[key] = 10000 ** (2 * (i // 2) / 128)
+    dim_t = _DIM_T[key]
+
+    def emb(c):
+        e = (c * (2 * math.pi))[:, :, None] / dim_t
+        return torch.stack((e[:, :, 0::2].sin(), e[:, :, 1::2].cos()), dim=3).flatten(2)
+
+    px, py = emb(pos[:, :, 0]), emb(pos[:, :, 1])
+    if pos.size(-1) == 2:
+        return torch.cat((py, px), dim=2)
+    if pos.size(-1) == 4:
+        return torch.cat((py, px, emb(pos[:, :, 2]), emb(pos[:, :, 3])), dim=2)
+    raise ValueError("Unknown pos_tensor shape(-1):{}".format(pos.size(-1)))
+
+
+def gen_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes_list):
+    """Two-stage proposals (transformer.py:525-575): grid centre / valid size with 0.05*2^l boxes, kept where all
+    four coordinates lie in (0.01, 0.99); padded / invalid rows get logit +inf and a zeroed memory row.
+    ``spatial_shapes_list`` is the host list [(H, W), ...] (no device sync)."""
+    N, S, C = memory.shape
+    proposals = []
+    cur = 0
+    for lvl, (H, W) in enumerate(spatial_shapes_list):
+        m = memory_padding_mask[:, cur:cur + H * W].view(N, H, W)
+        valid_h = (~m[:, :, 0]).sum(1)
+        valid_w = (~m[:, 0, :]).sum(1)
+        gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=memory.device),
+                                torch.arange(W, dtype=torch.float32, device=memory.device), indexing="ij")
+        grid = torch.stack([gx, gy], -1)
+        scale = torch.stack([valid_w, valid_h], 1).view(N, 1, 1, 2)
+        grid = (grid[None].expand(N, -1, -1, -1) + 0.5) / scale
+        wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
+        proposals.append(torch.cat((grid, wh), -1).view(N, -1, 4))
+        cur += H * W
+    prop = torch.cat(proposals, 1)
+    valid = ((prop > 0.01) & (prop < 0.99)).all(-1, keepdim=True)
+    prop = torch.log(prop / (1 - prop))
+    bad = memory_padding_mask.unsqueeze(-1) | ~valid
+    prop = prop.masked_fill(bad, float("inf"))
+    out_memory = memory.masked_fill(bad, 0.0)
+    return out_memory, prop
+
+
+class DINOTransformerEncoderLayer(nn.Module):
+    """MSDA self-attention + FFN, post-norm (transformer.py:578-642)."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        assert activation == "relu"
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
+        q = src if pos is None else src + pos
+        src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, key_padding_mask)
+        src = self.norm1(src + self.dropout1(src2))
+        src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
+        return self.norm2(src + self.dropout3(src2))
+
+
+class DINOTransformerEncoder(nn.Module):
+    """transformer.py:644-744"""
+
+    def __init__(self, encoder_layer, num_layers, norm=None, d_model=256):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.d_model = d_model
+
+    @staticmethod
+    def get_reference_points(spatial_shapes_list, valid_ratios, device):
+        """Pixel centres / (valid_ratio * size), then scaled by every level's valid ratio (transformer.py:676-691)."""
+        refs = []
+        for lvl, (H, W) in enumerate(spatial_shapes_list):
+            ry, rx = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=device),
+                                    torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=device), indexing="ij")
+            ry = ry.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H)
+            rx = rx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W)
+            refs.append(torch.stack((rx, ry), -1))
+        ref = torch.cat(refs, 1)
+        return ref[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, pos, spatial_shapes, level_start_index, valid_ratios, key_padding_mask,
+                spatial_shapes_list):
+        out = src
+        reference_points = self.get_reference_points(spatial_shapes_list, valid_ratios, src.device)
+        for layer in self.layers:
+            out = layer(out, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask)
+        if self.norm is not None:
+            out = self.norm(out)
+        return out
+
+
+class DINOTransformerDecoderLayer(nn.Module):
+    """self-attention (nn.MultiheadAttention) -> MSDA cross-attention -> FFN, post-norm (transformer.py:746-873)."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4,
+                 decoder_sa_type="sa", module_seq=("sa", "ca", "ffn")):
+        super().__init__()
+        assert activation == "relu" and decoder_sa_type == "sa"
+        assert sorted(module_seq) == ["ca", "ffn", "sa"]
+        self.module_seq = list(module_seq)
+        self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout3 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    def forward(self, tgt, query_pos, reference_points, memory, memory_key_padding_mask, level_start_index,
+                spatial_shapes, self_attn_mask=None):
+        """tgt / query_pos (nq, bs, C); reference_points (nq, bs, L, 4); memory (bs, S, C) batch-first."""
+        for name in self.module_seq:
+            if name == "sa":
+                qk = tgt + query_pos
+                tgt2 = self.self_attn(qk, qk, tgt, attn_mask=self_attn_mask, need_weights=False)[0]
+                tgt = self.norm2(tgt + self.dropout2(tgt2))
+            elif name == "ca":
+                tgt2 = self.cross_attn((tgt + query_pos).transpose(0, 1), reference_points.transpose(0, 1).contiguous(),
+                                       memory, spatial_shapes, level_start_index,
+                                       memory_key_padding_mask).transpose(0, 1)
+                tgt = self.norm1(tgt + self.dropout1(tgt2))
+            else:
+                tgt2 = self.linear2(self.dropout3(F.relu(self.linear1(tgt))))
+                tgt = self.norm3(tgt + self.dropout4(tgt2))
+        return tgt
+
+
+class DINOTransformerDecoder(nn.Module):
+    """Iterative box refinement decoder (transformer.py:875-1045)."""
+
+    def __init__(self, decoder_layer, num_layers, norm, d_model=256, query_dim=4, num_feature_levels=4):
+        super().__init__()
+        assert query_dim == 4
+        self.layers = nn.ModuleList([copy.deepcopy(decoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.query_dim = query_dim
+        self.num_feature_levels = num_feature_levels
+        self.ref_point_head = MLP(query_dim // 2 * d_model, d_model, d_model, 2)
+        self.d_model = d_model
+
+    def forward(self, tgt, memory, tgt_mask, memory_key_padding_mask, refpoints_unsigmoid, level_start_index,
+                spatial_shapes, valid_ratios, fc_reg):
+        """tgt (nq, bs, C); memory (bs, S, C); refpoints_unsigmoid (nq, bs, 4)
+        -> ([n_dec x (bs, nq, C)], [(n_dec+1) x (bs, nq, 4)])"""
+        output = tgt
+        intermediate = []
+        reference_points = refpoints_unsigmoid.sigmoid()
+        ref_points = [reference_points]
+        vr4 = torch.cat([valid_ratios, valid_ratios], -1)[None]          # (1, bs, L, 4)
+        for lid, layer in enumerate(self.layers):
+            ref_in = reference_points[:, :, None] * vr4                   # (nq, bs, L, 4)
+            query_pos = self.ref_point_head(gen_sineembed_for_position(ref_in[:, :, 0, :]))
+            output = layer(output, query_pos, ref_in, memory, memory_key_padding_mask, level_start_index,
+                           spatial_shapes, self_attn_mask=tgt_mask)
+            if fc_reg is not None:
+                new_ref = (fc_reg[lid](output) + inverse_sigmoid(reference_points)).sigmoid()
+                reference_points = new_ref.detach()
+                ref_points.append(new_ref)
+            intermediate.append(self.norm(output))
+        return [o.transpose(0, 1) for o in intermediate], [r.transpose(0, 1) for r in ref_points]
+
+
+@TRANSFORMER.register_module()
+class DINOTransformer(nn.Module):
+    """transformer.py:1047-1406 with the defaults the configs rely on (``transformer=dict(type='DINOTransformer')``)."""
+
+    def __init__(self, d_model=256, nhead=8, num_queries=900, num_encoder_layers=6, num_decoder_layers=6,
+                 dim_feedforward=2048, dropout=0.0, activation="relu", normalize_before=False,
+                 return_intermediate_dec=True, query_dim=4, num_feature_levels=4, enc_n_points=4, dec_n_points=4,
+                 two_stage_type="standard", embed_init_tgt=True, decoder_sa_type="sa",
+                 module_seq=("sa", "ca", "ffn"), **unsupported):
+        super().__init__()
+        for k, v in unsupported.items():
+            if v not in (None, False, 0, True) and k not in ("modulate_hw_attn", "deformable_encoder",
+                                                             "deformable_decoder", "learnable_tgt_init",
+                                                             "rm_enc_query_scale", "rm_dec_query_scale"):
+                raise NotImplementedError(f"DINOTransformer option {k}={v!r} is outside the shipped configs")
+        assert two_stage_type == "standard" and query_dim == 4 and return_intermediate_dec and embed_init_tgt
+        self.num_feature_levels = num_feature_levels
+        self.num_encoder_layers = num_encoder_layers
+        self.num_decoder_layers = num_decoder_layers
+        self.num_queries = num_queries
+        self.d_model = self.embed_dims = d_model
+        self.nhead = nhead
+        enc_layer = DINOTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
+                                                nhead, enc_n_points)
+        self.encoder = DINOTransformerEncoder(enc_layer, num_encoder_layers,
+                                              nn.LayerNorm(d_model) if normalize_before else None, d_model)
+        dec_layer = DINOTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
+                                                nhead, dec_n_points, decoder_sa_type, module_seq)
+        self.decoder = DINOTransformerDecoder(dec_layer, num_decoder_layers, nn.LayerNorm(d_model), d_model,
+                                              query_dim, num_feature_levels)
+        self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model)) if num_feature_levels > 1 else None
+        self.tgt_embed = nn.Embedding(num_queries, d_model)
+        self.enc_output = nn.Linear(d_model, d_model)
+        self.enc_output_norm = nn.LayerNorm(d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        if self.level_embed is not None:
+            nn.init.normal_(self.level_embed)
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        _, H, W = mask.shape
+        valid_h = (~mask[:, :, 0]).sum(1)
+        valid_w = (~mask[:, 0, :]).sum(1)
+        return torch.stack([valid_w.float() / W, valid_h.float() / H], -1)
+
+    def forward(self, srcs, masks, refpoint_embed, pos_embeds, tgt, attn_mask=None, fc_reg=None, fc_cls=None,
+                fc_enc_reg=None, fc_enc_cls=None):
+        """srcs / pos_embeds: L x (bs, C, H_l, W_l); masks: L x (bs, H_l, W_l) bool (True = padding);
+        refpoint_embed (bs, n_dn, 4) / tgt (bs, n_dn, C): the denoising part or None
+        -> hs [n_dec x (bs, nq, C)], references [(n_dec+1) x (bs, nq, 4)], hs_enc (1, bs, 900, C),
+           ref_enc (1, bs, 900, 4), init_box_proposal (bs, 900, 4)"""
+        src_l, mask_l, pos_l, shapes_list = [], [], [], []
+        for lvl, (src, mask, pos) in enumerate(zip(srcs, masks, pos_embeds)):
+            bs, c, h, w = src.shape
+            shapes_list.append((h, w))
+            pos = pos.flatten(2).transpose(1, 2)
+            if self.level_embed is not None:
+                pos = pos + self.level_embed[lvl].view(1, 1, -1)
+            src_l.append(src.flatten(2).transpose(1, 2))
+            mask_l.append(mask.flatten(1))
+            pos_l.append(pos)
+        src_flat = torch.cat(src_l, 1)
+        mask_flat = torch.cat(mask_l, 1)
+        pos_flat = torch.cat(pos_l, 1)
+        spatial_shapes = torch.as_tensor(shapes_list, dtype=torch.long, device=src_flat.device)
+        starts = [0]
+        for h, w in shapes_list[:-1]:
+            starts.append(starts[-1] + h * w)
+        level_start_index = torch.as_tensor(starts, dtype=torch.long, device=src_flat.device)
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+
+        memory = self.encoder(src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, mask_flat,
+                              shapes_list)
+
+        # two-stage query selection (transformer.py:1314-1346)
+        output_memory, output_proposals = gen_encoder_output_proposals(memory, mask_flat, shapes_list)
+        output_memory = self.enc_output_norm(self.enc_output(output_memory))
+        enc_cls = fc_enc_cls(output_memory)
+        enc_coord = fc_enc_reg(output_memory) + output_proposals
+        topk = torch.topk(enc_cls.max(-1)[0], self.num_queries, dim=1)[1]
+        idx4 = topk.unsqueeze(-1).expand(-1, -1, 4)
+        refpoint_undetach = torch.gather(enc_coord, 1, idx4)
+        refpoint_sel = refpoint_undetach.detach()
+        init_box_proposal = torch.gather(output_proposals, 1, idx4).sigmoid()
+        tgt_undetach = torch.gather(output_memory, 1, topk.unsqueeze(-1).expand(-1, -1, self.d_model))
+        bs = src_flat.shape[0]
+        tgt_sel = self.tgt_embed.weight[:self.num_queries][None].expand(bs, -1, -1)
+        if refpoint_embed is not None:
+            refpoint_embed = torch.cat([refpoint_embed, refpoint_sel], dim=1)
+            tgt = torch.cat([tgt, tgt_sel], dim=1)
+        else:
+            refpoint_embed, tgt = refpoint_sel, tgt_sel
+
+        hs, references = self.decoder(tgt.transpose(0, 1), memory, attn_mask, mask_flat,
+                                      refpoint_embed.transpose(0, 1), level_start_index, spatial_shapes,
+                                      valid_ratios, fc_reg)
+        hs_enc = tgt_undetach.unsqueeze(0)
+        ref_enc = refpoint_undetach.sigmoid().unsqueeze(0)
+        return hs, references, hs_enc, ref_enc, init_box_proposal

@@ -9,7 +9,7 @@ from oracle import msda_oracle as O
 pytestmark = pytest.mark.gpu
 
 GOLDEN = ["testpy", "small_d32", "wide_d32", "odd_d30", "d64_l5", "one_point"]
-FWD_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+FWD_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
 BWD_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 9]
 RTOL = 1e-3          # north star: attention tensors within 1e-3 relative of the reference's op
 
@@ -17,6 +17,16 @@ RTOL = 1e-3          # north star: attention tensors within 1e-3 relative of the
 def _relerr(a, b):
     a, b = a.double(), b.double()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _smooth_mask(loc, levels):
+    """grad_sampling_loc is the derivative of a piecewise-bilinear function: it jumps where a pixel coordinate
+    crosses an integer.  fp32 kernels (ours and the reference's) and the fp64 oracle can round such a coordinate
+    to different sides, so samples within 1e-3 px of an integer are left out of the grad_loc comparison."""
+    wh = torch.tensor([[w, h] for h, w in levels], dtype=torch.float64)[None, None, None, :, None, :]
+    px = loc.double().cpu() * wh - 0.5
+    near = (px - px.round()).abs() < 1e-3
+    return ~(near.any(-1, keepdim=True).expand_as(px))
 
 
 def _dev(c, k, dtype):
@@ -88,9 +98,13 @@ def test_backward_variants_vs_oracle(bv, mode, Lq):
         got = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["gout"], 64)
     finally:
         _lib.lib().sdb_msda_set_variant(0, 0)
+    mask = _smooth_mask(x["loc"], levels)
     for g, r, k in zip(got, (gv, gl, ga), ("grad_value", "grad_loc", "grad_attn")):
-        assert _relerr(g.cpu(), torch.from_numpy(r)) < 1e-5, k
-        np.testing.assert_allclose(g.cpu().numpy(), r, rtol=RTOL, atol=2e-3, err_msg=k)
+        g, r = g.cpu(), torch.from_numpy(r)
+        if k == "grad_loc":
+            g, r = g * mask, r * mask
+        assert _relerr(g, r) < 1e-5, k
+        np.testing.assert_allclose(g.numpy(), r.numpy(), rtol=RTOL, atol=2e-3, err_msg=k)
 
 
 def test_five_levels_and_odd_points():
@@ -105,8 +119,12 @@ def test_five_levels_and_odd_points():
         assert _relerr(out.cpu(), torch.from_numpy(ref)) < 1e-5
         gref = O.msda_backward(*a, x["gout"].cpu().numpy())
         got = MSDA.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["gout"], 64)
-        for g, r in zip(got, gref):
-            assert _relerr(g.cpu(), torch.from_numpy(r)) < 1e-5
+        mask = _smooth_mask(x["loc"], levels)
+        for i, (g, r) in enumerate(zip(got, gref)):
+            g, r = g.cpu(), torch.from_numpy(r)
+            if i == 1:
+                g, r = g * mask, r * mask
+            assert _relerr(g, r) < 1e-5
 
 
 def test_empty_inputs():
@@ -187,7 +205,10 @@ def test_full_size_against_reference_cuda_op(levels_name, mode):
     assert torch.allclose(out, ref, rtol=RTOL, atol=1e-4)
     got = MSDA.ms_deform_attn_backward(*args, x["gout"], 64)
     want = ref_cuda.backward(*args, x["gout"])
+    mask = _smooth_mask(x["loc"], levels).cuda()
     for g, r, k in zip(got, want, ("grad_value", "grad_loc", "grad_attn")):
+        if k == "grad_loc":
+            g, r = g * mask, r * mask
         assert _relerr(g, r) < 1e-4, k
         assert torch.allclose(g, r, rtol=RTOL, atol=1e-2 if k == "grad_loc" else 1e-3), k
 

@@ -68,8 +68,8 @@ def main():
     lib = _lib.lib()
     cases = [("micro_enc", MICROBENCH_LEVELS, "encoder", None), ("micro_uniform", MICROBENCH_LEVELS, "uniform", 17821),
              ("coco_enc", COCO_4SCALE_LEVELS, "encoder", None), ("coco_dec", COCO_4SCALE_LEVELS, "uniform", 1100)]
-    fvars = [0, 1, 2, 3, 4, 5, 6, 7, 9] if args.variants else [0]
-    bvars = [0, 1, 2, 3, 4, 5, 6, 9] if args.variants else [0]
+    fvars = [1, 2, 3, 4, 5, 6, 7, 8, 9] if args.variants else [0]
+    bvars = [1, 2, 3, 4, 5, 6, 9] if args.variants else [0]
     for name, levels, mode, Lq in cases:
         if args.only and args.only not in name:
             continue
