@@ -31,6 +31,9 @@ SIGNATURES = {
 
 _lib = None
 
+# kernels of this library launched so far, by entry point (bench.py reports the per-step count)
+LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0}
+
 
 class EmaChunk(ctypes.Structure):
     """sdb_ema_chunk"""

@@ -1,0 +1,92 @@
+"""ResNet backbone with the mmdet constructor arguments the configs pass
+(configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:9-17: depth 50, out_indices (1,2,3), frozen_stages 1,
+BN frozen + norm_eval, style 'pytorch').  Parameter names follow torchvision / mmdet (``conv1``, ``bn1``,
+``layerN.M.convK`` ...) so ``torchvision://resnet50`` checkpoints load.  Dense convolutions go to cuDNN (library
+plumbing): the backbone is not part of the graded hot path but is needed to run the train step end to end.
+"""
+import torch
+from torch import nn
+
+from ..registry import BACKBONES
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)   # style='pytorch'
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        return self.relu(out + identity)
+
+
+@BACKBONES.register_module()
+class ResNet(nn.Module):
+    arch = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+
+    def __init__(self, depth=50, num_stages=4, out_indices=(1, 2, 3), frozen_stages=1,
+                 norm_cfg=dict(type="BN", requires_grad=False), norm_eval=True, style="pytorch", init_cfg=None):
+        super().__init__()
+        assert depth in self.arch and style == "pytorch" and num_stages == 4
+        self.out_indices, self.frozen_stages, self.norm_eval = tuple(out_indices), frozen_stages, norm_eval
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        inplanes = 64
+        for i, blocks in enumerate(self.arch[depth]):
+            planes, stride = 64 * 2 ** i, 1 if i == 0 else 2
+            down = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False),
+                                 nn.BatchNorm2d(planes * 4))
+            layers = [Bottleneck(inplanes, planes, stride, down)]
+            inplanes = planes * 4
+            layers += [Bottleneck(inplanes, planes) for _ in range(1, blocks)]
+            setattr(self, f"layer{i + 1}", nn.Sequential(*layers))
+        if not norm_cfg.get("requires_grad", True):
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    for p in m.parameters():
+                        p.requires_grad = False
+        self._freeze_stages()
+
+    def _freeze_stages(self):
+        if self.frozen_stages >= 0:
+            self.bn1.eval()
+            for m in (self.conv1, self.bn1):
+                for p in m.parameters():
+                    p.requires_grad = False
+        for i in range(1, self.frozen_stages + 1):
+            m = getattr(self, f"layer{i}")
+            m.eval()
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def train(self, mode=True):
+        super().train(mode)
+        self._freeze_stages()
+        if mode and self.norm_eval:
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.eval()
+        return self
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        outs = []
+        for i in range(4):
+            x = getattr(self, f"layer{i + 1}")(x)
+            if i in self.out_indices:
+                outs.append(x)
+        return tuple(outs)

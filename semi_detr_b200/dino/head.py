@@ -1,0 +1,302 @@
+"""``DINODETRHead`` -- host-side mirror of detr_od/models/dense_heads/dino_detr_head.py:39-1046.
+
+Module tree / parameter names (``input_proj``, ``fc_cls``, ``fc_reg``, ``fc_enc_cls``, ``fc_enc_reg``, ``label_enc``,
+``transformer.*``), ``forward`` / ``forward_train`` / ``loss`` signatures and the 65-key loss dict are the
+reference's.  The body of ``loss`` is re-designed for the device:
+
+ * all (decoder layer + encoder) x image Hungarian problems of the step go through ONE cost kernel and ONE solver
+   kernel (``HungarianAssigner.assign_batch``) -- the reference runs ``multi_apply(_get_target_single)`` with a
+   ``.cpu()`` + scipy call per problem (dino_detr_head.py:895-980, 937);
+ * targets are gathered and the focal / L1 / GIoU terms evaluated for all layers in one batched pass and reduced
+   per layer, instead of 13 ``loss_single`` calls (dino_detr_head.py:546-582, 634-736);
+ * normalisers come from the host-known GT counts (every GT is matched when num_query >= num_gt), so no ``.item()``;
+   under data parallelism the one cross-rank mean (dino_detr_head.py:698-699, 720-723) is a single tiny all-reduce
+   whose result stays on the device.
+The arithmetic per element and per normaliser is the reference's.
+"""
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from ..matching import HungarianAssigner, MatchTargets  # noqa: F401  (registers the assigner)
+from ..matching.match_cost import bbox_cxcywh_to_xyxy, bbox_xyxy_to_cxcywh
+from ..registry import BBOX_ASSIGNERS, HEADS, LOSSES, POSITIONAL_ENCODING, TRANSFORMER
+from . import losses as _losses  # noqa: F401  (registers the losses)
+from . import positional_encoding as _pe  # noqa: F401
+from .dn_components import dn_post_process, prepare_for_cdn
+from .losses import giou_aligned, sigmoid_focal_elementwise
+from .transformer import MLP, inverse_sigmoid
+
+LOSS_PARTS = ("loss_cls", "loss_bbox", "loss_iou", "loss_bbox_xy", "loss_bbox_hw")
+
+
+def reduce_mean_scalar(value, device):
+    """mmdet core/utils/dist_utils.py:67-73 for a host scalar: mean over ranks, kept on the device (no .item())."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device)
+    dist.all_reduce(t.div_(dist.get_world_size()), op=dist.ReduceOp.SUM)
+    return t
+
+
+def _clamp_min1(x):
+    return x.clamp(min=1) if torch.is_tensor(x) else max(x, 1)
+
+
+@HEADS.register_module()
+class DINODETRHead(nn.Module):
+    def __init__(self, num_classes=80, in_channels=2048, num_query=900, num_reg_fcs=2, transformer=None,
+                 num_feature_levels=4, num_backbone_outs=3, backbone_channels=(512, 1024, 2048),
+                 sync_cls_avg_factor=False, iter_update=True, dn_number=100, dn_box_noise_scale=0.4,
+                 dn_label_noise_ratio=0.5, dn_labelbook_size=81, query_dim=4, dec_pred_class_embed_share=True,
+                 dec_pred_bbox_embed_share=True, two_stage_bbox_embed_share=False, two_stage_class_embed_share=False,
+                 bbox_embed_diff_each_layer=False, random_refpoints_xy=False,
+                 positional_encoding=dict(type="SinePositionalEncodingHW", num_feats=128, normalize=True,
+                                          temperatureH=20, temperatureW=20),
+                 loss_cls=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+                 loss_bbox=dict(type="L1Loss", loss_weight=5.0), loss_iou=dict(type="GIoULoss", loss_weight=2.0),
+                 train_cfg=dict(assigner=dict(type="HungarianAssigner",
+                                              cls_cost=dict(type="FocalLossCost", weight=2.0),
+                                              reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+                                              iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0))),
+                 test_cfg=dict(max_per_img=300), init_cfg=None, **kwargs):
+        super().__init__()
+        assert dec_pred_class_embed_share and dec_pred_bbox_embed_share and not bbox_embed_diff_each_layer
+        assert not two_stage_bbox_embed_share and not two_stage_class_embed_share and not sync_cls_avg_factor
+        self.bg_cls_weight = 0
+        if train_cfg:
+            assigner = train_cfg["assigner"]
+            # the reference asserts loss and matcher weights agree (dino_detr_head.py:130-141)
+            assert loss_cls["loss_weight"] == assigner["cls_cost"]["weight"]
+            assert loss_bbox["loss_weight"] == assigner["reg_cost"]["weight"]
+            assert loss_iou["loss_weight"] == assigner["iou_cost"]["weight"]
+            self.assigner = BBOX_ASSIGNERS.build(assigner)
+        self.num_query, self.num_classes, self.in_channels = num_query, num_classes, in_channels
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.loss_cls, self.loss_bbox, self.loss_iou = (LOSSES.build(c) for c in (loss_cls, loss_bbox, loss_iou))
+        self.num_feature_levels, self.num_backbone_outs = num_feature_levels, num_backbone_outs
+        self.backbone_channels = list(backbone_channels)
+        self.query_dim = query_dim
+        self.dn_number, self.dn_box_noise_scale = dn_number, dn_box_noise_scale
+        self.dn_label_noise_ratio, self.dn_labelbook_size = dn_label_noise_ratio, dn_labelbook_size
+        self.cls_out_channels = num_classes if self.loss_cls.use_sigmoid else num_classes + 1
+        self.positional_encoding = POSITIONAL_ENCODING.build(positional_encoding)
+        self.transformer = TRANSFORMER.build(transformer or dict(type="DINOTransformer"))
+        self.embed_dims = self.transformer.embed_dims
+        assert positional_encoding["num_feats"] * 2 == self.embed_dims
+        self._init_layers()
+        self.init_weights()
+
+    def _init_layers(self):
+        """dino_detr_head.py:215-282"""
+        proj = []
+        in_ch = self.backbone_channels[-1]
+        for i in range(self.num_backbone_outs):
+            in_ch = self.backbone_channels[i]
+            proj.append(nn.Sequential(nn.Conv2d(in_ch, self.embed_dims, kernel_size=1),
+                                      nn.GroupNorm(32, self.embed_dims)))
+        for _ in range(self.num_feature_levels - self.num_backbone_outs):
+            proj.append(nn.Sequential(nn.Conv2d(in_ch, self.embed_dims, kernel_size=3, stride=2, padding=1),
+                                      nn.GroupNorm(32, self.embed_dims)))
+            in_ch = self.embed_dims
+        self.input_proj = nn.ModuleList(proj)
+        cls_embed = nn.Linear(self.embed_dims, self.cls_out_channels)
+        box_embed = MLP(self.embed_dims, self.embed_dims, 4, 3)
+        cls_embed.bias.data = torch.ones(self.cls_out_channels) * (-math.log((1 - 0.01) / 0.01))
+        nn.init.constant_(box_embed.layers[-1].weight.data, 0)
+        nn.init.constant_(box_embed.layers[-1].bias.data, 0)
+        n_dec = self.transformer.num_decoder_layers
+        self.fc_reg = nn.ModuleList([box_embed for _ in range(n_dec)])      # shared across layers
+        self.fc_cls = nn.ModuleList([cls_embed for _ in range(n_dec)])
+        self.fc_enc_reg = copy.deepcopy(box_embed)
+        self.fc_enc_cls = copy.deepcopy(cls_embed)
+        self.label_enc = nn.Embedding(self.dn_labelbook_size + 1, self.embed_dims)
+
+    def init_weights(self):
+        for proj in self.input_proj:
+            nn.init.xavier_uniform_(proj[0].weight, gain=1)
+            nn.init.constant_(proj[0].bias, 0)
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, mlvl_feats, img_metas, input_query_label=None, input_query_bbox=None, attn_mask=None,
+                dn_meta=None):
+        """dino_detr_head.py:314-407 -> (outputs_class (n_dec, bs, Q, C), outputs_coord (n_dec, bs, Q, 4),
+        interm_outputs_class (bs, Q, C), interm_outputs_coord (bs, Q, 4), dn_outputs_class, dn_outputs_coord)"""
+        bs = mlvl_feats[0].size(0)
+        in_h, in_w = img_metas[0]["batch_input_shape"]
+        img_masks = mlvl_feats[0].new_ones((bs, in_h, in_w))
+        for i in range(bs):
+            h, w, _ = img_metas[i]["img_shape"]
+            img_masks[i, :h, :w] = 0
+        srcs, masks, poss = [], [], []
+        for lvl, feat in enumerate(mlvl_feats):
+            masks.append(F.interpolate(img_masks[None], size=feat.shape[-2:]).to(torch.bool).squeeze(0))
+            poss.append(self.positional_encoding(masks[-1]))
+            srcs.append(self.input_proj[lvl](feat))
+        for lvl in range(len(srcs), self.num_feature_levels):
+            src = self.input_proj[lvl](mlvl_feats[-1] if lvl == len(mlvl_feats) else srcs[-1])
+            srcs.append(src)
+            masks.append(F.interpolate(img_masks[None], size=src.shape[-2:]).to(torch.bool).squeeze(0))
+            poss.append(self.positional_encoding(masks[-1]))
+
+        hs, reference, hs_enc, ref_enc, _ = self.transformer(
+            srcs, masks, input_query_bbox, poss, input_query_label, attn_mask, fc_reg=self.fc_reg,
+            fc_cls=self.fc_cls, fc_enc_reg=self.fc_enc_reg, fc_enc_cls=self.fc_enc_cls)
+        hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0      # keeps label_enc in the graph without a DN part
+
+        hs_all = torch.stack(hs)                                # (n_dec, bs, nq, C); heads are shared across layers
+        ref_all = torch.stack(reference[:-1])
+        outputs_coord = (self.fc_reg[0](hs_all) + inverse_sigmoid(ref_all)).sigmoid()
+        outputs_class = self.fc_cls[0](hs_all)
+        interm_coord = ref_enc[-1]
+        interm_class = self.fc_enc_cls(hs_enc[-1])
+        if self.dn_number > 0 and dn_meta is not None:
+            outputs_class, outputs_coord, dn_class, dn_coord = dn_post_process(outputs_class, outputs_coord, dn_meta)
+        else:
+            dn_class, dn_coord = None, None
+        return outputs_class, outputs_coord, interm_class, interm_coord, dn_class, dn_coord
+
+    # ------------------------------------------------------------------------------------------------
+    def _batched_terms(self, cls, box, labels, box_t, pos, factor):
+        """Element-wise loss terms summed per problem.  cls (P,Q,C), box/box_t (P,Q,4), labels/pos (P,Q),
+        factor (P,1,4) -> dict of (P,) sums (un-normalised, un-weighted)."""
+        w = pos.unsqueeze(-1).to(box.dtype)
+        focal = sigmoid_focal_elementwise(cls, labels, self.num_classes, self.loss_cls.gamma, self.loss_cls.alpha)
+        l1 = (box - box_t).abs() * w
+        giou = giou_aligned(bbox_cxcywh_to_xyxy(box) * factor, bbox_cxcywh_to_xyxy(box_t) * factor, self.loss_iou.eps)
+        return dict(loss_cls=focal.sum((1, 2)), loss_bbox=l1.sum((1, 2)), loss_bbox_xy=l1[..., :2].sum((1, 2)),
+                    loss_bbox_hw=l1[..., 2:].sum((1, 2)), loss_iou=((1 - giou) * w.squeeze(-1)).sum(1))
+
+    def _finish(self, sums, layers, bs, cls_avg, reg_avg):
+        """(P,) per-problem sums -> per-layer losses with the reference's normalisers and weights."""
+        out = {}
+        for k, v in sums.items():
+            v = v.view(layers, bs).sum(1)
+            if k == "loss_cls":
+                out[k] = v / cls_avg * self.loss_cls.loss_weight
+            elif k == "loss_iou":
+                out[k] = v / reg_avg * self.loss_iou.loss_weight
+            else:
+                out[k] = v / reg_avg * self.loss_bbox.loss_weight
+        return out
+
+    def loss(self, all_cls_scores, all_bbox_preds, enc_cls_scores, enc_bbox_preds, dn_cls_scores, dn_bbox_preds,
+             gt_bboxes_list, gt_labels_list, gt_scores_list=None, img_metas=None, dn_metas=None,
+             gt_bboxes_ignore=None, decouple=False):
+        """Same inputs and the same 65 keys as dino_detr_head.py:506-632."""
+        assert gt_bboxes_ignore is None and gt_scores_list is None
+        all_cls_scores, all_bbox_preds = all_cls_scores.float(), all_bbox_preds.float()        # force_fp32
+        L, bs, Q, C = all_cls_scores.shape
+        dev = all_cls_scores.device
+        counts = [int(b.shape[0]) for b in gt_bboxes_list]
+        img_wh = [(m["img_shape"][1], m["img_shape"][0]) for m in img_metas]
+        has_enc = enc_cls_scores is not None
+
+        # --- matching part: L decoder layers (+ encoder proposals against class-0 labels, :574-577) -----------
+        gtb = list(gt_bboxes_list) + (list(gt_bboxes_list) if has_enc else [])
+        gtl = list(gt_labels_list) + ([torch.zeros_like(l) for l in gt_labels_list] if has_enc else [])
+        targets = MatchTargets(gtb, gtl, img_wh * (2 if has_enc else 1), dev)
+        cls_stack, box_stack = all_cls_scores, all_bbox_preds
+        if has_enc:
+            cls_stack = torch.cat([cls_stack, enc_cls_scores.float()[None]])
+            box_stack = torch.cat([box_stack, enc_bbox_preds.float()[None]])
+        layers = cls_stack.shape[0]
+        P = layers * bs
+        prob_seg = [(bs if (has_enc and l == L) else 0) + i for l in range(layers) for i in range(bs)]
+        gt_inds, labels = self.assigner.assign_batch(box_stack.view(P, Q, 4), cls_stack.view(P, Q, C), targets,
+                                                     prob_img=prob_seg)
+        # per-GT normalised cxcywh targets (dino_detr_head.py:969-976) and per-problem geometry
+        seg_of_gt = np.concatenate([np.full(c, s, dtype=np.int64) for s, c in enumerate(targets.counts)] +
+                                   [np.zeros(0, dtype=np.int64)])
+        meta = torch.from_numpy(np.concatenate([seg_of_gt, np.asarray(prob_seg, dtype=np.int64)])).to(dev, non_blocking=True)
+        seg_of_gt_d, prob_seg_d = meta[:len(seg_of_gt)], meta[len(seg_of_gt):]
+        wh4 = torch.cat([targets.img_wh, targets.img_wh], 1)                                     # (nseg, 4)
+        if len(seg_of_gt):
+            gt_norm = bbox_xyxy_to_cxcywh(targets.gt_bboxes / wh4[seg_of_gt_d])
+        else:
+            gt_norm = torch.zeros((1, 4), device=dev)
+        pos = gt_inds > 0
+        gidx = (targets.seg_offsets.long()[prob_seg_d][:, None] + gt_inds - 1).clamp(min=0)
+        box_t = gt_norm[gidx] * pos.unsqueeze(-1)
+        labels_t = torch.where(pos, labels, torch.full_like(labels, self.num_classes))
+        factor = wh4[prob_seg_d][:, None, :]
+        sums = self._batched_terms(cls_stack.view(P, Q, C), box_stack.view(P, Q, 4), labels_t, box_t, pos, factor)
+        num_pos = sum(min(c, Q) for c in counts)
+        reg_avg = _clamp_min1(reduce_mean_scalar(num_pos, dev))
+        main = self._finish(sums, layers, bs, max(num_pos * 1.0, 1), reg_avg)
+
+        # --- denoising part: targets follow from the CDN layout, no matcher (:739-819) -------------------------
+        if dn_cls_scores is not None and dn_bbox_preds is not None:
+            pad, groups = dn_metas["pad_size"], dn_metas["num_dn_group"]
+            single_pad = pad // groups            # = 2 * max_gt: positives then negatives of one group
+            half = single_pad // 2
+            total = sum(counts)
+            bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)] + [np.zeros(0, np.int64)])
+            within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts] + [np.zeros(0, np.int64)])
+            gtix = np.arange(total, dtype=np.int64)
+            b_ix = np.tile(bid, groups)
+            s_ix = np.concatenate([within + single_pad * g for g in range(groups)] + [np.zeros(0, np.int64)])
+            g_ix = np.tile(gtix, groups)
+            ix = torch.from_numpy(np.stack([b_ix, s_ix, g_ix])).to(dev, non_blocking=True)
+            dn_labels = torch.full((bs, pad), self.num_classes, dtype=torch.long, device=dev)
+            dn_pos = torch.zeros((bs, pad), dtype=torch.bool, device=dev)
+            dn_box_t = torch.zeros((bs, pad, 4), device=dev)
+            if total > 0:
+                real_labels = targets.gt_labels[:total]
+                dn_labels[ix[0], ix[1]] = real_labels[ix[2]]
+                dn_pos[ix[0], ix[1]] = True
+                dn_box_t[ix[0], ix[1]] = gt_norm[:total][ix[2]]
+            Ld = dn_cls_scores.shape[0]
+            Pd = Ld * bs
+            rep = lambda t: t[None].expand(Ld, *t.shape).reshape(Pd, *t.shape[1:])
+            dn_factor = wh4[:bs][:, None, :]
+            dsums = self._batched_terms(dn_cls_scores.float().reshape(Pd, pad, C),
+                                        dn_bbox_preds.float().reshape(Pd, pad, 4), rep(dn_labels), rep(dn_box_t),
+                                        rep(dn_pos), rep(dn_factor))
+            dn_num_pos = total * groups
+            dn = self._finish(dsums, Ld, bs, max(dn_num_pos * 1.0, 1), _clamp_min1(reduce_mean_scalar(dn_num_pos, dev)))
+            assert half >= 0
+        else:
+            dn = {k: torch.zeros(L, device=dev) for k in LOSS_PARTS}
+
+        loss_dict = {}
+        if has_enc:
+            for k in LOSS_PARTS:
+                loss_dict[f"enc_{k}"] = main[k][L]
+        for k in LOSS_PARTS:
+            loss_dict[k] = main[k][L - 1]
+        for k in LOSS_PARTS:
+            loss_dict[f"dn_{k}"] = dn[k][L - 1]
+        for l in range(L - 1):
+            for k in LOSS_PARTS:
+                loss_dict[f"d{l}.{k}"] = main[k][l]
+            for k in LOSS_PARTS:
+                loss_dict[f"d{l}.dn_{k}"] = dn[k][l]
+        return loss_dict
+
+    # ------------------------------------------------------------------------------------------------
+    def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None, proposal_cfg=None,
+                      **kwargs):
+        """dino_detr_head.py:983-1046"""
+        assert proposal_cfg is None, '"proposal_cfg" must be None'
+        counts = [int(b.shape[0]) for b in gt_bboxes]
+        if self.dn_number > 0 and max(counts) > 0:
+            boxes = []
+            for meta, b in zip(img_metas, gt_bboxes):
+                h, w, _ = meta["img_shape"]
+                boxes.append(bbox_xyxy_to_cxcywh(b) / b.new_tensor([w, h, w, h]))
+            q_label, q_bbox, attn_mask, dn_meta = prepare_for_cdn(
+                dn_args=(dict(labels=gt_labels, boxes=boxes), self.dn_number, self.dn_label_noise_ratio,
+                         self.dn_box_noise_scale),
+                training=True, num_queries=self.num_query, num_classes=self.num_classes,
+                hidden_dim=self.embed_dims, label_enc=self.label_enc)
+        else:
+            q_label = q_bbox = attn_mask = dn_meta = None
+        outs = self(x, img_metas, q_label, q_bbox, attn_mask, dn_meta)
+        return self.loss(*outs, gt_bboxes, gt_labels, img_metas=img_metas, dn_metas=dn_meta,
+                         gt_bboxes_ignore=gt_bboxes_ignore)

@@ -88,6 +88,7 @@ def linear_sum_assignment(cost):
                                            max(counts) if counts else 0, gt_inds.data_ptr(), None,
                                            status.data_ptr())
     _lib.check(rc, "lsap_solve")
+    _lib.LAUNCHES["lsap_solve"] += 1
     st = status.cpu()
     if (st == 1).any():
         raise ValueError("matrix contains invalid numeric entries")
@@ -153,6 +154,8 @@ class HungarianAssigner:
                 float(self.cls_cost.weight), float(self.reg_cost.weight), float(self.iou_cost.weight),
                 workspace.data_ptr(), _lib.ptr(cost_qg), gt_inds.data_ptr(), labels.data_ptr(), status.data_ptr())
         _lib.check(rc, "hungarian_assign")
+        _lib.LAUNCHES["match_cost"] += 1 if targets.max_gt > 0 else 0
+        _lib.LAUNCHES["lsap_solve"] += 1
         self.last_status = status
         if return_cost:
             costs = [cost_qg[cost_offs[p]:cost_offs[p + 1]].view(Q, targets.counts[prob_img[p]]) for p in range(P)]

@@ -15,6 +15,21 @@ from .. import _lib
 
 _FLOAT = (torch.float32, torch.float64)
 
+# Optional live timing (bench.py): when a list is installed here every launch is bracketed by CUDA events on the
+# launching stream and (kind, batch, spatial_size, num_query, start_event, end_event) is appended.
+EVENT_LOG = None
+
+
+def _timed(kind, b, s, q, launch):
+    if EVENT_LOG is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = launch()
+    e1.record()
+    EVENT_LOG.append((kind, b, s, q, e0, e1))
+    return rc
+
 
 def _check_inputs(named):
     # ms_deform_attn_cuda.cu:28-38 / :93-105 -- contiguity and device asserts, same messages
@@ -58,10 +73,12 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     out = torch.empty((b, q, m * d), dtype=value.dtype, device=value.device)   # every element is written
     fn = _lib.lib().sdb_msda_forward_f32 if value.dtype == torch.float32 else _lib.lib().sdb_msda_forward_f64
     with torch.cuda.device(value.device):
-        rc = fn(_lib.current_stream(value.device), value.data_ptr(), spatial_shapes.data_ptr(),
-                level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
-                b, s, m, d, l, q, p, out.data_ptr())
+        rc = _timed("fwd", b, s, q, lambda: fn(
+            _lib.current_stream(value.device), value.data_ptr(), spatial_shapes.data_ptr(),
+            level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+            b, s, m, d, l, q, p, out.data_ptr()))
     _lib.check(rc, "ms_deform_attn_forward")
+    _lib.LAUNCHES["msda_forward"] += 1
     return out
 
 
@@ -81,9 +98,11 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_attn = torch.empty_like(attn_weight)       # fully overwritten
     fn = _lib.lib().sdb_msda_backward_f32 if value.dtype == torch.float32 else _lib.lib().sdb_msda_backward_f64
     with torch.cuda.device(value.device):
-        rc = fn(_lib.current_stream(value.device), grad_output.data_ptr(), value.data_ptr(),
-                spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
-                attn_weight.data_ptr(), b, s, m, d, l, q, p, grad_value.data_ptr(), grad_loc.data_ptr(),
-                grad_attn.data_ptr())
+        rc = _timed("bwd", b, s, q, lambda: fn(
+            _lib.current_stream(value.device), grad_output.data_ptr(), value.data_ptr(),
+            spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            attn_weight.data_ptr(), b, s, m, d, l, q, p, grad_value.data_ptr(), grad_loc.data_ptr(),
+            grad_attn.data_ptr()))
     _lib.check(rc, "ms_deform_attn_backward")
+    _lib.LAUNCHES["msda_backward"] += 1
     return [grad_value, grad_loc, grad_attn]

@@ -52,3 +52,51 @@ def msda_bytes(N, S, Lq, M=8, D=32, L=4, P=4, elt=4):
     v, o = N * S * M * D, N * Lq * M * D
     loc, att = N * Lq * M * L * P * 2, N * Lq * M * L * P
     return elt * (v + loc + att + o), elt * (o + 2 * v + 2 * loc + 2 * att)
+
+
+# ---- DINO train-step inputs ----------------------------------------
+
+DINO_R50_4SCALE = dict(
+    type="DINODETR",
+    backbone=dict(type="ResNet", depth=50, num_stages=4, out_indices=(1, 2, 3), frozen_stages=1,
+                  norm_cfg=dict(type="BN", requires_grad=False), norm_eval=True, style="pytorch"),
+    bbox_head=dict(type="DINODETRHead", num_query=900, query_dim=4, random_refpoints_xy=False,
+                   bbox_embed_diff_each_layer=False, num_classes=80, in_channels=2048,
+                   transformer=dict(type="DINOTransformer"),
+                   positional_encoding=dict(type="SinePositionalEncodingHW", temperatureH=20, temperatureW=20,
+                                            num_feats=128, normalize=True),
+                   loss_cls=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+                   loss_bbox=dict(type="L1Loss", loss_weight=5.0), loss_iou=dict(type="GIoULoss", loss_weight=2.0)),
+    train_cfg=dict(assigner=dict(type="HungarianAssigner", cls_cost=dict(type="FocalLossCost", weight=2.0),
+                                 reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+                                 iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0))),
+    test_cfg=dict(max_per_img=300))
+"""The ``model`` dict of configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:7-45 (init_cfg / pretrained weights dropped:
+no network, random init)."""
+
+
+def coco_like_batch(batch_size=2, height=800, width=1333, seed=0, device="cpu", pin=False):
+    """Synthetic COCO-shape batch: images ~ N(0,1); per image G ~ clamp(Poisson(7), 1, 100) boxes with
+    cx,cy ~ U(.1,.9), w,h ~ U(.05,.5) clipped to the image, labels ~ U{0..79}."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(batch_size, 3, height, width, generator=g)
+    gt_bboxes, gt_labels, metas = [], [], []
+    for _ in range(batch_size):
+        n = int(torch.poisson(torch.tensor(7.0), generator=g).clamp(1, 100))
+        cxcy = torch.rand(n, 2, generator=g) * 0.8 + 0.1
+        wh = torch.rand(n, 2, generator=g) * 0.45 + 0.05
+        x1y1 = (cxcy - wh / 2).clamp(0, 1)
+        x2y2 = (cxcy + wh / 2).clamp(0, 1)
+        gt_bboxes.append(torch.cat([x1y1, x2y2], 1) * torch.tensor([width, height, width, height], dtype=torch.float32))
+        gt_labels.append(torch.randint(0, 80, (n,), generator=g))
+        metas.append(dict(img_shape=(height, width, 3), pad_shape=(height, width, 3), ori_shape=(height, width, 3),
+                          batch_input_shape=(height, width), scale_factor=1.0))
+    if pin:
+        img = img.pin_memory()
+        gt_bboxes = [b.pin_memory() for b in gt_bboxes]
+        gt_labels = [l.pin_memory() for l in gt_labels]
+    if device != "cpu":
+        img = img.to(device, non_blocking=True)
+        gt_bboxes = [b.to(device, non_blocking=True) for b in gt_bboxes]
+        gt_labels = [l.to(device, non_blocking=True) for l in gt_labels]
+    return dict(img=img, img_metas=metas, gt_bboxes=gt_bboxes, gt_labels=gt_labels)

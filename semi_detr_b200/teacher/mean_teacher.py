@@ -68,6 +68,7 @@ class EmaPlan:
             rc = _lib.lib().sdb_ema_update_f32(_lib.current_stream(dev), self._table.data_ptr(), self.num_chunks,
                                                float(momentum))
         _lib.check(rc, "ema_update")
+        _lib.LAUNCHES["ema_update"] += 1
 
 
 def _unwrap(model):

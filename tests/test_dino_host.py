@@ -1,0 +1,113 @@
+"""Host logic of the DINO path on the CPU (oracle ops injected): CDN layout, batched loss == per-problem
+reference-style loss, loss-dict keys, gradients reach every trainable parameter."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hungarian_oracle as H
+from oracle.cpu_path import reference_cpu_ops
+from semi_detr_b200 import dino  # noqa: F401
+from semi_detr_b200.dino.dn_components import prepare_for_cdn
+from semi_detr_b200.dino.losses import FocalLoss, GIoULoss, L1Loss
+from semi_detr_b200.matching.match_cost import bbox_cxcywh_to_xyxy, bbox_xyxy_to_cxcywh
+from semi_detr_b200.registry import DETECTORS
+from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch
+
+
+def test_cdn_layout_matches_reference_rules():
+    """SURVEY.md appendix A.5 / dn_components.py:21-112"""
+    torch.manual_seed(0)
+    labels = [torch.tensor([3, 7, 9]), torch.tensor([1])]
+    boxes = [torch.rand(3, 4) * 0.4 + 0.3, torch.rand(1, 4) * 0.4 + 0.3]
+    enc = torch.nn.Embedding(82, 16)
+    ql, qb, mask, meta = prepare_for_cdn((dict(labels=labels, boxes=boxes), 100, 0.5, 0.4), True, 900, 80, 16, enc)
+    groups = 200 // (3 * 2)
+    assert meta == dict(pad_size=3 * 2 * groups, num_dn_group=groups)
+    pad = meta["pad_size"]
+    assert ql.shape == (2, pad, 16) and qb.shape == (2, pad, 4) and mask.shape == (pad + 900, pad + 900)
+    # unused slots stay zero (image 1 has one GT: slots 1,2 of every repetition are empty)
+    assert not qb[1, 1:3].any() and not ql[1, 1:3].any() and qb[1, 0].any()
+    # positives (even repetitions) stay within half a box extent of the GT, negatives move at least that far
+    gt = boxes[0][0]
+    b = torch.sigmoid(qb[0, 0])                     # repetition 0, GT 0
+    xyxy_gt = torch.cat([gt[:2] - gt[2:] / 2, gt[:2] + gt[2:] / 2])
+    xyxy = torch.cat([b[:2] - b[2:] / 2, b[:2] + b[2:] / 2])
+    assert ((xyxy - xyxy_gt).abs() <= torch.cat([gt[2:], gt[2:]]) / 2 * 0.4 + 1e-4).all()
+    # mask: matching part never sees DN; groups are isolated; a group sees itself
+    assert mask[pad:, :pad].all() and not mask[pad:, pad:].any()
+    assert not mask[0:6, 0:6].any() and mask[0:6, 6:pad].all() and mask[6:12, 0:6].all()
+    assert not mask[:pad, pad:].any()
+
+
+def _reference_style_loss_single(cls, box, gtb, gtl, metas, num_classes=80):
+    """dino_detr_head.py:634-736 written out per image with the reference's losses (oracle assigner)."""
+    labels_l, box_t_l, w_l, fac_l = [], [], [], []
+    for i in range(cls.shape[0]):
+        h, w, _ = metas[i]["img_shape"]
+        gi, lb = H.hungarian_assign(box[i].detach(), cls[i].detach(), gtb[i], gtl[i], h, w)
+        pos = gi > 0
+        labels = torch.full((cls.shape[1],), num_classes, dtype=torch.long)
+        labels[pos] = gtl[i][gi[pos] - 1]
+        bt = torch.zeros_like(box[i])
+        bt[pos] = bbox_xyxy_to_cxcywh(gtb[i][gi[pos] - 1] / gtb[i].new_tensor([w, h, w, h]))
+        bw = torch.zeros_like(box[i])
+        bw[pos] = 1.0
+        labels_l.append(labels); box_t_l.append(bt); w_l.append(bw)
+        fac_l.append(box[i].new_tensor([w, h, w, h]).repeat(box.shape[1], 1))
+    labels, bt, bw, fac = torch.cat(labels_l), torch.cat(box_t_l), torch.cat(w_l), torch.cat(fac_l)
+    npos = float((bw.sum(-1) > 0).sum())
+    cls_avg, reg_avg = max(npos, 1), max(npos, 1)
+    lc = FocalLoss(loss_weight=2.0)(cls.reshape(-1, num_classes), labels, torch.ones(len(labels)), avg_factor=cls_avg)
+    bp = box.reshape(-1, 4)
+    li = GIoULoss(loss_weight=2.0)(bbox_cxcywh_to_xyxy(bp) * fac, bbox_cxcywh_to_xyxy(bt) * fac, bw, avg_factor=reg_avg)
+    lb_ = L1Loss(loss_weight=5.0)(bp, bt, bw, avg_factor=reg_avg)
+    return lc, lb_, li
+
+
+def test_batched_loss_equals_per_layer_reference_loss():
+    torch.manual_seed(1)
+    cfg = copy.deepcopy(DINO_R50_4SCALE)
+    head = DETECTORS.build(cfg).bbox_head
+    L, bs, Q, C = 3, 2, 60, 80
+    cls = torch.randn(L, bs, Q, C) - 2
+    box = torch.rand(L, bs, Q, 4) * 0.5 + 0.2
+    enc_cls, enc_box = torch.randn(bs, Q, C) - 2, torch.rand(bs, Q, 4) * 0.5 + 0.2
+    data = coco_like_batch(bs, 300, 400, seed=3)
+    with reference_cpu_ops():
+        out = head.loss(cls, box, enc_cls, enc_box, None, None, data["gt_bboxes"], data["gt_labels"],
+                        img_metas=data["img_metas"], dn_metas=None)
+    assert len(out) == 5 + 5 + 5 + (L - 1) * 10
+    for l in range(L):
+        lc, lb_, li = _reference_style_loss_single(cls[l], box[l], data["gt_bboxes"], data["gt_labels"], data["img_metas"])
+        pre = "" if l == L - 1 else f"d{l}."
+        assert torch.allclose(out[pre + "loss_cls"], lc, rtol=1e-5)
+        assert torch.allclose(out[pre + "loss_bbox"], lb_, rtol=1e-5)
+        assert torch.allclose(out[pre + "loss_iou"], li, rtol=1e-5)
+        assert torch.allclose(out[pre + "loss_bbox_xy"] + out[pre + "loss_bbox_hw"], lb_, rtol=1e-5)
+    zl = [torch.zeros_like(l) for l in data["gt_labels"]]       # encoder aux loss: class-0 labels (:574-577)
+    lc, lb_, li = _reference_style_loss_single(enc_cls, enc_box, data["gt_bboxes"], zl, data["img_metas"])
+    assert torch.allclose(out["enc_loss_cls"], lc, rtol=1e-5) and torch.allclose(out["enc_loss_iou"], li, rtol=1e-5)
+    assert float(out["dn_loss_cls"]) == 0.0
+
+
+def test_train_step_on_cpu_oracle_path():
+    torch.manual_seed(0)
+    model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE)).train()
+    data = coco_like_batch(2, 256, 320, seed=0)
+    with reference_cpu_ops():
+        out = model.train_step(data)
+        out["loss"].backward()
+    keys = list(out["log_vars"])
+    assert len(keys) == 66 and keys[-1] == "loss"          # 65 loss terms + total
+    for part in ("loss_cls", "loss_bbox", "loss_iou", "loss_bbox_xy", "loss_bbox_hw"):
+        for pre in ("", "enc_", "dn_", "d0.", "d4.dn_"):
+            assert pre + part in out["log_vars"]
+    total = sum(float(v) for k, v in out["log_vars"].items() if k != "loss")
+    assert abs(total - float(out["loss"])) < 1e-3 * total
+    assert np.isfinite(float(out["loss"]))
+    missing = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing
+    frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+    assert any("layer1" in n for n in frozen) and all("backbone" in n for n in frozen)
