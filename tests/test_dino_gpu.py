@@ -32,6 +32,13 @@ def test_train_step_matches_cpu_reference_path(cpu_noise):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     cpu_model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE)).train()
+    # At initialisation every sampling location sits exactly on a pixel centre (integer offsets from pixel-centre
+    # reference points), where the bilinear kernel's location-gradient is discontinuous and fp rounding decides the
+    # side -- the reference's CUDA op and its own python fallback disagree there too.  Move off the lattice.
+    with torch.no_grad():
+        for name, p in cpu_model.named_parameters():
+            if name.endswith("sampling_offsets.bias"):
+                p.add_(torch.randn_like(p) * 0.37)
     gpu_model = copy.deepcopy(cpu_model).cuda().train()
     data = coco_like_batch(2, 288, 352, seed=5)
     gdata = dict(img=data["img"].cuda(), img_metas=[dict(m) for m in data["img_metas"]],

@@ -1,0 +1,97 @@
+"""World-size-2 gloo checks of the data-parallel host logic (no GPU): the cross-rank loss normaliser
+(dino_detr_head.py:698-699, 720-723), log-var reduction (base.py:202-207) and DDP gradient averaging with the
+reference CPU ops injected."""
+import copy
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _small_cfg():
+    from semi_detr_b200.synthetic import DINO_R50_4SCALE
+    cfg = copy.deepcopy(DINO_R50_4SCALE)
+    cfg["bbox_head"]["num_query"] = 60
+    cfg["bbox_head"]["transformer"] = dict(type="DINOTransformer", num_queries=60, num_encoder_layers=1,
+                                           num_decoder_layers=2, dim_feedforward=64)
+    cfg["bbox_head"]["dn_number"] = 10
+    return cfg
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        from oracle.cpu_path import reference_cpu_ops
+        from semi_detr_b200 import dino  # noqa: F401
+        from semi_detr_b200.dino.head import reduce_mean_scalar
+        from semi_detr_b200.registry import DETECTORS
+        from semi_detr_b200.synthetic import coco_like_batch
+        # 1. normaliser: mean over ranks of a host scalar, returned as a tensor
+        m = reduce_mean_scalar(float(3 + 4 * rank), "cpu")
+        assert torch.is_tensor(m) and abs(float(m) - 5.0) < 1e-6
+        # 2. DDP step on different data per rank
+        torch.manual_seed(0)
+        model = DETECTORS.build(_small_cfg()).train()
+        ddp = torch.nn.parallel.DistributedDataParallel(model, broadcast_buffers=False)
+        data = coco_like_batch(1, 128, 160, seed=10 + rank)
+        with reference_cpu_ops():
+            losses = ddp(**data)
+            loss, log_vars = model._parse_losses(losses)
+            loss.backward()
+            _, reduced = model._parse_losses(losses, reduce_log_vars=True)
+        g = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+        gathered = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(gathered, g)
+        assert torch.equal(gathered[0], gathered[1]), "DDP must leave identical (averaged) gradients on all ranks"
+        losses_all = [torch.zeros(1) for _ in range(world)]
+        dist.all_gather(losses_all, loss.detach().reshape(1))
+        mean_loss = sum(float(x) for x in losses_all) / world
+        assert abs(reduced["loss"] - mean_loss) < 1e-4 * abs(mean_loss)
+        assert isinstance(reduced["loss_cls"], float) and len(reduced) == len(log_vars)
+        if rank == 0:
+            out.put(("ok", float(loss)))
+    except Exception as e:  # pragma: no cover
+        if rank == 0:
+            out.put(("fail", repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(280)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    status, val = q.get(timeout=5)
+    assert status == "ok", val
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs the reference arm; the other ranks exit 0 without work."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
