@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[1]): one supervised DINO-4scale R50 train step -- forward, 13-way Hungarian-matched
 loss with contrastive denoising, backward, grad-clip 0.1, AdamW -- on a synthetic COCO-shape batch of 2 images
 800x1333 per GPU, random-init weights (no network for checkpoints / datasets).  Data parallel over N GPUs of one
-node: one process per GPU, NCCL gradient all-reduce over NVLink (torch DDP), weak scaling.
+node: one process per GPU, one NCCL all-reduce of the flat gradient buffer over NVLink per step, weak scaling.
 
 Prints ONE JSON line on rank 0 (see README / DESIGN.md for the keys):
   value     images/s with the batch already resident in HBM (CUDA events, max over ranks)
@@ -152,7 +152,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from semi_detr_b200 import _lib
-    from semi_detr_b200.engine import SupervisedTrainStep, build_optimizer
+    from semi_detr_b200.engine import GraphedTrainStep, SupervisedTrainStep, build_optimizer
     from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
     from semi_detr_b200.synthetic import coco_like_batch, msda_bytes
 
@@ -171,10 +171,10 @@ def run_ours(args):
     torch.backends.cudnn.benchmark = True
 
     model = build_model(device)
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
-                                                          gradient_as_bucket_view=True)
-    step = SupervisedTrainStep(model, build_optimizer(model.module if world > 1 else model))
+    if world > 1:   # identical seeds give identical weights; broadcast anyway so the ranks cannot drift
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+    step = SupervisedTrainStep(model, build_optimizer(model, capturable=True), world_size=world)
     host = coco_like_batch(PER_GPU_BATCH, IMG_H, IMG_W, seed=rank, pin=True)
 
     def to_device(b):
@@ -198,39 +198,70 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(resident)
+    barrier()
+    # kernels of this library per step (python-side counters tick when the launchers run, i.e. in eager mode)
+    launches0 = sum(_lib.LAUNCHES.values())
+    step(resident)
+    launches_per_step = sum(_lib.LAUNCHES.values()) - launches0
+
+    graphed, graph_note = None, "eager"
+    if not args.no_graph:
+        try:
+            graphed = GraphedTrainStep(step, resident, warmup=2)
+            graph_note = "whole step captured in one CUDA graph, replayed"
+        except Exception as e:  # pragma: no cover - fall back loudly, never silently
+            graphed, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            print("WARNING: CUDA graph capture failed, running eagerly:", e, file=sys.stderr)
+            torch.cuda.synchronize()
+    run = (lambda: graphed()) if graphed else (lambda: step(resident))
+    for _ in range(warm):
+        run()
     barrier()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------------
-    MSDA.EVENT_LOG = []
-    launches0 = sum(_lib.LAUNCHES.values())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(resident)
+        run()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = sum(_lib.LAUNCHES.values()) - launches0
-    log, MSDA.EVENT_LOG = MSDA.EVENT_LOG, None
+    launches = launches_per_step * args.steps
 
     # ---- timed region 2: end to end (pinned host -> device every step, loss read back) -------------------
+    run_e2e = (lambda: graphed(host)) if graphed else (lambda: step(to_device(host)))
     for _ in range(2):
-        float(step(to_device(host))[0])
+        float(run_e2e()[0])
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = 0.0
     for _ in range(args.steps):
-        loss, _ = step(to_device(host))
+        loss, _ = run_e2e()
         last = float(loss)                        # device -> host read of the step's result
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     clocks = sampler.stop() if sampler else None
+
+    # ---- per-kernel timing for the roofline: CUDA events around every MSDA launch.  Events recorded inside a
+    # captured graph cannot be queried, so the same step runs eagerly for this part -----------------------
+    MSDA.EVENT_LOG = []
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_roof = min(args.steps, 5)
+    barrier()
+    e4.record()
+    for _ in range(n_roof):
+        step(resident)
+    e5.record()
+    barrier()
+    ms_roof = e4.elapsed_time(e5)
+    log, MSDA.EVENT_LOG = MSDA.EVENT_LOG, None
 
     if rank != 0:
         if world > 1:
@@ -252,7 +283,8 @@ def run_ours(args):
         nbytes = fb if kind == "fwd" else bb
         avg = sum(ts) / len(ts)
         kernels[f"msda_{kind}_{shape}"] = dict(launches=len(ts), avg_us=avg * 1e6, bytes=nbytes,
-                                               gbs=nbytes / avg / 1e9, total_ms=sum(ts) * 1e3)
+                                               gbs=nbytes / avg / 1e9, total_ms=sum(ts) * 1e3,
+                                               ms_per_step=sum(ts) * 1e3 / n_roof)
     dom_name = max(kernels, key=lambda k: kernels[k]["total_ms"]) if kernels else None
     roofline = None
     if dom_name:
@@ -260,10 +292,13 @@ def run_ours(args):
         roofline = dict(bound="hbm", kernel=dom_name, achieved=d["gbs"], peak=peak, unit="GB/s",
                         frac=d["gbs"] / peak, traffic=None, peak_source=peak_src, avg_launch_us=d["avg_us"],
                         algorithmic_bytes_per_launch=d["bytes"], launches_timed=d["launches"],
-                        share_of_step=d["total_ms"] / ms_total,
+                        share_of_step=d["ms_per_step"] / (ms_total / args.steps),
+                        timed_in="eager replica of the timed step (events inside a captured graph cannot be read); "
+                                 f"{n_roof} steps, {ms_roof / n_roof:.2f} ms/step eager",
                         all_msda={k: dict(avg_us=round(v["avg_us"], 2), gbs=round(v["gbs"], 1),
                                           frac=round(v["gbs"] / peak, 4), launches=v["launches"],
-                                          share_of_step=round(v["total_ms"] / ms_total, 4)) for k, v in kernels.items()})
+                                          share_of_step=round(v["ms_per_step"] / (ms_total / args.steps), 4))
+                                  for k, v in kernels.items()})
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -273,15 +308,16 @@ def run_ours(args):
                             sample=f"1 full train step, {PER_GPU_BATCH} images {IMG_H}x{IMG_W}, reference CPU path "
                                    f"(python ms_deform_attn fallback + host LSAP + torch-cpu), {threads} threads")
 
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32 (tf32 tensor-core matmul/conv; MSDA, matching and losses in f32)", data="synthetic",
                 config=dict(workload=WORKLOAD, global_batch=PER_GPU_BATCH * world, parallelism=f"dp{world}",
+                            execution=graph_note,
                             l2="per-step working set (activations + 25.6 MB input) exceeds the 126 MB L2"),
                 clocks=clocks,
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / args.steps, last_loss=last),
-                gpu_launches=launches, gpu_launches_per_step=launches / args.steps,
+                gpu_launches=launches, gpu_launches_per_step=launches_per_step,
                 roofline=roofline, cpu_baseline=cpu_baseline)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -295,6 +331,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

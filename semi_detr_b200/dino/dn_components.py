@@ -15,6 +15,7 @@ does not.
 import numpy as np
 import torch
 
+from ..consts import device_const
 from .transformer import inverse_sigmoid
 
 _MASK_CACHE = {}
@@ -86,7 +87,8 @@ def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, lab
         sign = _randint(0, 2, known_boxes.shape, device, generator).float() * 2.0 - 1.0
         part = _rand(known_boxes.shape, device, generator)
         # negatives (odd repetitions) are pushed one half-extent further out
-        neg = (torch.arange(reps, device=device) % 2 == 1).repeat_interleave(total)
+        neg = device_const(device, "cdn_neg", (reps, total),
+                           lambda: (torch.arange(reps) % 2 == 1).repeat_interleave(total))
         part = (part + neg[:, None].float()) * sign
         xyxy = (xyxy + part * diff * box_noise_scale).clamp(min=0.0, max=1.0)
         known_boxes = torch.cat([(xyxy[:, :2] + xyxy[:, 2:]) / 2, xyxy[:, 2:] - xyxy[:, :2]], 1)
@@ -96,11 +98,11 @@ def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, lab
     input_query_label = torch.zeros(bs, pad_size, hidden_dim, device=device)
     input_query_bbox = torch.zeros(bs, pad_size, 4, device=device)
     if total > 0:
-        bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)])
-        within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts])
-        bid = np.tile(bid, reps)
-        slot = np.concatenate([within + single_pad * i for i in range(reps)])
-        idx = torch.from_numpy(np.stack([bid, slot])).to(device, non_blocking=True)
+        def build_idx():
+            bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)])
+            within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts])
+            return np.stack([np.tile(bid, reps), np.concatenate([within + single_pad * i for i in range(reps)])])
+        idx = device_const(device, "cdn_idx", (tuple(counts), reps), build_idx)
         input_query_label[idx[0], idx[1]] = input_label_embed
         input_query_bbox[idx[0], idx[1]] = input_bbox_embed
 

@@ -23,6 +23,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
+from ..consts import device_const
 from ..matching import HungarianAssigner, MatchTargets  # noqa: F401  (registers the assigner)
 from ..matching.match_cost import bbox_cxcywh_to_xyxy, bbox_xyxy_to_cxcywh
 from ..registry import BBOX_ASSIGNERS, HEADS, LOSSES, POSITIONAL_ENCODING, TRANSFORMER
@@ -128,21 +129,39 @@ class DINODETRHead(nn.Module):
         """dino_detr_head.py:314-407 -> (outputs_class (n_dec, bs, Q, C), outputs_coord (n_dec, bs, Q, 4),
         interm_outputs_class (bs, Q, C), interm_outputs_coord (bs, Q, 4), dn_outputs_class, dn_outputs_coord)"""
         bs = mlvl_feats[0].size(0)
+        dev = mlvl_feats[0].device
         in_h, in_w = img_metas[0]["batch_input_shape"]
-        img_masks = mlvl_feats[0].new_ones((bs, in_h, in_w))
-        for i in range(bs):
-            h, w, _ = img_metas[i]["img_shape"]
-            img_masks[i, :h, :w] = 0
+        shapes_key = (in_h, in_w, tuple(tuple(m["img_shape"][:2]) for m in img_metas))
+
+        def build_img_masks():
+            m = torch.ones((bs, in_h, in_w), device=dev)
+            for i in range(bs):
+                h, w, _ = img_metas[i]["img_shape"]
+                m[i, :h, :w] = 0
+            return m
+
+        def mask_and_pos(size):
+            # padding masks and sine embeddings depend only on the image / feature geometry: built once per
+            # geometry (the reference rebuilds them every pass, dino_detr_head.py:321-347)
+            size = tuple(size)
+            mask = device_const(dev, "lvl_mask", (shapes_key, size), lambda: F.interpolate(
+                device_const(dev, "img_masks", shapes_key, build_img_masks)[None], size=size).to(torch.bool).squeeze(0))
+            pos = device_const(dev, "lvl_pos", (shapes_key, size, id(self.positional_encoding)),
+                               lambda: self.positional_encoding(mask))
+            return mask, pos
+
         srcs, masks, poss = [], [], []
         for lvl, feat in enumerate(mlvl_feats):
-            masks.append(F.interpolate(img_masks[None], size=feat.shape[-2:]).to(torch.bool).squeeze(0))
-            poss.append(self.positional_encoding(masks[-1]))
+            mk, ps = mask_and_pos(feat.shape[-2:])
+            masks.append(mk)
+            poss.append(ps)
             srcs.append(self.input_proj[lvl](feat))
         for lvl in range(len(srcs), self.num_feature_levels):
             src = self.input_proj[lvl](mlvl_feats[-1] if lvl == len(mlvl_feats) else srcs[-1])
             srcs.append(src)
-            masks.append(F.interpolate(img_masks[None], size=src.shape[-2:]).to(torch.bool).squeeze(0))
-            poss.append(self.positional_encoding(masks[-1]))
+            mk, ps = mask_and_pos(src.shape[-2:])
+            masks.append(mk)
+            poss.append(ps)
 
         hs, reference, hs_enc, ref_enc, _ = self.transformer(
             srcs, masks, input_query_bbox, poss, input_query_label, attn_mask, fc_reg=self.fc_reg,
@@ -211,12 +230,12 @@ class DINODETRHead(nn.Module):
         gt_inds, labels = self.assigner.assign_batch(box_stack.view(P, Q, 4), cls_stack.view(P, Q, C), targets,
                                                      prob_img=prob_seg)
         # per-GT normalised cxcywh targets (dino_detr_head.py:969-976) and per-problem geometry
-        seg_of_gt = np.concatenate([np.full(c, s, dtype=np.int64) for s, c in enumerate(targets.counts)] +
-                                   [np.zeros(0, dtype=np.int64)])
-        meta = torch.from_numpy(np.concatenate([seg_of_gt, np.asarray(prob_seg, dtype=np.int64)])).to(dev, non_blocking=True)
-        seg_of_gt_d, prob_seg_d = meta[:len(seg_of_gt)], meta[len(seg_of_gt):]
+        seg_counts = tuple(targets.counts)
+        seg_of_gt_d = device_const(dev, "seg_of_gt", seg_counts, lambda: np.concatenate(
+            [np.full(c, s, dtype=np.int64) for s, c in enumerate(seg_counts)] + [np.zeros(0, dtype=np.int64)]))
+        prob_seg_d = device_const(dev, "prob_seg64", tuple(prob_seg), lambda: np.asarray(prob_seg, dtype=np.int64))
         wh4 = torch.cat([targets.img_wh, targets.img_wh], 1)                                     # (nseg, 4)
-        if len(seg_of_gt):
+        if sum(seg_counts):
             gt_norm = bbox_xyxy_to_cxcywh(targets.gt_bboxes / wh4[seg_of_gt_d])
         else:
             gt_norm = torch.zeros((1, 4), device=dev)
@@ -236,13 +255,15 @@ class DINODETRHead(nn.Module):
             single_pad = pad // groups            # = 2 * max_gt: positives then negatives of one group
             half = single_pad // 2
             total = sum(counts)
-            bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)] + [np.zeros(0, np.int64)])
-            within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts] + [np.zeros(0, np.int64)])
-            gtix = np.arange(total, dtype=np.int64)
-            b_ix = np.tile(bid, groups)
-            s_ix = np.concatenate([within + single_pad * g for g in range(groups)] + [np.zeros(0, np.int64)])
-            g_ix = np.tile(gtix, groups)
-            ix = torch.from_numpy(np.stack([b_ix, s_ix, g_ix])).to(dev, non_blocking=True)
+
+            def build_ix():
+                z = [np.zeros(0, np.int64)]
+                bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)] + z)
+                within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts] + z)
+                return np.stack([np.tile(bid, groups),
+                                 np.concatenate([within + single_pad * g for g in range(groups)] + z),
+                                 np.tile(np.arange(total, dtype=np.int64), groups)])
+            ix = device_const(dev, "dn_loss_ix", (tuple(counts), groups, single_pad), build_ix)
             dn_labels = torch.full((bs, pad), self.num_classes, dtype=torch.long, device=dev)
             dn_pos = torch.zeros((bs, pad), dtype=torch.bool, device=dev)
             dn_box_t = torch.zeros((bs, pad, 4), device=dev)
@@ -289,7 +310,8 @@ class DINODETRHead(nn.Module):
             boxes = []
             for meta, b in zip(img_metas, gt_bboxes):
                 h, w, _ = meta["img_shape"]
-                boxes.append(bbox_xyxy_to_cxcywh(b) / b.new_tensor([w, h, w, h]))
+                fac = device_const(b.device, "whwh", (w, h), lambda: torch.tensor([w, h, w, h], dtype=torch.float32))
+                boxes.append(bbox_xyxy_to_cxcywh(b) / fac)
             q_label, q_bbox, attn_mask, dn_meta = prepare_for_cdn(
                 dn_args=(dict(labels=gt_labels, boxes=boxes), self.dn_number, self.dn_label_noise_ratio,
                          self.dn_box_noise_scale),

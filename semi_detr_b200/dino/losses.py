@@ -32,7 +32,7 @@ def weight_reduce_loss(loss, weight=None, reduction="mean", avg_factor=None):
 
 def sigmoid_focal_elementwise(pred, labels, num_classes, gamma=2.0, alpha=0.25):
     """pred (..., C) logits, labels (...) with ``num_classes`` = background -> (..., C) focal loss terms."""
-    target = F.one_hot(labels, num_classes + 1)[..., :num_classes].type_as(pred)
+    target = (labels.unsqueeze(-1) == torch.arange(num_classes, device=labels.device)).type_as(pred)
     p = pred.sigmoid()
     pt = (1 - p) * target + p * (1 - target)
     focal_weight = (alpha * target + (1 - alpha) * (1 - target)) * pt.pow(gamma)
@@ -45,10 +45,9 @@ def giou_aligned(a, b, eps=1e-6):
     area_b = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
     wh = (torch.min(a[..., 2:], b[..., 2:]) - torch.max(a[..., :2], b[..., :2])).clamp(min=0)
     overlap = wh[..., 0] * wh[..., 1]
-    e = a.new_tensor([eps])
-    union = torch.max(area_a + area_b - overlap, e)
+    union = (area_a + area_b - overlap).clamp(min=eps)
     ewh = (torch.max(a[..., 2:], b[..., 2:]) - torch.min(a[..., :2], b[..., :2])).clamp(min=0)
-    earea = torch.max(ewh[..., 0] * ewh[..., 1], e)
+    earea = (ewh[..., 0] * ewh[..., 1]).clamp(min=eps)
     return overlap / union - (earea - union) / earea
 
 

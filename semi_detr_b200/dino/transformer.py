@@ -18,6 +18,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ..consts import device_const
 from ..msda import MSDeformAttn
 from ..registry import TRANSFORMER
 
@@ -80,9 +81,11 @@ def gen_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes_lis
         m = memory_padding_mask[:, cur:cur + H * W].view(N, H, W)
         valid_h = (~m[:, :, 0]).sum(1)
         valid_w = (~m[:, 0, :]).sum(1)
-        gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=memory.device),
-                                torch.arange(W, dtype=torch.float32, device=memory.device), indexing="ij")
-        grid = torch.stack([gx, gy], -1)
+        def build_grid(H=H, W=W):
+            gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=memory.device),
+                                    torch.arange(W, dtype=torch.float32, device=memory.device), indexing="ij")
+            return torch.stack([gx, gy], -1)
+        grid = device_const(memory.device, "proposal_grid", (H, W), build_grid)
         scale = torch.stack([valid_w, valid_h], 1).view(N, 1, 1, 2)
         grid = (grid[None].expand(N, -1, -1, -1) + 0.5) / scale
         wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
@@ -135,10 +138,14 @@ class DINOTransformerEncoder(nn.Module):
         """Pixel centres / (valid_ratio * size), then scaled by every level's valid ratio (transformer.py:676-691)."""
         refs = []
         for lvl, (H, W) in enumerate(spatial_shapes_list):
-            ry, rx = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=device),
-                                    torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=device), indexing="ij")
-            ry = ry.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H)
-            rx = rx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W)
+            def grid(H=H, W=W):
+                ry, rx = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=device),
+                                        torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=device),
+                                        indexing="ij")
+                return torch.stack((rx.reshape(-1), ry.reshape(-1)))
+            g = device_const(device, "enc_ref_grid", (H, W), grid)
+            ry = g[1][None] / (valid_ratios[:, None, lvl, 1] * H)
+            rx = g[0][None] / (valid_ratios[:, None, lvl, 0] * W)
             refs.append(torch.stack((rx, ry), -1))
         ref = torch.cat(refs, 1)
         return ref[:, :, None] * valid_ratios[:, None]
@@ -302,11 +309,14 @@ class DINOTransformer(nn.Module):
         src_flat = torch.cat(src_l, 1)
         mask_flat = torch.cat(mask_l, 1)
         pos_flat = torch.cat(pos_l, 1)
-        spatial_shapes = torch.as_tensor(shapes_list, dtype=torch.long, device=src_flat.device)
         starts = [0]
         for h, w in shapes_list[:-1]:
             starts.append(starts[-1] + h * w)
-        level_start_index = torch.as_tensor(starts, dtype=torch.long, device=src_flat.device)
+        skey = tuple(shapes_list)
+        spatial_shapes = device_const(src_flat.device, "spatial_shapes", skey,
+                                      lambda: torch.as_tensor(shapes_list, dtype=torch.long))
+        level_start_index = device_const(src_flat.device, "level_start", skey,
+                                         lambda: torch.as_tensor(starts, dtype=torch.long))
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
 
         memory = self.encoder(src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, mask_flat,

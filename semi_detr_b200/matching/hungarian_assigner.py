@@ -14,6 +14,7 @@ shipped configs use (configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:40-44) rais
 import torch
 
 from .. import _lib
+from ..consts import device_const
 from ..registry import BBOX_ASSIGNERS
 from .match_cost import BBoxL1Cost, FocalLossCost, IoUCost, build_match_cost
 
@@ -50,9 +51,11 @@ class MatchTargets:
         else:
             self.gt_bboxes = torch.zeros((1, 4), dtype=torch.float32, device=device)
             self.gt_labels = torch.zeros((1,), dtype=torch.int64, device=device)
-        self.seg_offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
-        self.img_wh = torch.tensor([[float(w), float(h)] for (w, h) in img_wh_list],
-                                   dtype=torch.float32).reshape(-1, 2).to(device, non_blocking=True)
+        self.seg_offsets = device_const(device, "seg_offsets", tuple(offs),
+                                        lambda: torch.tensor(offs, dtype=torch.int32))
+        wh = tuple((float(w), float(h)) for (w, h) in img_wh_list)
+        self.img_wh = device_const(device, "img_wh", wh,
+                                   lambda: torch.tensor(wh, dtype=torch.float32).reshape(-1, 2))
 
 
 def linear_sum_assignment(cost):
@@ -137,9 +140,10 @@ class HungarianAssigner:
         cost_offs = [0]
         for p in range(P):
             cost_offs.append(cost_offs[-1] + Q * targets.counts[prob_img[p]])
-        meta = torch.tensor(list(prob_img) + [0], dtype=torch.int32)
-        prob_seg = meta[:P].to(dev, non_blocking=True)
-        cost_offsets = torch.tensor(cost_offs, dtype=torch.int64).to(dev, non_blocking=True)
+        prob_img = tuple(int(x) for x in prob_img)
+        prob_seg = device_const(dev, "prob_seg", prob_img, lambda: torch.tensor(prob_img, dtype=torch.int32))
+        cost_offsets = device_const(dev, "cost_offsets", tuple(cost_offs),
+                                    lambda: torch.tensor(cost_offs, dtype=torch.int64))
         total = max(cost_offs[-1], 1)
         workspace = torch.empty(total, dtype=torch.float32, device=dev)
         cost_qg = torch.empty(total, dtype=torch.float32, device=dev) if return_cost else None

@@ -27,10 +27,9 @@ def bbox_overlaps_giou(a, b, eps=1e-6):
     area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
     wh = (torch.min(a[:, None, 2:], b[None, :, 2:]) - torch.max(a[:, None, :2], b[None, :, :2])).clamp(min=0)
     overlap = wh[..., 0] * wh[..., 1]
-    e = a.new_tensor([eps])
-    union = torch.max(area_a[:, None] + area_b[None, :] - overlap, e)
+    union = (area_a[:, None] + area_b[None, :] - overlap).clamp(min=eps)
     ewh = (torch.max(a[:, None, 2:], b[None, :, 2:]) - torch.min(a[:, None, :2], b[None, :, :2])).clamp(min=0)
-    earea = torch.max(ewh[..., 0] * ewh[..., 1], e)
+    earea = (ewh[..., 0] * ewh[..., 1]).clamp(min=eps)
     return overlap / union - (earea - union) / earea
 
 

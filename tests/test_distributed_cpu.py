@@ -45,17 +45,26 @@ def _worker(rank, world, port, out):
         # 2. DDP step on different data per rank
         torch.manual_seed(0)
         model = DETECTORS.build(_small_cfg()).train()
-        ddp = torch.nn.parallel.DistributedDataParallel(model, broadcast_buffers=False)
+        from semi_detr_b200.engine import FlatGrads
+        grads = FlatGrads(list(model.parameters()))
         data = coco_like_batch(1, 128, 160, seed=10 + rank)
         with reference_cpu_ops():
-            losses = ddp(**data)
+            losses = model(**data)
             loss, log_vars = model._parse_losses(losses)
             loss.backward()
             _, reduced = model._parse_losses(losses, reduce_log_vars=True)
+        local = grads.flat.clone()
+        grads.all_reduce_mean(world)                       # the step's one gradient exchange
+        both = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(both, local)
+        assert torch.allclose(grads.flat, (both[0] + both[1]) / 2, rtol=1e-6, atol=1e-9)
+        norm_before = float(grads.flat.norm())
+        returned = float(grads.clip_(0.1))
+        assert abs(returned - norm_before) < 1e-5 * norm_before and float(grads.flat.norm()) <= 0.1 + 1e-5
         g = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
         gathered = [torch.zeros_like(g) for _ in range(world)]
         dist.all_gather(gathered, g)
-        assert torch.equal(gathered[0], gathered[1]), "DDP must leave identical (averaged) gradients on all ranks"
+        assert torch.equal(gathered[0], gathered[1]), "the exchange must leave identical (averaged) gradients on all ranks"
         losses_all = [torch.zeros(1) for _ in range(world)]
         dist.all_gather(losses_all, loss.detach().reshape(1))
         mean_loss = sum(float(x) for x in losses_all) / world
