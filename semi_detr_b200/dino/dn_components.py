@@ -46,14 +46,25 @@ def _attn_mask(single_pad, groups, num_queries, device):
     return m
 
 
-def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, label_enc, generator=None):
+def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, label_enc, generator=None,
+                    fill_empty=False):
     """dn_args = (targets{'labels': [..], 'boxes': [normalised cxcywh ..]}, dn_number, label_noise_ratio,
     box_noise_scale) -> input_query_label (bs, pad, C), input_query_bbox (bs, pad, 4) [inverse-sigmoid],
     attn_mask (pad+Q, pad+Q) bool, dn_meta {'pad_size', 'num_dn_group'}"""
     if not training:
         return None, None, None, None
     targets, dn_number, label_noise_ratio, box_noise_scale = dn_args
-    labels_list, boxes_list = targets["labels"], targets["boxes"]
+    labels_list, boxes_list = list(targets["labels"]), list(targets["boxes"])
+    empty = [int(t.shape[0]) == 0 for t in boxes_list]
+    if fill_empty and any(empty):
+        # prepare_for_cdn_plus (dn_components.py:137-160): an image without boxes gets one centred dummy box with a
+        # random label so the batch layout stays rectangular; its targets stay empty (all background)
+        dev0 = boxes_list[0].device
+        dummy = device_const(dev0, "cdn_dummy_box", (), lambda: torch.tensor([[0.5, 0.5, 0.5, 0.5]]))
+        for i, e in enumerate(empty):
+            if e:
+                boxes_list[i] = dummy
+                labels_list[i] = _randint(0, num_classes, (1,), dev0, generator)
     bs = len(labels_list)
     counts = [int(t.shape[0]) for t in labels_list]           # host ints
     device = boxes_list[0].device
@@ -108,6 +119,8 @@ def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, lab
 
     attn_mask = _attn_mask(single_pad, groups, num_queries, device)
     dn_meta = {"pad_size": pad_size, "num_dn_group": groups}
+    if fill_empty:
+        dn_meta["pad_mask"] = empty          # host flags: which images have no real box
     return input_query_label, input_query_bbox, attn_mask, dn_meta
 
 

@@ -124,10 +124,9 @@ class DINODETRHead(nn.Module):
             nn.init.constant_(proj[0].bias, 0)
 
     # ------------------------------------------------------------------------------------------------
-    def forward(self, mlvl_feats, img_metas, input_query_label=None, input_query_bbox=None, attn_mask=None,
-                dn_meta=None):
-        """dino_detr_head.py:314-407 -> (outputs_class (n_dec, bs, Q, C), outputs_coord (n_dec, bs, Q, 4),
-        interm_outputs_class (bs, Q, C), interm_outputs_coord (bs, Q, 4), dn_outputs_class, dn_outputs_coord)"""
+    def _decode(self, mlvl_feats, img_metas, input_query_label=None, input_query_bbox=None, attn_mask=None):
+        """Shared body of ``forward`` / ``forward_dummy``: -> hs (list of (bs, nq, C)), class logits and boxes of
+        every decoder layer for ALL queries (denoising part included), encoder proposals' class / box."""
         bs = mlvl_feats[0].size(0)
         dev = mlvl_feats[0].device
         in_h, in_w = img_metas[0]["batch_input_shape"]
@@ -174,6 +173,14 @@ class DINODETRHead(nn.Module):
         outputs_class = self.fc_cls[0](hs_all)
         interm_coord = ref_enc[-1]
         interm_class = self.fc_enc_cls(hs_enc[-1])
+        return hs, outputs_class, outputs_coord, interm_class, interm_coord
+
+    def forward(self, mlvl_feats, img_metas, input_query_label=None, input_query_bbox=None, attn_mask=None,
+                dn_meta=None):
+        """dino_detr_head.py:314-407 -> (outputs_class (n_dec, bs, Q, C), outputs_coord (n_dec, bs, Q, 4),
+        interm_outputs_class (bs, Q, C), interm_outputs_coord (bs, Q, 4), dn_outputs_class, dn_outputs_coord)"""
+        _, outputs_class, outputs_coord, interm_class, interm_coord = self._decode(
+            mlvl_feats, img_metas, input_query_label, input_query_bbox, attn_mask)
         if self.dn_number > 0 and dn_meta is not None:
             outputs_class, outputs_coord, dn_class, dn_coord = dn_post_process(outputs_class, outputs_coord, dn_meta)
         else:
@@ -181,11 +188,13 @@ class DINODETRHead(nn.Module):
         return outputs_class, outputs_coord, interm_class, interm_coord, dn_class, dn_coord
 
     # ------------------------------------------------------------------------------------------------
-    def _batched_terms(self, cls, box, labels, box_t, pos, factor):
+    def _batched_terms(self, cls, box, labels, box_t, pos, factor, cls_weight=None):
         """Element-wise loss terms summed per problem.  cls (P,Q,C), box/box_t (P,Q,4), labels/pos (P,Q),
-        factor (P,1,4) -> dict of (P,) sums (un-normalised, un-weighted)."""
+        factor (P,1,4), cls_weight (P,) or None -> dict of (P,) sums (un-normalised, un-weighted)."""
         w = pos.unsqueeze(-1).to(box.dtype)
         focal = sigmoid_focal_elementwise(cls, labels, self.num_classes, self.loss_cls.gamma, self.loss_cls.alpha)
+        if cls_weight is not None:
+            focal = focal * cls_weight[:, None, None]
         l1 = (box - box_t).abs() * w
         giou = giou_aligned(bbox_cxcywh_to_xyxy(box) * factor, bbox_cxcywh_to_xyxy(box_t) * factor, self.loss_iou.eps)
         return dict(loss_cls=focal.sum((1, 2)), loss_bbox=l1.sum((1, 2)), loss_bbox_xy=l1[..., :2].sum((1, 2)),
@@ -206,7 +215,7 @@ class DINODETRHead(nn.Module):
 
     def loss(self, all_cls_scores, all_bbox_preds, enc_cls_scores, enc_bbox_preds, dn_cls_scores, dn_bbox_preds,
              gt_bboxes_list, gt_labels_list, gt_scores_list=None, img_metas=None, dn_metas=None,
-             gt_bboxes_ignore=None, decouple=False):
+             gt_bboxes_ignore=None, decouple=False, zero_weight_empty_dn=False):
         """Same inputs and the same 65 keys as dino_detr_head.py:506-632."""
         assert gt_bboxes_ignore is None and gt_scores_list is None
         all_cls_scores, all_bbox_preds = all_cls_scores.float(), all_bbox_preds.float()        # force_fp32
@@ -251,40 +260,63 @@ class DINODETRHead(nn.Module):
 
         # --- denoising part: targets follow from the CDN layout, no matcher (:739-819) -------------------------
         if dn_cls_scores is not None and dn_bbox_preds is not None:
-            pad, groups = dn_metas["pad_size"], dn_metas["num_dn_group"]
-            single_pad = pad // groups            # = 2 * max_gt: positives then negatives of one group
-            half = single_pad // 2
-            total = sum(counts)
-
-            def build_ix():
-                z = [np.zeros(0, np.int64)]
-                bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)] + z)
-                within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts] + z)
-                return np.stack([np.tile(bid, groups),
-                                 np.concatenate([within + single_pad * g for g in range(groups)] + z),
-                                 np.tile(np.arange(total, dtype=np.int64), groups)])
-            ix = device_const(dev, "dn_loss_ix", (tuple(counts), groups, single_pad), build_ix)
-            dn_labels = torch.full((bs, pad), self.num_classes, dtype=torch.long, device=dev)
-            dn_pos = torch.zeros((bs, pad), dtype=torch.bool, device=dev)
-            dn_box_t = torch.zeros((bs, pad, 4), device=dev)
-            if total > 0:
-                real_labels = targets.gt_labels[:total]
-                dn_labels[ix[0], ix[1]] = real_labels[ix[2]]
-                dn_pos[ix[0], ix[1]] = True
-                dn_box_t[ix[0], ix[1]] = gt_norm[:total][ix[2]]
-            Ld = dn_cls_scores.shape[0]
-            Pd = Ld * bs
-            rep = lambda t: t[None].expand(Ld, *t.shape).reshape(Pd, *t.shape[1:])
-            dn_factor = wh4[:bs][:, None, :]
-            dsums = self._batched_terms(dn_cls_scores.float().reshape(Pd, pad, C),
-                                        dn_bbox_preds.float().reshape(Pd, pad, 4), rep(dn_labels), rep(dn_box_t),
-                                        rep(dn_pos), rep(dn_factor))
-            dn_num_pos = total * groups
-            dn = self._finish(dsums, Ld, bs, max(dn_num_pos * 1.0, 1), _clamp_min1(reduce_mean_scalar(dn_num_pos, dev)))
-            assert half >= 0
+            dn = self._dn_terms(dn_cls_scores, dn_bbox_preds, gt_bboxes_list, gt_labels_list, img_metas, dn_metas,
+                                zero_weight_empty_dn)
         else:
             dn = {k: torch.zeros(L, device=dev) for k in LOSS_PARTS}
+        return self._assemble(main, dn, L, has_enc)
 
+    def _dn_terms(self, dn_cls_scores, dn_bbox_preds, gt_bboxes_list, gt_labels_list, img_metas, dn_metas,
+                  zero_weight_empty_dn=False):
+        """Per-layer denoising losses.  Slot of GT k of image b in group g is g*single_pad + k (positives first,
+        negatives ``single_pad // 2`` later); everything else is background (dino_detr_head.py:739-819).  With
+        ``zero_weight_empty_dn`` an image without boxes contributes no classification loss
+        (dino_detr_ssod_head.py:921-924)."""
+        dev = dn_cls_scores.device
+        Ld, bs, pad, C = dn_cls_scores.shape
+        counts = [int(b.shape[0]) for b in gt_bboxes_list]
+        groups = dn_metas["num_dn_group"]
+        single_pad = pad // groups            # = 2 * max_gt: positives then negatives of one group
+        total = sum(counts)
+
+        def build_ix():
+            z = [np.zeros(0, np.int64)]
+            bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)] + z)
+            within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts] + z)
+            return np.stack([np.tile(bid, groups),
+                             np.concatenate([within + single_pad * g for g in range(groups)] + z),
+                             np.tile(np.arange(total, dtype=np.int64), groups)])
+        ix = device_const(dev, "dn_loss_ix", (tuple(counts), groups, single_pad), build_ix)
+        img_wh = tuple((float(m["img_shape"][1]), float(m["img_shape"][0])) for m in img_metas)
+        wh = device_const(dev, "img_wh", img_wh, lambda: torch.tensor(img_wh, dtype=torch.float32).reshape(-1, 2))
+        wh4 = torch.cat([wh, wh], 1)
+        dn_labels = torch.full((bs, pad), self.num_classes, dtype=torch.long, device=dev)
+        dn_pos = torch.zeros((bs, pad), dtype=torch.bool, device=dev)
+        dn_box_t = torch.zeros((bs, pad, 4), device=dev)
+        if total > 0:
+            seg_of_gt = device_const(dev, "seg_of_gt", tuple(counts), lambda: np.concatenate(
+                [np.full(c, s_, dtype=np.int64) for s_, c in enumerate(counts)]))
+            gt_all = torch.cat([b.reshape(-1, 4) for b in gt_bboxes_list]).to(dev, torch.float32)
+            lab_all = torch.cat([l.reshape(-1) for l in gt_labels_list]).to(dev, torch.long)
+            gt_norm = bbox_xyxy_to_cxcywh(gt_all / wh4[seg_of_gt])
+            dn_labels[ix[0], ix[1]] = lab_all[ix[2]]
+            dn_pos[ix[0], ix[1]] = torch.ones(ix.shape[1], dtype=torch.bool, device=dev)   # device value: graph-safe
+            dn_box_t[ix[0], ix[1]] = gt_norm[ix[2]]
+        Pd = Ld * bs
+        rep = lambda t: t[None].expand(Ld, *t.shape).reshape(Pd, *t.shape[1:])
+        cls_w = None
+        if zero_weight_empty_dn and any(c == 0 for c in counts):
+            cw = tuple(0.0 if c == 0 else 1.0 for c in counts)
+            cls_w = rep(device_const(dev, "dn_cls_w", cw, lambda: torch.tensor(cw, dtype=torch.float32)))
+        dsums = self._batched_terms(dn_cls_scores.float().reshape(Pd, pad, C),
+                                    dn_bbox_preds.float().reshape(Pd, pad, 4), rep(dn_labels), rep(dn_box_t),
+                                    rep(dn_pos), rep(wh4[:, None, :]), cls_w)
+        dn_num_pos = total * groups
+        return self._finish(dsums, Ld, bs, max(dn_num_pos * 1.0, 1), _clamp_min1(reduce_mean_scalar(dn_num_pos, dev)))
+
+    @staticmethod
+    def _assemble(main, dn, L, has_enc):
+        """Per-layer tensors -> the reference's loss dict (key order of dino_detr_head.py:584-632)."""
         loss_dict = {}
         if has_enc:
             for k in LOSS_PARTS:

@@ -1,0 +1,189 @@
+"""``DINODETRSSODHead`` -- host-side mirror of detr_od/models/dense_heads/dino_detr_ssod_head.py:42-1581.
+
+Two training phases keyed on ``curr_step`` (``warm_up_step`` = 60000 in the shipped config):
+ * warm-up   : ``assigner1`` = O2MAssigner (top-13 one-to-many) + ``loss_cls1`` = TaskAlignedFocalLoss, box losses
+               weighted by the normalised alignment metric (:665-738, :1110-1160);
+ * afterwards: ``assigner2`` = HungarianAssigner + ``loss_cls2`` = FocalLoss -- the batched device path of
+               ``DINODETRHead.loss`` (one cost launch + one solver launch for all layers x images).
+Also here: ``forward_dummy`` (returns the decoder states and splits off the consistency / denoising parts,
+:420-505), the pseudo-label decoding used on the teacher (sigmoid -> class-wise NMS 0.6, score > 0.01, top 300;
+:1332-1395), and the CDN variant that tolerates images without boxes (dn_components.py:128-274).
+"""
+import torch
+from torchvision.ops import batched_nms
+
+from ..consts import device_const
+from ..dino.dn_components import prepare_for_cdn
+from ..dino.head import LOSS_PARTS, DINODETRHead, _clamp_min1, reduce_mean_scalar
+from ..dino.losses import giou_aligned
+from ..matching.match_cost import bbox_cxcywh_to_xyxy, bbox_xyxy_to_cxcywh
+from ..registry import BBOX_ASSIGNERS, HEADS, LOSSES
+from . import o2m_assigner as _o2m  # noqa: F401  (registers O2MAssigner)
+from . import task_aligned_focal_loss as _tal  # noqa: F401
+from .o2m_assigner import normalized_alignment_metrics
+
+
+def _reduce_mean_tensor(t):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = t.clone()
+        dist.all_reduce(t.div_(dist.get_world_size()))
+    return t
+
+
+@HEADS.register_module()
+class DINODETRSSODHead(DINODETRHead):
+    def __init__(self, *args, loss_cls1=dict(type="TaskAlignedFocalLoss", use_sigmoid=True, gamma=2.0, loss_weight=2.0),
+                 loss_cls2=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+                 train_cfg=None, test_cfg=dict(max_per_img=300, warm_up_step=60000), **kwargs):
+        train_cfg = dict(train_cfg or {})
+        assigner1 = train_cfg.get("assigner1", dict(type="O2MAssigner"))
+        assigner2 = train_cfg.get("assigner2", dict(type="HungarianAssigner",
+                                                    cls_cost=dict(type="FocalLossCost", weight=2.0),
+                                                    reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+                                                    iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0)))
+        super().__init__(*args, loss_cls=loss_cls2, train_cfg=dict(assigner=assigner2), test_cfg=test_cfg, **kwargs)
+        self.loss_cls1 = LOSSES.build(loss_cls1)
+        self.loss_cls2 = self.loss_cls
+        self.assigner1 = BBOX_ASSIGNERS.build(assigner1)
+        self.assigner2 = self.assigner
+        self.warm_up_step = train_cfg.get("warm_up_step", (test_cfg or {}).get("warm_up_step", 60000))
+        self.in_warm_up = True
+        self.train_cfg = train_cfg
+
+    # ---------------------------------------------------------------------------------------------
+    def forward_dummy(self, mlvl_feats, img_metas, input_query_label=None, input_query_bbox=None, attn_mask=None,
+                      dn_meta=None):
+        """-> hs, outputs_class, outputs_coord, interm_class, interm_coord, consistency_class, consistency_coord,
+        dn_class, dn_coord   (dino_detr_ssod_head.py:420-505)"""
+        hs, cls_all, coord_all, interm_class, interm_coord = self._decode(mlvl_feats, img_metas, input_query_label,
+                                                                          input_query_bbox, attn_mask)
+        if self.dn_number > 0 and dn_meta is not None:
+            p1, p2 = dn_meta["pad_size_1"], dn_meta["pad_size_2"]
+            return (hs, cls_all[:, :, p1 + p2:], coord_all[:, :, p1 + p2:], interm_class, interm_coord,
+                    cls_all[:, :, :p1], coord_all[:, :, :p1], cls_all[:, :, p1:p1 + p2], coord_all[:, :, p1:p1 + p2])
+        return hs, cls_all, coord_all, interm_class, interm_coord, None, None, None, None
+
+    # ---------------------------------------------------------------------------------------------
+    def _warmup_terms(self, cls_stack, box_stack, gt_bboxes_list, gt_labels_list, img_metas, labels_override=None):
+        """O2M phase (:665-738): per (layer, image) assignment with the one-to-many assigner; returns per-layer
+        losses.  cls_stack (layers, bs, Q, C), box_stack (layers, bs, Q, 4)."""
+        layers, bs, Q, C = cls_stack.shape
+        dev = cls_stack.device
+        out = {k: [] for k in LOSS_PARTS}
+        for l in range(layers):
+            labels, box_t, box_w, metrics, facs = [], [], [], [], []
+            for i in range(bs):
+                gl = gt_labels_list[i] if labels_override is None or l < layers - 1 else labels_override[i]
+                h, w, _ = img_metas[i]["img_shape"]
+                fac = device_const(dev, "whwh", (w, h), lambda: torch.tensor([w, h, w, h], dtype=torch.float32))
+                res = self.assigner1.assign(box_stack[l, i].detach(), cls_stack[l, i].detach().sigmoid(),
+                                            gt_bboxes_list[i], gl, img_metas[i])
+                pos = res.gt_inds > 0
+                g = (res.gt_inds - 1).clamp(min=0)
+                if gt_bboxes_list[i].shape[0] > 0:
+                    lab = torch.where(pos, gl.long()[g], torch.full_like(g, self.num_classes))
+                    bt = bbox_xyxy_to_cxcywh(gt_bboxes_list[i][g] / fac) * pos[:, None]
+                    nm = normalized_alignment_metrics(res)
+                else:
+                    lab = torch.full((Q,), self.num_classes, dtype=torch.long, device=dev)
+                    bt = torch.zeros((Q, 4), device=dev)
+                    nm = torch.zeros((Q,), device=dev)
+                labels.append(lab); box_t.append(bt); metrics.append(nm)
+                box_w.append(nm[:, None].expand(-1, 4))
+                facs.append(fac[None].expand(Q, 4))
+            labels, box_t, box_w = torch.cat(labels), torch.cat(box_t), torch.cat(box_w)
+            metrics, facs = torch.cat(metrics), torch.cat(facs)
+            cls = cls_stack[l].reshape(-1, C)
+            box = box_stack[l].reshape(-1, 4)
+            sum_metrics = _reduce_mean_tensor(metrics.sum().reshape(1)).clamp(min=1.0)
+            out["loss_cls"].append(self.loss_cls1(cls.sigmoid(), labels, metrics, avg_factor=sum_metrics))
+            reg_avg = _reduce_mean_tensor(box_w[:, 0].sum().reshape(1)).clamp(min=1.0)
+            giou = giou_aligned(bbox_cxcywh_to_xyxy(box) * facs, bbox_cxcywh_to_xyxy(box_t) * facs, self.loss_iou.eps)
+            out["loss_iou"].append(((1 - giou) * box_w[:, 0]).sum() / reg_avg[0] * self.loss_iou.loss_weight)
+            l1 = (box - box_t).abs() * box_w
+            out["loss_bbox"].append(l1.sum() / reg_avg[0] * self.loss_bbox.loss_weight)
+            out["loss_bbox_xy"].append(l1[:, :2].sum() / reg_avg[0] * self.loss_bbox.loss_weight)
+            out["loss_bbox_hw"].append(l1[:, 2:].sum() / reg_avg[0] * self.loss_bbox.loss_weight)
+        return {k: torch.stack([x.reshape(()) for x in v]) for k, v in out.items()}
+
+    def loss(self, all_cls_scores, all_bbox_preds, enc_cls_scores, enc_bbox_preds, dn_cls_scores, dn_bbox_preds,
+             gt_bboxes_list, gt_labels_list, gt_scores_list=None, img_metas=None, dn_metas=None,
+             gt_bboxes_ignore=None, is_pseudo_label=False):
+        """dino_detr_ssod_head.py:508-625.  In the Hungarian phase ``gt_scores_list`` is accepted and -- like the
+        reference's ``_get_target_single`` (:1170-1205) -- not used for the weights."""
+        if not self.in_warm_up:
+            dn_meta = dn_metas
+            if dn_metas is not None and is_pseudo_label:
+                dn_meta = dict(pad_size=dn_metas["pad_size_2"], num_dn_group=dn_metas["num_dn_group_2"])
+            return super().loss(all_cls_scores, all_bbox_preds, enc_cls_scores, enc_bbox_preds, dn_cls_scores,
+                                dn_bbox_preds, gt_bboxes_list, gt_labels_list, None, img_metas=img_metas,
+                                dn_metas=dn_meta, gt_bboxes_ignore=gt_bboxes_ignore, zero_weight_empty_dn=True)
+        # ---- warm-up: O2M matching part; DN part as in the Hungarian phase (skipped for pseudo labels, :548-553)
+        L = all_cls_scores.shape[0]
+        cls_stack = torch.cat([all_cls_scores.float(), enc_cls_scores.float()[None]])
+        box_stack = torch.cat([all_bbox_preds.float(), enc_bbox_preds.float()[None]])
+        zero_labels = [torch.zeros_like(l) for l in gt_labels_list]
+        main = self._warmup_terms(cls_stack, box_stack, gt_bboxes_list, gt_labels_list, img_metas, zero_labels)
+        dev = cls_stack.device
+        if is_pseudo_label or dn_cls_scores is None:
+            dn = {k: torch.zeros(L, device=dev) for k in LOSS_PARTS}
+        else:
+            dn = self._dn_terms(dn_cls_scores, dn_bbox_preds, gt_bboxes_list, gt_labels_list, img_metas, dn_metas,
+                                zero_weight_empty_dn=True)
+        return self._assemble(main, dn, L, True)
+
+    # ---------------------------------------------------------------------------------------------
+    def forward_train(self, x, img_metas, gt_bboxes, gt_labels, gt_scores=None, gt_bboxes_ignore=None,
+                      proposal_cfg=None, curr_step=None, is_pseudo_label=False, **kwargs):
+        """dino_detr_ssod_head.py:1208-1279 (CDN that tolerates empty images, phase switch on curr_step)."""
+        assert proposal_cfg is None
+        if curr_step is not None:
+            self.in_warm_up = curr_step < self.warm_up_step
+        if self.dn_number > 0:
+            boxes = []
+            for meta, b in zip(img_metas, gt_bboxes):
+                h, w, _ = meta["img_shape"]
+                fac = device_const(b.device, "whwh", (w, h), lambda: torch.tensor([w, h, w, h], dtype=torch.float32))
+                boxes.append(bbox_xyxy_to_cxcywh(b) / fac)
+            q_label, q_bbox, attn_mask, dn_meta = prepare_for_cdn(
+                dn_args=(dict(labels=gt_labels, boxes=boxes), self.dn_number, self.dn_label_noise_ratio,
+                         self.dn_box_noise_scale),
+                training=True, num_queries=self.num_query, num_classes=self.num_classes, hidden_dim=self.embed_dims,
+                label_enc=self.label_enc, fill_empty=True)
+        else:
+            q_label = q_bbox = attn_mask = dn_meta = None
+        outs = self(x, img_metas, q_label, q_bbox, attn_mask, dn_meta)
+        return self.loss(*outs, gt_bboxes, gt_labels, gt_scores, img_metas=img_metas, dn_metas=dn_meta,
+                         gt_bboxes_ignore=gt_bboxes_ignore, is_pseudo_label=is_pseudo_label)
+
+    # ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def simple_test_bboxes(self, feats, img_metas, rescale=False, curr_step=None, for_pseudo_label=False):
+        """Teacher decoding for pseudo labels (:1281-1400): last decoder layer, sigmoid, class-wise NMS.
+        -> list of (det_bboxes (n, 5) [x1 y1 x2 y2 score], det_labels (n,))"""
+        if curr_step is not None:
+            self.in_warm_up = curr_step < self.warm_up_step
+        cls_all, coord_all = self.forward(feats, img_metas)[:2]
+        cls, box = cls_all[-1], coord_all[-1]
+        max_per_img = (self.test_cfg or {}).get("max_per_img", self.num_query)
+        results = []
+        for i, meta in enumerate(img_metas):
+            h, w = meta["img_shape"][:2]
+            scores = cls[i].sigmoid()
+            b = bbox_cxcywh_to_xyxy(box[i])
+            b = torch.stack([(b[:, 0] * w).clamp(0, w), (b[:, 1] * h).clamp(0, h),
+                             (b[:, 2] * w).clamp(0, w), (b[:, 3] * h).clamp(0, h)], -1)
+            if rescale:
+                b = b / b.new_tensor(meta["scale_factor"])
+            if self.in_warm_up or for_pseudo_label:
+                # mmdet multiclass_nms: every (query, class) pair above the score threshold competes
+                keep_mask = scores > 0.01
+                q_idx, c_idx = keep_mask.nonzero(as_tuple=True)
+                bb, ss = b[q_idx], scores[q_idx, c_idx]
+                keep = batched_nms(bb, ss, c_idx, 0.6)[:max_per_img]
+                results.append((torch.cat([bb[keep], ss[keep, None]], 1), c_idx[keep]))
+            else:
+                s, idx = scores.reshape(-1).topk(max_per_img)
+                results.append((torch.cat([b[idx // self.num_classes], s[:, None]], 1), idx % self.num_classes))
+        return results
