@@ -100,3 +100,54 @@ def coco_like_batch(batch_size=2, height=800, width=1333, seed=0, device="cpu", 
         gt_bboxes = [b.to(device, non_blocking=True) for b in gt_bboxes]
         gt_labels = [l.to(device, non_blocking=True) for l in gt_labels]
     return dict(img=img, img_metas=metas, gt_bboxes=gt_bboxes, gt_labels=gt_labels)
+
+
+# ---- Semi-DETR teacher-student step inputs -----------------------------
+
+def ssod_model_cfg(warm_up_step=60000):
+    """``semi_wrapper`` of configs/detr_ssod/detr_ssod_dino_detr_r50_coco_120k.py:27-39 around the model of
+    configs/dino_detr/dino_detr_ssod_r50_coco_120k.py:7-53."""
+    import copy
+    model = copy.deepcopy(DINO_R50_4SCALE)
+    head = model["bbox_head"]
+    head["type"] = "DINODETRSSODHead"
+    head["loss_cls1"] = dict(type="TaskAlignedFocalLoss", use_sigmoid=True, gamma=2.0, loss_weight=2.0)
+    head["loss_cls2"] = head.pop("loss_cls")
+    model["train_cfg"] = dict(assigner1=dict(type="O2MAssigner"), assigner2=model["train_cfg"]["assigner"],
+                              warm_up_step=warm_up_step)
+    model["test_cfg"] = dict(max_per_img=300, warm_up_step=warm_up_step)
+    return dict(type="DinoDetrSSOD", model=model,
+                train_cfg=dict(use_teacher_proposal=False, pseudo_label_initial_score_thr=0.4, min_pseduo_box_size=0,
+                               unsup_weight=4.0, aug_query=False),
+                test_cfg=dict(inference_on="student"))
+
+
+def ssod_batch(n_sup=1, n_unsup=4, height=800, width=1333, seed=0, device="cpu"):
+    """1 labelled + ``n_unsup`` unlabelled pairs per GPU (sample_ratio [1, 4], samples_per_gpu 5): the weak
+    (teacher) and strong (student) views are the same synthetic image, the strong one horizontally flipped, with the
+    3x3 ``transform_matrix`` each pipeline would have recorded."""
+    import numpy as np
+    sup = coco_like_batch(n_sup, height, width, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    weak = torch.randn(n_unsup, 3, height, width, generator=g)
+    strong = weak.flip(-1)
+    flip = np.array([[-1.0, 0.0, width], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]], dtype=np.float32)
+    metas, imgs = [], []
+    for m in sup["img_metas"]:
+        m.update(tag="sup", filename=f"sup{len(metas)}", transform_matrix=np.eye(3, dtype=np.float32))
+        metas.append(m)
+    shape = dict(img_shape=(height, width, 3), pad_shape=(height, width, 3), ori_shape=(height, width, 3),
+                 scale_factor=1.0)
+    for i in range(n_unsup):
+        metas.append(dict(shape, tag="unsup_teacher", filename=f"u{i}", transform_matrix=np.eye(3, dtype=np.float32)))
+    for i in range(n_unsup):
+        metas.append(dict(shape, tag="unsup_student", filename=f"u{i}", transform_matrix=flip))
+    img = torch.cat([sup["img"], weak, strong])
+    empty_b, empty_l = torch.zeros(0, 4), torch.zeros(0, dtype=torch.long)
+    gt_bboxes = sup["gt_bboxes"] + [empty_b.clone() for _ in range(2 * n_unsup)]
+    gt_labels = sup["gt_labels"] + [empty_l.clone() for _ in range(2 * n_unsup)]
+    if device != "cpu":
+        img = img.to(device)
+        gt_bboxes = [b.to(device) for b in gt_bboxes]
+        gt_labels = [l.to(device) for l in gt_labels]
+    return dict(img=img, img_metas=metas, gt_bboxes=gt_bboxes, gt_labels=gt_labels)

@@ -1,3 +1,3 @@
-from .mean_teacher import EmaPlan, MeanTeacher
+from .mean_teacher import EmaPlan, MeanTeacher, StepRecord
 
-__all__ = ["EmaPlan", "MeanTeacher"]
+__all__ = ["EmaPlan", "MeanTeacher", "StepRecord"]

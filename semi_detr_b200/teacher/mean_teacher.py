@@ -115,3 +115,17 @@ class MeanTeacher:
                                  [p.data for _, p in model.student.named_parameters()])
             self._plan_model = model
         self._plan.step(momentum)
+
+
+@HOOKS.register_module()
+class StepRecord:
+    """detr_ssod/utils/hooks/step_record.py:7-27: publishes the runner's iteration on the model."""
+
+    def __init__(self, normalize=True, name="curr_step"):
+        self.normalize, self.name = normalize, name
+
+    def before_train_iter(self, runner):
+        model = _unwrap(runner.model)
+        assert hasattr(model, self.name)
+        it = getattr(runner, "iter", None)
+        setattr(model, self.name, it / 10000 if self.normalize else it)
