@@ -172,6 +172,22 @@ typedef struct {
 int sdb_ema_update_f32(sdb_stream_t stream, const sdb_ema_chunk* chunks, int num_chunks,
                        double momentum);
 
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over d_model = 256 (the transformer's channel dimension), forward and backward.
+ *
+ * Replaces the nn.LayerNorm calls of the DINO encoder / decoder layers
+ * (detr_od/models/utils/transformer.py:606-642, 762-791, 1039): y = (x - mean) * rstd * gamma + beta with torch's
+ * statistics (biased variance, eps inside the square root).  `mean` / `rstd` (rows floats each) are saved by the
+ * forward for the backward.  The backward needs a scratch buffer of sdb_layernorm_bwd_workspace_floats() floats.
+ * cols other than 256 return SDB_ERR_UNSUPPORTED (the host layer then uses the library LayerNorm).
+ * ------------------------------------------------------------------------------------------ */
+int sdb_layernorm_bwd_workspace_floats(void);
+int sdb_layernorm_forward_f32(sdb_stream_t stream, const float* x, const float* gamma, const float* beta,
+                              int64_t rows, int cols, float eps, float* y, float* mean, float* rstd);
+int sdb_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float* x, const float* gamma,
+                               const float* mean, const float* rstd, int64_t rows, int cols, float* dx,
+                               float* dgamma, float* dbeta, float* workspace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,12 +27,16 @@ SIGNATURES = {
     "sdb_lsap_solve_f32": [c_void_p] * 6 + [c_int] * 3 + [c_void_p] * 3,
     "sdb_hungarian_assign_f32": [c_void_p] * 9 + [c_int] * 4 + [c_float] * 3 + [c_void_p] * 5,
     "sdb_ema_update_f32": [c_void_p, c_void_p, c_int, c_double],
+    "sdb_layernorm_bwd_workspace_floats": [],
+    "sdb_layernorm_forward_f32": [c_void_p] * 4 + [ctypes.c_int64, c_int, c_float] + [c_void_p] * 3,
+    "sdb_layernorm_backward_f32": [c_void_p] * 6 + [ctypes.c_int64, c_int] + [c_void_p] * 4,
 }
 
 _lib = None
 
 # kernels of this library launched so far, by entry point (bench.py reports the per-step count)
-LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0}
+LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,
+            "layernorm_forward": 0, "layernorm_backward": 0}
 
 
 class EmaChunk(ctypes.Structure):

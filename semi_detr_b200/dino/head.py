@@ -40,7 +40,8 @@ def reduce_mean_scalar(value, device):
     """mmdet core/utils/dist_utils.py:67-73 for a host scalar: mean over ranks, kept on the device (no .item())."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)
-    t = torch.tensor([float(value)], device=device)
+    v = float(value)
+    t = device_const(device, "scalar", v, lambda: torch.tensor([v], dtype=torch.float32)).clone()   # graph-safe
     dist.all_reduce(t.div_(dist.get_world_size()), op=dist.ReduceOp.SUM)
     return t
 

@@ -1,0 +1,54 @@
+"""``LayerNorm`` -- an ``nn.LayerNorm`` (same parameters / state dict, transformer.py:606-642, 762-791, 1039) whose
+CUDA path is the sm_100a kernel pair of ``csrc/layernorm.cu`` when normalising fp32 over d_model = 256.  Other
+widths / dtypes use the library LayerNorm (plumbing outside the shipped configs)."""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import _lib
+
+_WS = {}
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x2 = x.contiguous()
+        rows = x2.numel() // x2.shape[-1]
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().sdb_layernorm_forward_f32(_lib.current_stream(x.device), x2.data_ptr(), weight.data_ptr(),
+                                                      bias.data_ptr(), rows, x2.shape[-1], eps, y.data_ptr(),
+                                                      mean.data_ptr(), rstd.data_ptr())
+        _lib.check(rc, "layernorm_forward")
+        _lib.LAUNCHES["layernorm_forward"] += 1
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows = x.numel() // x.shape[-1]
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(weight)
+        dbeta = torch.empty_like(weight)
+        ws = torch.empty(_lib.lib().sdb_layernorm_bwd_workspace_floats(), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().sdb_layernorm_backward_f32(_lib.current_stream(x.device), dy.data_ptr(), x.data_ptr(),
+                                                       weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows,
+                                                       x.shape[-1], dx.data_ptr(), dgamma.data_ptr(),
+                                                       dbeta.data_ptr(), ws.data_ptr())
+        _lib.check(rc, "layernorm_backward")
+        _lib.LAUNCHES["layernorm_backward"] += 2
+        return dx, dgamma, dbeta, None
+
+
+class LayerNorm(nn.LayerNorm):
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and self.normalized_shape == (256,) and self.elementwise_affine
+                and self.weight.dtype == torch.float32):
+            return _LayerNormFn.apply(x, self.weight, self.bias, self.eps)
+        return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)

@@ -21,6 +21,7 @@ from torch import nn
 from ..consts import device_const
 from ..msda import MSDeformAttn
 from ..registry import TRANSFORMER
+from .layernorm import LayerNorm
 
 
 def inverse_sigmoid(x, eps=1e-5):
@@ -108,12 +109,12 @@ class DINOTransformerEncoderLayer(nn.Module):
         assert activation == "relu"
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
         self.dropout1 = nn.Dropout(dropout)
-        self.norm1 = nn.LayerNorm(d_model)
+        self.norm1 = LayerNorm(d_model)
         self.linear1 = nn.Linear(d_model, d_ffn)
         self.dropout2 = nn.Dropout(dropout)
         self.linear2 = nn.Linear(d_ffn, d_model)
         self.dropout3 = nn.Dropout(dropout)
-        self.norm2 = nn.LayerNorm(d_model)
+        self.norm2 = LayerNorm(d_model)
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
         q = src if pos is None else src + pos
@@ -172,15 +173,15 @@ class DINOTransformerDecoderLayer(nn.Module):
         self.module_seq = list(module_seq)
         self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
         self.dropout1 = nn.Dropout(dropout)
-        self.norm1 = nn.LayerNorm(d_model)
+        self.norm1 = LayerNorm(d_model)
         self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
         self.dropout2 = nn.Dropout(dropout)
-        self.norm2 = nn.LayerNorm(d_model)
+        self.norm2 = LayerNorm(d_model)
         self.linear1 = nn.Linear(d_model, d_ffn)
         self.dropout3 = nn.Dropout(dropout)
         self.linear2 = nn.Linear(d_ffn, d_model)
         self.dropout4 = nn.Dropout(dropout)
-        self.norm3 = nn.LayerNorm(d_model)
+        self.norm3 = LayerNorm(d_model)
 
     def forward(self, tgt, query_pos, reference_points, memory, memory_key_padding_mask, level_start_index,
                 spatial_shapes, self_attn_mask=None):
@@ -262,15 +263,15 @@ class DINOTransformer(nn.Module):
         enc_layer = DINOTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
                                                 nhead, enc_n_points)
         self.encoder = DINOTransformerEncoder(enc_layer, num_encoder_layers,
-                                              nn.LayerNorm(d_model) if normalize_before else None, d_model)
+                                              LayerNorm(d_model) if normalize_before else None, d_model)
         dec_layer = DINOTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
                                                 nhead, dec_n_points, decoder_sa_type, module_seq)
-        self.decoder = DINOTransformerDecoder(dec_layer, num_decoder_layers, nn.LayerNorm(d_model), d_model,
+        self.decoder = DINOTransformerDecoder(dec_layer, num_decoder_layers, LayerNorm(d_model), d_model,
                                               query_dim, num_feature_levels)
         self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model)) if num_feature_levels > 1 else None
         self.tgt_embed = nn.Embedding(num_queries, d_model)
         self.enc_output = nn.Linear(d_model, d_model)
-        self.enc_output_norm = nn.LayerNorm(d_model)
+        self.enc_output_norm = LayerNorm(d_model)
         self._reset_parameters()
 
     def _reset_parameters(self):
