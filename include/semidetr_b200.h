@@ -92,6 +92,27 @@ int sdb_msda_backward_f64(sdb_stream_t stream, const double* grad_out, const dou
                           int num_query, int num_point, double* grad_value,
                           double* grad_sampling_loc, double* grad_attn_weight);
 
+/* Fused prologue (NOT part of the reference surface, apply() stays the compatibility
+ * path).  Takes the module's RAW linear outputs instead of materialised locations / weights
+ * (modules/ms_deform_attn.py:96-112):
+ *   sampling_offsets (batch, num_query, num_heads, num_levels, num_point, 2)   sampling_offsets(query)
+ *   attn_logits      (batch, num_query, num_heads, num_levels * num_point)     attention_weights(query), pre-softmax
+ *   reference_points (batch, num_query, num_levels, ref_dim), ref_dim 2 (encoder) or 4 (decoder)
+ * and evaluates softmax + location arithmetic in registers.  The backward returns gradients w.r.t. value, the raw
+ * offsets and the raw logits (none w.r.t. the reference points: DINO detaches them, transformer.py:1030-1036).
+ * Built for channels 32, heads 8, points 4, levels*points <= 16; other shapes return SDB_ERR_UNSUPPORTED. */
+int sdb_msda_fused_forward_f32(sdb_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                               const int64_t* level_start_index, const float* reference_points, int ref_dim,
+                               const float* sampling_offsets, const float* attn_logits, int batch,
+                               int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                               int num_point, float* out);
+int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* grad_out, const float* value,
+                                const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                const float* reference_points, int ref_dim, const float* sampling_offsets,
+                                const float* attn_logits, int batch, int spatial_size, int num_heads,
+                                int channels, int num_levels, int num_query, int num_point, float* grad_value,
+                                float* grad_offsets, float* grad_attn_logits);
+
 /* Tuning knob for benchmarking kernel variants (0 = default heuristic).  Not part of the
  * reference surface; see DESIGN.md "MSDA forward variants". */
 int sdb_msda_set_variant(int forward_variant, int backward_variant);

@@ -108,7 +108,7 @@ __device__ __forceinline__ BwdPrep bwd_prep(const LevelTable& lt, int lvl, float
   BwdPrep r;
   r.lh = t.lh;
   r.lw = t.lw;
-  r.a = t.ok ? a : 0.f;
+  r.a = a;   // not masked: an out-of-range sample has no valid corner, so every term it feeds is already zero
   const int mask = (t.c00 ? 1 : 0) | (t.c01 ? 2 : 0) | (t.c10 ? 4 : 0) | (t.c11 ? 8 : 0);
   r.offm = ((lt.start[lvl] + t.h0 * W + t.w0) * px_stride) | mask;
   return r;
@@ -120,13 +120,15 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-template <int kThreads, int TH, int TW, int kMinBlocks>
+// kFused: `loc` / `attn` are the RAW sampling offsets / attention logits, (ref, ref_dim) the reference points, and
+// the outputs are the gradients w.r.t. those raw tensors (location arithmetic and softmax differentiated here).
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                     const float* __restrict__ loc, const float* __restrict__ attn, int batch, int S, int L,
                     int Lq, int tiled, float* __restrict__ grad_value, float* __restrict__ grad_loc,
-                    float* __restrict__ grad_attn) {
+                    float* __restrict__ grad_attn, const float* __restrict__ ref = nullptr, int ref_dim = 0) {
   constexpr int M = 8, P = 4;
   constexpr int px_stride = M * 32;
   __shared__ LevelTable lt;
@@ -166,10 +168,16 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
         const int pt = c0 + 2 * j;
         float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 a2 = make_float2(0.f, 0.f);
-        if (live && pt < LP) {
+        const long long nq = (long long)n * Lq + (live ? q : 0);
+        if (kFused) {
+          const FusedPoints fp = fused_prologue(lt, ref, ref_dim, loc, attn, nq, pair, L, P, LP, pt, live);
+          l4 = fp.loc;
+          a2 = fp.a;
+        } else if (live && pt < LP) {
           l4 = ld_stream_f4(reinterpret_cast<const float4*>(lp + 2 * pt));
           a2 = ld_stream_f2(reinterpret_cast<const float2*>(ap + pt));
         }
+        float sm_a[4] = {0.f, 0.f, 0.f, 0.f}, sm_g[4] = {0.f, 0.f, 0.f, 0.f};   // fused: softmax backward state
         const int lvj = min(pt / P, L - 1);   // both of this lane's points sit on one level (P = 4)
         const BwdPrep p0 = bwd_prep(lt, lvj, l4.x, l4.y, a2.x, px_stride);
         const BwdPrep p1 = bwd_prep(lt, lvj, l4.z, l4.w, a2.y, px_stride);
@@ -235,12 +243,33 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
           const int point = c0 + 4 * b + (j >> 1);
           if (live) {
             if ((j & 1) == 0) {
-              const float gx = (float)lt.W[lvl] * ka * (hh * (f[1] - f[0]) + klh * (f[3] - f[2]));
-              const float gy = (float)lt.H[lvl] * ka * (hw * (f[2] - f[0]) + klw * (f[3] - f[1]));
+              float gx = (float)lt.W[lvl] * ka * (hh * (f[1] - f[0]) + klh * (f[3] - f[2]));
+              float gy = (float)lt.H[lvl] * ka * (hw * (f[2] - f[0]) + klw * (f[3] - f[1]));
+              if (kFused) {   // chain through loc = ref + off * (sx, sy)
+                if (ref_dim == 2) {
+                  gx *= 1.f / (float)lt.W[lvl];
+                  gy *= 1.f / (float)lt.H[lvl];
+                } else {
+                  const float* rp = ref + (nq * L + lvl) * 4;
+                  gx *= rp[2] * 0.5f / (float)P;
+                  gy *= rp[3] * 0.5f / (float)P;
+                }
+              }
               st_stream_f2(reinterpret_cast<float2*>(grad_loc + (pair * LP + point) * 2), make_float2(gx, gy));
             } else {
-              grad_attn[pair * LP + point] = hh * (hw * f[0] + klw * f[1]) + klh * (hw * f[2] + klw * f[3]);
+              const float ga = hh * (hw * f[0] + klw * f[1]) + klh * (hw * f[2] + klw * f[3]);
+              if (kFused) { sm_a[b] = ka; sm_g[b] = ga; }
+              else grad_attn[pair * LP + point] = ga;
             }
+          }
+        }
+        if (kFused) {
+          // softmax backward over the pair's L*P points: dlogit_i = a_i * (ga_i - sum_j a_j ga_j)
+          const float dotp = group8_sum(sm_a[0] * sm_g[0] + sm_a[1] * sm_g[1] + sm_a[2] * sm_g[2] + sm_a[3] * sm_g[3]);
+          if (live && (j & 1)) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (b < nb) grad_attn[pair * LP + c0 + 4 * b + (j >> 1)] = sm_a[b] * (sm_g[b] - dotp);
           }
         }
       }
@@ -248,11 +277,12 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
   }
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks>
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false>
 static int launch_bwd_d32(cudaStream_t st, const float* grad_out, const float* value, const int64_t* shapes,
                           const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int M,
-                          int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn) {
-  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks>;
+                          int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn,
+                          const float* ref = nullptr, int ref_dim = 0) {
+  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kFused>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -266,7 +296,7 @@ static int launch_bwd_d32(cudaStream_t st, const float* grad_out, const float* v
   if (grid > approx_items) grid = approx_items;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, kThreads, 0, st>>>(grad_out, value, shapes, lsi, loc, attn, batch, S, L, Lq, tiled,
-                                           grad_value, grad_loc, grad_attn);
+                                           grad_value, grad_loc, grad_attn, ref, ref_dim);
   SDB_LAUNCH_CHECK("msda_bwd_d32_kernel");
   return SDB_OK;
 }
@@ -330,6 +360,35 @@ extern "C" int sdb_msda_backward_f32(sdb_stream_t stream, const float* grad_out,
                                    sampling_loc, attn_weight, batch, spatial_size, num_heads, channels,
                                    num_levels, num_query, num_point, grad_value, grad_sampling_loc,
                                    grad_attn_weight);
+}
+
+extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* grad_out, const float* value,
+                                           const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                           const float* reference_points, int ref_dim,
+                                           const float* sampling_offsets, const float* attn_logits, int batch,
+                                           int spatial_size, int num_heads, int channels, int num_levels,
+                                           int num_query, int num_point, float* grad_value, float* grad_offsets,
+                                           float* grad_attn_logits) {
+  using namespace sdb;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = spatial_size, M = num_heads, L = num_levels, Lq = num_query, P = num_point;
+  SDB_REQUIRE(batch >= 0 && S >= 0 && Lq >= 0, "msda_fused_backward: bad sizes");
+  if (!(channels == 32 && M == 8 && P == 4 && L * P <= 16 && L <= kMaxLevels && (ref_dim == 2 || ref_dim == 4) &&
+        (long long)S * M * channels < (1ll << 31))) {
+    set_error("msda_fused_backward: built for channels=32, heads=8, points=4, levels*points<=16, ref_dim 2|4");
+    return SDB_ERR_UNSUPPORTED;
+  }
+  const long long nv = (long long)batch * S * M * channels;
+  if (nv > 0) {
+    SDB_REQUIRE(grad_value, "msda_fused_backward: null grad_value");
+    SDB_CUDA(cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)nv, st));
+  }
+  if ((long long)batch * Lq == 0) return SDB_OK;
+  SDB_REQUIRE(grad_out && value && spatial_shapes && level_start_index && reference_points && sampling_offsets &&
+              attn_logits && grad_offsets && grad_attn_logits, "msda_fused_backward: null pointer");
+  return launch_bwd_d32<128, 4, 8, 6, true>(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets,
+                                            attn_logits, batch, S, M, L, Lq, P, grad_value, grad_offsets,
+                                            grad_attn_logits, reference_points, ref_dim);
 }
 
 extern "C" int sdb_msda_backward_f64(sdb_stream_t stream, const double* grad_out, const double* value,

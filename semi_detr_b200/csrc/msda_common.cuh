@@ -101,4 +101,70 @@ struct TileCursor {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Fused prologue: the module's softmax over the L*P attention logits and its
+// sampling-location arithmetic (modules/ms_deform_attn.py:98-112) evaluated by the lane that owns the two points,
+// so the (N, Lq, M, L, P, 2) locations and (N, Lq, M, L, P) weights are never materialised in HBM.
+//   ref_dim == 2 (encoder):  loc = ref + off / (W_l, H_l)
+//   ref_dim == 4 (decoder):  loc = ref_xy + off / P * ref_wh * 0.5
+// `sx`, `sy` return d(loc)/d(off) for the backward.  One chunk only: L*P <= 16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float group8_max(float v) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, 8));
+  return v;
+}
+__device__ __forceinline__ float group8_sum(float v) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 8);
+  return v;
+}
+
+struct FusedPoints {
+  float4 loc;   // x0 y0 x1 y1
+  float2 a;     // softmax weights of the two points
+  float sx, sy; // d loc / d offset (same for both points: they sit on one level)
+};
+
+__device__ __forceinline__ FusedPoints fused_prologue(const LevelTable& lt, const float* __restrict__ ref,
+                                                      int ref_dim, const float* __restrict__ offsets,
+                                                      const float* __restrict__ logits, long long nq, long long pair,
+                                                      int L, int P, int LP, int pt, bool live) {
+  FusedPoints r;
+  const bool on = live && pt < LP;
+  float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 lg = make_float2(live ? -INFINITY : 0.f, live ? -INFINITY : 0.f);
+  if (on) {
+    off = ld_stream_f4(reinterpret_cast<const float4*>(offsets + pair * LP * 2 + 2 * pt));
+    lg = ld_stream_f2(reinterpret_cast<const float2*>(logits + pair * LP + pt));
+  }
+  const float mx = group8_max(fmaxf(lg.x, lg.y));
+  const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx);
+  const float inv = 1.f / group8_sum(e0 + e1);
+  r.a = make_float2(on ? e0 * inv : 0.f, on ? e1 * inv : 0.f);
+  const int lvl = min(pt / P, L - 1);
+  const float* rp = ref + (nq * L + lvl) * ref_dim;
+  float rx = 0.f, ry = 0.f;
+  r.sx = r.sy = 0.f;
+  if (on) {
+    rx = rp[0];
+    ry = rp[1];
+    if (ref_dim == 2) {
+      r.sx = 1.f / (float)lt.W[lvl];
+      r.sy = 1.f / (float)lt.H[lvl];
+      r.loc = make_float4(rx + off.x / (float)lt.W[lvl], ry + off.y / (float)lt.H[lvl],
+                          rx + off.z / (float)lt.W[lvl], ry + off.w / (float)lt.H[lvl]);
+    } else {
+      const float rw = rp[2], rh = rp[3];
+      r.sx = rw * 0.5f / (float)P;
+      r.sy = rh * 0.5f / (float)P;
+      r.loc = make_float4(rx + off.x / (float)P * rw * 0.5f, ry + off.y / (float)P * rh * 0.5f,
+                          rx + off.z / (float)P * rw * 0.5f, ry + off.w / (float)P * rh * 0.5f);
+    }
+  } else {
+    r.loc = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return r;
+}
+
 }  // namespace sdb

@@ -101,12 +101,14 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep>
+// kFused: `loc` / `attn` hold the RAW sampling offsets / attention logits and (ref, ref_dim) the reference points;
+// locations and softmax weights are formed in registers (fused_prologue).
+template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep, bool kFused = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, int batch, int S, int M, int L, int Lq, int P,
-                    int tiled, float* __restrict__ out) {
+                    int tiled, float* __restrict__ out, const float* __restrict__ ref = nullptr, int ref_dim = 0) {
   __shared__ LevelTable lt;
   const int px_stride = kHeads > 0 ? kHeads * 32 : M * 32;
   load_levels<TH, TW>(lt, shapes, lsi, L, px_stride);
@@ -143,7 +145,12 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
         const int pt = c0 + 2 * j;
         float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 a2 = make_float2(0.f, 0.f);   // weight 0 -> a dead group / padded point gathers nothing
-        if (live && pt < LP) {
+        if (kFused) {
+          const FusedPoints fp = fused_prologue(lt, ref, ref_dim, loc, attn, (long long)n * Lq + (live ? q : 0), pair,
+                                                L, P, LP, pt, live);
+          l4 = fp.loc;
+          a2 = fp.a;
+        } else if (live && pt < LP) {
           l4 = ld_stream_f4(reinterpret_cast<const float4*>(lp + 2 * pt));
           a2 = ld_stream_f2(reinterpret_cast<const float2*>(ap + pt));
         }
@@ -196,11 +203,11 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
   }
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep>
+template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep, bool kFused = false>
 static int launch_fwd_d32(cudaStream_t st, const float* value, const int64_t* shapes, const int64_t* lsi,
                           const float* loc, const float* attn, int batch, int S, int M, int L, int Lq, int P,
-                          float* out) {
-  auto kern = msda_fwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kHeads, kPoints, kStep>;
+                          float* out, const float* ref = nullptr, int ref_dim = 0) {
+  auto kern = msda_fwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kHeads, kPoints, kStep, kFused>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     // all of the unified L1/shared array as cache: the kernel's reuse lives in L1
@@ -215,7 +222,8 @@ static int launch_fwd_d32(cudaStream_t st, const float* value, const int64_t* sh
   long long grid = (long long)sm_count() * blocks_per_sm;
   if (grid > approx_items) grid = approx_items;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, kThreads, 0, st>>>(value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, tiled, out);
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(value, shapes, lsi, loc, attn, batch, S, M, L, Lq, P, tiled, out, ref,
+                                           ref_dim);
   SDB_LAUNCH_CHECK("msda_fwd_d32_kernel");
   return SDB_OK;
 }
@@ -284,6 +292,33 @@ extern "C" int sdb_msda_forward_f64(sdb_stream_t stream, const double* value, co
   return sdb::msda_forward<double>((cudaStream_t)stream, value, spatial_shapes, level_start_index, sampling_loc,
                                    attn_weight, batch, spatial_size, num_heads, channels, num_levels, num_query,
                                    num_point, out);
+}
+
+extern "C" int sdb_msda_fused_forward_f32(sdb_stream_t stream, const float* value, const int64_t* spatial_shapes,
+                                          const int64_t* level_start_index, const float* reference_points,
+                                          int ref_dim, const float* sampling_offsets, const float* attn_logits,
+                                          int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                                          int num_query, int num_point, float* out) {
+  using namespace sdb;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = spatial_size, M = num_heads, L = num_levels, Lq = num_query, P = num_point;
+  SDB_REQUIRE(batch >= 0 && S >= 0 && Lq >= 0, "msda_fused_forward: bad sizes");
+  if (!(channels == 32 && M == 8 && P == 4 && L * P <= 16 && L <= kMaxLevels && (ref_dim == 2 || ref_dim == 4) &&
+        (long long)S * M * channels < (1ll << 31))) {
+    set_error("msda_fused_forward: built for channels=32, heads=8, points=4, levels*points<=16, ref_dim 2|4 "
+              "(got C=%d M=%d P=%d L=%d ref_dim=%d); use the unfused entry point", channels, M, P, L, ref_dim);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  if ((long long)batch * Lq == 0) return SDB_OK;
+  SDB_REQUIRE(value && spatial_shapes && level_start_index && reference_points && sampling_offsets && attn_logits &&
+              out, "msda_fused_forward: null pointer");
+  if (Lq == S)
+    return launch_fwd_d32<256, 8, 8, 3, 8, 4, 2, true>(st, value, spatial_shapes, level_start_index,
+                                                        sampling_offsets, attn_logits, batch, S, M, L, Lq, P, out,
+                                                        reference_points, ref_dim);
+  return launch_fwd_d32<256, 4, 8, 3, 8, 4, 2, true>(st, value, spatial_shapes, level_start_index, sampling_offsets,
+                                                      attn_logits, batch, S, M, L, Lq, P, out, reference_points,
+                                                      ref_dim);
 }
 
 extern "C" int sdb_msda_set_variant(int forward_variant, int backward_variant) {

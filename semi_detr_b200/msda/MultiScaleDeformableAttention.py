@@ -106,3 +106,54 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     _lib.check(rc, "ms_deform_attn_backward")
     _lib.LAUNCHES["msda_backward"] += 1
     return [grad_value, grad_loc, grad_attn]
+
+
+# ---- fused prologue (not part of the reference extension surface) ----------------------------------------
+
+def fused_supported(value, reference_points, n_levels, n_points):
+    b, s, m, d = value.shape
+    return (value.is_cuda and value.dtype == torch.float32 and d == 32 and m == 8 and n_points == 4
+            and n_levels * n_points <= 16 and reference_points.shape[-1] in (2, 4))
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                 attn_logits):
+    """value (N,S,M,D); reference_points (N,Lq,L,2|4); sampling_offsets (N,Lq,M,L,P,2) RAW; attn_logits
+    (N,Lq,M,L*P) RAW (pre-softmax) -> (N, Lq, M*D).  Softmax + location arithmetic happen inside the kernel."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("reference_points", reference_points), ("sampling_offsets", sampling_offsets),
+                   ("attn_logits", attn_logits)])
+    b, s, m, d = value.shape
+    l = spatial_shapes.shape[0]
+    q, p = sampling_offsets.shape[1], sampling_offsets.shape[4]
+    out = torch.empty((b, q, m * d), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _timed("fwd", b, s, q, lambda: _lib.lib().sdb_msda_fused_forward_f32(
+            _lib.current_stream(value.device), value.data_ptr(), spatial_shapes.data_ptr(),
+            level_start_index.data_ptr(), reference_points.data_ptr(), reference_points.shape[-1],
+            sampling_offsets.data_ptr(), attn_logits.data_ptr(), b, s, m, d, l, q, p, out.data_ptr()))
+    _lib.check(rc, "ms_deform_attn_fused_forward")
+    _lib.LAUNCHES["msda_fused_forward"] += 1
+    return out
+
+
+def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                  attn_logits, grad_output):
+    """-> [grad_value, grad_sampling_offsets, grad_attn_logits]"""
+    _check_inputs([("value", value), ("reference_points", reference_points), ("sampling_offsets", sampling_offsets),
+                   ("attn_logits", attn_logits), ("grad_output", grad_output)])
+    b, s, m, d = value.shape
+    l = spatial_shapes.shape[0]
+    q, p = sampling_offsets.shape[1], sampling_offsets.shape[4]
+    grad_value = torch.empty_like(value)
+    grad_off = torch.empty_like(sampling_offsets)
+    grad_logits = torch.empty_like(attn_logits)
+    with torch.cuda.device(value.device):
+        rc = _timed("bwd", b, s, q, lambda: _lib.lib().sdb_msda_fused_backward_f32(
+            _lib.current_stream(value.device), grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
+            level_start_index.data_ptr(), reference_points.data_ptr(), reference_points.shape[-1],
+            sampling_offsets.data_ptr(), attn_logits.data_ptr(), b, s, m, d, l, q, p, grad_value.data_ptr(),
+            grad_off.data_ptr(), grad_logits.data_ptr()))
+    _lib.check(rc, "ms_deform_attn_fused_backward")
+    _lib.LAUNCHES["msda_fused_backward"] += 1
+    return [grad_value, grad_off, grad_logits]

@@ -33,3 +33,30 @@ class MSDeformAttnFunction(Function):
             value, shapes, level_start, sampling_locations, attention_weights, grad_output.contiguous(),
             ctx.im2col_step)
         return grad_value, None, None, grad_loc, grad_attn, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """Same operator with the module's softmax and sampling-location arithmetic folded into the kernels
+    (``sdb_msda_fused_forward/backward_f32``): takes the raw ``sampling_offsets`` / ``attention_weights`` linear
+    outputs and the reference points, so neither ``sampling_locations`` nor the softmax weights are materialised.
+    The reference points get no gradient (DINO detaches them, transformer.py:1030-1036)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+                attention_logits):
+        output = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
+                                                   reference_points, sampling_offsets, attention_logits)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points,
+                              sampling_offsets, attention_logits)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, ref, offsets, logits = ctx.saved_tensors
+        if ctx.needs_input_grad[3]:
+            raise RuntimeError("MSDeformAttnFusedFunction: reference_points must not require grad "
+                               "(use MSDeformAttnFunction for that case)")
+        grad_value, grad_off, grad_logits = MSDA.ms_deform_attn_fused_backward(
+            value, shapes, level_start, ref, offsets, logits, grad_output.contiguous())
+        return grad_value, None, None, None, grad_off, grad_logits

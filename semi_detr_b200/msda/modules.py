@@ -15,7 +15,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .functions import MSDeformAttnFunction
+from . import MultiScaleDeformableAttention as MSDA
+from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
 def _is_power_of_2(n):
@@ -40,6 +41,8 @@ class MSDeformAttn(nn.Module):
         self.value_proj = nn.Linear(d_model, d_model)
         self.output_proj = nn.Linear(d_model, d_model)
         self._checked_shapes = None
+        # fold softmax + location arithmetic into the sampling kernels when the shape allows (same numerics)
+        self.fused_prologue = True
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -81,7 +84,16 @@ class MSDeformAttn(nn.Module):
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(N, S, M, self.d_model // M)
         offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
-        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        logits = self.attention_weights(query).view(N, Lq, M, L * P)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
+                reference_points.shape[-1]))
+        if (self.fused_prologue and not reference_points.requires_grad
+                and MSDA.fused_supported(value, reference_points, L, P)):
+            out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                  reference_points.contiguous(), offsets, logits)
+            return self.output_proj(out)
+        weights = F.softmax(logits, -1).view(N, Lq, M, L, P)
         ref = reference_points[:, :, None, :, None, :]
         if reference_points.shape[-1] == 2:
             wh = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)

@@ -1,0 +1,87 @@
+"""Fused-prologue MSDA (softmax + location arithmetic inside the kernels) against the unfused path and autograd
+through the module's own torch arithmetic."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(levels, N, Lq, ref_dim, seed):
+    from semi_detr_b200.synthetic import level_tensors
+    g = torch.Generator().manual_seed(seed)
+    L, M, D, P = len(levels), 8, 32, 4
+    S = sum(h * w for h, w in levels)
+    shapes, start = level_tensors(levels, "cuda")
+    value = torch.randn(N, S, M, D, generator=g).cuda()
+    if ref_dim == 2:
+        ref = torch.rand(N, Lq, L, 2, generator=g).cuda()
+        off = (torch.randn(N, Lq, M, L, P, 2, generator=g) * 3).cuda()
+    else:
+        ref = torch.cat([torch.rand(N, Lq, L, 2, generator=g), torch.rand(N, Lq, L, 2, generator=g) * 0.4 + 0.02], -1).cuda()
+        off = (torch.randn(N, Lq, M, L, P, 2, generator=g) * 2).cuda()
+    logits = (torch.randn(N, Lq, M, L * P, generator=g) * 2).cuda()
+    gout = torch.randn(N, Lq, M * D, generator=g).cuda()
+    return value, shapes, start, ref, off, logits, gout
+
+
+def _unfused(value, shapes, start, ref, off, logits, P=4):
+    from semi_detr_b200.msda import MSDeformAttnFunction
+    N, Lq, M, L = off.shape[:4]
+    w = F.softmax(logits, -1).view(N, Lq, M, L, P)
+    if ref.shape[-1] == 2:
+        wh = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
+    return MSDeformAttnFunction.apply(value, shapes, start, loc.contiguous(), w, 64)
+
+
+@pytest.mark.parametrize("levels,Lq,ref_dim", [([(19, 27), (10, 14), (5, 7), (3, 4)], None, 2),
+                                               ([(19, 27), (10, 14), (5, 7), (3, 4)], 211, 4),
+                                               ([(9, 8), (4, 5)], 37, 4), ([(6, 5)], None, 2)])
+def test_fused_matches_unfused(levels, Lq, ref_dim):
+    from semi_detr_b200.msda.functions import MSDeformAttnFusedFunction
+    S = sum(h * w for h, w in levels)
+    value, shapes, start, ref, off, logits, gout = _inputs(levels, 2, Lq or S, ref_dim, seed=len(levels) + ref_dim)
+    leaves = [t.clone().requires_grad_(True) for t in (value, off, logits)]
+    out = MSDeformAttnFusedFunction.apply(leaves[0], shapes, start, ref, leaves[1], leaves[2])
+    out.backward(gout)
+    ref_leaves = [t.clone().requires_grad_(True) for t in (value, off, logits)]
+    want = _unfused(ref_leaves[0], shapes, start, ref, ref_leaves[1], ref_leaves[2])
+    want.backward(gout)
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+    assert rel(out, want) < 1e-5
+    assert torch.allclose(out, want, rtol=1e-3, atol=1e-4)
+    for a, b, name in zip(leaves, ref_leaves, ("value", "offsets", "logits")):
+        assert rel(a.grad, b.grad) < 2e-4, name
+
+
+def test_module_uses_fused_path_and_matches_unfused_module():
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.msda import MSDeformAttn
+    from semi_detr_b200.synthetic import level_tensors
+    torch.manual_seed(0)
+    levels = [(20, 27), (10, 14), (5, 7), (3, 4)]
+    S = sum(h * w for h, w in levels)
+    shapes, start = level_tensors(levels, "cuda")
+    mod = MSDeformAttn().cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.05)
+        mod.sampling_offsets.bias.add_(torch.randn_like(mod.sampling_offsets.bias) * 0.3)
+    q = torch.randn(2, S, 256, device="cuda")
+    src = torch.randn(2, S, 256, device="cuda", requires_grad=True)
+    ref = torch.rand(2, S, 4, 2, device="cuda")
+    mask = torch.zeros(2, S, dtype=torch.bool, device="cuda")
+    mask[1, -50:] = True
+    before = _lib.LAUNCHES["msda_fused_forward"]
+    y1 = mod(q, ref, src, shapes, start, mask)
+    assert _lib.LAUNCHES["msda_fused_forward"] == before + 1
+    g1 = torch.autograd.grad(y1.square().sum(), [src] + list(mod.parameters()))
+    mod.fused_prologue = False
+    y2 = mod(q, ref, src, shapes, start, mask)
+    g2 = torch.autograd.grad(y2.square().sum(), [src] + list(mod.parameters()))
+    assert torch.allclose(y1, y2, rtol=1e-4, atol=1e-5)
+    for a, b in zip(g1, g2):
+        assert ((a - b).norm() / b.norm().clamp_min(1e-20)) < 1e-3
