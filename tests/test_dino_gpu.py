@@ -84,4 +84,6 @@ def test_full_size_step_runs_and_is_finite():
     assert torch.isfinite(l0) and torch.isfinite(l1)
     n = {k: _lib.LAUNCHES[k] - before[k] for k in before}
     # per step: 6 encoder + 6 decoder MSDA forward launches, as many backward, one cost build + one solve
-    assert n["msda_forward"] == 24 and n["msda_backward"] == 24 and n["lsap_solve"] == 2 and n["match_cost"] == 2
+    assert n["msda_forward"] + n["msda_fused_forward"] == 24 and n["msda_backward"] + n["msda_fused_backward"] == 24
+    assert n["msda_fused_forward"] == 24, "the shipped config takes the fused-prologue kernels"
+    assert n["lsap_solve"] == 2 and n["match_cost"] == 2 and n["layernorm_forward"] == 2 * 37

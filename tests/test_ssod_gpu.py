@@ -109,4 +109,5 @@ def test_full_size_ssod_step_runs():
     loss.backward()
     assert torch.isfinite(loss)
     n = {k: _lib.LAUNCHES[k] - before[k] for k in before}
-    assert n["ema_update"] == 1 and n["msda_forward"] >= 5 * 12 and n["msda_backward"] == 2 * 12
+    assert n["ema_update"] == 1 and n["msda_forward"] + n["msda_fused_forward"] >= 5 * 12
+    assert n["msda_backward"] + n["msda_fused_backward"] == 2 * 12
