@@ -49,6 +49,11 @@ class MLP(nn.Module):
 
 _DIM_T = {}
 
+# Decoder self-attention runs over ~1.1 k queries in fp32: for that size the plain matmul-softmax-matmul
+# ("math") scaled-dot-product backend beats the fused memory-efficient fp32 kernel torch picks by default on
+# sm_100 (measured in profiles/).  None = torch's default choice.
+SDPA_BACKEND = "math"
+
 
 def gen_sineembed_for_position(pos):
     """(nq, bs, 2|4) in [0,1] -> (nq, bs, 256|512); 128 dims per coordinate, temperature 10000, order y,x,w,h
@@ -189,7 +194,12 @@ class DINOTransformerDecoderLayer(nn.Module):
         for name in self.module_seq:
             if name == "sa":
                 qk = tgt + query_pos
-                tgt2 = self.self_attn(qk, qk, tgt, attn_mask=self_attn_mask, need_weights=False)[0]
+                if SDPA_BACKEND == "math" and tgt.is_cuda:
+                    from torch.nn.attention import SDPBackend, sdpa_kernel
+                    with sdpa_kernel([SDPBackend.MATH]):
+                        tgt2 = self.self_attn(qk, qk, tgt, attn_mask=self_attn_mask, need_weights=False)[0]
+                else:
+                    tgt2 = self.self_attn(qk, qk, tgt, attn_mask=self_attn_mask, need_weights=False)[0]
                 tgt = self.norm2(tgt + self.dropout2(tgt2))
             elif name == "ca":
                 tgt2 = self.cross_attn((tgt + query_pos).transpose(0, 1), reference_points.transpose(0, 1).contiguous(),
