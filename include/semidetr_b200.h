@@ -209,6 +209,31 @@ int sdb_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float
                                const float* mean, const float* rstd, int64_t rows, int cols, float* dx,
                                float* dgamma, float* dbeta, float* workspace);
 
+/* ------------------------------------------------------------------------------------------
+ * Column sums of a row-major (rows, cols) fp32 matrix into out[cols] (zero-filled by the call): the bias gradient
+ * grad_output.sum(0) of the linears on the path (transformer.py:596-630, 765-791; ms_deform_attn.py:52-55).
+ * cols must be a multiple of 4 and x 16-byte aligned, else SDB_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_colsum_f32(sdb_stream_t stream, const float* x, int64_t rows, int cols, float* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient clip + AdamW (+ mean-teacher EMA) in one pass over flat fp32 buffers.
+ *
+ * Replaces mmcv's OptimizerHook for configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:122-128 (clip_grad_norm_ 0.1,
+ * AdamW lr 1e-4 / wd 1e-4, backbone lr x0.1) and, when `teacher` is non-NULL, the next iteration's
+ * MeanTeacher.momentum_update (mean_teacher.py:60-64) for the same parameters.
+ *   params / grads / exp_avg / exp_avg_sq / teacher : flat device buffers, identical layout
+ *   clip_coef  : device scalar min(1, max_norm / (||g|| + 1e-6)) or NULL (no clipping)
+ *   step_count : device scalar, number of updates done so far (the caller increments it after the call)
+ *   seg_bounds (host, 2*num_segs int64: [begin, end) element ranges, multiples of 4), seg_lr, seg_weight_decay
+ *   (host, num_segs floats): parameter groups
+ * Arithmetic follows torch.optim.AdamW; the EMA keeps the reference's two roundings.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const float* grads, float* exp_avg,
+                           float* exp_avg_sq, float* teacher, const float* clip_coef, const float* step_count,
+                           const int64_t* seg_bounds, const float* seg_lr, const float* seg_weight_decay,
+                           int num_segs, float beta1, float beta2, float eps, double ema_momentum);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,9 +5,23 @@ BN frozen + norm_eval, style 'pytorch').  Parameter names follow torchvision / m
 plumbing): the backbone is not part of the graded hot path but is needed to run the train step end to end.
 """
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from ..registry import BACKBONES
+
+
+def conv_bn(conv, bn, x):
+    """conv -> BatchNorm.  With the statistics frozen (``norm_eval``; every shipped config) the normalisation is a
+    per-channel affine map that folds exactly into the convolution: conv(x, w * s) + t with s = gamma / sqrt(var +
+    eps), t = beta - mean * s.  That removes one elementwise pass over every backbone activation in forward and
+    backward (53 BN launches per step); gradients still reach ``w`` through the scale.  In training-statistics mode
+    the two modules run as written."""
+    if bn.training or not x.is_cuda:
+        return bn(conv(x))
+    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    t = bn.bias - bn.running_mean * s
+    return F.conv2d(x, conv.weight * s.view(-1, 1, 1, 1), t, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 class Bottleneck(nn.Module):
@@ -25,10 +39,10 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
+        identity = x if self.downsample is None else conv_bn(self.downsample[0], self.downsample[1], x)
+        out = self.relu(conv_bn(self.conv1, self.bn1, x))
+        out = self.relu(conv_bn(self.conv2, self.bn2, out))
+        out = conv_bn(self.conv3, self.bn3, out)
         return self.relu(out + identity)
 
 
@@ -83,7 +97,7 @@ class ResNet(nn.Module):
         return self
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(self.relu(conv_bn(self.conv1, self.bn1, x)))
         outs = []
         for i in range(4):
             x = getattr(self, f"layer{i + 1}")(x)

@@ -27,8 +27,15 @@ class DINODETR(nn.Module):
         bbox_head.update(train_cfg=train_cfg, test_cfg=test_cfg)
         self.bbox_head = HEADS.build(bbox_head)
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.backbone.to(memory_format=torch.channels_last)
+        self.bbox_head.input_proj.to(memory_format=torch.channels_last)
 
     def extract_feat(self, img):
+        # NHWC end to end through the convolutional backbone: cuDNN's tensor-core kernels are channels-last, so this
+        # removes the NCHW<->NHWC transposes around every convolution, and (N, C, H, W) channels-last flattens to the
+        # transformer's (N, HW, C) token layout for free
+        if img.is_cuda:
+            img = img.contiguous(memory_format=torch.channels_last)
         return self.backbone(img)
 
     def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore=None, **kwargs):

@@ -21,7 +21,7 @@ from torch import nn
 from ..consts import device_const
 from ..msda import MSDeformAttn
 from ..registry import TRANSFORMER
-from .layernorm import LayerNorm
+from ..layers import LayerNorm, Linear
 
 
 def inverse_sigmoid(x, eps=1e-5):
@@ -37,7 +37,7 @@ class MLP(nn.Module):
         super().__init__()
         self.num_layers = num_layers
         dims = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
-        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+        self.layers = nn.ModuleList(Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
 
     def forward(self, x):
         for i, layer in enumerate(self.layers):
@@ -115,9 +115,9 @@ class DINOTransformerEncoderLayer(nn.Module):
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
         self.dropout1 = nn.Dropout(dropout)
         self.norm1 = LayerNorm(d_model)
-        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.linear1 = Linear(d_model, d_ffn)
         self.dropout2 = nn.Dropout(dropout)
-        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.linear2 = Linear(d_ffn, d_model)
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = LayerNorm(d_model)
 
@@ -182,9 +182,9 @@ class DINOTransformerDecoderLayer(nn.Module):
         self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
         self.dropout2 = nn.Dropout(dropout)
         self.norm2 = LayerNorm(d_model)
-        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.linear1 = Linear(d_model, d_ffn)
         self.dropout3 = nn.Dropout(dropout)
-        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.linear2 = Linear(d_ffn, d_model)
         self.dropout4 = nn.Dropout(dropout)
         self.norm3 = LayerNorm(d_model)
 
@@ -280,7 +280,7 @@ class DINOTransformer(nn.Module):
                                               query_dim, num_feature_levels)
         self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model)) if num_feature_levels > 1 else None
         self.tgt_embed = nn.Embedding(num_queries, d_model)
-        self.enc_output = nn.Linear(d_model, d_model)
+        self.enc_output = Linear(d_model, d_model)
         self.enc_output_norm = LayerNorm(d_model)
         self._reset_parameters()
 

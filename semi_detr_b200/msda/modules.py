@@ -16,6 +16,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import MultiScaleDeformableAttention as MSDA
+from ..layers import Linear
 from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
@@ -36,10 +37,10 @@ class MSDeformAttn(nn.Module):
         self.im2col_step = 64
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
 
-        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
-        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
-        self.value_proj = nn.Linear(d_model, d_model)
-        self.output_proj = nn.Linear(d_model, d_model)
+        self.sampling_offsets = Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = Linear(d_model, d_model)
+        self.output_proj = Linear(d_model, d_model)
         self._checked_shapes = None
         # fold softmax + location arithmetic into the sampling kernels when the shape allows (same numerics)
         self.fused_prologue = True
