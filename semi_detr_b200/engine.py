@@ -118,3 +118,110 @@ class GraphedTrainStep:
             self.load(batch)
         self.graph.replay()
         return self.loss, self.log_vars
+
+
+class FusedAdamW:
+    """clip-by-global-norm + AdamW (+ optional mean-teacher EMA of the same parameters) as ONE kernel over flat
+    buffers (``sdb_adamw_ema_step_f32``).  Parameters are re-pointed into a flat fp32 buffer (layout preserved with
+    ``as_strided``), their ``.grad`` into a second one; the two moments are flat as well.  Param groups follow
+    ``build_optimizer`` (head/transformer at ``lr``, backbone at ``lr * backbone_lr_mult``).
+
+    Semantics match ``torch.nn.utils.clip_grad_norm_(max_norm)`` followed by ``torch.optim.AdamW.step()``; with
+    ``teacher_params`` the teacher is blended right after the update, which is what the reference's MeanTeacher hook
+    does at the start of the next iteration (mean_teacher.py:37-64)."""
+
+    def __init__(self, model, lr=1e-4, weight_decay=1e-4, backbone_lr_mult=0.1, betas=(0.9, 0.999), eps=1e-8,
+                 teacher_params=None):
+        from . import _lib
+        self._lib = _lib
+        groups = [[], []]
+        names = [[], []]
+        for name, p in model.named_parameters():
+            if p.requires_grad:
+                gi = 1 if "backbone" in name else 0
+                groups[gi].append(p)
+                names[gi].append(name)
+        self.params = groups[0] + groups[1]
+        self.param_names = names[0] + names[1]
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdamW needs CUDA parameters (no CPU path)")
+        sizes = [sum(p.numel() for p in g) for g in groups]
+        pad = [(-s) % 4 for s in sizes]
+        bounds, off = [], 0
+        for s, pd in zip(sizes, pad):
+            bounds.append((off, off + s + pd))
+            off += s + pd
+        total = off
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_t = torch.zeros(total, dtype=torch.float32, device=dev) if teacher_params is not None else None
+        teacher_by_name = dict(teacher_params) if teacher_params is not None else {}
+        for gi, g in enumerate(groups):
+            o = bounds[gi][0]
+            for name, p in zip(names[gi], g):
+                n = p.numel()
+                view = self.flat_p[o:o + n].as_strided(p.shape, p.stride())
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_g[o:o + n].as_strided(p.shape, p.stride())
+                if self.flat_t is not None:
+                    t = teacher_by_name[name]
+                    tv = self.flat_t[o:o + n].as_strided(t.shape, t.stride())
+                    tv.copy_(t.data)
+                    t.data = tv
+                o += n
+        import ctypes
+        self._bounds = (ctypes.c_int64 * 4)(bounds[0][0], bounds[0][1], bounds[1][0], bounds[1][1])
+        self._lr = (ctypes.c_float * 2)(lr, lr * backbone_lr_mult)
+        self._wd = (ctypes.c_float * 2)(weight_decay, weight_decay)
+        self.betas, self.eps = betas, eps
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.param_groups = [dict(params=groups[0], lr=lr), dict(params=groups[1], lr=lr * backbone_lr_mult)]
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def all_reduce_mean(self, world_size):
+        if world_size > 1:
+            dist.all_reduce(self.flat_g)
+            self.flat_g.div_(world_size)
+
+    def step(self, max_grad_norm=None, ema_momentum=None):
+        coef = None
+        if max_grad_norm is not None:
+            total_norm = torch.linalg.vector_norm(self.flat_g, 2)
+            coef = torch.clamp(max_grad_norm / (total_norm + 1e-6), max=1.0).reshape(1)
+        dev = self.flat_p.device
+        teacher = self.flat_t if (self.flat_t is not None and ema_momentum is not None) else None
+        with torch.cuda.device(dev):
+            rc = self._lib.lib().sdb_adamw_ema_step_f32(
+                self._lib.current_stream(dev), self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                self.flat_v.data_ptr(), self._lib.ptr(teacher), self._lib.ptr(coef), self.step_count.data_ptr(),
+                self._bounds, self._lr, self._wd, 2, self.betas[0], self.betas[1], self.eps,
+                float(ema_momentum) if ema_momentum is not None else 0.0)
+        self._lib.check(rc, "adamw_ema_step")
+        self._lib.LAUNCHES["adamw_ema_step"] += 1
+        self.step_count.add_(1.0)
+
+
+class FusedSupervisedTrainStep:
+    """``SupervisedTrainStep`` with the fused optimizer kernel (same step, fewer passes over the parameters)."""
+
+    def __init__(self, model, max_grad_norm=0.1, world_size=None, **opt_kw):
+        self.model, self.max_grad_norm = model, max_grad_norm
+        if world_size is None:
+            world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.world_size = world_size
+        self.opt = FusedAdamW(model, **opt_kw)
+
+    def __call__(self, data):
+        self.opt.zero_grad()
+        losses = self.model(**data)
+        loss, log_vars = self.model._parse_losses(losses)
+        loss.backward()
+        self.opt.all_reduce_mean(self.world_size)
+        self.opt.step(self.max_grad_norm)
+        return loss.detach(), log_vars
