@@ -45,7 +45,7 @@ class FlatGrads:
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            p.grad = self.flat[off:off + n].as_strided(p.shape, p.stride())   # same memory format as the parameter
             off += n
 
     def zero(self):
