@@ -113,6 +113,18 @@ int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* grad_out, cons
                                 int channels, int num_levels, int num_query, int num_point, float* grad_value,
                                 float* grad_offsets, float* grad_attn_logits);
 
+/* TMA-staged forward for encoder self-attention (num_query == spatial_size, channels 32, heads 8, points 4,
+ * levels <= 4): per (image, head, 8x8 query tile) one bulk tensor copy per level stages that head's value box in
+ * shared memory behind an mbarrier; out-of-box samples use global loads.  Same results as sdb_msda_forward_f32 /
+ * sdb_msda_fused_forward_f32 (fused != 0: raw offsets / logits + reference points).  `spatial_shapes_host` /
+ * `level_start_host` are HOST copies of the two index tensors (the TMA descriptors are encoded on the host). */
+int sdb_msda_forward_tma_f32(sdb_stream_t stream, int fused, const float* value, const int64_t* spatial_shapes,
+                             const int64_t* level_start_index, const int64_t* spatial_shapes_host,
+                             const int64_t* level_start_host, const float* reference_points, int ref_dim,
+                             const float* sampling_loc, const float* attn_weight, int batch, int spatial_size,
+                             int num_heads, int channels, int num_levels, int num_query, int num_point,
+                             float* out);
+
 /* Tuning knob for benchmarking kernel variants (0 = default heuristic).  Not part of the
  * reference surface; see DESIGN.md "MSDA forward variants". */
 int sdb_msda_set_variant(int forward_variant, int backward_variant);

@@ -23,6 +23,7 @@ SIGNATURES = {
     "sdb_msda_backward_f32": _MSDA_BWD,
     "sdb_msda_backward_f64": _MSDA_BWD,
     "sdb_msda_set_variant": [c_int, c_int],
+    "sdb_msda_forward_tma_f32": [c_void_p, c_int] + [c_void_p] * 6 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p],
     "sdb_msda_fused_forward_f32": [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p],
     "sdb_msda_fused_backward_f32": [c_void_p] * 6 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p] * 3,
     "sdb_match_cost_f32": [c_void_p] * 9 + [c_int] * 3 + [c_float] * 3 + [c_void_p] * 2,
@@ -39,7 +40,7 @@ SIGNATURES = {
 _lib = None
 
 # kernels of this library launched so far, by entry point (bench.py reports the per-step count)
-LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "msda_fused_forward": 0, "msda_fused_backward": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,
+LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "msda_fused_forward": 0, "msda_fused_backward": 0, "msda_forward_tma": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,
             "layernorm_forward": 0, "layernorm_backward": 0, "adamw_ema_step": 0, "colsum": 0}
 
 

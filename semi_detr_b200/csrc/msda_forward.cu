@@ -155,8 +155,8 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
           a2 = ld_stream_f2(reinterpret_cast<const float2*>(ap + pt));
         }
         int lv0, lv1;
-        if (kPoints > 0) { lv0 = pt / kPoints; lv1 = (pt + 1) / kPoints; }
-        else             { lv0 = pt / P;       lv1 = (pt + 1) / P; }
+        if constexpr (kPoints > 0) { lv0 = pt / kPoints; lv1 = (pt + 1) / kPoints; }
+        else                       { lv0 = pt / P;       lv1 = (pt + 1) / P; }
         lv0 = min(lv0, L - 1);
         lv1 = min(lv1, L - 1);
         const PointPrep p0 = prep_point(lt, lv0, l4.x, l4.y, a2.x, px_stride);
@@ -177,7 +177,7 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
             w[u][1] = __shfl_sync(kFull, src.w01, sl, 8);
             w[u][2] = __shfl_sync(kFull, src.w10, sl, 8);
             w[u][3] = __shfl_sync(kFull, src.w11, sl, 8);
-            if (kPoints > 0 && kPoints % kStep == 0) ws[u] = lt.wstr[min((c0 + s) / kPoints, L - 1)];
+            if constexpr (kPoints > 0 && kPoints % kStep == 0) ws[u] = lt.wstr[min((c0 + s) / kPoints, L - 1)];
             else ws[u] = __shfl_sync(kFull, src.wstr, sl, 8);
           }
           float4 v[kStep][4];

@@ -15,6 +15,44 @@ from .. import _lib
 
 _FLOAT = (torch.float32, torch.float64)
 
+# TMA-staged forward for encoder self-attention (num_query == spatial_size): see csrc/msda_forward_tma.cu.
+USE_TMA = True
+_HOST_INDEX = {}
+
+
+def _host_index(spatial_shapes, level_start_index):
+    """Host copies of the two index tensors (the TMA descriptors are encoded on the host): one device->host read
+    per distinct tensor, then cached."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version)
+    hit = _HOST_INDEX.get(key)
+    if hit is None:
+        if len(_HOST_INDEX) > 256:
+            _HOST_INDEX.clear()
+        hit = (spatial_shapes.cpu().contiguous(), level_start_index.cpu().contiguous())
+        _HOST_INDEX[key] = hit
+    return hit
+
+
+def _tma_ok(value, num_query, num_levels, num_point):
+    b, s, m, d = value.shape
+    return (USE_TMA and value.dtype == torch.float32 and d == 32 and m == 8 and num_point == 4 and num_levels <= 4
+            and num_query == s and value.data_ptr() % 128 == 0)
+
+
+def _forward_tma(fused, value, spatial_shapes, level_start_index, ref, loc, attn, out, dims):
+    b, s, m, d, l, q, p = dims
+    hs, hl = _host_index(spatial_shapes, level_start_index)
+    with torch.cuda.device(value.device):
+        rc = _timed("fwd", b, s, q, lambda: _lib.lib().sdb_msda_forward_tma_f32(
+            _lib.current_stream(value.device), 1 if fused else 0, value.data_ptr(), spatial_shapes.data_ptr(),
+            level_start_index.data_ptr(), hs.data_ptr(), hl.data_ptr(), _lib.ptr(ref),
+            ref.shape[-1] if ref is not None else 0, loc.data_ptr(), attn.data_ptr(), b, s, m, d, l, q, p,
+            out.data_ptr()))
+    _lib.check(rc, "ms_deform_attn_forward_tma")
+    _lib.LAUNCHES["msda_forward_tma"] += 1
+    return out
+
+
 # Optional live timing (bench.py): when a list is installed here every launch is bracketed by CUDA events on the
 # launching stream and (kind, batch, spatial_size, num_query, start_event, end_event) is appended.
 EVENT_LOG = None
@@ -71,6 +109,9 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
         raise RuntimeError("value, sampling_loc and attn_weight must share one floating dtype")
     b, s, m, d, l, q, p = _dims(value, spatial_shapes, sampling_loc, im2col_step)
     out = torch.empty((b, q, m * d), dtype=value.dtype, device=value.device)   # every element is written
+    if _tma_ok(value, q, l, p):
+        return _forward_tma(False, value, spatial_shapes, level_start_index, None, sampling_loc, attn_weight, out,
+                            (b, s, m, d, l, q, p))
     fn = _lib.lib().sdb_msda_forward_f32 if value.dtype == torch.float32 else _lib.lib().sdb_msda_forward_f64
     with torch.cuda.device(value.device):
         rc = _timed("fwd", b, s, q, lambda: fn(
@@ -127,6 +168,9 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, refer
     l = spatial_shapes.shape[0]
     q, p = sampling_offsets.shape[1], sampling_offsets.shape[4]
     out = torch.empty((b, q, m * d), dtype=value.dtype, device=value.device)
+    if _tma_ok(value, q, l, p):
+        return _forward_tma(True, value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                            attn_logits, out, (b, s, m, d, l, q, p))
     with torch.cuda.device(value.device):
         rc = _timed("fwd", b, s, q, lambda: _lib.lib().sdb_msda_fused_forward_f32(
             _lib.current_stream(value.device), value.data_ptr(), spatial_shapes.data_ptr(),

@@ -85,3 +85,49 @@ def test_module_uses_fused_path_and_matches_unfused_module():
     assert torch.allclose(y1, y2, rtol=1e-4, atol=1e-5)
     for a, b in zip(g1, g2):
         assert ((a - b).norm() / b.norm().clamp_min(1e-20)) < 1e-3
+
+
+# ---- TMA-staged forward (encoder self-attention) ---------------------------------------------------------
+
+@pytest.mark.parametrize("levels", [[(19, 27), (10, 14), (5, 7), (3, 4)], [(100, 134), (50, 67), (25, 34), (13, 17)],
+                                    [(9, 8), (4, 5)], [(6, 5)], [(33, 9), (17, 5), (9, 3), (5, 2)]])
+@pytest.mark.parametrize("mode", ["encoder", "wide"])
+def test_tma_forward_matches_l1_kernel(levels, mode):
+    """Same inputs through the TMA-staged kernel and the L1-gather kernel; 'wide' locations leave the staged boxes
+    (and the image), exercising the global fallback, the zero fill and the out-of-range test."""
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import msda_inputs
+    S = sum(h * w for h, w in levels)
+    x = msda_inputs(levels, N=2, mode="encoder", seed=7)
+    if mode == "wide":
+        g = torch.Generator().manual_seed(1)
+        x["loc"] = (torch.rand(x["loc"].shape, generator=g) * 1.6 - 0.3).cuda()
+    a = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"])
+    before = _lib.LAUNCHES["msda_forward_tma"]
+    MSDA.USE_TMA = True
+    got = MSDA.ms_deform_attn_forward(*a, 64)
+    assert _lib.LAUNCHES["msda_forward_tma"] == before + 1
+    MSDA.USE_TMA = False
+    try:
+        want = MSDA.ms_deform_attn_forward(*a, 64)
+    finally:
+        MSDA.USE_TMA = True
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), (got - want).abs().max()
+
+
+def test_tma_fused_forward_matches_fused_l1_kernel():
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    levels = [(40, 54), (20, 27), (10, 14), (5, 7)]
+    S = sum(h * w for h, w in levels)
+    value, shapes, start, ref, off, logits, _ = _inputs(levels, 2, S, 2, seed=3)
+    from semi_detr_b200.synthetic import encoder_reference_points
+    ref = encoder_reference_points(levels, "cuda")[None, :, None, :].expand(2, S, 4, 2).contiguous()
+    MSDA.USE_TMA = True
+    got = MSDA.ms_deform_attn_fused_forward(value, shapes, start, ref, off, logits)
+    MSDA.USE_TMA = False
+    try:
+        want = MSDA.ms_deform_attn_fused_forward(value, shapes, start, ref, off, logits)
+    finally:
+        MSDA.USE_TMA = True
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)

@@ -78,6 +78,12 @@ def main():
         q = x["loc"].shape[1]
         fb, bb = msda_bytes(args.n, S, q)
         a = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"])
+        MSDA.USE_TMA = True
+        if q == S:
+            med, best = timeit(lambda: MSDA.ms_deform_attn_forward(*a, 64), args.iters)
+            emit(op="msda_fwd_tma", case=name, n=args.n, us=round(med, 2), best_us=round(best, 2),
+                 gbs=round(fb / med / 1e3, 1), frac=round(fb / med / 1e3 / PEAK, 4))
+        MSDA.USE_TMA = False
         for v in fvars:
             lib.sdb_msda_set_variant(v, 0)
             med, best = timeit(lambda: MSDA.ms_deform_attn_forward(*a, 64), args.iters)
@@ -89,6 +95,7 @@ def main():
             emit(op="msda_bwd", case=name, n=args.n, variant=v, us=round(med, 2), best_us=round(best, 2),
                  gbs=round(bb / med / 1e3, 1), frac=round(bb / med / 1e3 / PEAK, 4))
         lib.sdb_msda_set_variant(0, 0)
+        MSDA.USE_TMA = True
         if args.ref:
             import ref_cuda
             if ref_cuda.available():
