@@ -152,7 +152,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from semi_detr_b200 import _lib
-    from semi_detr_b200.engine import GraphedTrainStep, SupervisedTrainStep, build_optimizer
+    from semi_detr_b200.engine import FusedSupervisedTrainStep, GraphedTrainStep, SupervisedTrainStep, build_optimizer
     from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
     from semi_detr_b200.synthetic import coco_like_batch, msda_bytes
 
@@ -174,7 +174,10 @@ def run_ours(args):
     if world > 1:   # identical seeds give identical weights; broadcast anyway so the ranks cannot drift
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
-    step = SupervisedTrainStep(model, build_optimizer(model, capturable=True), world_size=world)
+    if args.torch_optimizer:
+        step = SupervisedTrainStep(model, build_optimizer(model, capturable=True), world_size=world)
+    else:   # clip + AdamW as one kernel over flat buffers (sdb_adamw_ema_step_f32)
+        step = FusedSupervisedTrainStep(model, world_size=world)
     host = coco_like_batch(PER_GPU_BATCH, IMG_H, IMG_W, seed=rank, pin=True)
 
     def to_device(b):
@@ -341,6 +344,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--torch-optimizer", action="store_true",
+                    help="use torch.optim.AdamW(fused) + flat-buffer clip instead of the fused clip+AdamW kernel")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid (numbers printed in this mode are NOT bench values): 1 eager warm-up step + "
                          "1 eager step, nothing else, so an `ncu --metrics gpu__time_duration.sum` launch list stays short")

@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from semi_detr_b200 import dino  # noqa: E402,F401
-from semi_detr_b200.engine import SupervisedTrainStep, build_optimizer  # noqa: E402
+from semi_detr_b200.engine import FusedSupervisedTrainStep  # noqa: E402
 from semi_detr_b200.registry import DETECTORS  # noqa: E402
 from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch  # noqa: E402
 
@@ -17,7 +17,7 @@ torch.backends.cudnn.allow_tf32 = True
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE)).cuda().train()
-step = SupervisedTrainStep(model, build_optimizer(model))
+step = FusedSupervisedTrainStep(model)
 data = coco_like_batch(2, 800, 1333, seed=0, device="cuda")
 for _ in range(5):
     step(data)
