@@ -65,6 +65,14 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// Generic-address 16-byte load: the operand may point into the staged box (shared window) or into the image
+// (global); spelled in PTX so the compiler cannot specialise the address space from the __restrict__ parameters.
+__device__ __forceinline__ float4 ld_generic_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
 struct BoxOrigin {
   int x0[kTmaLevels], y0[kTmaLevels];
 };
@@ -86,7 +94,7 @@ __device__ __forceinline__ void box_origin(const LevelTable& lt, int L, int tlvl
 }
 
 struct TmaPrep {
-  int code;                  // bit 31 set: float offset inside the stage (in-box); else float offset in the image
+  int code;                  // < -2^30: INT_MIN + float offset inside the stage (in-box); else float offset in the image
   float w00, w01, w10, w11;  // corner weights * attention weight, 0 where the corner does not contribute
 };
 
@@ -109,8 +117,28 @@ __device__ __forceinline__ TmaPrep tma_prep(const LevelTable& lt, const BoxOrigi
   return r;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
+// Warp roles: warps 0..15 gather (4 queries of the tile each), warp 16 is the TMA producer.  Stages are handed
+// over with two mbarriers each -- full[s] (transaction count: the boxes have landed) and empty[s] (one arrival per
+// gather warp: the stage may be overwritten) -- so the gather warps are never synchronised with one another: a warp
+// that finishes an item early starts the next one as soon as its boxes are in.
+constexpr int kGatherWarps = 16;
+
+struct ItemOperands {      // this lane's two points of one item, loaded one item ahead
+  float4 l4;
+  float2 a2;
+};
+
 template <bool kFused>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+__global__ void __launch_bounds__(kTmaThreads + 32, 1)
 msda_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                     const float* __restrict__ loc, const float* __restrict__ attn, int batch, int S, int L, int Lq,
@@ -118,18 +146,20 @@ msda_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restric
   constexpr int M = 8, P = 4, px_stride = M * 32;
   extern __shared__ __align__(128) float stage[];           // 2 x kStageFloats
   __shared__ LevelTable lt;
-  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) uint64_t full[2], empty[2];
   load_levels<kTmaTile, kTmaTile>(lt, shapes, lsi, L, px_stride);
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
+    mbar_init(&empty[0], kGatherWarps);
+    mbar_init(&empty[1], kGatherWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int n_tiles = lt.tile_begin[L];
   const long long total = (long long)batch * n_tiles * M;
-  const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;     // 64 groups = the 64 queries of a tile
   const int LP = L * P;
+  const int warp = threadIdx.x >> 5;
 
   auto decode = [&](long long item, int& m, int& n, TileCursor<kTmaTile, kTmaTile>& cur) {
     m = (int)(item % M);
@@ -137,29 +167,67 @@ msda_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restric
     n = (int)(t2 / n_tiles);
     cur.seek(lt, L, (int)(t2 % n_tiles), true, Lq);
   };
-  auto issue = [&](long long item, int stage_idx) {          // one thread: L bulk tensor copies for `item`
+
+  if (warp == kGatherWarps) {
+    // ===== producer: one lane walks the CTA's items and keeps two stages in flight =====
+    if ((threadIdx.x & 31) == 0) {
+      int it = 0;
+      for (long long item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+        const int sidx = it & 1;
+        if (it >= 2) mbar_wait(&empty[sidx], (uint32_t)(((it >> 1) - 1) & 1));   // all gather warps released it
+        int m, n;
+        TileCursor<kTmaTile, kTmaTile> cur;
+        decode(item, m, n, cur);
+        BoxOrigin bo;
+        box_origin(lt, L, cur.lvl, cur.x0, cur.y0, bo);
+        float* dst = stage + sidx * kStageFloats;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int l = 0; l < kTmaLevels; ++l)
+          if (l < L) bytes += box_side(l) * box_side(l) * 128;
+        mbar_expect_tx(&full[sidx], bytes);
+        // constant indices: the descriptors must be addressed in kernel-parameter space, never through a local copy
+        tma_load_5d(dst + box_base(0), &maps.lvl[0], &full[sidx], 0, m, bo.x0[0], bo.y0[0], n);
+        if (L > 1) tma_load_5d(dst + box_base(1), &maps.lvl[1], &full[sidx], 0, m, bo.x0[1], bo.y0[1], n);
+        if (L > 2) tma_load_5d(dst + box_base(2), &maps.lvl[2], &full[sidx], 0, m, bo.x0[2], bo.y0[2], n);
+        if (L > 3) tma_load_5d(dst + box_base(3), &maps.lvl[3], &full[sidx], 0, m, bo.x0[3], bo.y0[3], n);
+      }
+    }
+    return;
+  }
+
+  // ===== gather warps =====
+  const int grp = threadIdx.x >> 3, j = threadIdx.x & 7;     // 64 groups = the 64 queries of a tile
+  const int pt = 2 * j;
+  const int lvj = min(pt / P, L - 1);
+
+  auto load_operands = [&](long long item, ItemOperands& o) {
+    o.l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    o.a2 = make_float2(0.f, 0.f);
+    if (item >= total) return;
     int m, n;
     TileCursor<kTmaTile, kTmaTile> cur;
     decode(item, m, n, cur);
-    BoxOrigin bo;
-    box_origin(lt, L, cur.lvl, cur.x0, cur.y0, bo);
-    float* dst = stage + stage_idx * kStageFloats;
-    uint32_t bytes = 0;
-#pragma unroll
-    for (int l = 0; l < kTmaLevels; ++l)
-      if (l < L) bytes += box_side(l) * box_side(l) * 128;
-    mbar_expect_tx(&full[stage_idx], bytes);
-#pragma unroll
-    for (int l = 0; l < kTmaLevels; ++l)
-      if (l < L) tma_load_5d(dst + box_base(l), &maps.lvl[l], &full[stage_idx], 0, m, bo.x0[l], bo.y0[l], n);
+    const int q = cur.query(grp, Lq);
+    const bool live = q >= 0;
+    const long long pair = ((long long)n * Lq + (live ? q : 0)) * M + m;
+    if (kFused) {
+      const FusedPoints fp = fused_prologue(lt, ref, ref_dim, loc, attn, (long long)n * Lq + (live ? q : 0), pair, L, P,
+                                            LP, pt, live);
+      o.l4 = fp.loc;
+      o.a2 = fp.a;
+    } else if (live && pt < LP) {
+      o.l4 = ld_stream_f4(reinterpret_cast<const float4*>(loc + pair * LP * 2 + 2 * pt));
+      o.a2 = ld_stream_f2(reinterpret_cast<const float2*>(attn + pair * LP + pt));
+    }
   };
 
-  long long item = blockIdx.x;
-  if (threadIdx.x == 0 && item < total) issue(item, 0);
-  for (int it = 0; item < total; item += gridDim.x, ++it) {
+  ItemOperands cur_op, next_op;
+  load_operands(blockIdx.x, cur_op);
+  int it = 0;
+  for (long long item = blockIdx.x; item < total; item += gridDim.x, ++it) {
     const int sidx = it & 1;
-    __syncthreads();                                        // everyone is done reading stage sidx^1 (item it-1)
-    if (threadIdx.x == 0 && item + gridDim.x < total) issue(item + gridDim.x, sidx ^ 1);
+    load_operands(item + gridDim.x, next_op);               // next item's locations / weights: latency hidden
     int m, n;
     TileCursor<kTmaTile, kTmaTile> cur;
     decode(item, m, n, cur);
@@ -167,25 +235,12 @@ msda_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restric
     box_origin(lt, L, cur.lvl, cur.x0, cur.y0, bo);
     const float* vhead = value + (long long)n * S * px_stride + m * 32 + 4 * j;
     const float* sbase = stage + sidx * kStageFloats + 4 * j;
-
+    const uint32_t sbase32 = smem_u32(sbase);
     const int q = cur.query(grp, Lq);
     const bool live = q >= 0;
     const long long pair = ((long long)n * Lq + (live ? q : 0)) * M + m;
-    const int pt = 2 * j;
-    float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 a2 = make_float2(0.f, 0.f);
-    if (kFused) {
-      const FusedPoints fp = fused_prologue(lt, ref, ref_dim, loc, attn, (long long)n * Lq + (live ? q : 0), pair, L, P,
-                                            LP, pt, live);
-      l4 = fp.loc;
-      a2 = fp.a;
-    } else if (live && pt < LP) {
-      l4 = ld_stream_f4(reinterpret_cast<const float4*>(loc + pair * LP * 2 + 2 * pt));
-      a2 = ld_stream_f2(reinterpret_cast<const float2*>(attn + pair * LP + pt));
-    }
-    const int lvj = min(pt / P, L - 1);
-    const TmaPrep p0 = tma_prep(lt, bo, lvj, l4.x, l4.y, a2.x, px_stride);
-    const TmaPrep p1 = tma_prep(lt, bo, lvj, l4.z, l4.w, a2.y, px_stride);
+    const TmaPrep p0 = tma_prep(lt, bo, lvj, cur_op.l4.x, cur_op.l4.y, cur_op.a2.x, px_stride);
+    const TmaPrep p1 = tma_prep(lt, bo, lvj, cur_op.l4.z, cur_op.l4.w, cur_op.a2.y, px_stride);
 
     mbar_wait(&full[sidx], (uint32_t)((it >> 1) & 1));      // this item's boxes have landed
 
@@ -204,18 +259,32 @@ msda_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restric
       w[0][2] = __shfl_sync(0xffffffffu, p0.w10, sl, 8); w[0][3] = __shfl_sync(0xffffffffu, p0.w11, sl, 8);
       w[1][0] = __shfl_sync(0xffffffffu, p1.w00, sl, 8); w[1][1] = __shfl_sync(0xffffffffu, p1.w01, sl, 8);
       w[1][2] = __shfl_sync(0xffffffffu, p1.w10, sl, 8); w[1][3] = __shfl_sync(0xffffffffu, p1.w11, sl, 8);
+      const bool in0 = code[0] < -(1 << 30), in1 = code[1] < -(1 << 30);   // image offsets can be slightly negative
       float4 v[2][4];
+      if (__all_sync(0xffffffffu, in0 && in1)) {
+        // whole warp inside the staged boxes: plain shared-memory loads with 32-bit addresses
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const bool inbox = code[u] < 0;
-        // staged box (shared memory) or the image itself (global): one generic pointer, no divergence
-        const float* p = inbox ? sbase + (code[u] & 0x7fffffff) : vhead + code[u];
-        const int dx = 32 * (inbox ? 1 : M);                // next pixel: 128 B in the box, M*128 B in the image
-        const int dy = inbox ? Bs : ws;
-        if (w[u][0] != 0.f) v[u][0] = *reinterpret_cast<const float4*>(p);
-        if (w[u][1] != 0.f) v[u][1] = *reinterpret_cast<const float4*>(p + dx);
-        if (w[u][2] != 0.f) v[u][2] = *reinterpret_cast<const float4*>(p + dy);
-        if (w[u][3] != 0.f) v[u][3] = *reinterpret_cast<const float4*>(p + dy + dx);
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t p = sbase32 + 4u * (uint32_t)(code[u] & 0x7fffffff);
+          v[u][0] = lds_f4(w[u][0] != 0.f ? p : sbase32);
+          v[u][1] = lds_f4(w[u][1] != 0.f ? p + 128u : sbase32);
+          v[u][2] = lds_f4(w[u][2] != 0.f ? p + 4u * Bs : sbase32);
+          v[u][3] = lds_f4(w[u][3] != 0.f ? p + 4u * Bs + 128u : sbase32);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool inbox = u ? in1 : in0;
+          // staged box (shared window) or the image (global): one generic pointer per corner, no divergence.  A
+          // corner that contributes nothing reads a harmless staged word; the accumulation below skips it.
+          const float* p = inbox ? sbase + (code[u] & 0x7fffffff) : vhead + code[u];
+          const int dx = 32 * (inbox ? 1 : M);              // next pixel: 128 B in the box, M*128 B in the image
+          const int dy = inbox ? Bs : ws;
+          v[u][0] = ld_generic_f4(w[u][0] != 0.f ? p : sbase);
+          v[u][1] = ld_generic_f4(w[u][1] != 0.f ? p + dx : sbase);
+          v[u][2] = ld_generic_f4(w[u][2] != 0.f ? p + dy : sbase);
+          v[u][3] = ld_generic_f4(w[u][3] != 0.f ? p + dy + dx : sbase);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u)
@@ -226,7 +295,10 @@ msda_fwd_tma_kernel(const __grid_constant__ TmaMaps maps, const float* __restric
             acc.z = fmaf(w[u][k], v[u][k].z, acc.z); acc.w = fmaf(w[u][k], v[u][k].w, acc.w);
           }
     }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[sidx]);  // this warp no longer reads the stage
     if (live) st_stream_f4(reinterpret_cast<float4*>(out + pair * 32 + 4 * j), acc);
+    cur_op = next_op;
   }
 }
 
@@ -290,10 +362,10 @@ int msda_forward_tma(cudaStream_t st, bool fused, const float* value, const int6
   if (grid > items) grid = items;
   if (grid < 1) grid = 1;
   if (fused)
-    k1<<<(unsigned)grid, kTmaThreads, smem, st>>>(maps, value, shapes_dev, lsi_dev, loc, attn, batch, S, L, Lq, out,
+    k1<<<(unsigned)grid, kTmaThreads + 32, smem, st>>>(maps, value, shapes_dev, lsi_dev, loc, attn, batch, S, L, Lq, out,
                                                  ref, ref_dim);
   else
-    k0<<<(unsigned)grid, kTmaThreads, smem, st>>>(maps, value, shapes_dev, lsi_dev, loc, attn, batch, S, L, Lq, out,
+    k0<<<(unsigned)grid, kTmaThreads + 32, smem, st>>>(maps, value, shapes_dev, lsi_dev, loc, attn, batch, S, L, Lq, out,
                                                  ref, ref_dim);
   SDB_LAUNCH_CHECK("msda_fwd_tma_kernel");
   return SDB_OK;
@@ -315,7 +387,7 @@ extern "C" int sdb_msda_forward_tma_f32(sdb_stream_t stream, int fused, const fl
   SDB_REQUIRE(batch >= 0 && spatial_size >= 0 && num_query >= 0, "msda_forward_tma: bad sizes");
   if (!(channels == 32 && num_heads == 8 && num_point == 4 && num_levels >= 1 && num_levels <= kTmaLevels &&
         num_query == spatial_size && (!fused || ref_dim == 2 || ref_dim == 4) &&
-        (long long)spatial_size * 256 < (1ll << 31))) {
+        (long long)spatial_size * 256 < (1ll << 30))) {
     set_error("msda_forward_tma: built for encoder self-attention with channels=32, heads=8, points=4, levels<=4 "
               "(got C=%d M=%d P=%d L=%d Lq=%d S=%d)", channels, num_heads, num_point, num_levels, num_query,
               spatial_size);

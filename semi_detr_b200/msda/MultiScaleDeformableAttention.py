@@ -16,19 +16,23 @@ from .. import _lib
 _FLOAT = (torch.float32, torch.float64)
 
 # TMA-staged forward for encoder self-attention (num_query == spatial_size): see csrc/msda_forward_tma.cu.
-USE_TMA = True
+# Bit-identical to the L1-gather kernel but measured slower on B200 (187 vs 138 us on the N=2 microbench: both are
+# bound by the same 128 B/clk/SM load data pipe and the staged variant keeps fewer warps resident), so it is opt-in.
+USE_TMA = False
 _HOST_INDEX = {}
 
 
 def _host_index(spatial_shapes, level_start_index):
     """Host copies of the two index tensors (the TMA descriptors are encoded on the host): one device->host read
-    per distinct tensor, then cached."""
+    per distinct tensor, then cached.  The cache entry keeps the device tensors alive so their addresses cannot be
+    handed to a different tensor while the entry exists (``_version`` covers in-place writes)."""
     key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version)
     hit = _HOST_INDEX.get(key)
     if hit is None:
         if len(_HOST_INDEX) > 256:
             _HOST_INDEX.clear()
-        hit = (spatial_shapes.cpu().contiguous(), level_start_index.cpu().contiguous())
+        hit = (spatial_shapes.cpu().contiguous(), level_start_index.cpu().contiguous(), spatial_shapes,
+               level_start_index)
         _HOST_INDEX[key] = hit
     return hit
 
@@ -36,12 +40,12 @@ def _host_index(spatial_shapes, level_start_index):
 def _tma_ok(value, num_query, num_levels, num_point):
     b, s, m, d = value.shape
     return (USE_TMA and value.dtype == torch.float32 and d == 32 and m == 8 and num_point == 4 and num_levels <= 4
-            and num_query == s and value.data_ptr() % 128 == 0)
+            and num_query == s and s * 256 < (1 << 30) and value.data_ptr() % 128 == 0)
 
 
 def _forward_tma(fused, value, spatial_shapes, level_start_index, ref, loc, attn, out, dims):
     b, s, m, d, l, q, p = dims
-    hs, hl = _host_index(spatial_shapes, level_start_index)
+    hs, hl = _host_index(spatial_shapes, level_start_index)[:2]
     with torch.cuda.device(value.device):
         rc = _timed("fwd", b, s, q, lambda: _lib.lib().sdb_msda_forward_tma_f32(
             _lib.current_stream(value.device), 1 if fused else 0, value.data_ptr(), spatial_shapes.data_ptr(),

@@ -69,6 +69,7 @@ class MSDeformAttn(nn.Module):
             total = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())
             assert total == len_in, f"sum(H*W)={total} does not match input length {len_in}"
             self._checked_shapes = key
+            self._checked_shapes_ref = spatial_shapes      # keeps the address from being reused while cached
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):

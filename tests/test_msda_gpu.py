@@ -79,7 +79,7 @@ def test_forward_variants_vs_oracle(fv, mode, Lq):
     try:
         out = MSDA.ms_deform_attn_forward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
     finally:
-        MSDA.USE_TMA = True
+        MSDA.USE_TMA = False
         _lib.lib().sdb_msda_set_variant(0, 0)
     assert _relerr(out.cpu(), torch.from_numpy(ref)) < 1e-5
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=1e-4)

@@ -95,7 +95,6 @@ def main():
             emit(op="msda_bwd", case=name, n=args.n, variant=v, us=round(med, 2), best_us=round(best, 2),
                  gbs=round(bb / med / 1e3, 1), frac=round(bb / med / 1e3 / PEAK, 4))
         lib.sdb_msda_set_variant(0, 0)
-        MSDA.USE_TMA = True
         if args.ref:
             import ref_cuda
             if ref_cuda.available():
