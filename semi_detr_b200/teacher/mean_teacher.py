@@ -38,8 +38,10 @@ class EmaPlan:
                 raise RuntimeError("MeanTeacher: parameters must live on a CUDA device (no CPU path)")
             if t.dtype != torch.float32 or s.dtype != torch.float32:
                 raise RuntimeError("MeanTeacher: fp32 parameters expected")
-            if t.numel() != s.numel() or not t.is_contiguous() or not s.is_contiguous():
-                raise RuntimeError("MeanTeacher: teacher/student parameters must be contiguous and congruent")
+            # the blend is elementwise over storage: any dense layout works as long as both sides share it
+            # (channels-last conv weights included)
+            if t.shape != s.shape or t.stride() != s.stride() or not _dense(t):
+                raise RuntimeError("MeanTeacher: teacher/student parameters must be dense and share one layout")
             n = t.numel()
             total += n
             tp, sp = t.data_ptr(), s.data_ptr()
@@ -69,6 +71,17 @@ class EmaPlan:
                                                float(momentum))
         _lib.check(rc, "ema_update")
         _lib.LAUNCHES["ema_update"] += 1
+
+
+def _dense(t):
+    """True when the tensor's elements occupy ``numel`` consecutive storage slots (any permutation of a contiguous
+    layout)."""
+    expect = 1
+    for size, stride in sorted(((sz, st) for sz, st in zip(t.shape, t.stride()) if sz > 1), key=lambda p: p[1]):
+        if stride != expect:
+            return False
+        expect *= size
+    return True
 
 
 def _unwrap(model):
