@@ -276,8 +276,7 @@ def run_ours(args):
     log, MSDA.EVENT_LOG = MSDA.EVENT_LOG, None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world)
         return
 
     imgs = PER_GPU_BATCH * world * args.steps
@@ -332,8 +331,21 @@ def run_ours(args):
                 gpu_launches=launches, gpu_launches_per_step=launches_per_step,
                 roofline=roofline, cpu_baseline=cpu_baseline)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _leave(world)
+
+
+def _leave(world):
+    """End a multi-rank run without NCCL teardown: destroying a communicator that a live CUDA graph still references
+    was observed to block (N=2, round 1), so every rank drains its device, meets the others at a host-side barrier
+    and exits immediately."""
+    if world <= 1:
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
