@@ -246,6 +246,30 @@ int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const float* grad
                            const int64_t* seg_bounds, const float* seg_lr, const float* seg_weight_decay,
                            int num_segs, float beta1, float beta2, float eps, double ema_momentum);
 
+/* ------------------------------------------------------------------------------------------
+ * Token-wise linear layers as tcgen05 (5th-generation tensor core) GEMMs, TF32 arithmetic on fp32 storage with
+ * fp32 accumulation in tensor memory -- the three products of the nn.Linear layers on the path
+ * (ms_deform_attn.py:61-65, 94-112 value_proj / sampling_offsets / attention_weights / output_proj;
+ * transformer.py:626-630, 878-882 FFN; :1277-1290 enc_output), which the reference runs through cuBLAS:
+ *
+ *   y[m,n] (row-major) = op(a)[m,k] . op(b)[k,n] (+ bias[n]) (ReLU) (rows with row_mask != 0 -> 0)
+ *
+ *   a_mn_major == 0 : a is stored (m, k) row-major          a_mn_major != 0 : a is stored (k, m) row-major
+ *   b_mn_major == 0 : b is stored (n, k) row-major (an nn.Linear weight)
+ *   b_mn_major != 0 : b is stored (k, n) row-major
+ *   forward  y = x W^T + b : (x, 0, W, 0)      grad x = dy W : (dy, 0, W, 1)      grad W = dy^T x : (dy, 1, x, 1)
+ *   row_mask : optional (m,) bytes -- value.masked_fill(input_padding_mask[..., None], 0) of ms_deform_attn.py:96-97
+ *   k_splits > 1 : the contraction is split into k_splits ranges whose partial products are REDUCE-ADDED into y
+ *                  (y must hold the initial value, e.g. zeros or the gradient being accumulated); no epilogue then.
+ *   round_mode : bit 0 / bit 1 -- round a / b to the nearest TF32 value (in shared memory, after the TMA load) before
+ *                the tensor core reads it.  The tensor core itself truncates (a systematic -7e-4 relative bias);
+ *                3 reproduces the unbiased round-to-nearest TF32 product of cuBLAS, 0 is the raw truncating product.
+ * Requirements: 16-byte aligned pointers, n % 4 == 0, and the contiguous dimension of every operand % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major, float* y,
+                  int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu, int k_splits,
+                  int round_mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,524 @@
+// Token-wise linears of the deformable transformer as tcgen05 tensor-core GEMMs (sm_100a).
+//
+//   Y[M,N] (row-major) = op(A)[M,K] . op(B)[K,N]  (+ bias[N]) (ReLU) (rows with row_mask != 0 -> 0)
+//
+// fp32 storage, TF32 tensor-core arithmetic (`tcgen05.mma.cta_group::1.kind::tf32`, fp32 accumulation in TMEM)
+// -- the arithmetic the reference's `nn.Linear`s get from cuBLAS with TF32 allowed
+// (detr_od/models/utils/ops/modules/ms_deform_attn.py:61-65 value_proj / sampling_offsets / attention_weights /
+// output_proj, detr_od/models/utils/transformer.py:626-630 and :878-882 FFN).  One kernel serves the three
+// products of a linear layer, selected by operand "majorness":
+//   forward   y  = x . W^T     A = x  (M,K) K-major         B = W  (N,K) K-major
+//   grad x    dx = dy . W      A = dy (M,K) K-major         B = W  (K,N) MN-major
+//   grad W    dW = dy^T . x    A = dy (K,M) MN-major        B = x  (K,N) MN-major     (split along K, reduce-add)
+//
+// Structure (one persistent CTA per SM, 320 threads -> 10 warps):
+//   warp 0   TMA producer: `cp.async.bulk.tensor.2d` boxes with the 128-byte swizzle into a 5-stage ring,
+//            completion on `full[s]` mbarriers (transaction bytes)
+//   warp 1   MMA issuer: one elected thread, 4 x `tcgen05.mma` (128x128x8) per 32-wide k-block, descriptors built
+//            from the stage address; `tcgen05.commit` releases the stage (`empty[s]`) and, after the last k-block,
+//            publishes the accumulator (`tmem_full[a]`).  It also owns the TMEM allocation (2 x 128 columns: the
+//            epilogue of tile i overlaps the main loop of tile i+1).
+//   warps 2-5  epilogue: `tcgen05.ld.32x32b.x32` (each thread owns one accumulator row), bias / ReLU / row mask in
+//            registers, 128B-swizzled staging tile in shared memory, `cp.async.bulk.tensor` store (or
+//            `cp.reduce.async.bulk.tensor ... .add` when the product is split along K), double-buffered.
+//   warps 6-9  operand rounding: the tensor core TRUNCATES fp32 words to TF32 (13 low mantissa bits ignored), a
+//            systematic -7e-4 relative shrink of every product.  These warps round each landed stage to nearest
+//            (`cvt.rna.tf32.f32`, in place, layout-agnostic) and hand it to the MMA warp through `ready[s]`, so the
+//            result is the unbiased round-to-nearest TF32 product cuBLAS computes.
+// K-major operands use the 128-byte swizzle; MN-major fp32 operands must use the "128B swizzle with 32-byte atoms"
+// (UMMA layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4 k-rows x 128 B per swizzle atom.
+// The path is HBM-bound for the shapes of this model (K = 256: 2 flop per byte moved would need ~12 TB/s to
+// saturate the tensor pipe), so the design goal is to keep TMA loads and stores continuously in flight.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sdb {
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;       // 32 fp32 = 128 B = one swizzle row
+constexpr int kStages = 5;
+constexpr int kResStages = 4;                       // A-only ring of the B-resident variant
+constexpr int kResKB = 8;                           // resident B: up to 8 k-blocks (K <= 256)
+constexpr int kTileBytes = kBM * kBK * 4;           // 16 KB per operand per stage
+constexpr int kStageBytes = 2 * kTileBytes;
+constexpr int kOutChunk = 32;                       // output columns per TMA store (128 B rows)
+constexpr int kOutBufBytes = kBM * kOutChunk * 4;   // 16 KB
+constexpr int kThreads = 320;
+constexpr int kXformThreads = 128;
+constexpr int kEpiThreads = 128;
+constexpr int kTmemCols = 2 * kBN;
+constexpr size_t kDynSmem = (size_t)kStages * kStageBytes + 2 * kOutBufBytes + 1024;   // + alignment slack
+constexpr size_t kDynSmemRes = (size_t)(kResKB + kResStages) * kTileBytes + 2 * kOutBufBytes + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug becomes a trap (an error the host sees), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 26)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.  Fields in 16-byte units:
+//   [0,14) start address   [16,30) leading byte offset   [32,46) stride byte offset   [46,48) version = 1
+//   [61,64) layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+// K-major operand (rows of 32 fp32 along K), SWIZZLE_128B: 8-row groups are 1024 B apart (SBO = 64); LBO unused (1).
+// MN-major operand (rows of 32 fp32 along M/N, one row per k), SWIZZLE_128B_BASE32B -- the only layout tcgen05
+// accepts for MN-major 32-bit operands: the 128 M/N elements of a tile are four boxes of (kBK rows x 128 B) = 4096 B
+// apart (LBO = 256); the swizzle atom holds 4 k-rows, so the two atoms of one MMA (k = 8) are 512 B apart (SBO = 32).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (uint64_t)(kBK * 128 / 16) : 1ull;
+  const uint64_t sbo = mn_major ? (uint64_t)(512 / 16) : (uint64_t)(1024 / 16);
+  const uint64_t type = mn_major ? 1ull : 2ull;
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
+}
+
+// Instruction descriptor, kind::tf32: c_format F32 (1 @ bit 4), a/b format TF32 (2 @ bits 7 / 10), a_major bit 15,
+// b_major bit 16, N >> 3 @ bit 17, M >> 4 @ bit 24.
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+struct GemmArgs {
+  int M, N, K;
+  int k_splits;           // > 1: every split reduce-adds its partial product into Y (Y must hold the initial value)
+  int k_blocks_per_split;
+  int relu;
+  int round_a, round_b;   // round the operand to nearest TF32 in shared memory before the MMA reads it
+  const float* bias;        // (N,) or null
+  const uint8_t* row_mask;  // (M,) or null; nonzero -> the output row is zero
+};
+
+// kBRes ("B resident"): for K <= 256 the whole (128 x K) B tile of one n-block -- the weight matrix of the
+// value / offset / attention / output projections -- stays in shared memory for the life of the CTA (128 KB), is
+// rounded once, and only A streams through a 4-stage ring.  L2 -> SM traffic drops from (A + B) per tile to A per tile.
+template <bool kAMn, bool kBMn, bool kBRes>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmY, const GemmArgs g) {
+  constexpr int kNS = kBRes ? kResStages : kStages;                  // ring depth
+  constexpr int kSB = kBRes ? kTileBytes : kStageBytes;              // bytes per ring stage
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * kStages + 6];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[2][kBN];
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bres = base;                                        // resident B: kResKB k-blocks of 16 KB
+  const uint32_t ring = kBRes ? base + kResKB * kTileBytes : base;
+  const uint32_t out_base = ring + kNS * kSB;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (3 * kStages + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (3 * kStages + 2 + a); };
+  const uint32_t bfull = bar0 + 8u * (3 * kStages + 4), bready = bar0 + 8u * (3 * kStages + 5);
+  // which operands the rounding warps touch per ring stage
+  const bool round_ring_a = g.round_a != 0, round_ring_b = !kBRes && g.round_b != 0;
+  const bool xform = round_ring_a || round_ring_b;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + kBM - 1) / kBM, n_tiles = (g.N + kBN - 1) / kBN;
+  const long long num_items = (long long)m_tiles * n_tiles * g.k_splits;
+  const int total_kb = (g.K + kBK - 1) / kBK;
+  // kBRes: the host sizes the grid as a multiple of n_tiles, so every item of this CTA has the same n-block
+  const int res_n0 = (int)(blockIdx.x % n_tiles) * kBN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+      mbar_init(ready(s), kXformThreads);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull(a), 1);
+      mbar_init(tempty(a), kEpiThreads);
+    }
+    mbar_init(bfull, 1);
+    mbar_init(bready, kXformThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      auto load_b = [&](uint32_t sb, int n0, int kb, uint32_t bar) {
+        if (kBMn) {
+#pragma unroll
+          for (int j = 0; j < kBN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, bar);
+        } else {
+          tma_load_2d(sb, &tmB, kb * kBK, n0, bar);
+        }
+      };
+      if (kBRes && blockIdx.x < num_items) {
+        mbar_expect_tx(bfull, (uint32_t)(total_kb * kTileBytes));
+        for (int kb = 0; kb < total_kb; ++kb) load_b(bres + kb * kTileBytes, res_n0, kb, bfull);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int ks = (int)(item % g.k_splits);
+        const long long t = item / g.k_splits;
+        const int n0 = (int)(t % n_tiles) * kBN, m0 = (int)(t / n_tiles) * kBM;
+        const int kb0 = ks * g.k_blocks_per_split;
+        const int kb1 = min(total_kb, kb0 + g.k_blocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          mbar_expect_tx(full(stage), kSB);
+          const uint32_t sa = ring + stage * kSB;
+          if (kAMn) {
+#pragma unroll
+            for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full(stage));
+          } else {
+            tma_load_2d(sa, &tmA, kb * kBK, m0, full(stage));
+          }
+          if (!kBRes) load_b(sa + kTileBytes, n0, kb, full(stage));
+          if (++stage == kNS) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = make_idesc(kAMn, kBMn);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      if (kBRes && blockIdx.x < num_items) mbar_wait(g.round_b ? bready : bfull, 0);
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int ks = (int)(item % g.k_splits);
+        const int kb0 = ks * g.k_blocks_per_split;
+        const int kb1 = min(total_kb, kb0 + g.k_blocks_per_split);
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(xform ? ready(stage) : full(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = ring + stage * kSB;
+          const uint32_t sb = kBRes ? bres + kb * kTileBytes : sa + kTileBytes;
+          const uint64_t adesc = make_desc(sa, kAMn), bdesc = make_desc(sb, kBMn);
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            // one MMA consumes 8 k: 32 B along a K-major row, or 8 rows (1024 B) of an MN-major box
+            const uint64_t ao = (uint64_t)((kAMn ? k * 1024 : k * 32) >> 4);
+            const uint64_t bo = (uint64_t)((kBMn ? k * 1024 : k * 32) >> 4);
+            tc_mma_tf32(d_tmem, adesc + ao, bdesc + bo, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty(stage));
+          if (++stage == kNS) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 6) {
+    // ---------------- operand rounding (warps 6..9) ----------------
+    const int t = threadIdx.x - 192;            // 0..127
+    auto round_region = [&](uint32_t p0, int n_vec) {   // n_vec x (128 threads x 16 B), in place
+#pragma unroll 4
+      for (int j = 0; j < n_vec; ++j) {
+        const uint32_t p = p0 + 16u * t + (uint32_t)(j * 16 * kXformThreads);
+        uint32_t a, b, c, d;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(p) : "memory");
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(__uint_as_float(a)));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(__uint_as_float(b)));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(__uint_as_float(c)));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(__uint_as_float(d)));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    };
+    constexpr int kVecPerTile = kTileBytes / (16 * kXformThreads);   // 8
+    if (kBRes && g.round_b && blockIdx.x < num_items) {
+      mbar_wait(bfull, 0);
+      round_region(bres, total_kb * kVecPerTile);
+      mbar_arrive(bready);
+    }
+    if (xform) {
+      const uint32_t first = round_ring_a ? 0u : (uint32_t)kTileBytes;
+      const int n_vec = ((round_ring_a ? 1 : 0) + (round_ring_b ? 1 : 0)) * kVecPerTile;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int ks = (int)(item % g.k_splits);
+        const int kb0 = ks * g.k_blocks_per_split;
+        const int kb1 = min(total_kb, kb0 + g.k_blocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full(stage), phase);
+          round_region(ring + stage * kSB + first, n_vec);
+          mbar_arrive(ready(stage));
+          if (++stage == kNS) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    const int t = threadIdx.x - 64;               // 0..127
+    const int quarter = warp & 3;                 // TMEM lanes this warp may read: 32*(warp % 4) .. +31
+    const int row = quarter * 32 + lane;          // accumulator row owned by this thread
+    const bool issuer = (t == 0);
+    int acc = 0, obuf = 0;
+    uint32_t acc_phase = 0;
+    for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int ks = (int)(item % g.k_splits);
+      const long long tt = item / g.k_splits;
+      const int n0 = (int)(tt % n_tiles) * kBN, m0 = (int)(tt / n_tiles) * kBM;
+      const bool has_k = ks * g.k_blocks_per_split < total_kb;
+      {
+        const int n = n0 + t;
+        bias_s[acc][t] = (g.bias != nullptr && ks == 0 && n < g.N) ? g.bias[n] : 0.f;
+      }
+      const bool masked = g.row_mask != nullptr && (m0 + row) < g.M && g.row_mask[m0 + row] != 0;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBN);
+#pragma unroll 1
+      for (int c = 0; c < kBN / kOutChunk; ++c) {
+        if (n0 + c * kOutChunk >= g.N) break;       // uniform over the CTA
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + (uint32_t)(c * kOutChunk))
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // the staging buffer written two chunks ago must have been read by its TMA store
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // also orders the bias_s writes before their reads
+        const uint32_t srow = out_base + obuf * kOutBufBytes + row * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = has_k ? __uint_as_float(v[4 * q + e]) : 0.f;
+            x += bias_s[acc][c * kOutChunk + 4 * q + e];
+            if (g.relu) x = fmaxf(x, 0.f);
+            op[e] = masked ? 0.f : x;
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)(((q ^ (row & 7)) << 4))),
+                       "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                       : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if (g.k_splits > 1)
+            tma_reduce_add_2d(&tmY, out_base + obuf * kOutBufBytes, n0 + c * kOutChunk, m0);
+          else
+            tma_store_2d(&tmY, out_base + obuf * kOutBufBytes, n0 + c * kOutChunk, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        obuf ^= 1;
+      }
+      tc_fence_before();
+      mbar_arrive(tempty(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major matrix (rows x cols), box (box_rows x 32 columns), 128-byte swizzle, zero fill out of bounds
+int make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, int box_rows, bool atom32,
+             const char* what) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("gemm_tf32: cuTensorMapEncodeTiled is not available from this driver");
+    return SDB_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tf32: cuTensorMapEncodeTiled failed for %s (CUresult %d, rows=%lld cols=%lld)", what, (int)r, rows,
+              cols);
+    return SDB_ERR_CUDA;
+  }
+  return SDB_OK;
+}
+
+template <bool kAMn, bool kBMn, bool kBRes>
+int launch(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const GemmArgs& g,
+           long long items, int n_tiles) {
+  static bool configured = false;
+  auto k = gemm_tf32_kernel<kAMn, kBMn, kBRes>;
+  const size_t smem = kBRes ? kDynSmemRes : kDynSmem;
+  if (!configured) {
+    SDB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  long long grid = sm_count();
+  if (grid > items) grid = items;
+  if (kBRes) grid -= grid % n_tiles;   // every CTA keeps one n-block: items of CTA c are c, c + grid, ...
+  k<<<(unsigned)grid, kThreads, smem, st>>>(a, b, y, g);
+  SDB_LAUNCH_CHECK("gemm_tf32_kernel");
+  return SDB_OK;
+}
+
+}  // namespace
+}  // namespace sdb
+
+extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
+                             float* y, int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu,
+                             int k_splits, int round_mode) {
+  using namespace sdb;
+  SDB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_tf32: negative size");
+  if (m == 0 || n == 0) return SDB_OK;
+  SDB_REQUIRE(a && b && y, "gemm_tf32: null pointer");
+  SDB_REQUIRE(k > 0, "gemm_tf32: k must be positive");
+  SDB_REQUIRE(m % 4 == 0 || !a_mn_major, "gemm_tf32: an MN-major A needs m %% 4 == 0 (16-byte row pitch)");
+  SDB_REQUIRE(n % 4 == 0, "gemm_tf32: n must be a multiple of 4 (16-byte row pitch of Y)");
+  SDB_REQUIRE(k % 4 == 0 || (a_mn_major && b_mn_major), "gemm_tf32: K-major operands need k %% 4 == 0");
+  SDB_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+              "gemm_tf32: operands must be 16-byte aligned");
+  SDB_REQUIRE(k_splits >= 1, "gemm_tf32: k_splits must be >= 1");
+  SDB_REQUIRE(round_mode >= 0 && round_mode <= 3, "gemm_tf32: round_mode is a bit mask (1 = a, 2 = b)");
+  SDB_REQUIRE(k_splits == 1 || (!bias && !relu && !row_mask) , "gemm_tf32: a split product cannot carry an epilogue");
+  CUtensorMap ta, tb, ty;
+  int rc;
+  if (a_mn_major) rc = make_map(&ta, a, k, m, kBK, true, "A (k,m)");
+  else rc = make_map(&ta, a, m, k, kBM, false, "A (m,k)");
+  if (rc) return rc;
+  if (b_mn_major) rc = make_map(&tb, b, k, n, kBK, true, "B (k,n)");
+  else rc = make_map(&tb, b, n, k, kBN, false, "B (n,k)");
+  if (rc) return rc;
+  rc = make_map(&ty, y, m, n, kBM, false, "Y (m,n)");
+  if (rc) return rc;
+  GemmArgs g;
+  g.M = m; g.N = n; g.K = k;
+  const int total_kb = (k + kBK - 1) / kBK;
+  if (k_splits > total_kb) k_splits = total_kb;
+  g.k_blocks_per_split = (total_kb + k_splits - 1) / k_splits;
+  g.k_splits = (total_kb + g.k_blocks_per_split - 1) / g.k_blocks_per_split;   // no empty split
+  g.relu = relu;
+  g.round_a = (round_mode & 1) != 0;
+  g.round_b = (round_mode & 2) != 0;
+  g.bias = bias;
+  g.row_mask = row_mask;
+  const long long items = (long long)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) * g.k_splits;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_tiles = (n + kBN - 1) / kBN;
+  // B-resident variant: the whole K extent of one n-block fits the 128 KB resident region, and there is enough work
+  // for every CTA to amortise loading it (at least two m-tiles per CTA on a full grid)
+  const bool res = g.k_splits == 1 && total_kb <= kResKB && n_tiles <= sm_count() &&
+                   items >= 2ll * sm_count();
+  if (res) {
+    if (a_mn_major) return b_mn_major ? launch<true, true, true>(st, ta, tb, ty, g, items, n_tiles) : launch<true, false, true>(st, ta, tb, ty, g, items, n_tiles);
+    return b_mn_major ? launch<false, true, true>(st, ta, tb, ty, g, items, n_tiles) : launch<false, false, true>(st, ta, tb, ty, g, items, n_tiles);
+  }
+  if (a_mn_major) return b_mn_major ? launch<true, true, false>(st, ta, tb, ty, g, items, n_tiles) : launch<true, false, false>(st, ta, tb, ty, g, items, n_tiles);
+  return b_mn_major ? launch<false, true, false>(st, ta, tb, ty, g, items, n_tiles) : launch<false, false, false>(st, ta, tb, ty, g, items, n_tiles);
+}

@@ -41,9 +41,7 @@ class MLP(nn.Module):
 
     def forward(self, x):
         for i, layer in enumerate(self.layers):
-            x = layer(x)
-            if i < self.num_layers - 1:
-                x = F.relu(x)
+            x = layer(x, relu=i < self.num_layers - 1)
         return x
 
 
@@ -125,7 +123,7 @@ class DINOTransformerEncoderLayer(nn.Module):
         q = src if pos is None else src + pos
         src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, key_padding_mask)
         src = self.norm1(src + self.dropout1(src2))
-        src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
+        src2 = self.linear2(self.dropout2(self.linear1(src, relu=True)))
         return self.norm2(src + self.dropout3(src2))
 
 
@@ -207,7 +205,7 @@ class DINOTransformerDecoderLayer(nn.Module):
                                        memory_key_padding_mask).transpose(0, 1)
                 tgt = self.norm1(tgt + self.dropout1(tgt2))
             else:
-                tgt2 = self.linear2(self.dropout3(F.relu(self.linear1(tgt))))
+                tgt2 = self.linear2(self.dropout3(self.linear1(tgt, relu=True)))
                 tgt = self.norm3(tgt + self.dropout4(tgt2))
         return tgt
 

@@ -1,0 +1,77 @@
+"""Host side of ``sdb_gemm_tf32`` (``csrc/gemm_tf32.cu``): the three products of an ``nn.Linear`` on tcgen05 tensor
+cores, TF32 arithmetic on fp32 storage.
+
+    y = x W^T + b   -> linear_forward(x, W, b)            (optional ReLU / zeroed rows in the epilogue)
+    dx = dy W       -> linear_grad_input(dy, W)
+    dW = dy^T x     -> linear_grad_weight(dy, x)          (split along the token axis, reduce-added by TMA)
+
+Reference call sites: ``ms_deform_attn.py:61-65, 94-112`` (value_proj with ``masked_fill``, sampling_offsets,
+attention_weights, output_proj) and the FFNs of ``transformer.py:626-630, 878-882``.  No CPU path: CPU tensors raise.
+"""
+import torch
+
+from .. import _lib
+
+_SMS = {}
+
+
+def _sm_count(device):
+    i = device.index if device.index is not None else torch.cuda.current_device()
+    if i not in _SMS:
+        _SMS[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _SMS[i]
+
+
+def _check(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"gemm_tf32: {name} is not a CUDA tensor (Not implemented on the CPU)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError(f"gemm_tf32: {name} must be contiguous float32")
+
+
+def gemm_tf32(a, a_mn_major, b, b_mn_major, m, n, k, bias=None, row_mask=None, relu=False, out=None, k_splits=1, round_mode=3):
+    """Raw entry: see include/semidetr_b200.h.  ``out`` (m, n) is allocated when None (zero-filled if k_splits > 1).
+    round_mode 3 (default): both operands rounded to nearest TF32 -- the unbiased product cuBLAS-TF32 computes."""
+    _check(a, "a")
+    _check(b, "b")
+    if out is None:
+        out = (torch.zeros if k_splits > 1 else torch.empty)((m, n), dtype=torch.float32, device=a.device)
+    else:
+        _check(out, "out")
+    if bias is not None:
+        _check(bias, "bias")
+    if row_mask is not None:
+        if row_mask.dtype == torch.bool:
+            row_mask = row_mask.view(torch.uint8)
+        if not row_mask.is_cuda or row_mask.dtype != torch.uint8 or not row_mask.is_contiguous() or row_mask.numel() != m:
+            raise RuntimeError("gemm_tf32: row_mask must be a contiguous (m,) bool / uint8 CUDA tensor")
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().sdb_gemm_tf32(_lib.current_stream(a.device), a.data_ptr(), int(a_mn_major), b.data_ptr(),
+                                      int(b_mn_major), out.data_ptr(), m, n, k, _lib.ptr(bias), _lib.ptr(row_mask),
+                                      int(relu), int(k_splits), int(round_mode))
+    _lib.check(rc, "gemm_tf32")
+    _lib.LAUNCHES["gemm_tf32"] += 1
+    return out
+
+
+def linear_forward(x2d, weight, bias=None, relu=False, row_mask=None):
+    """x2d (tokens, in) . weight (out, in)^T + bias -> (tokens, out)"""
+    m, k = x2d.shape
+    n = weight.shape[0]
+    return gemm_tf32(x2d, 0, weight, 0, m, n, k, bias=bias, row_mask=row_mask, relu=relu)
+
+
+def linear_grad_input(g2d, weight):
+    """g2d (tokens, out) . weight (out, in) -> (tokens, in)"""
+    m, k = g2d.shape
+    n = weight.shape[1]
+    return gemm_tf32(g2d, 0, weight, 1, m, n, k)
+
+
+def linear_grad_weight(g2d, x2d):
+    """g2d (tokens, out)^T . x2d (tokens, in) -> (out, in); the token axis is split over the SMs."""
+    k, m = g2d.shape
+    n = x2d.shape[1]
+    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+    splits = max(1, min((k + 31) // 32, (2 * _sm_count(g2d.device)) // tiles))
+    return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits)

@@ -81,9 +81,8 @@ class MSDeformAttn(nn.Module):
         M, L, P = self.n_heads, self.n_levels, self.n_points
         self._check_len(input_spatial_shapes, S)
 
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        # value_proj + masked_fill(padding) (ms_deform_attn.py:94-97): the mask is applied in the GEMM epilogue
+        value = self.value_proj(input_flatten, row_mask=input_padding_mask)
         value = value.view(N, S, M, self.d_model // M)
         offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
         logits = self.attention_weights(query).view(N, Lq, M, L * P)

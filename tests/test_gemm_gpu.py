@@ -1,0 +1,121 @@
+"""tcgen05 TF32 GEMM (sdb_gemm_tf32) against an fp64 product of the TF32-rounded operands.
+
+The kernel rounds both operands to the nearest TF32 value (cvt.rna) before the tensor core reads them; products are
+exact in fp32 and accumulated in fp32, so against the fp64 product of the rounded operands only the accumulation
+order differs (round_mode 0 -- the raw truncating tensor-core product -- is checked the same way).  Tolerance: 2e-5 of
+the largest output magnitude (k <= 44448 fp32 accumulations), far inside the 1e-3 relative the north star asks of the
+attention tensors; cuBLAS-TF32 (what the reference's nn.Linear runs on) is checked against the same bound."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trunc(t):
+    """cvt.rna.tf32.f32: nearest TF32, ties away from zero"""
+    return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _close(y, ref, tol=2e-5):
+    scale = ref.abs().max().item() + 1e-30
+    err = (y.double() - ref).abs().max().item() / scale
+    assert err < tol, err
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (256, 256, 64), (1000, 384, 256), (77, 132, 36), (4446, 256, 256),
+                                   (4446, 2048, 256), (4446, 256, 2048), (44446, 256, 256)])
+@pytest.mark.parametrize("epilogue", ["plain", "bias", "bias_relu_mask"])
+def test_forward(m, n, k, epilogue):
+    from semi_detr_b200.layers import gemm as G
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    x = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) * 0.1
+    b = torch.randn(n, device="cuda", generator=g) if epilogue != "plain" else None
+    mask = (torch.rand(m, device="cuda", generator=g) < 0.2) if epilogue == "bias_relu_mask" else None
+    y = G.linear_forward(x, w, b, relu=epilogue == "bias_relu_mask", row_mask=mask)
+    ref = _trunc(x).double() @ _trunc(w).double().t()
+    if b is not None:
+        ref = ref + b.double()
+    if epilogue == "bias_relu_mask":
+        ref = torch.relu(ref).masked_fill(mask[:, None], 0.0)
+        assert (y[mask] == 0).all()
+    _close(y, ref)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (1000, 256, 384), (4446, 256, 2048), (4446, 2048, 256), (44446, 256, 256),
+                                   (900, 4, 256)])
+def test_grad_input(m, n, k):
+    from semi_detr_b200.layers import gemm as G
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    dy = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    _close(G.linear_grad_input(dy, w), _trunc(dy).double() @ _trunc(w).double())
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 256, 1000), (256, 256, 44446), (2048, 256, 4446), (256, 2048, 4446),
+                                   (384, 256, 44448), (132, 36, 76)])
+def test_grad_weight(m, n, k):
+    from semi_detr_b200.layers import gemm as G
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    dy = torch.randn(k, m, device="cuda", generator=g)
+    x = torch.randn(k, n, device="cuda", generator=g)
+    _close(G.linear_grad_weight(dy, x), _trunc(dy).double().t() @ _trunc(x).double())
+
+
+def test_split_product_accumulates_into_out():
+    from semi_detr_b200.layers import gemm as G
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dy = torch.randn(3000, 256, device="cuda", generator=g)
+    x = torch.randn(3000, 128, device="cuda", generator=g)
+    init = torch.randn(256, 128, device="cuda", generator=g)
+    out = init.clone()
+    G.gemm_tf32(dy, 1, x, 1, 256, 128, 3000, out=out, k_splits=7)
+    _close(out, init.double() + _trunc(dy).double().t() @ _trunc(x).double())
+
+
+def test_truncating_mode_is_the_raw_tensor_core_product():
+    from semi_detr_b200.layers import gemm as G
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(1000, 256, device="cuda", generator=g)
+    w = torch.randn(256, 256, device="cuda", generator=g)
+    chop = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    y = G.gemm_tf32(x, 0, w, 0, 1000, 256, 256, round_mode=0)
+    _close(y, chop(x).double() @ chop(w).double().t())
+
+
+def test_rejects_cpu_and_bad_shapes():
+    from semi_detr_b200.layers import gemm as G
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        G.linear_forward(torch.randn(8, 8), torch.randn(8, 8).cuda())
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        G.linear_forward(torch.randn(8, 8).cuda(), torch.randn(6, 8).cuda())
+    with pytest.raises(RuntimeError, match="epilogue"):
+        G.gemm_tf32(torch.randn(64, 8).cuda(), 1, torch.randn(64, 8).cuda(), 1, 8, 8, 64, bias=torch.randn(8).cuda(), k_splits=2)
+
+
+def test_linear_layer_matches_torch_autograd():
+    """Linear (forward + all three gradients through the tcgen05 GEMM) against nn.Linear in fp32 (no TF32):
+    1e-3 relative of the tensor's scale, the north star's bound."""
+    from semi_detr_b200.layers.linear import Linear
+    torch.manual_seed(0)
+    lin = Linear(256, 384).cuda()
+    ref = torch.nn.Linear(256, 384).cuda()
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(2, 3000, 256, device="cuda", requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    gy = torch.randn(2, 3000, 384, device="cuda")
+    from semi_detr_b200 import _lib
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        yr = ref(xr)
+        yr.backward(gy)
+        torch.backends.cuda.matmul.allow_tf32 = True      # the switch that selects the tcgen05 kernel
+        before = _lib.LAUNCHES["gemm_tf32"]
+        y = lin(x)
+        y.backward(gy)
+        assert _lib.LAUNCHES["gemm_tf32"] - before == 3, "forward, grad-input and grad-weight run on the tcgen05 kernel"
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    for a, b in ((y, yr), (x.grad, xr.grad), (lin.weight.grad, ref.weight.grad), (lin.bias.grad, ref.bias.grad)):
+        assert (a - b).abs().max().item() <= 1e-3 * b.abs().max().item()
