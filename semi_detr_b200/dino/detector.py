@@ -55,14 +55,21 @@ class DINODETR(nn.Module):
         """-> (total loss tensor, log_vars): ``log_vars`` maps names to 0-dim device tensors; pass
         ``reduce_log_vars=True`` to average them over ranks (one all-reduce) and get python floats."""
         log_vars = OrderedDict()
-        for name, value in losses.items():
-            if torch.is_tensor(value):
-                log_vars[name] = value.mean()
-            elif isinstance(value, (list, tuple)):
-                log_vars[name] = sum(v.mean() for v in value)
-            else:
-                raise TypeError(f"{name} is not a tensor or list of tensors")
-        loss = sum(v for k, v in log_vars.items() if "loss" in k)
+        total = getattr(losses, "total", None)
+        if total is not None:
+            # the head already summed its entries (dino.head.LossDict): log the scalars as they are
+            assert all(torch.is_tensor(v) and v.dim() == 0 and "loss" in k for k, v in losses.items())
+            log_vars.update((k, v.detach()) for k, v in losses.items())
+            loss = total
+        else:
+            for name, value in losses.items():
+                if torch.is_tensor(value):
+                    log_vars[name] = value.mean()
+                elif isinstance(value, (list, tuple)):
+                    log_vars[name] = sum(v.mean() for v in value)
+                else:
+                    raise TypeError(f"{name} is not a tensor or list of tensors")
+            loss = sum(v for k, v in log_vars.items() if "loss" in k)
         log_vars["loss"] = loss
         if reduce_log_vars:
             vec = torch.stack([v.detach() for v in log_vars.values()])

@@ -36,6 +36,21 @@ from .transformer import MLP, inverse_sigmoid
 LOSS_PARTS = ("loss_cls", "loss_bbox", "loss_iou", "loss_bbox_xy", "loss_bbox_hw")
 
 
+class LossDict(dict):
+    """The reference's loss dict (name -> scalar tensor) plus ``total``: the sum of every entry whose name contains
+    "loss" -- what mmdet's ``_parse_losses`` (base.py:176-209) computes entry by entry -- precomputed by the head.
+    Adding or replacing an entry afterwards drops ``total`` (the slow entry-by-entry sum is then used)."""
+    total = None
+
+    def __setitem__(self, key, value):
+        self.total = None
+        super().__setitem__(key, value)
+
+    def update(self, *args, **kwargs):
+        self.total = None
+        super().update(*args, **kwargs)
+
+
 def reduce_mean_scalar(value, device):
     """mmdet core/utils/dist_utils.py:67-73 for a host scalar: mean over ranks, kept on the device (no .item())."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -317,8 +332,10 @@ class DINODETRHead(nn.Module):
 
     @staticmethod
     def _assemble(main, dn, L, has_enc):
-        """Per-layer tensors -> the reference's loss dict (key order of dino_detr_head.py:584-632)."""
-        loss_dict = {}
+        """Per-layer tensors -> the reference's loss dict (key order of dino_detr_head.py:584-632).  The dict also
+        carries ``total`` -- the sum of all its entries, taken from the per-layer vectors with one concatenate + one
+        reduction -- so ``_parse_losses`` need not add 65 scalars one kernel at a time (nor autograd undo them)."""
+        loss_dict = LossDict()
         if has_enc:
             for k in LOSS_PARTS:
                 loss_dict[f"enc_{k}"] = main[k][L]
@@ -331,6 +348,7 @@ class DINODETRHead(nn.Module):
                 loss_dict[f"d{l}.{k}"] = main[k][l]
             for k in LOSS_PARTS:
                 loss_dict[f"d{l}.dn_{k}"] = dn[k][l]
+        loss_dict.total = torch.cat([main[k] for k in LOSS_PARTS] + [dn[k] for k in LOSS_PARTS]).sum()
         return loss_dict
 
     # ------------------------------------------------------------------------------------------------

@@ -6,11 +6,20 @@ Used for the token-wise linears of the transformer (FFN, MSDA projections, enc_o
 and ``value.masked_fill(padding_mask[..., None], 0)`` (``ms_deform_attn.py:96-97``) into the GEMM epilogue.
 
 The tcgen05 kernel computes in TF32, so it is taken exactly when torch's own switch for TF32 matrix products
-(``torch.backends.cuda.matmul.allow_tf32``) is on -- with the switch off the products are full-fp32 library GEMMs,
-which is what the parity tests against the fp32 CPU oracle use.  Small or oddly shaped products (a few hundred rows,
-4-wide box heads) and -- until the 2-CTA variant of the kernel lands -- the 2048-wide FFN products also stay library
-GEMMs: plumbing, like the convolutions.  ``SDB_LINEAR=cublas`` sends everything to the library and
-``SDB_LINEAR=tcgen05_all`` everything eligible to the kernel (A/B comparisons only).
+(``torch.backends.cuda.matmul.allow_tf32``) is on -- with the switch off every product is a full-fp32 library GEMM,
+which is what the parity tests against the fp32 CPU oracle use.
+
+Which of a layer's three products run on the kernel is a measured choice (``profiles/gemm_r1_*.jsonl``, B200,
+44 446 tokens), ``SDB_LINEAR`` selects the policy:
+
+* ``auto`` (default) -- every product where the kernel is at least as fast as the library: the split-K weight
+  gradients of the 256-wide projection family (1.7-1.9x faster than cuBLAS), every forward whose epilogue absorbs a
+  separate elementwise pass (value_proj + padding mask, FFN linear1 + ReLU), and nothing else;
+* ``tcgen05`` -- all three products of the projection family (value / offsets / weights / output projections,
+  enc_output); ``tcgen05_all`` -- additionally the 2048-wide FFN products; ``cublas`` -- library only.
+
+Small or oddly shaped products (a few hundred rows, 4-wide box heads) always stay library GEMMs: plumbing, like the
+convolutions.
 """
 import os
 
@@ -23,14 +32,29 @@ from . import gemm
 
 # products smaller than this many rows are latency-bound either way; keep them on the library path
 MIN_ROWS = 1024
-
-
-# widest layer the kernel takes by default: the projection family (value / offsets / weights / output, enc_output)
+# widest layer of the projection family
 MAX_FEATURES = 512
 
 
-def use_tcgen05():
-    return os.environ.get("SDB_LINEAR", "tcgen05") != "cublas" and torch.backends.cuda.matmul.allow_tf32
+def policy():
+    p = os.environ.get("SDB_LINEAR", "auto")
+    if p not in ("auto", "tcgen05", "tcgen05_all", "cublas"):
+        raise RuntimeError(f"SDB_LINEAR={p!r}: expected auto, tcgen05, tcgen05_all or cublas")
+    return p
+
+
+def product_plan(in_features, out_features, fused_epilogue):
+    """-> (forward, grad_input, grad_weight) on the tcgen05 kernel?  None: the whole layer stays on the library."""
+    p = policy()
+    if p == "cublas" or not torch.backends.cuda.matmul.allow_tf32:
+        return None
+    family = max(in_features, out_features) <= MAX_FEATURES
+    if p == "tcgen05_all" or (p == "tcgen05" and family):
+        return True, True, True
+    if p == "tcgen05":
+        return None
+    plan = (fused_epilogue, False, family)          # auto
+    return plan if any(plan) else None
 
 
 def column_sum(x2d):
@@ -69,18 +93,24 @@ class _LinearFn(torch.autograd.Function):
 
 
 class _TensorCoreLinearFn(torch.autograd.Function):
-    """y = [mask rows](relu)(x W^T + b) with all three products on sdb_gemm_tf32."""
+    """y = [mask rows](relu)(x W^T + b); ``plan`` says which of the three products run on sdb_gemm_tf32."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, row_mask):
+    def forward(ctx, x, weight, bias, relu, row_mask, plan):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         mask = None if row_mask is None else row_mask.reshape(-1).contiguous()
-        y = gemm.linear_forward(x2, weight, bias, relu=relu, row_mask=mask)
+        if plan[0]:
+            y = gemm.linear_forward(x2, weight, bias, relu=relu, row_mask=mask)
+        else:
+            y = torch.addmm(bias, x2, weight.t())
+            if relu:
+                y = y.relu_()
+            if mask is not None:
+                y = y.masked_fill_(mask.view(torch.bool)[:, None], 0.0)
         ctx.save_for_backward(x2, weight, y if relu else None, mask)
-        ctx.relu = relu
-        ctx.x_shape = x.shape
+        ctx.relu, ctx.plan, ctx.x_shape = relu, plan, x.shape
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
@@ -95,27 +125,28 @@ class _TensorCoreLinearFn(torch.autograd.Function):
             g2 = g2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm.linear_grad_input(g2, weight).view(ctx.x_shape)
+            gx = (gemm.linear_grad_input(g2, weight) if ctx.plan[1] else g2 @ weight).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            gw = gemm.linear_grad_weight(g2, x2)
+            gw = gemm.linear_grad_weight(g2, x2) if ctx.plan[2] else g2.t() @ x2
         if ctx.needs_input_grad[2]:
             gb = column_sum(g2)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class Linear(nn.Linear):
-    def _tensor_core_ok(self, x):
-        return (x.is_cuda and x.dtype == torch.float32 and self.bias is not None and self.weight.dtype == torch.float32
+    def _plan(self, x, fused_epilogue):
+        if not (x.is_cuda and x.dtype == torch.float32 and self.bias is not None and self.weight.dtype == torch.float32
                 and self.in_features % 4 == 0 and self.out_features % 4 == 0 and self.in_features >= 64
-                and self.out_features >= 64 and x.numel() // self.in_features >= MIN_ROWS and use_tcgen05()
-                and (max(self.in_features, self.out_features) <= MAX_FEATURES
-                     or os.environ.get("SDB_LINEAR") == "tcgen05_all"))
+                and self.out_features >= 64 and x.numel() // self.in_features >= MIN_ROWS):
+            return None
+        return product_plan(self.in_features, self.out_features, fused_epilogue)
 
     def forward(self, x, relu=False, row_mask=None):
         """relu / row_mask (bool, one entry per row of x): applied to the output, inside the GEMM epilogue when the
-        product runs on the tcgen05 kernel."""
-        if self._tensor_core_ok(x):
-            return _TensorCoreLinearFn.apply(x, self.weight, self.bias, relu, row_mask)
+        forward product runs on the tcgen05 kernel."""
+        plan = self._plan(x, relu or row_mask is not None)
+        if plan is not None:
+            return _TensorCoreLinearFn.apply(x, self.weight, self.bias, relu, row_mask, plan)
         if (x.is_cuda and x.dtype == torch.float32 and self.bias is not None and self.out_features % 4 == 0
                 and x.numel() >= (1 << 16) and torch.is_grad_enabled()):
             y = _LinearFn.apply(x, self.weight, self.bias)

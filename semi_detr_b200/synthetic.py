@@ -75,6 +75,19 @@ DINO_R50_4SCALE = dict(
 no network, random init)."""
 
 
+def dino_r50_5scale():
+    """the 5-scale variant -- all four ResNet stages feed the transformer plus one
+    stride-2 extra level (head kwargs ``dino_detr_head.py:80-82``: num_feature_levels=5, num_backbone_outs=4,
+    backbone_channels=[256, 512, 1024, 2048]; transformer num_feature_levels=5).  The reference ships no such config
+    file; the head and transformer take these kwargs unchanged."""
+    import copy
+    cfg = copy.deepcopy(DINO_R50_4SCALE)
+    cfg["backbone"]["out_indices"] = (0, 1, 2, 3)
+    cfg["bbox_head"].update(num_feature_levels=5, num_backbone_outs=4, backbone_channels=[256, 512, 1024, 2048],
+                            transformer=dict(type="DINOTransformer", num_feature_levels=5))
+    return cfg
+
+
 def coco_like_batch(batch_size=2, height=800, width=1333, seed=0, device="cpu", pin=False):
     """Synthetic COCO-shape batch: images ~ N(0,1); per image G ~ clamp(Poisson(7), 1, 100) boxes with
     cx,cy ~ U(.1,.9), w,h ~ U(.05,.5) clipped to the image, labels ~ U{0..79}."""

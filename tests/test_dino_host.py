@@ -111,3 +111,51 @@ def test_train_step_on_cpu_oracle_path():
     assert not missing
     frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
     assert any("layer1" in n for n in frozen) and all("backbone" in n for n in frozen)
+
+
+def test_five_scale_config_steps_on_cpu_oracle_path():
+    """BASELINE config 4 plumbing: 5 feature levels (4 backbone stages + 1 extra stride-2 level)."""
+    import torch
+    from oracle.cpu_path import reference_cpu_ops
+    from semi_detr_b200 import dino  # noqa: F401
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import coco_like_batch, dino_r50_5scale
+    torch.manual_seed(0)
+    model = DETECTORS.build(dino_r50_5scale()).train()
+    assert model.bbox_head.transformer.num_feature_levels == 5 and len(model.bbox_head.input_proj) == 5
+    assert model.bbox_head.transformer.encoder.layers[0].self_attn.n_levels == 5
+    with reference_cpu_ops():
+        out = model.train_step(coco_like_batch(1, 128, 160, seed=5))
+    assert torch.isfinite(out["loss"]) and len(out["log_vars"]) == 66
+    out["loss"].backward()
+    assert model.bbox_head.transformer.level_embed.grad.shape == (5, 256)
+
+
+def test_loss_dict_total_equals_entry_by_entry_sum():
+    """The head's precomputed ``LossDict.total`` against mmdet's entry-by-entry ``_parse_losses`` sum
+    (base.py:176-209): same value, same gradients, same log keys; editing the dict drops the shortcut."""
+    import copy
+    import torch
+    from oracle.cpu_path import reference_cpu_ops
+    from semi_detr_b200 import dino  # noqa: F401
+    from semi_detr_b200.dino.head import LossDict
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch
+    torch.manual_seed(0)
+    model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE)).train()
+    data = coco_like_batch(1, 288, 352, seed=5)
+    with reference_cpu_ops():
+        losses = model(**data)
+        assert isinstance(losses, LossDict) and losses.total is not None and len(losses) == 65
+        fast, lv_fast = model._parse_losses(losses)
+        slow, lv_slow = model._parse_losses(dict(losses))
+        assert list(lv_fast) == list(lv_slow)
+        assert abs(float(fast) - float(slow)) <= 1e-5 * abs(float(slow))
+        for k in lv_slow:
+            assert abs(float(lv_fast[k]) - float(lv_slow[k])) <= 1e-5 * abs(float(lv_slow[k])) + 1e-7
+        w = model.bbox_head.fc_cls[0].weight
+        g_fast = torch.autograd.grad(fast, w, retain_graph=True)[0]
+        g_slow = torch.autograd.grad(slow, w)[0]
+        assert (g_fast - g_slow).abs().max() <= 1e-5 * g_slow.abs().max()
+    losses["extra_loss"] = torch.zeros(())
+    assert losses.total is None

@@ -93,7 +93,8 @@ def test_rejects_cpu_and_bad_shapes():
         G.gemm_tf32(torch.randn(64, 8).cuda(), 1, torch.randn(64, 8).cuda(), 1, 8, 8, 64, bias=torch.randn(8).cuda(), k_splits=2)
 
 
-def test_linear_layer_matches_torch_autograd():
+def test_linear_layer_matches_torch_autograd(monkeypatch):
+    monkeypatch.setenv("SDB_LINEAR", "tcgen05")
     """Linear (forward + all three gradients through the tcgen05 GEMM) against nn.Linear in fp32 (no TF32):
     1e-3 relative of the tensor's scale, the north star's bound."""
     from semi_detr_b200.layers.linear import Linear
@@ -119,3 +120,36 @@ def test_linear_layer_matches_torch_autograd():
         torch.backends.cuda.matmul.allow_tf32 = prev
     for a, b in ((y, yr), (x.grad, xr.grad), (lin.weight.grad, ref.weight.grad), (lin.bias.grad, ref.bias.grad)):
         assert (a - b).abs().max().item() <= 1e-3 * b.abs().max().item()
+
+
+def test_auto_policy_mixes_kernel_and_library(monkeypatch):
+    """SDB_LINEAR=auto: masked value projection -> forward + grad-weight on the kernel, grad-input on the library;
+    same numbers as the all-kernel policy to TF32 accuracy."""
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.layers.linear import Linear, product_plan
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        monkeypatch.setenv("SDB_LINEAR", "auto")
+        assert product_plan(256, 256, True) == (True, False, True) and product_plan(256, 256, False) == (False, False, True)
+        assert product_plan(256, 2048, True) == (True, False, False) and product_plan(2048, 256, False) is None
+        torch.manual_seed(1)
+        lin = Linear(256, 256).cuda()
+        x = torch.randn(2, 2000, 256, device="cuda", requires_grad=True)
+        mask = torch.rand(2, 2000, device="cuda") < 0.3
+        gy = torch.randn(2, 2000, 256, device="cuda")
+        before = _lib.LAUNCHES["gemm_tf32"]
+        y = lin(x, row_mask=mask)
+        y.backward(gy)
+        assert _lib.LAUNCHES["gemm_tf32"] - before == 2
+        assert (y[mask] == 0).all()
+        got = (y.detach().clone(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+        monkeypatch.setenv("SDB_LINEAR", "cublas")
+        x.grad = None
+        lin.zero_grad()
+        y2 = lin(x, row_mask=mask)
+        y2.backward(gy)
+        for a, b in zip(got, (y2, x.grad, lin.weight.grad, lin.bias.grad)):
+            assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
