@@ -300,8 +300,19 @@ def run_ours(args):
     roofline = None
     if dom_name:
         d = kernels[dom_name]
+        # DRAM bytes per launch of the same kernel at the same shape, from the committed `ncu --set full` capture of
+        # `bench.py --ncu` (profiles/ncu_msda_step_r1.txt); ncu cannot run inside the timed region.
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_msda_traffic_r1.json")) as f:
+                tj = json.load(f)
+            traffic = tj["kernels"][dom_name]["dram_bytes_per_launch"]
+            traffic_src = tj["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = dict(bound="hbm", kernel=dom_name, achieved=d["gbs"], peak=peak, unit="GB/s",
-                        frac=d["gbs"] / peak, traffic=None, peak_source=peak_src, avg_launch_us=d["avg_us"],
+                        frac=d["gbs"] / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
+                        avg_launch_us=d["avg_us"],
                         algorithmic_bytes_per_launch=d["bytes"], launches_timed=d["launches"],
                         share_of_step=d["ms_per_step"] / (ms_total / args.steps),
                         timed_in="eager replica of the timed step (events inside a captured graph cannot be read); "

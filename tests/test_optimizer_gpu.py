@@ -51,3 +51,39 @@ def test_fused_adamw_matches_torch(with_teacher):
             for (n, t), (_, u) in zip(teacher_ref.named_parameters(), teacher_mine.named_parameters()):
                 assert torch.allclose(t, u, rtol=2e-5, atol=2e-7), (it, n)
     assert float(opt.step_count) == 4
+
+
+def test_gathered_gradients_equal_accumulated_ones():
+    """FusedSupervisedTrainStep: autograd.grad + multi-tensor pack into the flat buffer gives the gradients that
+    backward() accumulates into the zeroed .grad views (unused parameters -> zeros; shared modules summed)."""
+    from semi_detr_b200.engine import FusedSupervisedTrainStep
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = torch.nn.Conv2d(3, 8, 3).to(memory_format=torch.channels_last)
+            self.shared = torch.nn.Linear(8, 8)
+            self.unused = torch.nn.Linear(4, 4)
+
+        def forward(self, img):
+            f = self.backbone(img).mean((2, 3))
+            return {"loss_a": self.shared(self.shared(f)).pow(2).mean(), "loss_b": f.abs().mean()}
+
+        @staticmethod
+        def _parse_losses(losses):
+            return sum(losses.values()), dict(losses)
+
+    torch.manual_seed(0)
+    a = Toy().cuda()
+    b = copy.deepcopy(a)
+    sa = FusedSupervisedTrainStep(a, gather_grads=True, lr=0.0)
+    sb = FusedSupervisedTrainStep(b, gather_grads=False, lr=0.0)
+    img = torch.randn(2, 3, 16, 16, device="cuda")
+    for st in (sa, sb):           # stale gradients must not leak into either mode
+        for p in st.opt.params:
+            p.grad.fill_(7.0)
+    la, _ = sa(dict(img=img))
+    lb, _ = sb(dict(img=img))
+    assert torch.allclose(la, lb)
+    assert torch.allclose(sa.opt.flat_g, sb.opt.flat_g, rtol=1e-6, atol=1e-8)
+    assert sa.opt.flat_g.abs().sum() > 0
