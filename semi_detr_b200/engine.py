@@ -158,6 +158,7 @@ class FusedAdamW:
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_t = torch.zeros(total, dtype=torch.float32, device=dev) if teacher_params is not None else None
+        # parameters without a teacher twin (e.g. the SSOD projector) blend into a scratch slot nobody reads
         teacher_by_name = dict(teacher_params) if teacher_params is not None else {}
         for gi, g in enumerate(groups):
             o = bounds[gi][0]
@@ -167,8 +168,10 @@ class FusedAdamW:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_g[o:o + n].as_strided(p.shape, p.stride())
-                if self.flat_t is not None:
+                if self.flat_t is not None and name in teacher_by_name:
                     t = teacher_by_name[name]
+                    if t.shape != p.shape or t.stride() != p.stride():
+                        raise RuntimeError(f"FusedAdamW: teacher parameter {name} does not share the student's layout")
                     tv = self.flat_t[o:o + n].as_strided(t.shape, t.stride())
                     tv.copy_(t.data)
                     t.data = tv
@@ -249,4 +252,50 @@ class FusedSupervisedTrainStep:
             loss.backward()
         self.opt.all_reduce_mean(self.world_size)
         self.opt.step(self.max_grad_norm)
+        return loss.detach(), log_vars
+
+
+class FusedSSODTrainStep:
+    """The teacher-student iteration of configs/detr_ssod (``DinoDetrSSOD`` wrapper + ``MeanTeacher`` hook +
+    OptimizerHook) with the student's clip + AdamW and the teacher's EMA blend in one pass over flat buffers.
+
+    The reference blends at the START of iteration i with ``m_i = min(momentum, 1 - (1 + warm_up) / (i + 1 +
+    warm_up))`` (mean_teacher.py:37-50); here the blend with ``m_{i+1}`` rides on the optimizer kernel at the END of
+    iteration i -- the same teacher for every forward pass.  Student parameters that are frozen (stem, layer1, BN
+    affine) are still blended (the reference has no ``requires_grad`` filter, :60-64) by a second, small
+    ``sdb_ema_update_f32`` launch.  ``before_run``'s momentum-0 copy happens in the constructor."""
+
+    def __init__(self, model, momentum=0.999, warm_up=0, max_grad_norm=0.1, world_size=None, start_iter=0, **opt_kw):
+        from .teacher.mean_teacher import EmaPlan
+        self.model, self.max_grad_norm = model, max_grad_norm
+        self.momentum, self.warm_up = momentum, warm_up
+        if world_size is None:
+            world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.world_size = world_size
+        student = dict(model.student.named_parameters())
+        teacher = dict(model.teacher.named_parameters())
+        with torch.no_grad():
+            for n, t in teacher.items():            # before_run: teacher <- student
+                t.copy_(student[n])
+        self.opt = FusedAdamW(model, teacher_params={"student." + n: t for n, t in teacher.items()}, **opt_kw)
+        frozen = [n for n, p in student.items() if not p.requires_grad]
+        self.frozen_plan = EmaPlan([teacher[n].data for n in frozen], [student[n].data for n in frozen])
+        self.iter = start_iter
+
+    def momentum_at(self, it):
+        return min(self.momentum, 1 - (1 + self.warm_up) / (it + 1 + self.warm_up))
+
+    _pack = FusedSupervisedTrainStep._pack
+
+    def __call__(self, data):
+        self.model.curr_step = self.iter            # StepRecord hook (step_record.py:7-27)
+        losses = self.model(**data)
+        loss, log_vars = self.model._parse_losses(losses)
+        self._pack(torch.autograd.grad(loss, self.opt.params, allow_unused=True))
+        self.opt.all_reduce_mean(self.world_size)
+        m = self.momentum_at(self.iter + 1)
+        self.opt.step(self.max_grad_norm, ema_momentum=m)
+        self.frozen_plan.step(m)
+        self.iter += 1
+        log_vars["ema_momentum"] = m
         return loss.detach(), log_vars

@@ -111,3 +111,42 @@ def test_full_size_ssod_step_runs():
     n = {k: _lib.LAUNCHES[k] - before[k] for k in before}
     assert n["ema_update"] == 1 and n["msda_forward"] + n["msda_fused_forward"] >= 5 * 12
     assert n["msda_backward"] + n["msda_fused_backward"] == 2 * 12
+
+
+def test_fused_ssod_engine_keeps_the_hook_semantics():
+    """FusedSSODTrainStep (student clip+AdamW and teacher EMA in one pass, frozen parameters through the EMA kernel)
+    against the reference's ordering: teacher <- student at start; after every step
+    teacher == m * teacher_prev + (1 - m) * student_new with the hook's momentum schedule, for every parameter
+    (trainable, frozen, and nothing for the projector)."""
+    from semi_detr_b200 import dino, ssod  # noqa: F401
+    from semi_detr_b200.engine import FusedSSODTrainStep
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import ssod_batch, ssod_model_cfg
+    torch.manual_seed(0)
+    cfg = ssod_model_cfg()
+    cfg["model"]["bbox_head"]["transformer"] = dict(type="DINOTransformer", num_encoder_layers=1, num_decoder_layers=2)
+    model = DETECTORS.build(cfg).cuda().train()
+    with torch.no_grad():                      # make the teacher differ from the student before the engine copies
+        for p in model.teacher.parameters():
+            p.add_(1.0)
+    step = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, start_iter=70000, lr=1e-3)
+    for (n, s), (_, t) in zip(model.student.named_parameters(), model.teacher.named_parameters()):
+        assert torch.equal(s, t), n
+    data = ssod_batch(1, 2, 256, 320, seed=3, device="cuda")
+    for it in range(2):
+        t_prev = {n: p.detach().clone() for n, p in model.teacher.named_parameters()}
+        s_prev = {n: p.detach().clone() for n, p in model.student.named_parameters()}
+        loss, log_vars = step(data)
+        assert torch.isfinite(loss) and model.curr_step == 70000 + it
+        m = min(0.999, 1 - 1 / (70000 + it + 2))
+        assert log_vars["ema_momentum"] == m
+        moved = 0
+        for (n, s), (_, t) in zip(model.student.named_parameters(), model.teacher.named_parameters()):
+            want = t_prev[n] * m + s.detach() * (1 - m)
+            assert torch.allclose(t, want, rtol=1e-6, atol=1e-7), n
+            if s.requires_grad:
+                moved += int(not torch.equal(s, s_prev[n]))
+            else:
+                assert torch.equal(s, s_prev[n]), n
+        assert moved > 100
+    assert all(not p.requires_grad for p in model.teacher.parameters())

@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--curr-step", type=int, default=60000)
+ap.add_argument("--engine", default="fused", choices=["fused", "hook"])
 args = ap.parse_args()
 torch.backends.cuda.matmul.allow_tf32 = True
 torch.backends.cudnn.allow_tf32 = True
@@ -27,24 +28,33 @@ torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 model = DETECTORS.build(ssod_model_cfg()).cuda().train()
 model.curr_step = args.curr_step
-opt = build_optimizer(model)
-grads = FlatGrads([p for g in opt.param_groups for p in g["params"]])
-runner = type("R", (), dict(model=model, iter=0, log_buffer=type("B", (), {"output": {}})()))()
-hook = MeanTeacher(momentum=0.999, interval=1, warm_up=0)
-hook.before_run(runner)
 data = ssod_batch(1, 4, 800, 1333, seed=0, device="cuda")
+if args.engine == "fused":
+    # clip + AdamW + EMA in one pass, gradients gathered with autograd.grad (engine.FusedSSODTrainStep)
+    from semi_detr_b200.engine import FusedSSODTrainStep  # noqa: E402
+    fused = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, start_iter=args.curr_step)
 
+    def step(i):
+        fused.iter = args.curr_step          # stay in the requested phase
+        return fused(data)[0]
+else:
+    # the reference's structure: MeanTeacher hook, backward() into flat .grad views, clip, torch AdamW
+    opt = build_optimizer(model)
+    grads = FlatGrads([p for g in opt.param_groups for p in g["params"]])
+    runner = type("R", (), dict(model=model, iter=0, log_buffer=type("B", (), {"output": {}})()))()
+    hook = MeanTeacher(momentum=0.999, interval=1, warm_up=0)
+    hook.before_run(runner)
 
-def step(i):
-    runner.iter = i
-    hook.before_train_iter(runner)            # fused EMA
-    grads.zero()
-    losses = model(**data)
-    loss, _ = model._parse_losses(losses)
-    loss.backward()
-    grads.clip_(0.1)
-    opt.step()
-    return loss
+    def step(i):
+        runner.iter = i
+        hook.before_train_iter(runner)            # fused EMA
+        grads.zero()
+        losses = model(**data)
+        loss, _ = model._parse_losses(losses)
+        loss.backward()
+        grads.clip_(0.1)
+        opt.step()
+        return loss
 
 
 for i in range(args.warmup):
@@ -59,6 +69,6 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.steps
 print(json.dumps(dict(workload="configs[2] shape: Semi-DETR teacher-student step, 1 sup + 4 unsup pairs 800x1333, 1 GPU, eager",
-                      phase="warm-up (O2M)" if args.curr_step < 60000 else "Hungarian", ms_per_step=ms,
+                      phase="warm-up (O2M)" if args.curr_step < 60000 else "Hungarian", engine=args.engine, ms_per_step=ms,
                       images_per_s=5 / (ms / 1e3), loss=float(loss),
                       launches_per_step={k: (_lib.LAUNCHES[k] - l0[k]) / args.steps for k in l0})))
