@@ -264,11 +264,14 @@ int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const float* grad
  *   round_mode : bit 0 / bit 1 -- round a / b to the nearest TF32 value (in shared memory, after the TMA load) before
  *                the tensor core reads it.  The tensor core itself truncates (a systematic -7e-4 relative bias);
  *                3 reproduces the unbiased round-to-nearest TF32 product of cuBLAS, 0 is the raw truncating product.
+ *   a_column_sums : optional (m,) fp32, only with a_mn_major != 0 -- sum_k a[k, :] is ADDED to it (zero it first): the
+ *                bias gradient grad_output.sum(0) of the same layer, taken from the tiles the grad-weight product
+ *                stages anyway instead of a separate pass over grad_output.
  * Requirements: 16-byte aligned pointers, n % 4 == 0, and the contiguous dimension of every operand % 4 == 0.
  * ------------------------------------------------------------------------------------------ */
 int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major, float* y,
                   int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu, int k_splits,
-                  int round_mode);
+                  int round_mode, float* a_column_sums);
 
 #ifdef __cplusplus
 }

@@ -154,6 +154,7 @@ struct GemmArgs {
   int k_blocks_per_split;
   int relu;
   int round_a, round_b;   // round the operand to nearest TF32 in shared memory before the MMA reads it
+  float* a_colsum;          // (M,) or null: column sums of an MN-major A are ADDED here (bias gradient)
   const float* bias;        // (N,) or null
   const uint8_t* row_mask;  // (M,) or null; nonzero -> the output row is zero
 };
@@ -170,6 +171,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * kStages + 6];
   __shared__ uint32_t tmem_slot;
+  __shared__ float colsum_s[kBM];
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bres = base;                                        // resident B: kResKB k-blocks of 16 KB
@@ -184,7 +186,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t bfull = bar0 + 8u * (3 * kStages + 4), bready = bar0 + 8u * (3 * kStages + 5);
   // which operands the rounding warps touch per ring stage
   const bool round_ring_a = g.round_a != 0, round_ring_b = !kBRes && g.round_b != 0;
-  const bool xform = round_ring_a || round_ring_b;
+  const bool xform = round_ring_a || round_ring_b || (kAMn && g.a_colsum != nullptr);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + kBM - 1) / kBM, n_tiles = (g.N + kBN - 1) / kBN;
@@ -324,22 +326,75 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_arrive(bready);
     }
     if (xform) {
-      const uint32_t first = round_ring_a ? 0u : (uint32_t)kTileBytes;
-      const int n_vec = ((round_ring_a ? 1 : 0) + (round_ring_b ? 1 : 0)) * kVecPerTile;
+      // Column sums of an MN-major A (the bias gradient dy^T.1 of the grad-weight product): these warps read every
+      // element of A anyway.  Thread t always lands on the same physical 16-byte slot of a 128-byte k-row and on
+      // rows with the same (row % 4), so under the 32-byte-atom swizzle (32 B chunk index ^= row % 4) it always sees
+      // the same four m-columns of each of the tile's four 32-column boxes: 16 register accumulators per thread,
+      // folded through shared-memory atomics once per work item and added to global memory by the n-block-0 items.
+      const bool do_colsum = kAMn && g.a_colsum != nullptr;
+      const int m_in_box = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 3) + ((t & 1) << 2);
+      float cs[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cs[i][e] = 0.f;
+      if (do_colsum) {
+        colsum_s[t] = 0.f;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int ks = (int)(item % g.k_splits);
+        const long long tt = item / g.k_splits;
+        const int n0 = (int)(tt % n_tiles) * kBN, m0 = (int)(tt / n_tiles) * kBM;
         const int kb0 = ks * g.k_blocks_per_split;
         const int kb1 = min(total_kb, kb0 + g.k_blocks_per_split);
+        const bool sum_item = do_colsum && n0 == 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full(stage), phase);
-          round_region(ring + stage * kSB + first, n_vec);
+          const uint32_t sa = ring + stage * kSB;
+          if (round_ring_a || sum_item) {
+#pragma unroll
+            for (int j = 0; j < kVecPerTile; ++j) {
+              const uint32_t p = sa + 16u * t + (uint32_t)(j * 16 * kXformThreads);
+              uint32_t a, b, c, d;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(p) : "memory");
+              if (sum_item) {            // row = t / 8 + 16 j -> box j / 2
+                cs[j >> 1][0] += __uint_as_float(a);
+                cs[j >> 1][1] += __uint_as_float(b);
+                cs[j >> 1][2] += __uint_as_float(c);
+                cs[j >> 1][3] += __uint_as_float(d);
+              }
+              if (round_ring_a) {
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(__uint_as_float(a)));
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(__uint_as_float(b)));
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(__uint_as_float(c)));
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(__uint_as_float(d)));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+              }
+            }
+          }
+          if (round_ring_b) round_region(sa + kTileBytes, kVecPerTile);
+          else if (round_ring_a) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive(ready(stage));
           if (++stage == kNS) {
             stage = 0;
             phase ^= 1u;
           }
+        }
+        if (sum_item) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              atomicAdd(&colsum_s[32 * i + m_in_box + e], cs[i][e]);
+              cs[i][e] = 0.f;
+            }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (m0 + t < g.M) atomicAdd(g.a_colsum + m0 + t, colsum_s[t]);
+          colsum_s[t] = 0.f;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
         }
       }
     }
@@ -480,7 +535,7 @@ int launch(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CU
 
 extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
                              float* y, int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu,
-                             int k_splits, int round_mode) {
+                             int k_splits, int round_mode, float* a_column_sums) {
   using namespace sdb;
   SDB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_tf32: negative size");
   if (m == 0 || n == 0) return SDB_OK;
@@ -493,6 +548,7 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
               "gemm_tf32: operands must be 16-byte aligned");
   SDB_REQUIRE(k_splits >= 1, "gemm_tf32: k_splits must be >= 1");
   SDB_REQUIRE(round_mode >= 0 && round_mode <= 3, "gemm_tf32: round_mode is a bit mask (1 = a, 2 = b)");
+  SDB_REQUIRE(!a_column_sums || a_mn_major, "gemm_tf32: column sums are taken of an MN-major a (the grad-weight product)");
   SDB_REQUIRE(k_splits == 1 || (!bias && !relu && !row_mask) , "gemm_tf32: a split product cannot carry an epilogue");
   CUtensorMap ta, tb, tyw;
   int rc;
@@ -515,6 +571,7 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
   g.round_b = (round_mode & 2) != 0;
   g.bias = bias;
   g.row_mask = row_mask;
+  g.a_colsum = a_column_sums;
   const long long items = (long long)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) * g.k_splits;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tiles = (n + kBN - 1) / kBN;

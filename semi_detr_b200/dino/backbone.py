@@ -11,6 +11,59 @@ from torch import nn
 from ..registry import BACKBONES
 
 
+class _ConvBiasAct(torch.autograd.Function):
+    """relu(conv(x, w) + b [+ z]) as ONE cuDNN fused convolution-bias-activation call (``cudnn_convolution_relu`` /
+    ``cudnn_convolution_add_relu``: library plumbing, like the convolution itself) instead of a convolution and two
+    or three elementwise passes over the activation; backward = ReLU mask + the library's convolution backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, z, stride, padding, dilation, groups):
+        if z is None:
+            y = torch.cudnn_convolution_relu(x, w, b, stride, padding, dilation, groups)
+        else:
+            y = torch.cudnn_convolution_add_relu(x, w, z, 1.0, b, stride, padding, dilation, groups)
+        ctx.save_for_backward(x, w, y)
+        ctx.conf = (stride, padding, dilation, groups, z is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        stride, padding, dilation, groups, has_z = ctx.conf
+        g = torch.ops.aten.threshold_backward(gy, y, 0.0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gx, gw, _ = torch.ops.aten.convolution_backward(
+                g, x, w, None, list(stride), list(padding), list(dilation), False, [0, 0], groups,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        if ctx.needs_input_grad[2]:
+            gb = g.sum((0, 2, 3))
+        gz = g if (has_z and ctx.needs_input_grad[3]) else None
+        return gx, gw, gb, gz, None, None, None, None
+
+
+def fused_conv_enabled():
+    import os
+    return os.environ.get("SDB_FUSED_CONV", "1") != "0"
+
+
+def conv_bn_relu(conv, bn, x, identity=None):
+    """relu(BN(conv(x)) [+ identity]) -- with frozen statistics on the device: one fused cuDNN call."""
+    if bn.training or not x.is_cuda or not fused_conv_enabled():
+        out = conv_bn(conv, bn, x)
+        return F.relu(out if identity is None else out + identity, inplace=True)
+    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    t = bn.bias - bn.running_mean * s
+    w = conv.weight * s.view(-1, 1, 1, 1)
+    args = (tuple(conv.stride), tuple(conv.padding), tuple(conv.dilation), conv.groups)
+    if not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or
+                                         (identity is not None and identity.requires_grad))):
+        if identity is None:
+            return torch.cudnn_convolution_relu(x, w, t, *args)
+        return torch.cudnn_convolution_add_relu(x, w, identity, 1.0, t, *args)
+    return _ConvBiasAct.apply(x, w, t, identity, *args)
+
+
 def conv_bn(conv, bn, x):
     """conv -> BatchNorm.  With the statistics frozen (``norm_eval``; every shipped config) the normalisation is a
     per-channel affine map that folds exactly into the convolution: conv(x, w * s) + t with s = gamma / sqrt(var +
@@ -40,10 +93,9 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         identity = x if self.downsample is None else conv_bn(self.downsample[0], self.downsample[1], x)
-        out = self.relu(conv_bn(self.conv1, self.bn1, x))
-        out = self.relu(conv_bn(self.conv2, self.bn2, out))
-        out = conv_bn(self.conv3, self.bn3, out)
-        return self.relu(out + identity)
+        out = conv_bn_relu(self.conv1, self.bn1, x)
+        out = conv_bn_relu(self.conv2, self.bn2, out)
+        return conv_bn_relu(self.conv3, self.bn3, out, identity)
 
 
 @BACKBONES.register_module()
@@ -97,7 +149,7 @@ class ResNet(nn.Module):
         return self
 
     def forward(self, x):
-        x = self.maxpool(self.relu(conv_bn(self.conv1, self.bn1, x)))
+        x = self.maxpool(conv_bn_relu(self.conv1, self.bn1, x))
         outs = []
         for i in range(4):
             x = getattr(self, f"layer{i + 1}")(x)

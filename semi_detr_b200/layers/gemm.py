@@ -29,7 +29,8 @@ def _check(t, name):
         raise RuntimeError(f"gemm_tf32: {name} must be contiguous float32")
 
 
-def gemm_tf32(a, a_mn_major, b, b_mn_major, m, n, k, bias=None, row_mask=None, relu=False, out=None, k_splits=1, round_mode=3):
+def gemm_tf32(a, a_mn_major, b, b_mn_major, m, n, k, bias=None, row_mask=None, relu=False, out=None, k_splits=1,
+              a_column_sums=None, round_mode=3):
     """Raw entry: see include/semidetr_b200.h.  ``out`` (m, n) is allocated when None (zero-filled if k_splits > 1).
     round_mode 3 (default): both operands rounded to nearest TF32 -- the unbiased product cuBLAS-TF32 computes."""
     _check(a, "a")
@@ -48,7 +49,7 @@ def gemm_tf32(a, a_mn_major, b, b_mn_major, m, n, k, bias=None, row_mask=None, r
     with torch.cuda.device(a.device):
         rc = _lib.lib().sdb_gemm_tf32(_lib.current_stream(a.device), a.data_ptr(), int(a_mn_major), b.data_ptr(),
                                       int(b_mn_major), out.data_ptr(), m, n, k, _lib.ptr(bias), _lib.ptr(row_mask),
-                                      int(relu), int(k_splits), int(round_mode))
+                                      int(relu), int(k_splits), int(round_mode), _lib.ptr(a_column_sums))
     _lib.check(rc, "gemm_tf32")
     _lib.LAUNCHES["gemm_tf32"] += 1
     return out
@@ -68,10 +69,14 @@ def linear_grad_input(g2d, weight):
     return gemm_tf32(g2d, 0, weight, 1, m, n, k)
 
 
-def linear_grad_weight(g2d, x2d):
-    """g2d (tokens, out)^T . x2d (tokens, in) -> (out, in); the token axis is split over the SMs."""
+def linear_grad_weight(g2d, x2d, with_bias_grad=False):
+    """g2d (tokens, out)^T . x2d (tokens, in) -> (out, in); the token axis is split over the SMs.
+    with_bias_grad: also return g2d.sum(0), accumulated by the same launch from the tiles of g2d it stages."""
     k, m = g2d.shape
     n = x2d.shape[1]
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
     splits = max(1, min((k + 31) // 32, (2 * _sm_count(g2d.device)) // tiles))
-    return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits)
+    if not with_bias_grad:
+        return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits)
+    gb = torch.zeros(m, dtype=torch.float32, device=g2d.device)
+    return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits, a_column_sums=gb), gb

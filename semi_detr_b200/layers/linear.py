@@ -126,10 +126,13 @@ class _TensorCoreLinearFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = (gemm.linear_grad_input(g2, weight) if ctx.plan[1] else g2 @ weight).view(ctx.x_shape)
-        if ctx.needs_input_grad[1]:
-            gw = gemm.linear_grad_weight(g2, x2) if ctx.plan[2] else g2.t() @ x2
-        if ctx.needs_input_grad[2]:
-            gb = column_sum(g2)
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and ctx.plan[2]:
+            gw, gb = gemm.linear_grad_weight(g2, x2, with_bias_grad=True)   # bias gradient from the same launch
+        else:
+            if ctx.needs_input_grad[1]:
+                gw = gemm.linear_grad_weight(g2, x2) if ctx.plan[2] else g2.t() @ x2
+            if ctx.needs_input_grad[2]:
+                gb = column_sum(g2)
         return gx, gw, gb, None, None, None
 
 

@@ -113,9 +113,11 @@ def test_linear_layer_matches_torch_autograd(monkeypatch):
         yr.backward(gy)
         torch.backends.cuda.matmul.allow_tf32 = True      # the switch that selects the tcgen05 kernel
         before = _lib.LAUNCHES["gemm_tf32"]
+        colsum_before = _lib.LAUNCHES["colsum"]
         y = lin(x)
         y.backward(gy)
         assert _lib.LAUNCHES["gemm_tf32"] - before == 3, "forward, grad-input and grad-weight run on the tcgen05 kernel"
+        assert _lib.LAUNCHES["colsum"] == colsum_before, "the bias gradient comes out of the grad-weight launch"
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     for a, b in ((y, yr), (x.grad, xr.grad), (lin.weight.grad, ref.weight.grad), (lin.bias.grad, ref.bias.grad)):
@@ -153,3 +155,16 @@ def test_auto_policy_mixes_kernel_and_library(monkeypatch):
             assert (a - b).abs().max().item() <= 2e-3 * b.abs().max().item()
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 256, 44446), (384, 256, 4448), (132, 36, 76), (2048, 256, 4446)])
+def test_grad_weight_with_fused_bias_gradient(m, n, k):
+    """The column sums of dy (bias gradient) taken by the grad-weight launch from the tiles it stages: exact fp32
+    values (before the TF32 rounding), every column exactly once whatever the number of n-blocks and k-splits."""
+    from semi_detr_b200.layers import gemm as G
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    dy = torch.randn(k, m, device="cuda", generator=g) + 0.25
+    x = torch.randn(k, n, device="cuda", generator=g)
+    gw, gb = G.linear_grad_weight(dy, x, with_bias_grad=True)
+    _close(gw, _trunc(dy).double().t() @ _trunc(x).double())
+    _close(gb, dy.double().sum(0), tol=1e-5)
