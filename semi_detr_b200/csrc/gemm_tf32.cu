@@ -171,7 +171,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[3 * kStages + 6];
   __shared__ uint32_t tmem_slot;
-  __shared__ float colsum_s[kBM];
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bres = base;                                        // resident B: kResKB k-blocks of 16 KB
@@ -330,7 +329,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // element of A anyway.  Thread t always lands on the same physical 16-byte slot of a 128-byte k-row and on
       // rows with the same (row % 4), so under the 32-byte-atom swizzle (32 B chunk index ^= row % 4) it always sees
       // the same four m-columns of each of the tile's four 32-column boxes: 16 register accumulators per thread,
-      // folded through shared-memory atomics once per work item and added to global memory by the n-block-0 items.
+      // folded over the warp with two shuffles each once per work item and added to global memory (one 16-byte
+      // reduction per m-group and warp) by the n-block-0 items.
       const bool do_colsum = kAMn && g.a_colsum != nullptr;
       const int m_in_box = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 3) + ((t & 1) << 2);
       float cs[4][4];
@@ -338,10 +338,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) cs[i][e] = 0.f;
-      if (do_colsum) {
-        colsum_s[t] = 0.f;
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
       int stage = 0;
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -384,17 +380,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (sum_item) {
+          // The four lanes of a warp that saw the same m-columns differ in (row % 4) = lane >> 3 and, through the
+          // swizzle, in their physical chunk: lane ^ 10 and lane ^ 20 walk exactly that set.
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              atomicAdd(&colsum_s[32 * i + m_in_box + e], cs[i][e]);
-              cs[i][e] = 0.f;
+              float v = cs[i][e];
+              v += __shfl_xor_sync(0xffffffffu, v, 10);
+              v += __shfl_xor_sync(0xffffffffu, v, 20);
+              cs[i][e] = v;
             }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (m0 + t < g.M) atomicAdd(g.a_colsum + m0 + t, colsum_s[t]);
-          colsum_s[t] = 0.f;
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int m = m0 + 32 * i + m_in_box;
+            if ((t & 31) < 8 && m < g.M)          // one writer per m-group and warp; M % 4 == 0
+              red_add_f4(g.a_colsum + m, make_float4(cs[i][0], cs[i][1], cs[i][2], cs[i][3]));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cs[i][e] = 0.f;
+          }
         }
       }
     }

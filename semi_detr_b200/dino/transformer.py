@@ -47,10 +47,9 @@ class MLP(nn.Module):
 
 _DIM_T = {}
 
-# Decoder self-attention runs over ~1.1 k queries in fp32: for that size the plain matmul-softmax-matmul
-# ("math") scaled-dot-product backend beats the fused memory-efficient fp32 kernel torch picks by default on
-# sm_100 (measured in profiles/).  None = torch's default choice.
-SDPA_BACKEND = "math"
+# Decoder self-attention runs over ~1.1 k queries in fp32: for that size plain matmul-softmax-matmul beats the fused
+# memory-efficient fp32 kernel torch's SDPA picks on sm_100 (measured in profiles/), so the layer writes it out
+# (DINOTransformerDecoderLayer._self_attention).
 
 
 def gen_sineembed_for_position(pos):
@@ -186,18 +185,39 @@ class DINOTransformerDecoderLayer(nn.Module):
         self.dropout4 = nn.Dropout(dropout)
         self.norm3 = LayerNorm(d_model)
 
+    def _self_attention(self, qk, value, attn_mask):
+        """``self.self_attn(qk, qk, value, attn_mask=attn_mask)[0]`` (nn.MultiheadAttention, transformer.py:795-803)
+        written out on the module's own parameters: q and k share one projection GEMM, the (T, T) mask is added by
+        the ``baddbmm`` that forms the scores instead of a separate pass over the (N*H, T, T) tensor, and the
+        fully-masked-row guard of torch's math SDPA (three more passes) is dropped -- the denoising mask never
+        masks a whole row (dn_components.py:97-113).  Scaling follows the reference's torch (q * d^-0.5 first)."""
+        mha = self.self_attn
+        T, N, C = qk.shape
+        H = mha.num_heads
+        d = C // H
+        w, b = mha.in_proj_weight, mha.in_proj_bias
+        q, k = F.linear(qk, w[:2 * C], b[:2 * C]).split(C, -1)
+        v = F.linear(value, w[2 * C:], b[2 * C:])
+        q = (q * (float(d) ** -0.5)).reshape(T, N * H, d).transpose(0, 1)
+        k = k.reshape(T, N * H, d).transpose(0, 1)
+        v = v.reshape(T, N * H, d).transpose(0, 1)
+        if attn_mask is None:
+            scores = torch.bmm(q, k.transpose(1, 2))
+        else:
+            if attn_mask.dtype == torch.bool:
+                attn_mask = torch.zeros(attn_mask.shape, dtype=q.dtype, device=q.device).masked_fill_(
+                    attn_mask, float("-inf"))
+            scores = torch.baddbmm(attn_mask, q, k.transpose(1, 2))
+        probs = F.dropout(F.softmax(scores, -1), mha.dropout, self.training)
+        out = torch.bmm(probs, v).transpose(0, 1).reshape(T, N, C)
+        return F.linear(out, mha.out_proj.weight, mha.out_proj.bias)
+
     def forward(self, tgt, query_pos, reference_points, memory, memory_key_padding_mask, level_start_index,
                 spatial_shapes, self_attn_mask=None):
         """tgt / query_pos (nq, bs, C); reference_points (nq, bs, L, 4); memory (bs, S, C) batch-first."""
         for name in self.module_seq:
             if name == "sa":
-                qk = tgt + query_pos
-                if SDPA_BACKEND == "math" and tgt.is_cuda:
-                    from torch.nn.attention import SDPBackend, sdpa_kernel
-                    with sdpa_kernel([SDPBackend.MATH]):
-                        tgt2 = self.self_attn(qk, qk, tgt, attn_mask=self_attn_mask, need_weights=False)[0]
-                else:
-                    tgt2 = self.self_attn(qk, qk, tgt, attn_mask=self_attn_mask, need_weights=False)[0]
+                tgt2 = self._self_attention(tgt + query_pos, tgt, self_attn_mask)
                 tgt = self.norm2(tgt + self.dropout2(tgt2))
             elif name == "ca":
                 tgt2 = self.cross_attn((tgt + query_pos).transpose(0, 1), reference_points.transpose(0, 1).contiguous(),

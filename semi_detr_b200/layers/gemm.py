@@ -78,5 +78,7 @@ def linear_grad_weight(g2d, x2d, with_bias_grad=False):
     splits = max(1, min((k + 31) // 32, (2 * _sm_count(g2d.device)) // tiles))
     if not with_bias_grad:
         return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits)
-    gb = torch.zeros(m, dtype=torch.float32, device=g2d.device)
-    return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits, a_column_sums=gb), gb
+    buf = torch.zeros(m * n + m, dtype=torch.float32, device=g2d.device)      # one fill for both outputs
+    gw, gb = buf[:m * n].view(m, n), buf[m * n:]
+    gemm_tf32(g2d, 1, x2d, 1, m, n, k, out=gw, k_splits=splits, a_column_sums=gb)
+    return gw, gb

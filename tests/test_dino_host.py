@@ -159,3 +159,24 @@ def test_loss_dict_total_equals_entry_by_entry_sum():
         assert (g_fast - g_slow).abs().max() <= 1e-5 * g_slow.abs().max()
     losses["extra_loss"] = torch.zeros(())
     assert losses.total is None
+
+
+def test_decoder_self_attention_equals_multihead_attention():
+    """The written-out decoder self-attention against nn.MultiheadAttention itself (same parameters, bool mask)."""
+    import torch
+    from semi_detr_b200.dino.transformer import DINOTransformerDecoderLayer
+    torch.manual_seed(0)
+    layer = DINOTransformerDecoderLayer(d_model=256, d_ffn=64, dropout=0.0).eval()
+    T, N = 50, 3
+    qk, v = torch.randn(T, N, 256), torch.randn(T, N, 256)
+    mask = torch.rand(T, T) < 0.4
+    mask.fill_diagonal_(False)                      # never a fully masked row (as in the CDN mask)
+    want = layer.self_attn(qk, qk, v, attn_mask=mask, need_weights=False)[0]
+    got = layer._self_attention(qk, v, mask)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(layer._self_attention(qk, v, None), layer.self_attn(qk, qk, v, need_weights=False)[0],
+                          rtol=1e-5, atol=1e-6)
+    qk.requires_grad_(True)
+    g1 = torch.autograd.grad(layer._self_attention(qk, v, mask).square().sum(), qk)[0]
+    g2 = torch.autograd.grad(layer.self_attn(qk, qk, v, attn_mask=mask, need_weights=False)[0].square().sum(), qk)[0]
+    assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-5)
