@@ -351,6 +351,8 @@ def _leave(world):
     and exits immediately."""
     if world <= 1:
         return
+    import torch
+    import torch.distributed as dist
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
