@@ -164,6 +164,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout: ONE JSON line there
         dist.init_process_group("nccl", device_id=device)
     _lib.lib()  # fail loudly if the extension is missing
     torch.backends.cuda.matmul.allow_tf32 = True

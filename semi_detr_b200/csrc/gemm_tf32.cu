@@ -56,6 +56,15 @@ constexpr int kTmemCols = 2 * kBN;
 constexpr size_t kDynSmem = (size_t)kStages * kStageBytes + 2 * kOutBufBytes + 1024;   // + alignment slack
 constexpr size_t kDynSmemRes = (size_t)(kResKB + kResStages) * kTileBytes + 2 * kOutBufBytes + 1024;
 
+__device__ __forceinline__ void stamp(unsigned long long* trace, int slot) {
+  if (trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    trace[(size_t)blockIdx.x * 64 + slot] = t;
+    asm volatile("" ::: "memory");
+  }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -154,6 +163,7 @@ struct GemmArgs {
   int k_blocks_per_split;
   int relu;
   int round_a, round_b;   // round the operand to nearest TF32 in shared memory before the MMA reads it
+  unsigned long long* trace;  // debug: 64 globaltimer stamps per CTA (sdb_gemm_tf32_set_trace), or null
   float* a_colsum;          // (M,) or null: column sums of an MN-major A are ADDED here (bias gradient)
   const float* bias;        // (N,) or null
   const uint8_t* row_mask;  // (M,) or null; nonzero -> the output row is zero
@@ -195,6 +205,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int res_n0 = (int)(blockIdx.x % n_tiles) * kBN;
 
   if (threadIdx.x == 0) {
+    stamp(g.trace, 0);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full(s), 1);
       mbar_init(empty(s), 1);
@@ -221,6 +232,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) stamp(g.trace, 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -236,7 +248,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (kBRes && blockIdx.x < num_items) {
         mbar_expect_tx(bfull, (uint32_t)(total_kb * kTileBytes));
         for (int kb = 0; kb < total_kb; ++kb) load_b(bres + kb * kTileBytes, res_n0, kb, bfull);
+        stamp(g.trace, 2);
       }
+      int tile_no = 0;
       int stage = 0;
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -247,6 +261,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb1 = min(total_kb, kb0 + g.k_blocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty(stage), phase ^ 1u);
+          if (kb == kb0 && tile_no < 6) stamp(g.trace, 3 + 2 * tile_no);
           mbar_expect_tx(full(stage), kSB);
           const uint32_t sa = ring + stage * kSB;
           if (kAMn) {
@@ -261,6 +276,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             phase ^= 1u;
           }
         }
+        if (tile_no < 6) stamp(g.trace, 4 + 2 * tile_no);
+        ++tile_no;
       }
     }
   } else if (warp == 1) {
@@ -270,6 +287,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       if (kBRes && blockIdx.x < num_items) mbar_wait(g.round_b ? bready : bfull, 0);
+      stamp(g.trace, 16);
+      int tile_no = 0;
       for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int ks = (int)(item % g.k_splits);
         const int kb0 = ks * g.k_blocks_per_split;
@@ -279,6 +298,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(xform ? ready(stage) : full(stage), phase);
+          if (kb == kb0 && tile_no < 6) stamp(g.trace, 17 + 2 * tile_no);
           tc_fence_after();
           const uint32_t sa = ring + stage * kSB;
           const uint32_t sb = kBRes ? bres + kb * kTileBytes : sa + kTileBytes;
@@ -297,6 +317,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         tc_commit(tfull(acc));
+        if (tile_no < 6) stamp(g.trace, 18 + 2 * tile_no);
+        ++tile_no;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -321,8 +343,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kVecPerTile = kTileBytes / (16 * kXformThreads);   // 8
     if (kBRes && g.round_b && blockIdx.x < num_items) {
       mbar_wait(bfull, 0);
+      if (t == 0) stamp(g.trace, 48);
       round_region(bres, total_kb * kVecPerTile);
       mbar_arrive(bready);
+      if (t == 0) stamp(g.trace, 49);
     }
     if (xform) {
       // Column sums of an MN-major A (the bias gradient dy^T.1 of the grad-weight product): these warps read every
@@ -404,7 +428,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---------------- epilogue (warps 2..5) ----------------
     const int quarter = warp & 3;                 // TMEM lanes this warp may read: 32*(warp % 4) .. +31
     const int row = quarter * 32 + lane;          // accumulator row owned by this thread
-    int acc = 0, obuf = 0;
+    int acc = 0, obuf = 0, epi_tile = 0;
     uint32_t acc_phase = 0;
     for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int ks = (int)(item % g.k_splits);
@@ -412,6 +436,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = (int)(tt % n_tiles) * kBN, m0 = (int)(tt / n_tiles) * kBM;
       const bool masked = g.row_mask != nullptr && (m0 + row) < g.M && g.row_mask[m0 + row] != 0;
       mbar_wait(tfull(acc), acc_phase);
+      if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 32 + 2 * epi_tile);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBN);
       {
@@ -458,18 +483,317 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(tempty(acc));
+      if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 33 + 2 * epi_tile);
+      ++epi_tile;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (warp == 2 && lane == 0) stamp(g.trace, 62);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(g.trace, 63);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols)
                  : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Weights-in-TMEM variant ("wres"): y[M,N] = a[M,K] . op(b)[K,N] for K <= 256 and a K-major a -- the forward and the
+// grad-input products of every 256-wide projection (value / offsets / weights / output, enc_output), FFN linear1
+// forward and FFN linear2 grad-input.
+//
+// Measured on the shared-memory-resident variant above (%globaltimer stamps per warp role, tools/trace_gemm.py): the
+// main loop is LATENCY-bound -- 128 KB of resident weights leave room for four 16 KB stages, and four stages per
+// ~1.6 us memory round trip are ~420 ns per k-block, twice the tensor time.  So the roles are swapped: the product is
+// computed transposed, y^T[N,M] = op(b)^T . a^T, with the WEIGHTS as the MMA's A operand held in tensor memory
+// (`tcgen05.mma ... [d_tmem], [a_tmem], b_desc`): the CTA's 128 x K weight block is loaded once through registers
+// (rounded to TF32 on the way, any source layout), parked in 256 TMEM columns next to the two 128-column
+// accumulators -- all 512 columns in use -- and shared memory is left to a 10-deep ring of activation tiles
+// (160 KB in flight per SM) plus the epilogue's staging tiles.
+// The accumulator is y^T: TMEM lane = output feature, column = token.  Each epilogue thread owns one output feature
+// (one bias value), transposes through its warp's private staging tile and the warp stores 32x32 sub-tiles of y by TMA.
+constexpr int kWStages = 10;
+constexpr int kWEpiBufs = 4;                        // staging tiles per epilogue warp: one per 32-token chunk
+constexpr size_t kDynSmemW = (size_t)kWStages * kTileBytes + 4 * kWEpiBufs * 4096 + 1024;
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+struct WresArgs {
+  int M, N, K;            // y is (M tokens, N features); contraction K <= 256
+  int relu, round_a, round_b;
+  int b_mn;               // weights stored (K, N) row-major instead of (N, K)
+  const float* b;         // weights
+  const float* bias;      // (N,) or null
+  const uint8_t* row_mask;  // (M,) or null
+  unsigned long long* trace;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmYw,
+                      const WresArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * kWStages + 5];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_base = base + kWStages * kTileBytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kWStages + s); };
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kWStages + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (3 * kWStages + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (3 * kWStages + 2 + a); };
+  const uint32_t wready = bar0 + 8u * (3 * kWStages + 4);
+  const bool xform = g.round_a != 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + kBM - 1) / kBM, n_tiles = (g.N + kBN - 1) / kBN;
+  const long long num_items = (long long)m_tiles * n_tiles;
+  const int total_kb = (g.K + kBK - 1) / kBK;
+  const int n0 = (int)(blockIdx.x % n_tiles) * kBN;     // grid is a multiple of n_tiles: one n-block per CTA
+
+  if (threadIdx.x == 0) {
+    stamp(g.trace, 0);
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+      mbar_init(ready(s), kXformThreads);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull(a), 1);
+      mbar_init(tempty(a), kEpiThreads);
+    }
+    mbar_init(wready, kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYw) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t w_tmem = tmem_base + 256u;            // columns [256, 512): the weight block, column = k
+  if (threadIdx.x == 0) stamp(g.trace, 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: activation tiles only ----------------
+      int stage = 0, tile_no = 0;
+      uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int m0 = (int)(item / n_tiles) * kBM;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          if (kb == 0 && tile_no < 6) stamp(g.trace, 3 + 2 * tile_no);
+          mbar_expect_tx(full(stage), kTileBytes);
+          tma_load_2d(base + stage * kTileBytes, &tmA, kb * kBK, m0, full(stage));
+          if (++stage == kWStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (tile_no < 6) stamp(g.trace, 4 + 2 * tile_no);
+        ++tile_no;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer: D[feature, token] += W_tmem[feature, k] . a_smem[token, k]^T ----------------
+      const uint32_t idesc = make_idesc(false, false);
+      int stage = 0, acc = 0, tile_no = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      mbar_wait(wready, 0);
+      tc_fence_after();
+      stamp(g.trace, 16);
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(xform ? ready(stage) : full(stage), phase);
+          if (kb == 0 && tile_no < 6) stamp(g.trace, 17 + 2 * tile_no);
+          tc_fence_after();
+          const uint64_t bdesc = make_desc(base + stage * kTileBytes, false);
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k)
+            tc_mma_tf32_ts(d_tmem, w_tmem + (uint32_t)(kb * kBK + k * 8), bdesc + (uint64_t)((k * 32) >> 4), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit(empty(stage));
+          if (++stage == kWStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull(acc));
+        if (tile_no < 6) stamp(g.trace, 18 + 2 * tile_no);
+        ++tile_no;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 6) {
+    // ---------------- activation rounding (warps 6..9) ----------------
+    if (xform) {
+      const int t = threadIdx.x - 192;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(full(stage), phase);
+          const uint32_t sa = base + stage * kTileBytes;
+#pragma unroll
+          for (int j = 0; j < kTileBytes / (16 * kXformThreads); ++j) {
+            const uint32_t p = sa + 16u * t + (uint32_t)(j * 16 * kXformThreads);
+            uint32_t a, b, c, d;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(p) : "memory");
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(__uint_as_float(a)));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(__uint_as_float(b)));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(__uint_as_float(c)));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(__uint_as_float(d)));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(ready(stage));
+          if (++stage == kWStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- weight load, then epilogue (warps 2..5) ----------------
+    const int quarter = warp & 3;
+    const int feat = n0 + quarter * 32 + lane;            // output feature owned by this thread (TMEM lane)
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    {
+      // This thread's weight row (TMEM lane = feature): element k is b[feat, k] (K-major source) or b[k, feat]
+      // (MN-major source), zero past N / K.  The MN-major source is read coalesced as it is; the K-major source is
+      // read coalesced row by row into the warp's staging tile and transposed there (33-float pitch).
+      const bool live = feat < g.N;
+      const uint32_t scratch = out_base + (uint32_t)(quarter * kWEpiBufs) * 4096u;
+      for (int c = 0; c < kResKB; ++c) {                  // 32 k per tcgen05.st
+        uint32_t v[32];
+        if (g.b_mn) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int k = c * 32 + e;
+            v[e] = (live && k < g.K) ? __float_as_uint(__ldg(g.b + (size_t)k * g.N + feat)) : 0u;
+          }
+        } else {
+          const int k = c * 32 + lane;
+          float w[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {                  // 32 independent coalesced loads in flight
+            const int row = n0 + quarter * 32 + i;
+            w[i] = (row < g.N && k < g.K) ? __ldg(g.b + (size_t)row * g.K + k) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + (uint32_t)((i * 33 + lane) * 4)), "f"(w[i]) : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[e]) : "r"(scratch + (uint32_t)((lane * 33 + e) * 4)) : "memory");
+          __syncwarp();
+        }
+        if (g.round_b) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[e]) : "f"(__uint_as_float(v[e])));
+        }
+        tmem_st32(w_tmem + lane_addr + (uint32_t)(c * 32), v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(wready);
+      if (warp == 2 && lane == 0) stamp(g.trace, 49);
+    }
+    const float bias = (g.bias != nullptr && feat < g.N) ? __ldg(g.bias + feat) : 0.f;
+    const uint32_t wbuf = out_base + (uint32_t)(quarter * kWEpiBufs) * 4096u;
+    int acc = 0, epi_tile = 0;
+    uint32_t acc_phase = 0;
+    for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int m0 = (int)(item / n_tiles) * kBM;
+      mbar_wait(tfull(acc), acc_phase);
+      if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 32 + 2 * epi_tile);
+      tc_fence_after();
+      // the staging tiles of the previous work item must have been read by their TMA stores
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * kBN);
+#pragma unroll 1
+      for (int c = 0; c < kBM / 32; ++c) {                // 32 tokens per chunk
+        if (m0 + c * 32 >= g.M) break;
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t mask_bits = 0;
+        if (g.row_mask != nullptr) {                      // one byte per token, the same for every lane
+          const int tok = m0 + c * 32 + lane;
+          mask_bits = __ballot_sync(0xffffffffu, tok < g.M && g.row_mask[tok] != 0);
+        }
+        const uint32_t sbuf = wbuf + (uint32_t)c * 4096u;  // [32 tokens][32 features] fp32, 128-byte rows
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float x = __uint_as_float(v[e]) + bias;
+          if (g.relu) x = fmaxf(x, 0.f);
+          if ((mask_bits >> e) & 1u) x = 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbuf + (uint32_t)(e * 128 + lane * 4)), "f"(x) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && n0 + quarter * 32 < g.N) {
+          tma_store_2d(&tmYw, sbuf, n0 + quarter * 32, m0 + c * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty(acc));
+      if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 33 + 2 * epi_tile);
+      ++epi_tile;
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (warp == 2 && lane == 0) stamp(g.trace, 62);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) stamp(g.trace, 63);
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -492,7 +816,7 @@ EncodeTiledFn encode_fn() {
 
 // 2-D fp32 row-major matrix (rows x cols), box (box_rows x 32 columns), 128-byte swizzle, zero fill out of bounds
 int make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, int box_rows, bool atom32,
-             const char* what) {
+             const char* what, bool no_swizzle = false) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     set_error("gemm_tf32: cuTensorMapEncodeTiled is not available from this driver");
@@ -503,7 +827,9 @@ int make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, i
   const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                    : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -534,6 +860,15 @@ int launch(cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CU
 
 }  // namespace
 }  // namespace sdb
+
+static unsigned long long* g_gemm_trace = nullptr;
+
+// Debug hook (not part of the reference-facing surface): a device buffer of 64 x gridDim.x uint64 that the next launches
+// fill with %globaltimer stamps per warp role (tools/trace_gemm.py prints the timeline); NULL switches it off.
+extern "C" int sdb_gemm_tf32_set_trace(unsigned long long* device_buffer) {
+  g_gemm_trace = device_buffer;
+  return SDB_OK;
+}
 
 extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
                              float* y, int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu,
@@ -574,9 +909,42 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
   g.bias = bias;
   g.row_mask = row_mask;
   g.a_colsum = a_column_sums;
+  g.trace = g_gemm_trace;
   const long long items = (long long)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) * g.k_splits;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tiles = (n + kBN - 1) / kBN;
+  // Weights-in-TMEM variant: K-major streamed operand, K <= 256, no split, enough m-tiles per CTA to amortise the
+  // weight load.  Opt-in (SDB_GEMM_WRES=1): parity-green, but measured on par with the shared-memory-resident
+  // variant (32 vs 30 us on the projection shape) -- the main loop of both runs at ~185 cycles per 128x128x8 MMA
+  // against ~100-125 for the bare instruction stream (tools/umma_rate.py), so the ring depth it buys is not what
+  // limits them; see DESIGN.md section 4.
+  static int wres_enabled = -1;
+  if (wres_enabled < 0) {
+    const char* e = getenv("SDB_GEMM_WRES");
+    wres_enabled = (e && strcmp(e, "1") == 0) ? 1 : 0;
+  }
+  if (wres_enabled && !a_mn_major && g.k_splits == 1 && total_kb <= kResKB && n_tiles <= sm_count() &&
+      items >= 2ll * sm_count() && !a_column_sums) {
+    CUtensorMap tyn;
+    rc = make_map(&tyn, y, m, n, 32, false, "Y (m,n), 32x32 boxes", true);
+    if (rc) return rc;
+    WresArgs w;
+    w.M = m; w.N = n; w.K = k;
+    w.relu = relu; w.round_a = g.round_a; w.round_b = g.round_b;
+    w.b_mn = b_mn_major ? 1 : 0;
+    w.b = b; w.bias = bias; w.row_mask = row_mask; w.trace = g_gemm_trace;
+    static bool configured = false;
+    if (!configured) {
+      SDB_CUDA(cudaFuncSetAttribute(gemm_tf32_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemW));
+      configured = true;
+    }
+    long long grid = sm_count();
+    if (grid > items) grid = items;
+    grid -= grid % n_tiles;
+    gemm_tf32_wres_kernel<<<(unsigned)grid, kThreads, kDynSmemW, st>>>(ta, tyn, w);
+    SDB_LAUNCH_CHECK("gemm_tf32_wres_kernel");
+    return SDB_OK;
+  }
   // B-resident variant: the whole K extent of one n-block fits the 128 KB resident region, and there is enough work
   // for every CTA to amortise loading it (at least two m-tiles per CTA on a full grid)
   const bool res = g.k_splits == 1 && total_kb <= kResKB && n_tiles <= sm_count() &&

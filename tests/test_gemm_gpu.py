@@ -168,3 +168,37 @@ def test_grad_weight_with_fused_bias_gradient(m, n, k):
     gw, gb = G.linear_grad_weight(dy, x, with_bias_grad=True)
     _close(gw, _trunc(dy).double().t() @ _trunc(x).double())
     _close(gb, dy.double().sum(0), tol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["fwd", "dx"])
+def test_weights_in_tmem_variant(kind):
+    """The opt-in variant that parks the weight block in tensor memory and computes y^T = W . x^T (TS-form
+    tcgen05.mma, tcgen05.st, transposing epilogue): same result as the default path.  Runs in a subprocess because the
+    variant is selected once per process (SDB_GEMM_WRES=1)."""
+    import os
+    import subprocess
+    import sys
+    code = f"""
+import torch
+from semi_detr_b200.layers import gemm as G
+g = torch.Generator(device="cuda").manual_seed(3)
+rna = lambda t: ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+m, n, k = 40000, 384, 256
+x = torch.randn(m, k, device="cuda", generator=g)
+if "{kind}" == "fwd":
+    w = torch.randn(n, k, device="cuda", generator=g) * 0.1
+    b = torch.randn(n, device="cuda", generator=g)
+    mask = torch.rand(m, device="cuda", generator=g) < 0.2
+    y = G.linear_forward(x, w, b, relu=True, row_mask=mask)
+    ref = torch.relu(rna(x).double() @ rna(w).double().t() + b.double()).masked_fill(mask[:, None], 0.0)
+else:
+    w = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    y = G.linear_grad_input(x, w)
+    ref = rna(x).double() @ rna(w).double()
+err = float((y.double() - ref).abs().max() / ref.abs().max())
+assert err < 2e-5, err
+print("ok", err)
+"""
+    env = dict(os.environ, SDB_GEMM_WRES="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
