@@ -228,6 +228,12 @@ int sdb_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float
  * ------------------------------------------------------------------------------------------ */
 int sdb_colsum_f32(sdb_stream_t stream, const float* x, int64_t rows, int cols, float* out);
 
+/* ReLU backward fused with the bias gradient of the linear layer in front of it (FFN linear1 -> ReLU,
+ * transformer.py:628, 880): g = dy where y > 0 else 0, colsum[c] = sum_r g[r, c] (zero-filled by the call), one pass.
+ * Same shape / alignment requirements as sdb_colsum_f32; g must not alias the inputs. */
+int sdb_relu_backward_colsum_f32(sdb_stream_t stream, const float* dy, const float* y, int64_t rows, int cols,
+                                 float* g, float* colsum);
+
 /* ------------------------------------------------------------------------------------------
  * Gradient clip + AdamW (+ mean-teacher EMA) in one pass over flat fp32 buffers.
  *

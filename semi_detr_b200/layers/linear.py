@@ -68,6 +68,19 @@ def column_sum(x2d):
     return out
 
 
+def relu_backward_colsum(dy2d, y2d):
+    """-> (dy * (y > 0), its column sums): ReLU backward and the bias gradient of the layer before it in one pass"""
+    rows, cols = y2d.shape
+    g = torch.empty_like(y2d)
+    out = torch.empty(cols, dtype=torch.float32, device=y2d.device)
+    with torch.cuda.device(y2d.device):
+        rc = _lib.lib().sdb_relu_backward_colsum_f32(_lib.current_stream(y2d.device), dy2d.data_ptr(), y2d.data_ptr(),
+                                                     rows, cols, g.data_ptr(), out.data_ptr())
+    _lib.check(rc, "relu_backward_colsum")
+    _lib.LAUNCHES["relu_backward_colsum"] += 1
+    return g, out
+
+
 class _LinearFn(torch.autograd.Function):
     """Library GEMMs + column-sum bias gradient (the small-shape path)."""
 
@@ -117,8 +130,12 @@ class _TensorCoreLinearFn(torch.autograd.Function):
     def backward(ctx, g):
         x2, weight, y, mask = ctx.saved_tensors
         g2 = g.reshape(-1, g.shape[-1])
+        gb_fused = None
         if ctx.relu:
-            g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)   # also zeroes masked rows (their y is 0)
+            if ctx.needs_input_grad[2] and g2.is_contiguous() and g2.shape[1] % 4 == 0:
+                g2, gb_fused = relu_backward_colsum(g2, y)       # masked rows have y == 0: zeroed as well
+            else:
+                g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)
         elif mask is not None:
             g2 = g2.masked_fill(mask.view(torch.bool)[:, None], 0.0)
         elif not g2.is_contiguous():
@@ -126,7 +143,11 @@ class _TensorCoreLinearFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = (gemm.linear_grad_input(g2, weight) if ctx.plan[1] else g2 @ weight).view(ctx.x_shape)
-        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and ctx.plan[2]:
+        if gb_fused is not None:
+            gb = gb_fused
+            if ctx.needs_input_grad[1]:
+                gw = gemm.linear_grad_weight(g2, x2) if ctx.plan[2] else g2.t() @ x2
+        elif ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and ctx.plan[2]:
             gw, gb = gemm.linear_grad_weight(g2, x2, with_bias_grad=True)   # bias gradient from the same launch
         else:
             if ctx.needs_input_grad[1]:

@@ -202,3 +202,47 @@ print("ok", err)
     env = dict(os.environ, SDB_GEMM_WRES="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("rows,cols", [(44446, 2048), (2184, 2048), (1000, 256), (7, 4)])
+def test_relu_backward_colsum(rows, cols):
+    from semi_detr_b200.layers.linear import relu_backward_colsum
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    dy = torch.randn(rows, cols, device="cuda", generator=g)
+    y = torch.relu(torch.randn(rows, cols, device="cuda", generator=g))
+    got, gb = relu_backward_colsum(dy, y)
+    want = torch.ops.aten.threshold_backward(dy, y, 0.0)
+    assert torch.equal(got, want)
+    ref = want.double().sum(0)
+    assert float((gb.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-6
+
+
+def test_ffn_layer_uses_fused_relu_backward(monkeypatch):
+    """FFN linear1 + ReLU under the default policy: forward on the tcgen05 kernel (ReLU in the epilogue), backward =
+    one fused ReLU-backward + bias-gradient pass, library products; same numbers as nn.Linear + relu."""
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.layers.linear import Linear
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        monkeypatch.setenv("SDB_LINEAR", "auto")
+        torch.manual_seed(2)
+        lin = Linear(256, 2048).cuda()
+        x = torch.randn(2, 1500, 256, device="cuda", requires_grad=True)
+        gy = torch.randn(2, 1500, 2048, device="cuda")
+        before = dict(_lib.LAUNCHES)
+        y = lin(x, relu=True)
+        y.backward(gy)
+        assert _lib.LAUNCHES["gemm_tf32"] - before["gemm_tf32"] == 1
+        assert _lib.LAUNCHES["relu_backward_colsum"] - before["relu_backward_colsum"] == 1
+        assert _lib.LAUNCHES["colsum"] == before["colsum"]
+        xr = x.detach().clone().requires_grad_(True)
+        yr = torch.relu(torch.nn.functional.linear(xr, lin.weight.detach(), lin.bias.detach()))
+        w2 = lin.weight.detach().clone().requires_grad_(True)
+        b2 = lin.bias.detach().clone().requires_grad_(True)
+        yr = torch.relu(torch.nn.functional.linear(xr, w2, b2))
+        yr.backward(gy)
+        for a, b in ((y, yr), (x.grad, xr.grad), (lin.weight.grad, w2.grad), (lin.bias.grad, b2.grad)):
+            assert (a - b).abs().max().item() <= 3e-3 * b.abs().max().item()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
