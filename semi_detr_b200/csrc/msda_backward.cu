@@ -386,9 +386,18 @@ extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* gra
   if ((long long)batch * Lq == 0) return SDB_OK;
   SDB_REQUIRE(grad_out && value && spatial_shapes && level_start_index && reference_points && sampling_offsets &&
               attn_logits && grad_offsets && grad_attn_logits, "msda_fused_backward: null pointer");
-  return launch_bwd_d32<128, 4, 8, 6, true>(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets,
-                                            attn_logits, batch, S, M, L, Lq, P, grad_value, grad_offsets,
-                                            grad_attn_logits, reference_points, ref_dim);
+#define SDB_FBWD_ARGS st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, batch, S, M, L, \
+                      Lq, P, grad_value, grad_offsets, grad_attn_logits, reference_points, ref_dim
+  switch (g_bwd_variant) {     // sdb_msda_set_variant: register budget / occupancy trade-off (tools/microbench.py)
+    // measured at the train-step shapes (profiles/msda_bwd_variants_r1.txt): 582 / 536 / 527 / 534 / 546 us (encoder)
+    // for 6 / 5 / 4 / 3 CTAs of 128 threads and 2 of 256 per SM -- the spill-free 115-register build wins
+    case 2: return launch_bwd_d32<256, 4, 8, 2, true>(SDB_FBWD_ARGS);
+    case 3: return launch_bwd_d32<128, 4, 8, 3, true>(SDB_FBWD_ARGS);   // 143 registers, 12 warps / SM
+    case 5: return launch_bwd_d32<128, 4, 8, 5, true>(SDB_FBWD_ARGS);   // 96 registers (spills 20 B), 20 warps / SM
+    case 6: return launch_bwd_d32<128, 4, 8, 6, true>(SDB_FBWD_ARGS);   // 80 registers (spills 108 B), 24 warps / SM
+    default: return launch_bwd_d32<128, 4, 8, 4, true>(SDB_FBWD_ARGS);  // 115 registers, no spills, 16 warps / SM
+  }
+#undef SDB_FBWD_ARGS
 }
 
 extern "C" int sdb_msda_backward_f64(sdb_stream_t stream, const double* grad_out, const double* value,
