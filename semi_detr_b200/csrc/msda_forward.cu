@@ -312,13 +312,23 @@ extern "C" int sdb_msda_fused_forward_f32(sdb_stream_t stream, const float* valu
   if ((long long)batch * Lq == 0) return SDB_OK;
   SDB_REQUIRE(value && spatial_shapes && level_start_index && reference_points && sampling_offsets && attn_logits &&
               out, "msda_fused_forward: null pointer");
-  if (Lq == S)
-    return launch_fwd_d32<256, 8, 8, 3, 8, 4, 2, true>(st, value, spatial_shapes, level_start_index,
-                                                        sampling_offsets, attn_logits, batch, S, M, L, Lq, P, out,
-                                                        reference_points, ref_dim);
-  return launch_fwd_d32<256, 4, 8, 3, 8, 4, 2, true>(st, value, spatial_shapes, level_start_index, sampling_offsets,
-                                                      attn_logits, batch, S, M, L, Lq, P, out, reference_points,
-                                                      ref_dim);
+#define SDB_FFWD_ARGS st, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, batch, S, M, L, Lq, P, \
+                      out, reference_points, ref_dim
+  if (Lq == S) {
+    switch (g_fwd_variant) {   // sdb_msda_set_variant: register budget / points in flight (tools/bwd_variants.py)
+      case 3: return launch_fwd_d32<256, 8, 8, 2, 8, 4, 4, true>(SDB_FFWD_ARGS);
+      case 5: return launch_fwd_d32<512, 8, 8, 1, 8, 4, 4, true>(SDB_FFWD_ARGS);
+      case 6: return launch_fwd_d32<128, 8, 8, 4, 8, 4, 4, true>(SDB_FFWD_ARGS);
+      case 8: return launch_fwd_d32<256, 8, 8, 2, 8, 4, 2, true>(SDB_FFWD_ARGS);
+      default: return launch_fwd_d32<256, 8, 8, 3, 8, 4, 2, true>(SDB_FFWD_ARGS);
+    }
+  }
+  switch (g_fwd_variant) {
+    case 3: return launch_fwd_d32<256, 4, 8, 2, 8, 4, 4, true>(SDB_FFWD_ARGS);
+    case 6: return launch_fwd_d32<128, 4, 8, 4, 8, 4, 4, true>(SDB_FFWD_ARGS);
+    default: return launch_fwd_d32<256, 4, 8, 3, 8, 4, 2, true>(SDB_FFWD_ARGS);
+  }
+#undef SDB_FFWD_ARGS
 }
 
 extern "C" int sdb_msda_set_variant(int forward_variant, int backward_variant) {

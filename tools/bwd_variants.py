@@ -1,4 +1,4 @@
-"""Fused MSDA backward at the train-step encoder / decoder shapes for the register-budget variants
+"""Fused MSDA backward and forward at the train-step encoder / decoder shapes for the register-budget variants
 (sdb_msda_set_variant): median of 30 L2-flushed launches."""
 import os
 import sys
@@ -40,4 +40,19 @@ for name, Lq, refdim in (("enc", S, 2), ("dec", 1092, 4)):
             ts.append(e0.elapsed_time(e1) * 1e3)
         ts = sorted(ts[3:])
         print(f"{name} Lq={Lq} backward variant {variant}: median {ts[len(ts) // 2]:.1f} us  min {ts[0]:.1f}")
+    for variant in (0, 3, 5, 6, 8):
+        if name == "dec" and variant in (5, 8):
+            continue
+        _lib.lib().sdb_msda_set_variant(variant, 0)
+        ts = []
+        for _ in range(33):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            MSDA.ms_deform_attn_fused_forward(value, shapes, start, ref, off, logits)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts = sorted(ts[3:])
+        print(f"{name} Lq={Lq} forward variant {variant}: median {ts[len(ts) // 2]:.1f} us  min {ts[0]:.1f}")
 _lib.lib().sdb_msda_set_variant(0, 0)
