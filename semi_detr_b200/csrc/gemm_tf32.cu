@@ -27,11 +27,17 @@
 //   warps 6-9  operand rounding: the tensor core TRUNCATES fp32 words to TF32 (13 low mantissa bits ignored), a
 //            systematic -7e-4 relative shrink of every product.  These warps round each landed stage to nearest
 //            (`cvt.rna.tf32.f32`, in place, layout-agnostic) and hand it to the MMA warp through `ready[s]`, so the
-//            result is the unbiased round-to-nearest TF32 product cuBLAS computes.
+//            result is the unbiased round-to-nearest TF32 product.  For an MN-major A (the grad-weight product) the
+//            same warps also accumulate its column sums -- the bias gradient -- in registers (`a_column_sums`).
 // K-major operands use the 128-byte swizzle; MN-major fp32 operands must use the "128B swizzle with 32-byte atoms"
 // (UMMA layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4 k-rows x 128 B per swizzle atom.
-// The path is HBM-bound for the shapes of this model (K = 256: 2 flop per byte moved would need ~12 TB/s to
-// saturate the tensor pipe), so the design goal is to keep TMA loads and stores continuously in flight.
+//
+// Three variants share the roles: the streaming kernel above; `kBRes` (K <= 256: the CTA's 128 x K block of B stays
+// in shared memory for the life of the CTA, only A streams through a 4-stage ring); and `gemm_tf32_wres_kernel`
+// (opt-in: the weight block lives in TENSOR memory as the MMA's A operand, see its header).
+// In HBM terms the projections are bandwidth-bound (K = 256: 91 MB per 44 446 x 256 x 256 product = 14 us at the
+// measured peak vs 5 us of tensor time); measured, the main loop sustains one 128x128x8 MMA per ~185 cycles against
+// 97-127 for the bare instruction stream (tools/umma_rate.py), see DESIGN.md section 4.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
