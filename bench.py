@@ -247,6 +247,9 @@ def run_ours(args):
     launches = launches_per_step * args.steps
 
     # ---- timed region 2: end to end (pinned host -> device every step, loss read back) -------------------
+    # Every step's inputs cross PCIe inside the timed region; with the graph engine the copy of step i+1 is issued
+    # (side stream, staging buffers) right after step i is enqueued, so it overlaps step i's compute like a
+    # prefetching data loader would -- K copies for K steps, the first one exposed.
     run_e2e = (lambda: graphed(host)) if graphed else (lambda: step(to_device(host)))
     for _ in range(2):
         float(run_e2e()[0])
@@ -254,9 +257,17 @@ def run_ours(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = 0.0
-    for _ in range(args.steps):
-        loss, _ = run_e2e()
-        last = float(loss)                        # device -> host read of the step's result
+    if graphed:
+        graphed.prefetch(host)
+        for i in range(args.steps):
+            loss, _ = graphed(prefetched=True)
+            if i + 1 < args.steps:
+                graphed.prefetch(host)
+            last = float(loss)                    # device -> host read of the step's result
+    else:
+        for _ in range(args.steps):
+            loss, _ = run_e2e()
+            last = float(loss)
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))

@@ -113,8 +113,34 @@ class GraphedTrainStep:
         for dst, src in zip(d["gt_labels"], batch["gt_labels"]):
             dst.copy_(src, non_blocking=True)
 
-    def __call__(self, batch=None):
-        if batch is not None:
+    def prefetch(self, batch):
+        """Start the host->device copy of the NEXT batch (pinned host memory) on a side stream into staging buffers,
+        so it overlaps the replay of the current step; ``__call__(prefetched=True)`` then moves it into the graph's
+        input buffers with device-to-device copies (a few microseconds)."""
+        if getattr(self, "_stage", None) is None:
+            d = self.data
+            self._stage = dict(img=torch.empty_like(d["img"]), gt_bboxes=[torch.empty_like(t) for t in d["gt_bboxes"]],
+                               gt_labels=[torch.empty_like(t) for t in d["gt_labels"]])
+            self._copy_stream = torch.cuda.Stream()
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        st = self._stage
+        self._copy_stream.wait_event(self._consumed)      # the previous staged batch has been moved out
+        with torch.cuda.stream(self._copy_stream):
+            st["img"].copy_(batch["img"], non_blocking=True)
+            for dst, src in zip(st["gt_bboxes"], batch["gt_bboxes"]):
+                dst.copy_(src, non_blocking=True)
+            for dst, src in zip(st["gt_labels"], batch["gt_labels"]):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record()
+
+    def __call__(self, batch=None, prefetched=False):
+        if prefetched:
+            torch.cuda.current_stream().wait_event(self._staged)
+            self.load(self._stage)
+            self._consumed.record()
+        elif batch is not None:
             self.load(batch)
         self.graph.replay()
         return self.loss, self.log_vars
