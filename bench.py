@@ -164,8 +164,19 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout: ONE JSON line there
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner to file descriptor 1 when the first communicator is created: point fd 1 at
+        # stderr until then, so stdout carries exactly ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     _lib.lib()  # fail loudly if the extension is missing
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
