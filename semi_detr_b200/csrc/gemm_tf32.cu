@@ -803,6 +803,289 @@ gemm_tf32_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (`cta_group::2`): the two CTAs of a cluster compute ONE 256 x 256 output tile.  Each CTA stages
+// its own 128 rows of A and its own 128-column half of B (the same 32 KB per stage as the 1-CTA kernel), and one
+// thread of the leader CTA issues `tcgen05.mma.cta_group::2` 256 x 256 x 8: each SM's tensor core multiplies its 128
+// rows by all 256 columns, reading the other half of B from the peer's shared memory -- twice the flops per byte
+// staged and per shared-memory byte read, which is what the measurements on the 1-CTA kernels ask for (DESIGN.md
+// section 4).  Each CTA's accumulator (128 lanes x 256 columns, double-buffered = all 512 TMEM columns) is drained
+// by its own epilogue warps.
+// Barrier protocol: `full[s]` / `empty[s]` / `tfull[a]` are local to each CTA (TMA completion; `tcgen05.commit`
+// multicast to both CTAs); `ready[s]` and `tempty[a]` live in the LEADER and count the rounding / epilogue threads of
+// BOTH CTAs (remote `mbarrier.arrive` through `mapa`), because only the leader issues MMAs.
+constexpr int kPairBN = 256;
+constexpr size_t kDynSmem2 = (size_t)kStages * kStageBytes + 16 * 4096 + 1024;   // ring + 4 x 4 staging tiles
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\tmapa.shared::cluster.u32 r, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool kAMn, bool kBMn>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmYw, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[3 * kStages + 4];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_base = base + kStages * kStageBytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (3 * kStages + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (3 * kStages + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_tiles = (g.M + 2 * kBM - 1) / (2 * kBM), n_tiles = (g.N + kPairBN - 1) / kPairBN;
+  const long long num_items = (long long)m_tiles * n_tiles;
+  const int total_kb = (g.K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    stamp(g.trace, 0);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+      mbar_init(ready(s), 2 * kXformThreads / 32); // used in the leader only: one arrival per rounding warp of both CTAs
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull(a), 1);
+      mbar_init(tempty(a), 2 * kEpiThreads / 32);  // used in the leader only: one arrival per epilogue warp of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmYw) : "memory");
+  }
+  if (warp == 1) {      // the same warp of both CTAs allocates collectively
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) stamp(g.trace, 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: this CTA's 128 rows of A and its 128-column half of B ----------------
+      int stage = 0, tile_no = 0;
+      uint32_t phase = 0;
+      for (long long item = pair; item < num_items; item += n_pairs) {
+        const int n0 = (int)(item % n_tiles) * kPairBN + (int)rank * kBN;
+        const int m0 = (int)(item / n_tiles) * 2 * kBM + (int)rank * kBM;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          if (tile_no == 0 && kb < 8) stamp(g.trace, 3 + kb);          // first tile: issue time of k-blocks 0..7
+          mbar_expect_tx(full(stage), kStageBytes);
+          const uint32_t sa = base + stage * kStageBytes, sb = sa + kTileBytes;
+          if (kAMn) {
+#pragma unroll
+            for (int j = 0; j < kBM / 32; ++j) tma_load_2d(sa + j * (kBK * 128), &tmA, m0 + 32 * j, kb * kBK, full(stage));
+          } else {
+            tma_load_2d(sa, &tmA, kb * kBK, m0, full(stage));
+          }
+          if (kBMn) {
+#pragma unroll
+            for (int j = 0; j < kBN / 32; ++j) tma_load_2d(sb + j * (kBK * 128), &tmB, n0 + 32 * j, kb * kBK, full(stage));
+          } else {
+            tma_load_2d(sb, &tmB, kb * kBK, n0, full(stage));
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ++tile_no;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------- MMA issuer (leader CTA only): 256 x 256 x 8 across the pair ----------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)kAMn << 15) | ((uint32_t)kBMn << 16) |
+                             ((uint32_t)(kPairBN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
+      int stage = 0, acc = 0, tile_no = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long item = pair; item < num_items; item += n_pairs) {
+        mbar_wait_cluster(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kPairBN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait_cluster(ready(stage), phase);
+          if (tile_no == 0 && kb < 8) stamp(g.trace, 17 + kb);         // first tile: k-block kb ready for the MMA
+          tc_fence_after();
+          const uint32_t sa = base + stage * kStageBytes, sb = sa + kTileBytes;
+          const uint64_t adesc = make_desc(sa, kAMn), bdesc = make_desc(sb, kBMn);
+#pragma unroll
+          for (int k = 0; k < kBK / 8; ++k) {
+            const uint64_t ao = (uint64_t)((kAMn ? k * 1024 : k * 32) >> 4);
+            const uint64_t bo = (uint64_t)((kBMn ? k * 1024 : k * 32) >> 4);
+            tc_mma_tf32_pair(d_tmem, adesc + ao, bdesc + bo, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_pair(empty(stage));
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit_pair(tfull(acc));
+        if (tile_no < 4) stamp(g.trace, 26 + tile_no);                   // tile committed
+        ++tile_no;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 6) {
+    // ---------------- operand rounding (warps 6..9): round the local stage, report to the leader ----------------
+    const int t = threadIdx.x - 192;
+    constexpr int kVecPerTile = kTileBytes / (16 * kXformThreads);
+    const uint32_t first = g.round_a ? 0u : (uint32_t)kTileBytes;
+    const int n_vec = ((g.round_a ? 1 : 0) + (g.round_b ? 1 : 0)) * kVecPerTile;
+    int stage = 0, xf_tile = 0;
+    uint32_t phase = 0;
+    for (long long item = pair; item < num_items; item += n_pairs, ++xf_tile) {
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(full(stage), phase);
+        if (t == 0 && xf_tile == 0 && kb < 8) stamp(g.trace, 40 + kb);   // first tile: k-block kb landed locally
+        const uint32_t p0 = base + stage * kStageBytes + first + 16u * t;
+#pragma unroll 4
+        for (int j = 0; j < n_vec; ++j) {
+          const uint32_t p = p0 + (uint32_t)(j * 16 * kXformThreads);
+          uint32_t a, b, c, d;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(p) : "memory");
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(__uint_as_float(a)));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(__uint_as_float(b)));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(__uint_as_float(c)));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(__uint_as_float(d)));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ready(stage), 0);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5): this CTA's 128 rows x 256 columns ----------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long item = pair; item < num_items; item += n_pairs) {
+      const int n0 = (int)(item % n_tiles) * kPairBN;
+      const int m0 = (int)(item / n_tiles) * 2 * kBM + (int)rank * kBM;
+      const bool masked = g.row_mask != nullptr && (m0 + row) < g.M && g.row_mask[m0 + row] != 0;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kPairBN);
+      const bool add_bias = g.bias != nullptr;
+      const uint32_t wbuf = out_base + (uint32_t)(quarter * 4) * 4096u;   // four 4 KB staging tiles per warp
+      constexpr int kChunks = kPairBN / kOutChunk;
+      uint32_t v[2][32];
+      tmem_ld32(taddr, v[0]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 1 < kChunks) tmem_ld32(taddr + (uint32_t)((c + 1) * kOutChunk), v[(c + 1) & 1]);   // next chunk in flight
+        if (n0 + c * kOutChunk < g.N) {
+          // the staging tile written four chunks ago must have been read by its TMA store
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          __syncwarp();
+          const uint32_t sbuf = wbuf + (uint32_t)(c & 3) * 4096u;
+          const uint32_t srow = sbuf + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int col = n0 + c * kOutChunk + 4 * q;
+            if (add_bias && col < g.N) o = __ldg(reinterpret_cast<const float4*>(g.bias + col));
+            float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(v[c & 1][4 * q + e]) + op[e];
+              if (g.relu) x = fmaxf(x, 0.f);
+              op[e] = masked ? 0.f : x;
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)(((q ^ (lane & 7)) << 4))),
+                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmYw, sbuf, n0 + c * kOutChunk, m0 + quarter * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty(acc), 0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  // nobody leaves (or frees tensor memory) while the peer may still read this CTA's shared memory or signal its barriers
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -832,12 +1115,19 @@ int make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, i
   const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
   const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  static int promo = -1;       // SDB_GEMM_L2PROMO=0..3: none / 64 B / 128 B / 256 B (experiments; default 256 B)
+  if (promo < 0) {
+    const char* e = getenv("SDB_GEMM_L2PROMO");
+    promo = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+  }
+  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE,
                          no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
                                     : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tf32: cuTensorMapEncodeTiled failed for %s (CUresult %d, rows=%lld cols=%lld)", what, (int)r, rows,
               cols);
@@ -919,6 +1209,26 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
   const long long items = (long long)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) * g.k_splits;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tiles = (n + kBN - 1) / kBN;
+  // CTA-pair variant (cta_group::2, 256 x 256 tiles): opt-in with SDB_GEMM_2CTA=1 until it has been through the full
+  // parity suite on hardware; no split-K, no fused column sums.
+  static int pair_enabled = -1;
+  if (pair_enabled < 0) {
+    const char* e = getenv("SDB_GEMM_2CTA");
+    pair_enabled = (e && strcmp(e, "1") == 0) ? 1 : 0;
+  }
+  if (pair_enabled && g.k_splits == 1 && !a_column_sums && sm_count() >= 2) {
+    const long long pair_items = (long long)((m + 2 * kBM - 1) / (2 * kBM)) * ((n + kPairBN - 1) / kPairBN);
+    long long pairs = sm_count() / 2;
+    if (pairs > pair_items) pairs = pair_items;
+    auto launch_pair = [&](auto kern) -> int {
+      SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem2));
+      kern<<<(unsigned)(2 * pairs), kThreads, kDynSmem2, st>>>(ta, tb, tyw, g);
+      SDB_LAUNCH_CHECK("gemm_tf32_pair_kernel");
+      return SDB_OK;
+    };
+    if (a_mn_major) return b_mn_major ? launch_pair(gemm_tf32_pair_kernel<true, true>) : launch_pair(gemm_tf32_pair_kernel<true, false>);
+    return b_mn_major ? launch_pair(gemm_tf32_pair_kernel<false, true>) : launch_pair(gemm_tf32_pair_kernel<false, false>);
+  }
   // Weights-in-TMEM variant: K-major streamed operand, K <= 256, no split, enough m-tiles per CTA to amortise the
   // weight load.  Opt-in (SDB_GEMM_WRES=1): parity-green, but measured on par with the shared-memory-resident
   // variant (32 vs 30 us on the projection shape) -- the main loop of both runs at ~185 cycles per 128x128x8 MMA
