@@ -248,3 +248,37 @@ def test_ffn_layer_uses_fused_relu_backward(monkeypatch):
             assert float((a - b).norm() / b.norm()) <= 5e-3
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("kind", ["fwd", "dx"])
+def test_cta_pair_variant(kind):
+    """The opt-in cta_group::2 kernel (one 256 x 256 tile per CTA pair, leader-issued tcgen05.mma.cta_group::2,
+    multicast commit, remote barrier arrives): same result as the default path, ragged shapes included.  Subprocess:
+    the variant is selected once per process (SDB_GEMM_2CTA=1)."""
+    import os
+    import subprocess
+    import sys
+    code = f"""
+import torch
+from semi_detr_b200.layers import gemm as G
+g = torch.Generator(device="cuda").manual_seed(4)
+rna = lambda t: ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+for m, n, k in ((77, 132, 36), (1000, 384, 256), (20000, 256, 512)):
+    x = torch.randn(m, k, device="cuda", generator=g)
+    if "{kind}" == "fwd":
+        w = torch.randn(n, k, device="cuda", generator=g) * 0.1
+        b = torch.randn(n, device="cuda", generator=g)
+        mask = torch.rand(m, device="cuda", generator=g) < 0.2
+        y = G.linear_forward(x, w, b, relu=True, row_mask=mask)
+        ref = torch.relu(rna(x).double() @ rna(w).double().t() + b.double()).masked_fill(mask[:, None], 0.0)
+    else:
+        w = torch.randn(k, n, device="cuda", generator=g) * 0.1
+        y = G.linear_grad_input(x, w)
+        ref = rna(x).double() @ rna(w).double()
+    err = float((y.double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, (m, n, k, err)
+print("ok")
+"""
+    env = dict(os.environ, SDB_GEMM_2CTA="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
