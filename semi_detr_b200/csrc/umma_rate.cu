@@ -1,6 +1,8 @@
 // Debug microbenchmark: issue rate of tcgen05.mma kind::tf32 on fixed shared-memory / tensor-memory operands (no
 // loads, garbage data), one CTA per SM.  Answers "how long does one 128xNx8 TF32 MMA take back to back?" for the
 // GEMM kernel's design (csrc/gemm_tf32.cu).  Not part of the reference-facing surface.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace sdb {
@@ -132,8 +134,108 @@ umma_rate_pair_kernel(int iters, long long* cycles_out) {
   }
 }
 
+// ---- TMA feed-rate microbenchmark -------------------------------------------------------------------------
+// What the GEMM traces point at: how fast can ONE SM pull K-major fp32 tiles (boxes of
+// `box_rows` rows x 128 bytes, 128B swizzle) through a ring of `stages` stages when nothing consumes them?  A producer
+// thread issues `boxes_per_stage` boxes per stage, a consumer thread frees every stage as soon as it has landed.
+// Every CTA walks its own row tiles over the whole K extent, like the GEMM's A operand.
+__device__ __forceinline__ void spin_wait_(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && spin > (1u << 26)) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(64, 1)
+tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int rows_total, int k_total, int box_rows, int boxes_per_stage,
+                int stages, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * 16];
+  const uint32_t base = (smem_u32_(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32_(bars);
+  const int stage_bytes = boxes_per_stage * box_rows * 128;
+  const int tile_rows = boxes_per_stage * box_rows;
+  const int n_tiles = (rows_total + tile_rows - 1) / tile_rows;
+  const int kbs = k_total / 32;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * s));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * (16 + s)));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  if (threadIdx.x == 0) {                       // producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int kb = 0; kb < kbs; ++kb) {
+        spin_wait_(bar0 + 8u * (16 + stage), phase ^ 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * stage), "r"((uint32_t)stage_bytes) : "memory");
+        for (int b = 0; b < boxes_per_stage; ++b)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(base + (uint32_t)(stage * stage_bytes + b * box_rows * 128)), "l"(&tm), "r"(bar0 + 8u * stage),
+                         "r"(kb * 32), "r"(tile * tile_rows + b * box_rows) : "memory");
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+  } else if (threadIdx.x == 32) {               // consumer: free the stage the moment it lands
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int kb = 0; kb < kbs; ++kb) {
+        spin_wait_(bar0 + 8u * stage, phase);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * (16 + stage)) : "memory");
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles_out[0] = clock64() - t0;
+}
+
 }  // namespace
 }  // namespace sdb
+
+// Streams a (rows x k) fp32 row-major matrix once through every SM's shared memory with TMA and reports the SM cycles
+// CTA 0 needed (the host times the launch with events for GB/s).  box_rows in {8..256}, boxes_per_stage >= 1,
+// stages <= 16, boxes_per_stage * box_rows * 128 * stages <= 200 KB, k % 32 == 0.
+extern "C" int sdb_debug_tma_rate(sdb_stream_t stream, const float* x, int rows, int k, int box_rows, int boxes_per_stage,
+                                  int stages, int grid, long long* cycles_out) {
+  using namespace sdb;
+  SDB_REQUIRE(x && cycles_out && rows > 0 && k > 0 && k % 32 == 0 && box_rows >= 8 && box_rows <= 256 &&
+              boxes_per_stage >= 1 && stages >= 1 && stages <= 16 && grid > 0, "debug_tma_rate: bad arguments");
+  const size_t ring = (size_t)boxes_per_stage * box_rows * 128 * stages;
+  SDB_REQUIRE(ring <= 200 * 1024, "debug_tma_rate: ring larger than 200 KB");
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess) {
+    set_error("debug_tma_rate: cuTensorMapEncodeTiled is not available");
+    return SDB_ERR_CUDA;
+  }
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)k * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = ((EncodeTiledFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)x, dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("debug_tma_rate: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return SDB_ERR_CUDA;
+  }
+  const size_t smem = ring + 1024;
+  SDB_CUDA(cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tma_rate_kernel<<<grid, 64, smem, (cudaStream_t)stream>>>(tm, rows, k, box_rows, boxes_per_stage, stages, cycles_out);
+  SDB_LAUNCH_CHECK("tma_rate_kernel");
+  return SDB_OK;
+}
 
 // n: 128 or 256 (MMA N); mode bit 0: A from tensor memory, bit 1: two accumulators alternate; grid: CTAs (<= SMs).
 // cycles_out (device, int64): SM cycles CTA 0 needed for `iters` back-to-back 128 x n x 8 MMAs.
