@@ -288,10 +288,10 @@ int sdb_gemm_tf32_set_trace(unsigned long long* device_buffer);
 int sdb_debug_umma_rate(sdb_stream_t stream, int n, int mode, int iters, int grid, long long* cycles_out);
 
 /* Debug microbenchmark (csrc/umma_rate.cu): streams a (rows, k) fp32 row-major matrix through every SM's shared memory
- * with TMA boxes of box_rows x 128 bytes, boxes_per_stage boxes per stage, a ring of `stages` stages and no consumer
+ * with TMA boxes of box_rows x 128 bytes x kblocks_per_box k-blocks, boxes_per_stage boxes per stage, a ring of `stages` stages and no consumer
  * work -- the feed rate the GEMM main loop can count on.  cycles_out: SM cycles of CTA 0. */
-int sdb_debug_tma_rate(sdb_stream_t stream, const float* x, int rows, int k, int box_rows, int boxes_per_stage, int stages,
-                       int grid, long long* cycles_out);
+int sdb_debug_tma_rate(sdb_stream_t stream, const float* x, int rows, int k, int box_rows, int boxes_per_stage,
+                       int kblocks_per_box, int stages, int grid, long long* cycles_out);
 
 #ifdef __cplusplus
 }

@@ -150,15 +150,16 @@ __device__ __forceinline__ void spin_wait_(uint32_t bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(64, 1)
 tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int rows_total, int k_total, int box_rows, int boxes_per_stage,
-                int stages, long long* cycles_out) {
+                int kblocks_per_box, int stages, long long* cycles_out) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * 16];
   const uint32_t base = (smem_u32_(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32_(bars);
-  const int stage_bytes = boxes_per_stage * box_rows * 128;
+  const int box_bytes = box_rows * 128 * kblocks_per_box;          // smem image of one box: [k-block][row][32 floats]
+  const int stage_bytes = boxes_per_stage * box_bytes;
   const int tile_rows = boxes_per_stage * box_rows;
   const int n_tiles = (rows_total + tile_rows - 1) / tile_rows;
-  const int kbs = k_total / 32;
+  const int kbs = (k_total / 32 + kblocks_per_box - 1) / kblocks_per_box;   // stage loads per row tile
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * s));
@@ -175,10 +176,10 @@ tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int rows_total, int k_to
       for (int kb = 0; kb < kbs; ++kb) {
         spin_wait_(bar0 + 8u * (16 + stage), phase ^ 1u);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * stage), "r"((uint32_t)stage_bytes) : "memory");
-        for (int b = 0; b < boxes_per_stage; ++b)
-          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                       ::"r"(base + (uint32_t)(stage * stage_bytes + b * box_rows * 128)), "l"(&tm), "r"(bar0 + 8u * stage),
-                         "r"(kb * 32), "r"(tile * tile_rows + b * box_rows) : "memory");
+        for (int b = 0; b < boxes_per_stage; ++b)      // 3-D map {32 floats, rows, k-blocks}: one box = several k-blocks
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                       ::"r"(base + (uint32_t)(stage * stage_bytes + b * box_bytes)), "l"(&tm), "r"(bar0 + 8u * stage),
+                         "r"(0), "r"(tile * tile_rows + b * box_rows), "r"(kb * kblocks_per_box) : "memory");
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
   } else if (threadIdx.x == 32) {               // consumer: free the stage the moment it lands
@@ -200,13 +201,15 @@ tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int rows_total, int k_to
 
 // Streams a (rows x k) fp32 row-major matrix once through every SM's shared memory with TMA and reports the SM cycles
 // CTA 0 needed (the host times the launch with events for GB/s).  box_rows in {8..256}, boxes_per_stage >= 1,
-// stages <= 16, boxes_per_stage * box_rows * 128 * stages <= 200 KB, k % 32 == 0.
+// kblocks_per_box >= 1 (one TMA instruction fetches that many 128-byte k-blocks of every row of the box), stages <= 16,
+// ring <= 200 KB, k % 32 == 0.
 extern "C" int sdb_debug_tma_rate(sdb_stream_t stream, const float* x, int rows, int k, int box_rows, int boxes_per_stage,
-                                  int stages, int grid, long long* cycles_out) {
+                                  int kblocks_per_box, int stages, int grid, long long* cycles_out) {
   using namespace sdb;
   SDB_REQUIRE(x && cycles_out && rows > 0 && k > 0 && k % 32 == 0 && box_rows >= 8 && box_rows <= 256 &&
-              boxes_per_stage >= 1 && stages >= 1 && stages <= 16 && grid > 0, "debug_tma_rate: bad arguments");
-  const size_t ring = (size_t)boxes_per_stage * box_rows * 128 * stages;
+              boxes_per_stage >= 1 && kblocks_per_box >= 1 && kblocks_per_box <= 64 && stages >= 1 && stages <= 16 &&
+              grid > 0, "debug_tma_rate: bad arguments");
+  const size_t ring = (size_t)boxes_per_stage * box_rows * 128 * kblocks_per_box * stages;
   SDB_REQUIRE(ring <= 200 * 1024, "debug_tma_rate: ring larger than 200 KB");
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -219,11 +222,13 @@ extern "C" int sdb_debug_tma_rate(sdb_stream_t stream, const float* x, int rows,
     return SDB_ERR_CUDA;
   }
   CUtensorMap tm;
-  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)k * 4};
-  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = ((EncodeTiledFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)x, dims, strides, box, estr,
+  // the matrix seen as {32 floats of one k-block, rows, k-blocks}: a box of kblocks_per_box k-blocks lands as that many
+  // consecutive K-major 128B-swizzled tiles
+  const cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(k / 32)};
+  const cuuint64_t strides[2] = {(cuuint64_t)k * 4, 128};
+  const cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)kblocks_per_box};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((EncodeTiledFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, estr,
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -232,7 +237,8 @@ extern "C" int sdb_debug_tma_rate(sdb_stream_t stream, const float* x, int rows,
   }
   const size_t smem = ring + 1024;
   SDB_CUDA(cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tma_rate_kernel<<<grid, 64, smem, (cudaStream_t)stream>>>(tm, rows, k, box_rows, boxes_per_stage, stages, cycles_out);
+  tma_rate_kernel<<<grid, 64, smem, (cudaStream_t)stream>>>(tm, rows, k, box_rows, boxes_per_stage, kblocks_per_box, stages,
+                                                             cycles_out);
   SDB_LAUNCH_CHECK("tma_rate_kernel");
   return SDB_OK;
 }
