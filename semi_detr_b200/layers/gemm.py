@@ -75,9 +75,7 @@ def linear_grad_weight(g2d, x2d, with_bias_grad=False):
     k, m = g2d.shape
     n = x2d.shape[1]
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
-    # about two work items per SM, but never fewer than 8 k-blocks per split: every split reduce-adds a full output
-    # tile (64 KB of L2 atomics), which must stay small against the operand bytes it streams
-    splits = max(1, min(((k + 31) // 32) // 8, (2 * _sm_count(g2d.device)) // tiles))
+    splits = max(1, min((k + 31) // 32, (2 * _sm_count(g2d.device)) // tiles))
     if not with_bias_grad:
         return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits)
     buf = torch.zeros(m * n + m, dtype=torch.float32, device=g2d.device)      # one fill for both outputs
