@@ -104,3 +104,58 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _ssod_worker(rank, world, port, out):
+    """Cross-rank couplings of the teacher-student step: the pooled matched costs behind the GMM
+    threshold (dino_detr_ssod.py:303, dist_utils.py:5-30) -- ragged lengths, an empty rank, truncation at the buffer
+    size -- must give every rank the same pool, hence the same threshold."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from semi_detr_b200.ssod.dino_detr_ssod import concat_all_gather_1d
+        from semi_detr_b200.ssod.gmm import fit_gmm_threshold
+        g = torch.Generator().manual_seed(7)
+        pools = [torch.randn(37, generator=g) - 2.0, torch.randn(5, generator=g) + 1.5]   # rank 0 / rank 1 costs
+        got = concat_all_gather_1d(pools[rank])
+        assert torch.equal(got, torch.cat(pools)), "rank order and values of the pooled costs"
+        thr = fit_gmm_threshold(got.numpy())
+        both = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(both, torch.tensor([thr], dtype=torch.float64))
+        assert float(both[0]) == float(both[1]) == fit_gmm_threshold(torch.cat(pools).numpy())
+        # one rank without a single pseudo box: the other rank's costs alone decide
+        mine = pools[0] if rank == 0 else torch.zeros(0)
+        got = concat_all_gather_1d(mine)
+        assert torch.equal(got, pools[0])
+        # nothing anywhere: empty pool, threshold 0 (gmm.py), no hang
+        got = concat_all_gather_1d(torch.zeros(0))
+        assert got.numel() == 0 and fit_gmm_threshold(got.numpy()) == 0.0
+        # longer than the fixed buffer: each rank contributes its first max_len costs
+        long = torch.arange(10, dtype=torch.float32) + 100 * rank
+        got = concat_all_gather_1d(long, max_len=4)
+        assert torch.equal(got, torch.tensor([0., 1., 2., 3., 100., 101., 102., 103.]))
+        assert np.isfinite(thr)
+        if rank == 0:
+            out.put(("ok", thr))
+    except Exception as e:  # pragma: no cover
+        if rank == 0:
+            out.put(("fail", repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_ssod_cost_pool_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ssod_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(280)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    status, val = q.get(timeout=5)
+    assert status == "ok", val
