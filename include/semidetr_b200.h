@@ -92,6 +92,24 @@ int sdb_msda_backward_f64(sdb_stream_t stream, const double* grad_out, const dou
                           int num_query, int num_point, double* grad_value,
                           double* grad_sampling_loc, double* grad_attn_weight);
 
+/* bf16 storage variant (BASELINE.json configs[3]: "bf16 value / output, fp32 sampling math").  The reference op has no
+ * bf16 path (AT_DISPATCH_FLOATING_TYPES, ms_deform_attn_cuda.cu:64,134), so these extend the surface rather than
+ * replace something.  `value`, `out` and `grad_out` hold bf16 bit patterns (uint16_t); locations, weights and ALL
+ * three gradients are fp32 -- grad_value is accumulated with fp32 reductions and narrowed by the caller if needed.
+ * Built for channels == 32, num_heads == 8, num_point == 4; anything else returns SDB_ERR_UNSUPPORTED.  value / out /
+ * grad_out must be 8-byte aligned, the fp32 tensors 16-byte aligned. */
+int sdb_msda_forward_bf16(sdb_stream_t stream, const uint16_t* value, const int64_t* spatial_shapes,
+                          const int64_t* level_start_index, const float* sampling_loc, const float* attn_weight,
+                          int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                          int num_query, int num_point, uint16_t* out);
+
+int sdb_msda_backward_bf16(sdb_stream_t stream, const uint16_t* grad_out, const uint16_t* value,
+                           const int64_t* spatial_shapes, const int64_t* level_start_index,
+                           const float* sampling_loc, const float* attn_weight, int batch,
+                           int spatial_size, int num_heads, int channels, int num_levels,
+                           int num_query, int num_point, float* grad_value,
+                           float* grad_sampling_loc, float* grad_attn_weight);
+
 /* Fused prologue (NOT part of the reference surface, apply() stays the compatibility
  * path).  Takes the module's RAW linear outputs instead of materialised locations / weights
  * (modules/ms_deform_attn.py:96-112):

@@ -22,6 +22,8 @@ SIGNATURES = {
     "sdb_msda_forward_f64": _MSDA_FWD,
     "sdb_msda_backward_f32": _MSDA_BWD,
     "sdb_msda_backward_f64": _MSDA_BWD,
+    "sdb_msda_forward_bf16": _MSDA_FWD,
+    "sdb_msda_backward_bf16": _MSDA_BWD,
     "sdb_msda_set_variant": [c_int, c_int],
     "sdb_msda_forward_tma_f32": [c_void_p, c_int] + [c_void_p] * 6 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p],
     "sdb_msda_fused_forward_f32": [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p],

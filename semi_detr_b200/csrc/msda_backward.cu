@@ -122,9 +122,10 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // kFused: `loc` / `attn` are the RAW sampling offsets / attention logits, (ref, ref_dim) the reference points, and
 // the outputs are the gradients w.r.t. those raw tensors (location arithmetic and softmax differentiated here).
-template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false>
+// V: storage type of `grad_out` and `value` (float or __nv_bfloat16); every gradient is accumulated and written in fp32.
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
+msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                     const float* __restrict__ loc, const float* __restrict__ attn, int batch, int S, int L,
                     int Lq, int tiled, float* __restrict__ grad_value, float* __restrict__ grad_loc,
@@ -150,7 +151,7 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
     TileCursor<TH, TW> cur;
     cur.seek(lt, L, tile, tiled != 0, Lq);
     const long long img = (long long)n * S * px_stride + m * 32 + 4 * j;
-    const float* vhead = value + img;
+    const V* vhead = value + img;
     float* gvhead = grad_value + img;
 
 #pragma unroll 1
@@ -161,7 +162,7 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
       const float* lp = loc + pair * LP * 2;
       const float* ap = attn + pair * LP;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) g = ld_stream_f4(reinterpret_cast<const float4*>(grad_out + pair * 32 + 4 * j));
+      if (live) g = Chan4<V>::stream_in(grad_out + pair * 32 + 4 * j);
 
 #pragma unroll 1
       for (int c0 = 0; c0 < LP; c0 += 16) {
@@ -201,14 +202,14 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
             const float hh = 1.f - lh, hw = 1.f - lw;
             const float4 tg = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
             const int off = offm & ~15;
-            const float* pv = vhead + off;
+            const V* pv = vhead + off;
             float* pg = gvhead + off;
             float4 v00, v01, v10, v11;
             const bool q00 = offm & 1, q01 = offm & 2, q10 = offm & 4, q11 = offm & 8;
-            if (q00) v00 = __ldg(reinterpret_cast<const float4*>(pv));
-            if (q01) v01 = __ldg(reinterpret_cast<const float4*>(pv + px_stride));
-            if (q10) v10 = __ldg(reinterpret_cast<const float4*>(pv + ws));
-            if (q11) v11 = __ldg(reinterpret_cast<const float4*>(pv + ws + px_stride));
+            if (q00) v00 = Chan4<V>::gather(pv);
+            if (q01) v01 = Chan4<V>::gather(pv + px_stride);
+            if (q10) v10 = Chan4<V>::gather(pv + ws);
+            if (q11) v11 = Chan4<V>::gather(pv + ws + px_stride);
             {
               // the reductions need no loaded data: they fill the wait for the four corner loads
               const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
@@ -277,12 +278,12 @@ msda_bwd_d32_kernel(const float* __restrict__ grad_out, const float* __restrict_
   }
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false>
-static int launch_bwd_d32(cudaStream_t st, const float* grad_out, const float* value, const int64_t* shapes,
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float>
+static int launch_bwd_d32(cudaStream_t st, const V* grad_out, const V* value, const int64_t* shapes,
                           const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int M,
                           int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn,
                           const float* ref = nullptr, int ref_dim = 0) {
-  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kFused>;
+  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kFused, V>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -398,6 +399,44 @@ extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* gra
     default: return launch_bwd_d32<128, 4, 8, 4, true>(SDB_FBWD_ARGS);  // 115 registers, no spills, 16 warps / SM
   }
 #undef SDB_FBWD_ARGS
+}
+
+// bf16 storage for `grad_out` and `value`; the three gradients are fp32 (grad_value is accumulated with fp32
+// reductions -- the caller narrows it if it needs a bf16 gradient).
+extern "C" int sdb_msda_backward_bf16(sdb_stream_t stream, const uint16_t* grad_out, const uint16_t* value,
+                                      const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                      const float* sampling_loc, const float* attn_weight, int batch,
+                                      int spatial_size, int num_heads, int channels, int num_levels,
+                                      int num_query, int num_point, float* grad_value, float* grad_sampling_loc,
+                                      float* grad_attn_weight) {
+  using namespace sdb;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = spatial_size, M = num_heads, L = num_levels, Lq = num_query, P = num_point;
+  SDB_REQUIRE(batch >= 0 && S >= 0 && M > 0 && channels > 0 && L > 0 && Lq >= 0 && P > 0,
+              "msda_backward_bf16: bad sizes batch=%d spatial=%d heads=%d channels=%d levels=%d query=%d point=%d",
+              batch, S, M, channels, L, Lq, P);
+  if (!(channels == 32 && M == 8 && P == 4 && L <= kMaxLevels && (long long)S * M * channels < (1ll << 31))) {
+    set_error("msda_backward_bf16: built for channels=32, heads=8, points=4, levels<=%d (got C=%d M=%d P=%d L=%d)",
+              kMaxLevels, channels, M, P, L);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  const long long nv = (long long)batch * S * M * channels;
+  if (nv > 0) {
+    SDB_REQUIRE(grad_value, "msda_backward_bf16: null grad_value");
+    SDB_CUDA(cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)nv, st));
+  }
+  if ((long long)batch * Lq == 0) return SDB_OK;
+  SDB_REQUIRE(grad_out && value && spatial_shapes && level_start_index && sampling_loc && attn_weight &&
+              grad_sampling_loc && grad_attn_weight, "msda_backward_bf16: null pointer");
+  SDB_REQUIRE(((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(grad_out)) & 7) == 0 &&
+              ((reinterpret_cast<uintptr_t>(sampling_loc) | reinterpret_cast<uintptr_t>(attn_weight) |
+                reinterpret_cast<uintptr_t>(grad_value) | reinterpret_cast<uintptr_t>(grad_sampling_loc) |
+                reinterpret_cast<uintptr_t>(grad_attn_weight)) & 15) == 0,
+              "msda_backward_bf16: value/grad_out must be 8-byte aligned, the fp32 tensors 16-byte aligned");
+  return launch_bwd_d32<128, 4, 8, 4, false, __nv_bfloat16>(
+      st, reinterpret_cast<const __nv_bfloat16*>(grad_out), reinterpret_cast<const __nv_bfloat16*>(value),
+      spatial_shapes, level_start_index, sampling_loc, attn_weight, batch, S, M, L, Lq, P, grad_value,
+      grad_sampling_loc, grad_attn_weight);
 }
 
 extern "C" int sdb_msda_backward_f64(sdb_stream_t stream, const double* grad_out, const double* value,

@@ -103,12 +103,14 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // kFused: `loc` / `attn` hold the RAW sampling offsets / attention logits and (ref, ref_dim) the reference points;
 // locations and softmax weights are formed in registers (fused_prologue).
-template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep, bool kFused = false>
+// V: storage type of `value` and `out` (float, or __nv_bfloat16 for the bf16 configuration; arithmetic is fp32).
+template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep, bool kFused = false,
+          typename V = float>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+msda_fwd_d32_kernel(const V* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, int batch, int S, int M, int L, int Lq, int P,
-                    int tiled, float* __restrict__ out, const float* __restrict__ ref = nullptr, int ref_dim = 0) {
+                    int tiled, V* __restrict__ out, const float* __restrict__ ref = nullptr, int ref_dim = 0) {
   __shared__ LevelTable lt;
   const int px_stride = kHeads > 0 ? kHeads * 32 : M * 32;
   load_levels<TH, TW>(lt, shapes, lsi, L, px_stride);
@@ -127,7 +129,7 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
     const int n = (int)(t2 / n_tiles);
     TileCursor<TH, TW> cur;
     cur.seek(lt, L, tile, tiled != 0, Lq);
-    const float* vhead = value + (long long)n * S * px_stride + m * 32 + 4 * j;
+    const V* vhead = value + (long long)n * S * px_stride + m * 32 + 4 * j;
 
     // every group of the warp runs the same trip counts: shuffles stay full-mask and convergent
     static_assert(TQ % kGroups == 0, "tile must be a whole number of CTA passes");
@@ -183,13 +185,13 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
           float4 v[kStep][4];
 #pragma unroll
           for (int u = 0; u < kStep; ++u) {
-            const float* pa = vhead + off[u];
-            const float* pa2 = pa + ws[u];
+            const V* pa = vhead + off[u];
+            const V* pa2 = pa + ws[u];
             // a corner with zero weight (outside the map, or a dead / padded point) is neither loaded nor used
-            if (w[u][0] != 0.f) v[u][0] = __ldg(reinterpret_cast<const float4*>(pa));
-            if (w[u][1] != 0.f) v[u][1] = __ldg(reinterpret_cast<const float4*>(pa + px_stride));
-            if (w[u][2] != 0.f) v[u][2] = __ldg(reinterpret_cast<const float4*>(pa2));
-            if (w[u][3] != 0.f) v[u][3] = __ldg(reinterpret_cast<const float4*>(pa2 + px_stride));
+            if (w[u][0] != 0.f) v[u][0] = Chan4<V>::gather(pa);
+            if (w[u][1] != 0.f) v[u][1] = Chan4<V>::gather(pa + px_stride);
+            if (w[u][2] != 0.f) v[u][2] = Chan4<V>::gather(pa2);
+            if (w[u][3] != 0.f) v[u][3] = Chan4<V>::gather(pa2 + px_stride);
           }
 #pragma unroll
           for (int u = 0; u < kStep; ++u)
@@ -198,16 +200,17 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
               if (w[u][k] != 0.f) fma4(acc, w[u][k], v[u][k]);
         }
       }
-      if (live) st_stream_f4(reinterpret_cast<float4*>(out + pair * 32 + 4 * j), acc);
+      if (live) Chan4<V>::stream_out(out + pair * 32 + 4 * j, acc);
     }
   }
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep, bool kFused = false>
-static int launch_fwd_d32(cudaStream_t st, const float* value, const int64_t* shapes, const int64_t* lsi,
+template <int kThreads, int TH, int TW, int kMinBlocks, int kHeads, int kPoints, int kStep, bool kFused = false,
+          typename V = float>
+static int launch_fwd_d32(cudaStream_t st, const V* value, const int64_t* shapes, const int64_t* lsi,
                           const float* loc, const float* attn, int batch, int S, int M, int L, int Lq, int P,
-                          float* out, const float* ref = nullptr, int ref_dim = 0) {
-  auto kern = msda_fwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kHeads, kPoints, kStep, kFused>;
+                          V* out, const float* ref = nullptr, int ref_dim = 0) {
+  auto kern = msda_fwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kHeads, kPoints, kStep, kFused, V>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     // all of the unified L1/shared array as cache: the kernel's reuse lives in L1
@@ -292,6 +295,40 @@ extern "C" int sdb_msda_forward_f64(sdb_stream_t stream, const double* value, co
   return sdb::msda_forward<double>((cudaStream_t)stream, value, spatial_shapes, level_start_index, sampling_loc,
                                    attn_weight, batch, spatial_size, num_heads, channels, num_levels, num_query,
                                    num_point, out);
+}
+
+// bf16 storage for `value` and `out` (BASELINE.json configs[3]: bf16 value / output, fp32 sampling math).  Tuned
+// shape only -- the reference op has no bf16 path at all, so there is nothing generic to mirror.
+extern "C" int sdb_msda_forward_bf16(sdb_stream_t stream, const uint16_t* value, const int64_t* spatial_shapes,
+                                     const int64_t* level_start_index, const float* sampling_loc,
+                                     const float* attn_weight, int batch, int spatial_size, int num_heads,
+                                     int channels, int num_levels, int num_query, int num_point, uint16_t* out) {
+  using namespace sdb;
+  const int S = spatial_size, M = num_heads, L = num_levels, Lq = num_query, P = num_point;
+  SDB_REQUIRE(batch >= 0 && S >= 0 && M > 0 && channels > 0 && L > 0 && Lq >= 0 && P > 0,
+              "msda_forward_bf16: bad sizes batch=%d spatial=%d heads=%d channels=%d levels=%d query=%d point=%d",
+              batch, S, M, channels, L, Lq, P);
+  if (!(channels == 32 && M == 8 && P == 4 && L <= kMaxLevels && (long long)S * M * channels < (1ll << 31))) {
+    set_error("msda_forward_bf16: built for channels=32, heads=8, points=4, levels<=%d (got C=%d M=%d P=%d L=%d)",
+              kMaxLevels, channels, M, P, L);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  if ((long long)batch * Lq == 0) return SDB_OK;
+  SDB_REQUIRE(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
+              "msda_forward_bf16: null pointer");
+  SDB_REQUIRE(((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(out)) & 7) == 0 &&
+              ((reinterpret_cast<uintptr_t>(sampling_loc) | reinterpret_cast<uintptr_t>(attn_weight)) & 15) == 0,
+              "msda_forward_bf16: value/out must be 8-byte aligned, sampling_loc/attn_weight 16-byte aligned");
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(value);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Lq == S)
+    return launch_fwd_d32<256, 8, 8, 3, 8, 4, 2, false, __nv_bfloat16>(st, v, spatial_shapes, level_start_index,
+                                                                      sampling_loc, attn_weight, batch, S, M, L, Lq,
+                                                                      P, o);
+  return launch_fwd_d32<256, 4, 8, 3, 8, 4, 2, false, __nv_bfloat16>(st, v, spatial_shapes, level_start_index,
+                                                                    sampling_loc, attn_weight, batch, S, M, L, Lq, P,
+                                                                    o);
 }
 
 extern "C" int sdb_msda_fused_forward_f32(sdb_stream_t stream, const float* value, const int64_t* spatial_shapes,

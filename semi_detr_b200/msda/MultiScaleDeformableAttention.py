@@ -14,6 +14,9 @@ import torch
 from .. import _lib
 
 _FLOAT = (torch.float32, torch.float64)
+# bf16 storage for value / output / grad_output with fp32 locations, weights and gradients (BASELINE.json configs[3]).
+# The reference op has no such path (AT_DISPATCH_FLOATING_TYPES); this extends the surface, it replaces nothing.
+_BF16 = torch.bfloat16
 
 # TMA-staged forward for encoder self-attention (num_query == spatial_size): see csrc/msda_forward_tma.cu.
 # Bit-identical to the L1-gather kernel but measured slower on B200 (187 vs 138 us on the N=2 microbench: both are
@@ -107,6 +110,8 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
     _index_tensors(spatial_shapes, level_start_index)
+    if value.dtype == _BF16:
+        return _forward_bf16(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
     if value.dtype not in _FLOAT:
         raise RuntimeError(f'"ms_deform_attn_forward_cuda" not implemented for \'{value.dtype}\'')
     if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
@@ -133,6 +138,9 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
     _index_tensors(spatial_shapes, level_start_index)
+    if value.dtype == _BF16:
+        return _backward_bf16(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                              im2col_step)
     if value.dtype not in _FLOAT:
         raise RuntimeError(f'"ms_deform_attn_backward_cuda" not implemented for \'{value.dtype}\'')
     if not (sampling_loc.dtype == attn_weight.dtype == grad_output.dtype == value.dtype):
@@ -151,6 +159,54 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     _lib.check(rc, "ms_deform_attn_backward")
     _lib.LAUNCHES["msda_backward"] += 1
     return [grad_value, grad_loc, grad_attn]
+
+
+# ---- bf16 storage (not part of the reference extension surface) -------------------------------------------
+
+def _bf16_dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step, what):
+    if sampling_loc.dtype != torch.float32 or attn_weight.dtype != torch.float32:
+        raise RuntimeError(f"{what}: with a bfloat16 value, sampling_loc and attn_weight must be float32 "
+                           "(the sampling arithmetic stays fp32)")
+    dims = _dims(value, spatial_shapes, sampling_loc, im2col_step)
+    b, s, m, d, l, q, p = dims
+    if not (d == 32 and m == 8 and p == 4):
+        raise RuntimeError(f"{what}: the bfloat16 kernels are built for 8 heads x 32 channels x 4 points "
+                           f"(got {m} x {d} x {p}); use float32")
+    return dims
+
+
+def _forward_bf16(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    b, s, m, d, l, q, p = _bf16_dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step,
+                                     "ms_deform_attn_forward")
+    out = torch.empty((b, q, m * d), dtype=_BF16, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _timed("fwd", b, s, q, lambda: _lib.lib().sdb_msda_forward_bf16(
+            _lib.current_stream(value.device), value.data_ptr(), spatial_shapes.data_ptr(),
+            level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+            b, s, m, d, l, q, p, out.data_ptr()))
+    _lib.check(rc, "ms_deform_attn_forward (bf16)")
+    _lib.LAUNCHES["msda_forward"] += 1
+    return out
+
+
+def _backward_bf16(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step):
+    """-> [grad_value (bf16, narrowed from the fp32 accumulation), grad_sampling_loc fp32, grad_attn_weight fp32]"""
+    if grad_output.dtype != _BF16:
+        raise RuntimeError("ms_deform_attn_backward: grad_output must be bfloat16 like value")
+    b, s, m, d, l, q, p = _bf16_dims(value, spatial_shapes, sampling_loc, attn_weight, im2col_step,
+                                     "ms_deform_attn_backward")
+    grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)   # zero-filled by the call
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device):
+        rc = _timed("bwd", b, s, q, lambda: _lib.lib().sdb_msda_backward_bf16(
+            _lib.current_stream(value.device), grad_output.data_ptr(), value.data_ptr(),
+            spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+            attn_weight.data_ptr(), b, s, m, d, l, q, p, grad_value.data_ptr(), grad_loc.data_ptr(),
+            grad_attn.data_ptr()))
+    _lib.check(rc, "ms_deform_attn_backward (bf16)")
+    _lib.LAUNCHES["msda_backward"] += 1
+    return [grad_value.to(_BF16), grad_loc, grad_attn]
 
 
 # ---- fused prologue (not part of the reference extension surface) ----------------------------------------

@@ -59,3 +59,31 @@ def test_empty_query_and_out_of_range():
     assert not gv.any() and not gl.any() and not ga.any()
     out0 = O.msda_forward(value, shapes, start, loc[:, :0], attn[:, :0])
     assert out0.shape == (1, 0, 8)
+
+
+def test_bf16_rounding_is_torch_round_to_nearest_even():
+    """The bf16-storage oracle (configs[3]) rounds exactly like ``tensor.to(torch.bfloat16)`` / ``cvt.rn.bf16.f32``."""
+    import torch
+    rng = np.random.default_rng(0)
+    x = np.concatenate([(rng.standard_normal(100000) * 10.0 ** rng.uniform(-30, 30, 100000)).astype(np.float32),
+                        np.array([0., -0., np.inf, -np.inf, 1.00390625, 1.01171875, 3.3895314e38, 1e-40, -1e-45],
+                                 np.float32)])
+    got = O.bf16_round(x)
+    want = torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.isnan(O.bf16_round(np.array([np.nan], np.float32))[0])
+
+
+def test_bf16_variant_is_the_fp_op_on_rounded_inputs(msda_golden):
+    """bf16 storage changes what is stored, not the arithmetic: forward = round(exact op on rounded value),
+    backward = exact adjoint on rounded value / grad_output."""
+    c = msda_golden["small_d32"]
+    levels = [tuple(int(v) for v in r) for r in c["shapes"]]
+    rounded, exact = O.msda_forward_bf16(c["value"], levels, c["start"], c["loc"], c["attn"])
+    want = O.msda_forward(O.bf16_round(c["value"]), levels, c["start"], c["loc"], c["attn"])
+    assert np.array_equal(exact, want)
+    assert np.allclose(rounded, exact, rtol=2.0 ** -8, atol=1e-30)
+    gv, gl, ga = O.msda_backward_bf16(c["value"], levels, c["start"], c["loc"], c["attn"], c["gout"])
+    wv, wl, wa = O.msda_backward(O.bf16_round(c["value"]), levels, c["start"], c["loc"], c["attn"],
+                                 O.bf16_round(c["gout"]))
+    assert np.array_equal(gv, wv) and np.array_equal(gl, wl) and np.array_equal(ga, wa)
