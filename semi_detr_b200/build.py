@@ -22,7 +22,7 @@ EXTRA = {
     # the matching cost must round like torch's separately-rounded elementwise kernels
     "hungarian.cu": ["-fmad=false"],
 }
-SOURCES = ["abi.cu", "msda_forward.cu", "msda_forward_tma.cu", "msda_backward.cu", "hungarian.cu", "ema.cu", "layernorm.cu", "optimizer.cu", "colsum.cu", "gemm_tf32.cu", "umma_rate.cu"]
+SOURCES = ["abi.cu", "msda_forward.cu", "msda_forward_tma.cu", "msda_backward.cu", "msda_backward_x8.cu", "hungarian.cu", "ema.cu", "layernorm.cu", "optimizer.cu", "colsum.cu", "gemm_tf32.cu", "umma_rate.cu"]
 
 
 def _stale():
