@@ -128,7 +128,8 @@ constexpr unsigned kFull = 0xffffffffu;
 // kFused: `loc` / `attn` are the RAW sampling offsets / attention logits, (ref, ref_dim) the reference points, and
 // the outputs are the gradients w.r.t. those raw tensors (location arithmetic and softmax differentiated here).
 // V: storage type of `grad_out` and `value` (float or __nv_bfloat16); every gradient is accumulated and written in fp32.
-template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float>
+// kDepth: points whose corner loads are in flight before the first use (1 = the validated default; 2 / 4 experimental).
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float, int kDepth = 1>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -195,6 +196,7 @@ msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
           const int ws = lt.wstr[lvl];
           float d[4][4];
           float klh = 0.f, klw = 0.f, ka = 0.f;   // the point this lane finalises: batch index j >> 1
+          if constexpr (kDepth == 1) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int sl = 2 * b + (r >> 1);
@@ -227,6 +229,49 @@ msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
             d[r][1] = q01 ? dot4(g, v01) : 0.f;
             d[r][2] = q10 ? dot4(g, v10) : 0.f;
             d[r][3] = q11 ? dot4(g, v11) : 0.f;
+          }
+          } else {
+            // kDepth points in flight: the corner loads (and reductions) of kDepth points are issued before the first
+            // dot product waits for data.  In the kDepth == 1 form every point exposes one full load latency (ncu
+            // source view: 32 % of the stall samples sit on the first FMUL after each point's loads, 4 loads in
+            // flight per warp -- profiles/ncu_msda_stalls_r1.txt).
+            static_assert(4 % kDepth == 0, "kDepth must divide the batch of 4 points");
+#pragma unroll
+            for (int r0 = 0; r0 < 4; r0 += kDepth) {
+              float4 v[kDepth][4];
+              int okm[kDepth];
+#pragma unroll
+              for (int u = 0; u < kDepth; ++u) {
+                const int r = r0 + u;
+                const int sl = 2 * b + (r >> 1);
+                const BwdPrep& src = (r & 1) ? p1 : p0;
+                const int offm = __shfl_sync(kFull, src.offm, sl, 8);
+                const float lh = __shfl_sync(kFull, src.lh, sl, 8);
+                const float lw = __shfl_sync(kFull, src.lw, sl, 8);
+                const float a = __shfl_sync(kFull, src.a, sl, 8);
+                if ((j >> 1) == r) { klh = lh; klw = lw; ka = a; }
+                const float hh = 1.f - lh, hw = 1.f - lw;
+                const float4 tg = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+                const int off = offm & ~15;
+                const V* pv = vhead + off;
+                float* pg = gvhead + off;
+                okm[u] = offm;
+                const bool q00 = offm & 1, q01 = offm & 2, q10 = offm & 4, q11 = offm & 8;
+                if (q00) v[u][0] = Chan4<V>::gather(pv);
+                if (q01) v[u][1] = Chan4<V>::gather(pv + px_stride);
+                if (q10) v[u][2] = Chan4<V>::gather(pv + ws);
+                if (q11) v[u][3] = Chan4<V>::gather(pv + ws + px_stride);
+                const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
+                red_add_f4_if(q00, pg, w00 * tg.x, w00 * tg.y, w00 * tg.z, w00 * tg.w);
+                red_add_f4_if(q01, pg + px_stride, w01 * tg.x, w01 * tg.y, w01 * tg.z, w01 * tg.w);
+                red_add_f4_if(q10, pg + ws, w10 * tg.x, w10 * tg.y, w10 * tg.z, w10 * tg.w);
+                red_add_f4_if(q11, pg + ws + px_stride, w11 * tg.x, w11 * tg.y, w11 * tg.z, w11 * tg.w);
+              }
+#pragma unroll
+              for (int u = 0; u < kDepth; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[r0 + u][k] = (okm[u] >> k) & 1 ? dot4(g, v[u][k]) : 0.f;
+            }
           }
           // reduce-scatter over the 8 lanes: afterwards lanes (j, j^1) hold the sums of point j >> 1
           float e[2][4], f[4];
@@ -283,12 +328,12 @@ msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
   }
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float>
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float, int kDepth = 1>
 static int launch_bwd_d32(cudaStream_t st, const V* grad_out, const V* value, const int64_t* shapes,
                           const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int M,
                           int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn,
                           const float* ref = nullptr, int ref_dim = 0) {
-  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kFused, V>;
+  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kFused, V, kDepth>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -343,6 +388,10 @@ static int msda_backward(cudaStream_t st, const T* grad_out, const T* value, con
         case 5: return launch_bwd_d32<128, 4, 8, 4>(SDB_BWD_ARGS);
         case 7: return msda_backward_x8(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, Lq, grad_value,
                                         grad_loc, grad_attn, nullptr, 0);
+        // experimental (not yet run on hardware): 2 / 4 points of corner loads in flight per warp
+        case 10: return launch_bwd_d32<128, 4, 8, 4, false, float, 2>(SDB_BWD_ARGS);
+        case 11: return launch_bwd_d32<128, 4, 8, 3, false, float, 2>(SDB_BWD_ARGS);
+        case 12: return launch_bwd_d32<128, 4, 8, 3, false, float, 4>(SDB_BWD_ARGS);
         default: return launch_bwd_d32<512, 8, 8, 1>(SDB_BWD_ARGS);
       }
     }
@@ -406,6 +455,10 @@ extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* gra
     case 7: return msda_backward_x8(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets,
                                     attn_logits, batch, S, L, Lq, grad_value, grad_offsets, grad_attn_logits,
                                     reference_points, ref_dim);   // experimental: 4 lanes x 8 channels per pair
+    // experimental (not yet run on hardware): 2 / 4 points of corner loads in flight per warp
+    case 10: return launch_bwd_d32<128, 4, 8, 4, true, float, 2>(SDB_FBWD_ARGS);
+    case 11: return launch_bwd_d32<128, 4, 8, 3, true, float, 2>(SDB_FBWD_ARGS);
+    case 12: return launch_bwd_d32<128, 4, 8, 3, true, float, 4>(SDB_FBWD_ARGS);
     default: return launch_bwd_d32<128, 4, 8, 4, true>(SDB_FBWD_ARGS);  // 115 registers, no spills, 16 warps / SM
   }
 #undef SDB_FBWD_ARGS

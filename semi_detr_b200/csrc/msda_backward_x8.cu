@@ -58,6 +58,17 @@ __device__ __forceinline__ float dot8(const float4& a0, const float4& a1, const 
 
 constexpr unsigned kAll = 0xffffffffu;
 
+// both 16-byte halves of a lane's 8 channels under ONE branch (ptxas turns a predicated vector `red` into a branch
+// region of its own anyway: see profiles/sass_msda_bwd_by_line_r1.txt)
+__device__ __forceinline__ void red_add_f8_if(bool pred, float* p, float w, const float4& t0, const float4& t1) {
+  if (pred)
+    asm volatile(
+        "red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n\t"
+        "red.global.add.v4.f32 [%0+16], {%5,%6,%7,%8};"
+        ::"l"(p), "f"(w * t0.x), "f"(w * t0.y), "f"(w * t0.z), "f"(w * t0.w), "f"(w * t1.x), "f"(w * t1.y),
+          "f"(w * t1.z), "f"(w * t1.w));   // no "memory" clobber: grad_value is write-only here
+}
+
 __device__ __forceinline__ float group4_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(kAll, v, 2, 4));
   return fmaxf(v, __shfl_xor_sync(kAll, v, 1, 4));
@@ -195,14 +206,10 @@ msda_bwd_x8_kernel(const float* __restrict__ grad_out, const float* __restrict__
             {
               // the reductions need no loaded data: they fill the wait for the corner loads
               const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
-              red_add_f4_if(q00, pg, w00 * t0.x, w00 * t0.y, w00 * t0.z, w00 * t0.w);
-              red_add_f4_if(q00, pg + 4, w00 * t1.x, w00 * t1.y, w00 * t1.z, w00 * t1.w);
-              red_add_f4_if(q01, pg + px_stride, w01 * t0.x, w01 * t0.y, w01 * t0.z, w01 * t0.w);
-              red_add_f4_if(q01, pg + px_stride + 4, w01 * t1.x, w01 * t1.y, w01 * t1.z, w01 * t1.w);
-              red_add_f4_if(q10, pg + ws, w10 * t0.x, w10 * t0.y, w10 * t0.z, w10 * t0.w);
-              red_add_f4_if(q10, pg + ws + 4, w10 * t1.x, w10 * t1.y, w10 * t1.z, w10 * t1.w);
-              red_add_f4_if(q11, pg + ws + px_stride, w11 * t0.x, w11 * t0.y, w11 * t0.z, w11 * t0.w);
-              red_add_f4_if(q11, pg + ws + px_stride + 4, w11 * t1.x, w11 * t1.y, w11 * t1.z, w11 * t1.w);
+              red_add_f8_if(q00, pg, w00, t0, t1);
+              red_add_f8_if(q01, pg + px_stride, w01, t0, t1);
+              red_add_f8_if(q10, pg + ws, w10, t0, t1);
+              red_add_f8_if(q11, pg + ws + px_stride, w11, t0, t1);
             }
             d[r][0] = q00 ? dot8(g0, g1, a00, b00) : 0.f;
             d[r][1] = q01 ? dot8(g0, g1, a01, b01) : 0.f;

@@ -51,6 +51,17 @@ def test_sass_is_sm100a_only(libpath):
     assert archs == {"sm_100a"}, archs
 
 
+def test_validated_kernels_are_unchanged(libpath):
+    """Kernels whose parity and timing were measured on a B200 must still compile to the same SASS: work done without a
+    GPU (new template parameters, shared headers, new opt-in variants) may add kernels but not alter validated ones
+    (tools/sass_fingerprint.py, profiles/sass_validated_r1.json; hashes are per nvcc version)."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_fingerprint.py")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "validated kernels unchanged" in r.stdout or "fingerprints do not apply" in r.stdout
+
+
 def test_argument_errors_without_gpu(libpath):
     """Argument validation happens before any CUDA call, so it is checkable on the CPU box."""
     from semi_detr_b200 import _lib

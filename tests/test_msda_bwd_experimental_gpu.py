@@ -1,9 +1,16 @@
-"""Experimental MSDA backward with 4 lanes x 8 channels per (query, head) pair (csrc/msda_backward_x8.cu, backward
-variant 7) against the oracle and against the validated 8-lane kernels.
+"""Experimental MSDA backward variants against the oracle and against the validated default kernel:
+
+  7       4 lanes x 8 channels per (query, head) pair (csrc/msda_backward_x8.cu): 0.56x the instructions per pair
+  10, 11  the 8-lane kernel with the corner loads of 2 points in flight per warp (4 / 3 CTAs per SM)
+  12      ... of 4 points in flight (3 CTAs per SM)
+
+Motivation (profiles/ncu_msda_stalls_r1.txt, ncu source view of the encoder backward): the default kernel has 4 loads
+in flight per warp and waits one L2 latency per point (32 % of the stall samples sit on the first FMUL after each
+point's loads), issues 46 % of its slots, and misses the instruction cache (hit rate 85.7 %).
 
 NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent); runs only with SDB_RUN_UNVALIDATED=1:
 
-    SDB_RUN_UNVALIDATED=1 python -m pytest tests/test_msda_x8_gpu.py -m gpu -q && python tools/bwd_variants.py
+    SDB_RUN_UNVALIDATED=1 python -m pytest tests/test_msda_bwd_experimental_gpu.py -m gpu -q && python tools/bwd_variants.py
 """
 import os
 
@@ -15,9 +22,10 @@ from oracle import msda_oracle as O
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("SDB_RUN_UNVALIDATED") != "1",
-                                 reason="x8 backward kernel has not run on hardware yet (set SDB_RUN_UNVALIDATED=1)")]
+                                 reason="experimental backward variants have not run on hardware yet "
+                                        "(set SDB_RUN_UNVALIDATED=1)")]
 
-X8 = 7
+VARIANTS = [7, 10, 11, 12]
 
 
 def _relerr(a, b):
@@ -48,12 +56,13 @@ class _variant:
 @pytest.mark.parametrize("levels", [[(19, 27), (10, 14), (5, 7), (3, 4)], [(38, 54), (19, 27), (10, 14), (5, 7), (3, 4)],
                                     [(9, 8), (4, 5)], [(6, 5)]], ids=["4lvl", "5lvl", "2lvl", "1lvl"])
 @pytest.mark.parametrize("mode,Lq", [("encoder", None), ("wide", 300), ("uniform", 77)])
-def test_unfused_vs_oracle_and_default_kernel(levels, mode, Lq):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_unfused_vs_oracle_and_default_kernel(variant, levels, mode, Lq):
     from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
     from semi_detr_b200.synthetic import msda_inputs
     x = msda_inputs(levels, N=2, Lq=Lq, mode=mode, seed=21)
     args = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["gout"], 64)
-    with _variant(X8):
+    with _variant(variant):
         got = MSDA.ms_deform_attn_backward(*args)
     base = MSDA.ms_deform_attn_backward(*args)
     gv, gl, ga = O.msda_backward(x["value"].cpu().numpy(), levels, x["start"].cpu().numpy(), x["loc"].cpu().numpy(),
@@ -65,18 +74,19 @@ def test_unfused_vs_oracle_and_default_kernel(levels, mode, Lq):
             g, b, r = g * mask, b * mask, r * mask
         assert _relerr(g, r) < 1e-5, k
         np.testing.assert_allclose(g.numpy(), r.numpy(), rtol=1e-3, atol=2e-3, err_msg=k)
-        assert _relerr(g, b) < 1e-5, k + " vs the 8-lane kernel"     # same arithmetic, different summation order
+        assert _relerr(g, b) < 1e-5, k + " vs the default kernel"     # same arithmetic, different summation order
 
 
 @pytest.mark.parametrize("levels,Lq,ref_dim", [([(19, 27), (10, 14), (5, 7), (3, 4)], None, 2),
                                                ([(19, 27), (10, 14), (5, 7), (3, 4)], 211, 4),
                                                ([(9, 8), (4, 5)], 37, 4), ([(6, 5)], None, 2)])
-def test_fused_vs_default_fused_kernel(levels, Lq, ref_dim):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_fused_vs_default_fused_kernel(variant, levels, Lq, ref_dim):
     from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
     from tests_fused_inputs import fused_inputs
     S = sum(h * w for h, w in levels)
     value, shapes, start, ref, off, logits, gout = fused_inputs(levels, 2, Lq or S, ref_dim, seed=len(levels) + ref_dim)
-    with _variant(X8):
+    with _variant(variant):
         got = MSDA.ms_deform_attn_fused_backward(value, shapes, start, ref, off, logits, gout)
     base = MSDA.ms_deform_attn_fused_backward(value, shapes, start, ref, off, logits, gout)
     for g, b, k in zip(got, base, ("grad_value", "grad_offsets", "grad_logits")):
@@ -84,14 +94,15 @@ def test_fused_vs_default_fused_kernel(levels, Lq, ref_dim):
         assert torch.allclose(g, b, rtol=1e-3, atol=2e-3 * float(b.abs().max())), k
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_full_size_properties(variant):
     """Train-step encoder shape: grad_value conserves mass (sum over pixels = sum_q a * w * grad_out over valid
     corners is the same number the 8-lane kernel produces), every output finite."""
     from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
     from semi_detr_b200.synthetic import COCO_4SCALE_LEVELS, msda_inputs
     x = msda_inputs(COCO_4SCALE_LEVELS, N=2, mode="encoder", seed=1)
     args = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["gout"], 64)
-    with _variant(X8):
+    with _variant(variant):
         got = MSDA.ms_deform_attn_backward(*args)
     base = MSDA.ms_deform_attn_backward(*args)
     for g, b in zip(got, base):

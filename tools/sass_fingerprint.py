@@ -1,0 +1,101 @@
+"""Guard for kernels that were validated on hardware: a hash of each kernel's SASS (instruction text without addresses
+and encodings) is kept in profiles/sass_validated_r1.json; `--check` (default) reports validated kernels whose SASS is no
+longer produced by the current build.
+
+    python tools/sass_fingerprint.py            # check the built objects against the committed fingerprints
+    python tools/sass_fingerprint.py --write    # regenerate (only after the kernels ran green on a B200)
+
+Why: work that happens without a GPU (new template parameters, shared headers, new variants) must not silently change
+the code of kernels whose parity and timing were measured.  Kernels are matched by hash, not by name, so adding a
+defaulted template parameter (which changes the mangled name but not the code) passes.  The fingerprints are specific
+to the nvcc version recorded in the file.
+"""
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJDIR = os.path.join(ROOT, "semi_detr_b200", "lib", "obj")
+OUT = os.path.join(ROOT, "profiles", "sass_validated_r1.json")
+
+
+def nvcc_version():
+    out = subprocess.run(["nvcc", "--version"], capture_output=True, text=True, check=True).stdout
+    return re.search(r"release [\d.]+, V([\d.]+)", out).group(1)
+
+
+def kernels(obj):
+    """-> {mangled name: sha1 of the normalised SASS}"""
+    text = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+    res, cur, lines = {}, None, []
+    for line in text.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            if cur:
+                res[cur] = hashlib.sha1("\n".join(lines).encode()).hexdigest()
+            cur, lines = m.group(1), []
+            continue
+        if cur is None or re.match(r"^\s*/\* 0x[0-9a-f]+ \*/\s*$", line):
+            continue
+        ins = re.sub(r"/\*[0-9a-f]+\*/", "", line)          # address and encoding comments
+        ins = re.sub(r"0x7f[0-9a-f]{10}", "ADDR", ins).strip()
+        if ins:
+            lines.append(ins)
+    if cur:
+        res[cur] = hashlib.sha1("\n".join(lines).encode()).hexdigest()
+    return res
+
+
+def demangle(names):
+    out = subprocess.run(["cu++filt"] + names, capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    names = []
+    for d in out:
+        d = d.replace("void ", "", 1)
+        m = re.match(r"(.*>)\(", d)            # template kernel: cut the parameter list after the last `>(`
+        names.append(m.group(1) if m else d.split("(", 1)[0])
+    return names
+
+
+def current():
+    res = {}
+    for f in sorted(os.listdir(OBJDIR)):
+        if f.endswith(".o"):
+            k = kernels(os.path.join(OBJDIR, f))
+            if k:
+                res[f] = dict(zip(demangle(list(k.keys())), k.values()))
+    return res
+
+
+def main():
+    if "--write" in sys.argv:
+        skip = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--skip=")]
+        cur = current()
+        data = {"nvcc": nvcc_version(), "objects": {
+            obj: {h: n for n, h in ks.items() if not any(re.search(p, n) for p in skip)} for obj, ks in cur.items()}}
+        data["objects"] = {o: k for o, k in data["objects"].items() if k}
+        with open(OUT, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+        print("wrote", OUT, sum(len(k) for k in data["objects"].values()), "kernels")
+        return 0
+    want = json.load(open(OUT))
+    if want["nvcc"] != nvcc_version():
+        print(f"nvcc {nvcc_version()} != {want['nvcc']} recorded: fingerprints do not apply")
+        return 0
+    cur = current()
+    bad = 0
+    for obj, ks in want["objects"].items():
+        have = set(cur.get(obj, {}).values())
+        for h, name in ks.items():
+            if h not in have:
+                bad += 1
+                print(f"CHANGED  {obj}: {name}")
+    total = sum(len(k) for k in want["objects"].values())
+    print(f"{total - bad} of {total} validated kernels unchanged")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
