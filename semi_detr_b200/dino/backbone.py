@@ -47,14 +47,57 @@ def fused_conv_enabled():
     return os.environ.get("SDB_FUSED_CONV", "1") != "0"
 
 
+def enable_frozen_bn_fold_cache(module, enabled=True):
+    """Opt the BatchNorm layers of ``module`` into caching their folded affine map (``folded_conv``).  Call it for a
+    model whose frozen BN tensors are written only through torch (``load_state_dict``, ``copy_`` ... bump the version
+    counters the cache is keyed on) -- the train-step engines do.  Do NOT enable it for an EMA teacher: its tensors are
+    rewritten by ``sdb_ema_update_f32`` through raw pointers, which no version counter sees."""
+    for m in module.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m._sdb_cache_fold = bool(enabled)
+            m.__dict__.pop("_sdb_fold", None)
+    return module
+
+
+def _fold_key(*tensors):
+    return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+def folded_conv(conv, bn):
+    """-> (w, t): conv(x, w) + t == BN_eval(conv(x)), with s = gamma / sqrt(var + eps), w = weight * s, t = beta - mean * s.
+
+    With frozen BN parameters (``requires_grad=False``; every shipped config) ``s`` and ``t`` are the same numbers every
+    step, and so is ``w`` for a frozen convolution (stem + ``frozen_stages``): recomputing them cost 6 tiny kernels per
+    convolution per step (53 convolutions -> ~300 of the step's ~2 700 launches).  When the layer has been opted in
+    (``enable_frozen_bn_fold_cache``) they are computed once and reused until one of the tensors is written (data
+    pointer + version counter).  An existing entry is used during CUDA-graph capture (it is ordinary device memory,
+    like the parameters); a new one is never created there (it would live in the graph's private pool).  Nothing that
+    requires grad is cached."""
+    cacheable = getattr(bn, "_sdb_cache_fold", False) and not bn.weight.requires_grad and not bn.bias.requires_grad
+    key = None
+    if cacheable:
+        key = _fold_key(bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        hit = bn.__dict__.get("_sdb_fold")
+        if hit is not None and hit[0] == key:
+            s, t, w, wkey = hit[1]
+            if w is not None and wkey == _fold_key(conv.weight):
+                return w, t
+            return conv.weight * s.view(-1, 1, 1, 1), t
+    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    t = bn.bias - bn.running_mean * s
+    w = conv.weight * s.view(-1, 1, 1, 1)
+    if cacheable and not (s.is_cuda and torch.cuda.is_current_stream_capturing()):
+        frozen_w = not conv.weight.requires_grad
+        bn.__dict__["_sdb_fold"] = (key, (s, t, w if frozen_w else None, _fold_key(conv.weight) if frozen_w else None))
+    return w, t
+
+
 def conv_bn_relu(conv, bn, x, identity=None):
     """relu(BN(conv(x)) [+ identity]) -- with frozen statistics on the device: one fused cuDNN call."""
     if bn.training or not x.is_cuda or not fused_conv_enabled():
         out = conv_bn(conv, bn, x)
         return F.relu(out if identity is None else out + identity, inplace=True)
-    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-    t = bn.bias - bn.running_mean * s
-    w = conv.weight * s.view(-1, 1, 1, 1)
+    w, t = folded_conv(conv, bn)
     args = (tuple(conv.stride), tuple(conv.padding), tuple(conv.dilation), conv.groups)
     if not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or
                                          (identity is not None and identity.requires_grad))):
@@ -72,9 +115,8 @@ def conv_bn(conv, bn, x):
     the two modules run as written."""
     if bn.training or not x.is_cuda:
         return bn(conv(x))
-    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-    t = bn.bias - bn.running_mean * s
-    return F.conv2d(x, conv.weight * s.view(-1, 1, 1, 1), t, conv.stride, conv.padding, conv.dilation, conv.groups)
+    w, t = folded_conv(conv, bn)
+    return F.conv2d(x, w, t, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 class Bottleneck(nn.Module):

@@ -180,7 +180,7 @@ class DINODETRHead(nn.Module):
 
         hs, reference, hs_enc, ref_enc, _ = self.transformer(
             srcs, masks, input_query_bbox, poss, input_query_label, attn_mask, fc_reg=self.fc_reg,
-            fc_cls=self.fc_cls, fc_enc_reg=self.fc_enc_reg, fc_enc_cls=self.fc_enc_cls)
+            fc_cls=self.fc_cls, fc_enc_reg=self.fc_enc_reg, fc_enc_cls=self.fc_enc_cls, geometry_key=shapes_key)
         hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0      # keeps label_enc in the graph without a DN part
 
         hs_all = torch.stack(hs)                                # (n_dec, bs, nq, C); heads are shared across layers

@@ -13,6 +13,7 @@ Host-side differences that do not change numerics:
 """
 import copy
 import math
+from collections import OrderedDict
 
 import torch
 import torch.nn.functional as F
@@ -46,6 +47,7 @@ class MLP(nn.Module):
 
 
 _DIM_T = {}
+_GEOMETRY = OrderedDict()     # (device, host geometry key, level shapes) -> mask-derived tensors (_mask_geometry)
 
 # Decoder self-attention runs over ~1.1 k queries in fp32: for that size plain matmul-softmax-matmul beats the fused
 # memory-efficient fp32 kernel torch's SDPA picks on sm_100 (measured in profiles/), so the layer writes it out
@@ -54,30 +56,33 @@ _DIM_T = {}
 
 def gen_sineembed_for_position(pos):
     """(nq, bs, 2|4) in [0,1] -> (nq, bs, 256|512); 128 dims per coordinate, temperature 10000, order y,x,w,h
-    (transformer.py:467-493)."""
-    key = pos.device
+    (transformer.py:467-493).
+
+    The reference embeds each coordinate on its own (scale, divide, ``sin`` of the even slots, ``cos`` of the odd
+    ones, stack, flatten: ~6 small kernels per coordinate, 25 per call, 6 calls per pass).  Here all coordinates go
+    through ONE scale / divide / sin / cos / select: the same elementwise values (``sin`` and ``cos`` of the same
+    quotient, picked by slot parity), 6 kernels per call."""
+    n = pos.size(-1)
+    if n not in (2, 4):
+        raise ValueError("Unknown pos_tensor shape(-1):{}".format(n))
+    dev = pos.device
+    key = str(dev)
     if key not in _DIM_T:
-        i = torch.arange(128, dtype=torch.float32, device=pos.device)
-        _DIM_T[key] = 10000 ** (2 * (i // 2) / 128)
-    dim_t = _DIM_T[key]
-
-    def emb(c):
-        e = (c * (2 * math.pi))[:, :, None] / dim_t
-        return torch.stack((e[:, :, 0::2].sin(), e[:, :, 1::2].cos()), dim=3).flatten(2)
-
-    px, py = emb(pos[:, :, 0]), emb(pos[:, :, 1])
-    if pos.size(-1) == 2:
-        return torch.cat((py, px), dim=2)
-    if pos.size(-1) == 4:
-        return torch.cat((py, px, emb(pos[:, :, 2]), emb(pos[:, :, 3])), dim=2)
-    raise ValueError("Unknown pos_tensor shape(-1):{}".format(pos.size(-1)))
+        i = torch.arange(128, dtype=torch.float32, device=dev)
+        _DIM_T[key] = (10000 ** (2 * (i // 2) / 128), (torch.arange(128, device=dev) % 2) == 0,
+                       {2: torch.tensor([1, 0], device=dev), 4: torch.tensor([1, 0, 2, 3], device=dev)})
+    dim_t, even, order = _DIM_T[key]
+    p = pos.index_select(-1, order[n])                                  # y, x(, w, h)
+    e = (p * (2 * math.pi))[..., None] / dim_t                          # (nq, bs, n, 128)
+    return torch.where(even, e.sin(), e.cos()).flatten(2)
 
 
-def gen_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes_list):
-    """Two-stage proposals (transformer.py:525-575): grid centre / valid size with 0.05*2^l boxes, kept where all
-    four coordinates lie in (0.01, 0.99); padded / invalid rows get logit +inf and a zeroed memory row.
-    ``spatial_shapes_list`` is the host list [(H, W), ...] (no device sync)."""
-    N, S, C = memory.shape
+def encoder_proposals(memory_padding_mask, spatial_shapes_list):
+    """The mask-only part of the two-stage proposals (transformer.py:525-575): grid centre / valid size with
+    0.05*2^l boxes in logit space, +inf where the row is padded or a coordinate leaves (0.01, 0.99)
+    -> (proposals (N, S, 4), bad (N, S, 1) bool).  Depends on the padding masks alone, i.e. on the batch geometry."""
+    N = memory_padding_mask.shape[0]
+    device = memory_padding_mask.device
     proposals = []
     cur = 0
     for lvl, (H, W) in enumerate(spatial_shapes_list):
@@ -85,10 +90,10 @@ def gen_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes_lis
         valid_h = (~m[:, :, 0]).sum(1)
         valid_w = (~m[:, 0, :]).sum(1)
         def build_grid(H=H, W=W):
-            gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=memory.device),
-                                    torch.arange(W, dtype=torch.float32, device=memory.device), indexing="ij")
+            gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=device),
+                                    torch.arange(W, dtype=torch.float32, device=device), indexing="ij")
             return torch.stack([gx, gy], -1)
-        grid = device_const(memory.device, "proposal_grid", (H, W), build_grid)
+        grid = device_const(device, "proposal_grid", (H, W), build_grid)
         scale = torch.stack([valid_w, valid_h], 1).view(N, 1, 1, 2)
         grid = (grid[None].expand(N, -1, -1, -1) + 0.5) / scale
         wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
@@ -98,9 +103,14 @@ def gen_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes_lis
     valid = ((prop > 0.01) & (prop < 0.99)).all(-1, keepdim=True)
     prop = torch.log(prop / (1 - prop))
     bad = memory_padding_mask.unsqueeze(-1) | ~valid
-    prop = prop.masked_fill(bad, float("inf"))
-    out_memory = memory.masked_fill(bad, 0.0)
-    return out_memory, prop
+    return prop.masked_fill(bad, float("inf")), bad
+
+
+def gen_encoder_output_proposals(memory, memory_padding_mask, spatial_shapes_list):
+    """Two-stage proposals (transformer.py:525-575): ``encoder_proposals`` + the memory rows of padded / invalid
+    positions zeroed.  ``spatial_shapes_list`` is the host list [(H, W), ...] (no device sync)."""
+    prop, bad = encoder_proposals(memory_padding_mask, spatial_shapes_list)
+    return memory.masked_fill(bad, 0.0), prop
 
 
 class DINOTransformerEncoderLayer(nn.Module):
@@ -154,9 +164,10 @@ class DINOTransformerEncoder(nn.Module):
         return ref[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, pos, spatial_shapes, level_start_index, valid_ratios, key_padding_mask,
-                spatial_shapes_list):
+                spatial_shapes_list, reference_points=None):
         out = src
-        reference_points = self.get_reference_points(spatial_shapes_list, valid_ratios, src.device)
+        if reference_points is None:
+            reference_points = self.get_reference_points(spatial_shapes_list, valid_ratios, src.device)
         for layer in self.layers:
             out = layer(out, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask)
         if self.norm is not None:
@@ -319,13 +330,38 @@ class DINOTransformer(nn.Module):
         valid_w = (~mask[:, 0, :]).sum(1)
         return torch.stack([valid_w.float() / W, valid_h.float() / H], -1)
 
+    def _mask_geometry(self, masks, shapes_list, geometry_key):
+        """Everything the pass derives from the padding masks alone: flattened mask, valid ratios, encoder reference
+        points, two-stage proposals.  The masks are per-geometry constants (``dino/head.py`` builds them once per
+        ``(batch_input_shape, img_shapes)``), so with that host key the derived tensors are built once as well (~110
+        small launches per step otherwise); without a key they are computed as written."""
+        def build():
+            mask_flat = torch.cat([m.flatten(1) for m in masks], 1)
+            valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+            ref = DINOTransformerEncoder.get_reference_points(shapes_list, valid_ratios, mask_flat.device)
+            prop, bad = encoder_proposals(mask_flat, shapes_list)
+            return mask_flat, valid_ratios, ref, prop, bad
+        if geometry_key is None:
+            return build()
+        k = (str(masks[0].device), geometry_key, tuple(shapes_list))
+        hit = _GEOMETRY.get(k)
+        if hit is None:
+            hit = build()
+            if not (masks[0].is_cuda and torch.cuda.is_current_stream_capturing()):   # never keep graph-pool memory
+                _GEOMETRY[k] = hit
+                if len(_GEOMETRY) > 64:
+                    _GEOMETRY.popitem(last=False)
+        else:
+            _GEOMETRY.move_to_end(k)
+        return hit
+
     def forward(self, srcs, masks, refpoint_embed, pos_embeds, tgt, attn_mask=None, fc_reg=None, fc_cls=None,
-                fc_enc_reg=None, fc_enc_cls=None):
+                fc_enc_reg=None, fc_enc_cls=None, geometry_key=None):
         """srcs / pos_embeds: L x (bs, C, H_l, W_l); masks: L x (bs, H_l, W_l) bool (True = padding);
         refpoint_embed (bs, n_dn, 4) / tgt (bs, n_dn, C): the denoising part or None
         -> hs [n_dec x (bs, nq, C)], references [(n_dec+1) x (bs, nq, 4)], hs_enc (1, bs, 900, C),
            ref_enc (1, bs, 900, 4), init_box_proposal (bs, 900, 4)"""
-        src_l, mask_l, pos_l, shapes_list = [], [], [], []
+        src_l, pos_l, shapes_list = [], [], []
         for lvl, (src, mask, pos) in enumerate(zip(srcs, masks, pos_embeds)):
             bs, c, h, w = src.shape
             shapes_list.append((h, w))
@@ -333,11 +369,11 @@ class DINOTransformer(nn.Module):
             if self.level_embed is not None:
                 pos = pos + self.level_embed[lvl].view(1, 1, -1)
             src_l.append(src.flatten(2).transpose(1, 2))
-            mask_l.append(mask.flatten(1))
             pos_l.append(pos)
         src_flat = torch.cat(src_l, 1)
-        mask_flat = torch.cat(mask_l, 1)
         pos_flat = torch.cat(pos_l, 1)
+        mask_flat, valid_ratios, enc_refs, output_proposals, bad_rows = self._mask_geometry(masks, shapes_list,
+                                                                                            geometry_key)
         starts = [0]
         for h, w in shapes_list[:-1]:
             starts.append(starts[-1] + h * w)
@@ -346,13 +382,13 @@ class DINOTransformer(nn.Module):
                                       lambda: torch.as_tensor(shapes_list, dtype=torch.long))
         level_start_index = device_const(src_flat.device, "level_start", skey,
                                          lambda: torch.as_tensor(starts, dtype=torch.long))
-        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
 
         memory = self.encoder(src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, mask_flat,
-                              shapes_list)
+                              shapes_list, reference_points=enc_refs)
 
-        # two-stage query selection (transformer.py:1314-1346)
-        output_memory, output_proposals = gen_encoder_output_proposals(memory, mask_flat, shapes_list)
+        # two-stage query selection (transformer.py:1314-1346; gen_encoder_output_proposals with its mask-only part
+        # taken from the geometry cache)
+        output_memory = memory.masked_fill(bad_rows, 0.0)
         output_memory = self.enc_output_norm(self.enc_output(output_memory))
         enc_cls = fc_enc_cls(output_memory)
         enc_coord = fc_enc_reg(output_memory) + output_proposals

@@ -34,6 +34,14 @@ def build_optimizer(model, lr=1e-4, weight_decay=1e-4, backbone_lr_mult=0.1, fus
                              capturable=capturable and fused)
 
 
+def _cache_student_bn_folds(model):
+    """The engines own the parameter updates of the model they train: frozen BatchNorm tensors are never written per
+    step, so their folded affine maps are computed once (dino/backbone.py ``folded_conv``).  For the teacher-student
+    wrapper only the student opts in -- the EMA teacher is rewritten through raw pointers every step."""
+    from .dino.backbone import enable_frozen_bn_fold_cache
+    enable_frozen_bn_fold_cache(model.student if hasattr(model, "student") and hasattr(model, "teacher") else model)
+
+
 class FlatGrads:
     """One contiguous gradient buffer; every trainable parameter's ``.grad`` is a view into it."""
 
@@ -73,6 +81,7 @@ class SupervisedTrainStep:
             world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.world_size = world_size
         self.grads = FlatGrads([p for g in optimizer.param_groups for p in g["params"]])
+        _cache_student_bn_folds(model)
 
     def __call__(self, data):
         self.grads.zero()
@@ -251,6 +260,7 @@ class FusedSupervisedTrainStep:
         self.world_size = world_size
         self.opt = FusedAdamW(model, **opt_kw)
         self.gather_grads = gather_grads
+        _cache_student_bn_folds(model)
 
     def _pack(self, grads):
         """grads (one per parameter, None for unused ones) -> the flat gradient buffer"""
@@ -307,6 +317,7 @@ class FusedSSODTrainStep:
         frozen = [n for n, p in student.items() if not p.requires_grad]
         self.frozen_plan = EmaPlan([teacher[n].data for n in frozen], [student[n].data for n in frozen])
         self.iter = start_iter
+        _cache_student_bn_folds(model)
 
     def momentum_at(self, it):
         return min(self.momentum, 1 - (1 + self.warm_up) / (it + 1 + self.warm_up))

@@ -180,3 +180,149 @@ def test_decoder_self_attention_equals_multihead_attention():
     g1 = torch.autograd.grad(layer._self_attention(qk, v, mask).square().sum(), qk)[0]
     g2 = torch.autograd.grad(layer.self_attn(qk, qk, v, attn_mask=mask, need_weights=False)[0].square().sum(), qk)[0]
     assert torch.allclose(g1, g2, rtol=1e-4, atol=1e-5)
+
+
+def test_frozen_bn_fold_is_cached_and_tracks_writes():
+    """dino/backbone.py ``folded_conv``: conv(x, w) + t equals BN_eval(conv(x)); with the cache enabled the fold is
+    computed once per layer, reused (same tensor objects) and recomputed after any torch-side write to a BN tensor or
+    a frozen convolution weight; trainable convolution weights are re-scaled every call and keep their gradient."""
+    import torch.nn.functional as F
+    from torch import nn
+    from semi_detr_b200.dino.backbone import enable_frozen_bn_fold_cache, folded_conv
+    torch.manual_seed(0)
+    conv = nn.Conv2d(5, 7, 3, padding=1, bias=False)
+    bn = nn.BatchNorm2d(7).eval()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    for p in bn.parameters():
+        p.requires_grad = False
+    x = torch.randn(2, 5, 9, 8)
+    want = bn(conv(x))
+    w, t = folded_conv(conv, bn)                       # cache off: plain computation
+    assert torch.allclose(F.conv2d(x, w, t, padding=1), want, rtol=1e-5, atol=1e-6)
+    assert "_sdb_fold" not in bn.__dict__
+    enable_frozen_bn_fold_cache(nn.Sequential(conv, bn))
+    w1, t1 = folded_conv(conv, bn)
+    w2, t2 = folded_conv(conv, bn)
+    assert t2 is t1 and w2 is not w1 and w2.requires_grad      # trainable weight: fresh product, gradient reaches it
+    assert torch.equal(w1, w) and torch.equal(t1, t)
+    F.conv2d(x, w2, t2, padding=1).sum().backward()
+    ref = conv.weight.grad.clone()
+    conv.weight.grad = None
+    bn(conv(x)).sum().backward()
+    assert torch.allclose(conv.weight.grad, ref, rtol=1e-4, atol=1e-5)
+    with torch.no_grad():
+        conv.weight.mul_(1.5)                          # an optimizer step (no version bump needed: never cached)
+    w3, _ = folded_conv(conv, bn)
+    assert torch.allclose(w3, w * 1.5)
+    conv.weight.requires_grad = False                  # frozen stage: the scaled weight is cached too
+    bn.__dict__.pop("_sdb_fold")
+    w4, t4 = folded_conv(conv, bn)
+    w5, t5 = folded_conv(conv, bn)
+    assert w5 is w4 and t5 is t4
+    with torch.no_grad():
+        conv.weight.add_(1.0)                          # torch-side write -> version bump -> recomputed
+    w6, _ = folded_conv(conv, bn)
+    assert w6 is not w4 and torch.allclose(w6, w4 + torch.rsqrt(bn.running_var + bn.eps).mul(bn.weight).view(-1, 1, 1, 1))
+    with torch.no_grad():
+        bn.running_var.mul_(2.0)                       # e.g. load_state_dict
+    w7, t7 = folded_conv(conv, bn)
+    assert t7 is not t4
+    assert torch.allclose(F.conv2d(x, w7, t7, padding=1), bn(conv(x)), rtol=1e-4, atol=1e-4)
+    bn.weight.requires_grad = True                     # trainable BN: never cached
+    a = folded_conv(conv, bn)
+    b = folded_conv(conv, bn)
+    assert a[1] is not b[1] and a[1].requires_grad
+
+
+def test_engines_enable_the_bn_fold_cache_for_the_student_only():
+    from semi_detr_b200.dino.backbone import enable_frozen_bn_fold_cache
+    from semi_detr_b200.engine import _cache_student_bn_folds
+    from torch import nn
+
+    class Wrapper(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.student = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
+            self.teacher = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
+    m = Wrapper()
+    _cache_student_bn_folds(m)
+    assert m.student[1]._sdb_cache_fold and not getattr(m.teacher[1], "_sdb_cache_fold", False)
+    plain = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
+    _cache_student_bn_folds(plain)
+    assert plain[1]._sdb_cache_fold
+    enable_frozen_bn_fold_cache(plain, False)
+    assert not plain[1]._sdb_cache_fold
+
+
+def test_mask_geometry_cache_changes_nothing():
+    """dino/transformer.py ``_mask_geometry``: valid ratios, encoder reference points and two-stage proposals depend on
+    the padding masks alone; with the head's host geometry key they are built once and reused -- bit-identical losses
+    with the cache cold, warm, and bypassed, and one entry per distinct geometry."""
+    import copy
+    from semi_detr_b200.dino import transformer as T
+    from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch
+    cfg = copy.deepcopy(DINO_R50_4SCALE)
+    cfg["bbox_head"]["num_query"] = 60
+    cfg["bbox_head"]["transformer"] = dict(type="DINOTransformer", num_queries=60, num_encoder_layers=1,
+                                           num_decoder_layers=2, dim_feedforward=64)
+    cfg["bbox_head"]["dn_number"] = 10
+    torch.manual_seed(0)
+    model = DETECTORS.build(cfg).train()
+
+    def run(data, seed=3):
+        torch.manual_seed(seed)
+        with reference_cpu_ops():
+            out = model(**data)
+        return {k: v.detach().clone() for k, v in out.items() if torch.is_tensor(v)}
+
+    data = coco_like_batch(2, 128, 160, seed=1)
+    data["img_metas"][1]["img_shape"] = (100, 120, 3)            # a padded image: valid ratios < 1, masked proposals
+    T._GEOMETRY.clear()
+    cold = run(data)
+    assert len(T._GEOMETRY) == 1
+    entry = next(iter(T._GEOMETRY.values()))
+    warm = run(data)
+    assert next(iter(T._GEOMETRY.values())) is entry and len(T._GEOMETRY) == 1
+    orig = T.DINOTransformer.forward
+    try:
+        T.DINOTransformer.forward = lambda self, *a, geometry_key=None, **k: orig(self, *a, geometry_key=None, **k)
+        bypass = run(data)
+    finally:
+        T.DINOTransformer.forward = orig
+    assert cold.keys() == warm.keys() == bypass.keys() and len(cold) > 10
+    for k in cold:
+        assert torch.equal(cold[k], warm[k]) and torch.equal(cold[k], bypass[k]), k
+    other = coco_like_batch(2, 128, 160, seed=1)                  # same tensors, no padding: a second geometry
+    run(other)
+    assert len(T._GEOMETRY) == 2
+    plain = run(other)
+    assert any(not torch.equal(plain[k], cold[k]) for k in cold)
+
+
+def test_sine_embedding_equals_the_per_coordinate_form():
+    """gen_sineembed_for_position: one pass over all coordinates is bit-identical to the reference's per-coordinate
+    sin / cos / stack / flatten (transformer.py:467-493)."""
+    import math
+    from semi_detr_b200.dino.transformer import gen_sineembed_for_position
+
+    def reference(pos):
+        dim_t = 10000 ** (2 * (torch.arange(128, dtype=torch.float32) // 2) / 128)
+
+        def emb(c):
+            e = (c * (2 * math.pi))[:, :, None] / dim_t
+            return torch.stack((e[:, :, 0::2].sin(), e[:, :, 1::2].cos()), dim=3).flatten(2)
+        px, py = emb(pos[:, :, 0]), emb(pos[:, :, 1])
+        if pos.size(-1) == 2:
+            return torch.cat((py, px), dim=2)
+        return torch.cat((py, px, emb(pos[:, :, 2]), emb(pos[:, :, 3])), dim=2)
+
+    g = torch.Generator().manual_seed(0)
+    for n in (2, 4):
+        pos = torch.rand(37, 3, n, generator=g)
+        got, want = gen_sineembed_for_position(pos), reference(pos)
+        assert got.shape == want.shape == (37, 3, 128 * n) and torch.equal(got, want)
+        nc = pos.transpose(0, 1).contiguous().transpose(0, 1)          # non-contiguous input, as the decoder passes
+        assert torch.equal(gen_sineembed_for_position(nc), want)
+    with pytest.raises(ValueError):
+        gen_sineembed_for_position(torch.rand(2, 2, 3))
