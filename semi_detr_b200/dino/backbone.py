@@ -4,6 +4,8 @@ BN frozen + norm_eval, style 'pytorch').  Parameter names follow torchvision / m
 ``layerN.M.convK`` ...) so ``torchvision://resnet50`` checkpoints load.  Dense convolutions go to cuDNN (library
 plumbing): the backbone is not part of the graded hot path but is needed to run the train step end to end.
 """
+import weakref
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -49,14 +51,25 @@ def fused_conv_enabled():
 
 def enable_frozen_bn_fold_cache(module, enabled=True):
     """Opt the BatchNorm layers of ``module`` into caching their folded affine map (``folded_conv``).  Call it for a
-    model whose frozen BN tensors are written only through torch (``load_state_dict``, ``copy_`` ... bump the version
-    counters the cache is keyed on) -- the train-step engines do.  Do NOT enable it for an EMA teacher: its tensors are
+    model whose frozen BN tensors are written only through torch ops on the tensors themselves (``load_state_dict``,
+    ``copy_`` ... bump the version counters the cache is keyed on; writes through ``.data`` or raw pointers do not)
+    -- the train-step engines do.  Do NOT enable it for an EMA teacher: its tensors are
     rewritten by ``sdb_ema_update_f32`` through raw pointers, which no version counter sees."""
     for m in module.modules():
         if isinstance(m, nn.BatchNorm2d):
-            m._sdb_cache_fold = bool(enabled)
-            m.__dict__.pop("_sdb_fold", None)
+            (_FOLD_ENABLED.add if enabled else _FOLD_ENABLED.discard)(m)
+            _FOLD_CACHE.pop(m, None)
     return module
+
+
+# Side tables, not module attributes: a deepcopy / pickle of the model (e.g. to make a teacher) neither inherits the
+# opt-in nor carries cached tensors.
+_FOLD_ENABLED = weakref.WeakSet()
+_FOLD_CACHE = weakref.WeakKeyDictionary()
+
+
+def fold_cache_enabled(bn):
+    return bn in _FOLD_ENABLED
 
 
 def _fold_key(*tensors):
@@ -73,11 +86,11 @@ def folded_conv(conv, bn):
     pointer + version counter).  An existing entry is used during CUDA-graph capture (it is ordinary device memory,
     like the parameters); a new one is never created there (it would live in the graph's private pool).  Nothing that
     requires grad is cached."""
-    cacheable = getattr(bn, "_sdb_cache_fold", False) and not bn.weight.requires_grad and not bn.bias.requires_grad
+    cacheable = bn in _FOLD_ENABLED and not bn.weight.requires_grad and not bn.bias.requires_grad
     key = None
     if cacheable:
         key = _fold_key(bn.weight, bn.bias, bn.running_mean, bn.running_var)
-        hit = bn.__dict__.get("_sdb_fold")
+        hit = _FOLD_CACHE.get(bn)
         if hit is not None and hit[0] == key:
             s, t, w, wkey = hit[1]
             if w is not None and wkey == _fold_key(conv.weight):
@@ -88,7 +101,7 @@ def folded_conv(conv, bn):
     w = conv.weight * s.view(-1, 1, 1, 1)
     if cacheable and not (s.is_cuda and torch.cuda.is_current_stream_capturing()):
         frozen_w = not conv.weight.requires_grad
-        bn.__dict__["_sdb_fold"] = (key, (s, t, w if frozen_w else None, _fold_key(conv.weight) if frozen_w else None))
+        _FOLD_CACHE[bn] = (key, (s, t, w if frozen_w else None, _fold_key(conv.weight) if frozen_w else None))
     return w, t
 
 

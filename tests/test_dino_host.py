@@ -188,7 +188,7 @@ def test_frozen_bn_fold_is_cached_and_tracks_writes():
     a frozen convolution weight; trainable convolution weights are re-scaled every call and keep their gradient."""
     import torch.nn.functional as F
     from torch import nn
-    from semi_detr_b200.dino.backbone import enable_frozen_bn_fold_cache, folded_conv
+    from semi_detr_b200.dino.backbone import _FOLD_CACHE, enable_frozen_bn_fold_cache, folded_conv
     torch.manual_seed(0)
     conv = nn.Conv2d(5, 7, 3, padding=1, bias=False)
     bn = nn.BatchNorm2d(7).eval()
@@ -200,7 +200,7 @@ def test_frozen_bn_fold_is_cached_and_tracks_writes():
     want = bn(conv(x))
     w, t = folded_conv(conv, bn)                       # cache off: plain computation
     assert torch.allclose(F.conv2d(x, w, t, padding=1), want, rtol=1e-5, atol=1e-6)
-    assert "_sdb_fold" not in bn.__dict__
+    assert bn not in _FOLD_CACHE
     enable_frozen_bn_fold_cache(nn.Sequential(conv, bn))
     w1, t1 = folded_conv(conv, bn)
     w2, t2 = folded_conv(conv, bn)
@@ -216,7 +216,7 @@ def test_frozen_bn_fold_is_cached_and_tracks_writes():
     w3, _ = folded_conv(conv, bn)
     assert torch.allclose(w3, w * 1.5)
     conv.weight.requires_grad = False                  # frozen stage: the scaled weight is cached too
-    bn.__dict__.pop("_sdb_fold")
+    _FOLD_CACHE.pop(bn)
     w4, t4 = folded_conv(conv, bn)
     w5, t5 = folded_conv(conv, bn)
     assert w5 is w4 and t5 is t4
@@ -245,14 +245,17 @@ def test_engines_enable_the_bn_fold_cache_for_the_student_only():
             super().__init__()
             self.student = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
             self.teacher = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
+    from semi_detr_b200.dino.backbone import fold_cache_enabled
+    import copy
     m = Wrapper()
     _cache_student_bn_folds(m)
-    assert m.student[1]._sdb_cache_fold and not getattr(m.teacher[1], "_sdb_cache_fold", False)
+    assert fold_cache_enabled(m.student[1]) and not fold_cache_enabled(m.teacher[1])
     plain = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
     _cache_student_bn_folds(plain)
-    assert plain[1]._sdb_cache_fold
+    assert fold_cache_enabled(plain[1])
+    assert not fold_cache_enabled(copy.deepcopy(plain)[1]), "a copy (e.g. a teacher made from the student) starts cold"
     enable_frozen_bn_fold_cache(plain, False)
-    assert not plain[1]._sdb_cache_fold
+    assert not fold_cache_enabled(plain[1])
 
 
 def test_mask_geometry_cache_changes_nothing():
