@@ -264,6 +264,10 @@ class DINOTransformerDecoder(nn.Module):
         reference_points = refpoints_unsigmoid.sigmoid()
         ref_points = [reference_points]
         vr4 = torch.cat([valid_ratios, valid_ratios], -1)[None]          # (1, bs, L, 4)
+        if tgt_mask is not None and tgt_mask.dtype == torch.bool:
+            # the additive form every layer's score product needs: built once per pass, not once per layer
+            tgt_mask = torch.zeros(tgt_mask.shape, dtype=tgt.dtype, device=tgt.device).masked_fill_(tgt_mask,
+                                                                                                  float("-inf"))
         for lid, layer in enumerate(self.layers):
             ref_in = reference_points[:, :, None] * vr4                   # (nq, bs, L, 4)
             query_pos = self.ref_point_head(gen_sineembed_for_position(ref_in[:, :, 0, :]))
