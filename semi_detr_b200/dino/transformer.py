@@ -69,8 +69,9 @@ def gen_sineembed_for_position(pos):
     key = str(dev)
     if key not in _DIM_T:
         i = torch.arange(128, dtype=torch.float32, device=dev)
+        yx = torch.arange(1, -1, -1, device=dev)                  # device-side construction only: stays capturable
         _DIM_T[key] = (10000 ** (2 * (i // 2) / 128), (torch.arange(128, device=dev) % 2) == 0,
-                       {2: torch.tensor([1, 0], device=dev), 4: torch.tensor([1, 0, 2, 3], device=dev)})
+                       {2: yx, 4: torch.cat([yx, torch.arange(2, 4, device=dev)])})
     dim_t, even, order = _DIM_T[key]
     p = pos.index_select(-1, order[n])                                  # y, x(, w, h)
     e = (p * (2 * math.pi))[..., None] / dim_t                          # (nq, bs, n, 128)

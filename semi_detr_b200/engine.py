@@ -113,6 +113,12 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.log_vars = step(static_data)
+        # The captured kernels read the per-geometry constants by address; the caches that own them are bounded (LRU),
+        # so the graph keeps its own references -- an eviction can then never free memory a replay still reads.
+        from . import consts
+        from .dino import backbone, transformer
+        self._keepalive = (list(consts._CACHE.values()), list(transformer._GEOMETRY.values()),
+                           list(backbone._FOLD_CACHE.values()))
 
     def load(self, batch):
         d = self.data
