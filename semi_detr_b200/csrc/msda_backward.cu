@@ -25,7 +25,8 @@ extern int g_bwd_variant;
 // experimental 4-lanes-per-pair mapping (msda_backward_x8.cu), backward variant 7
 int msda_backward_x8(cudaStream_t st, const float* grad_out, const float* value, const int64_t* shapes,
                      const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int L, int Lq,
-                     float* grad_value, float* grad_loc, float* grad_attn, const float* ref, int ref_dim);
+                     float* grad_value, float* grad_loc, float* grad_attn, const float* ref, int ref_dim,
+                     bool rolled);
 
 // ------------------------------------------------------------------------------------------------
 // generic kernel: any channel count, float or double.  One warp per (n, q, m).
@@ -386,8 +387,9 @@ static int msda_backward(cudaStream_t st, const T* grad_out, const T* value, con
         case 3: return launch_bwd_d32<256, 4, 8, 2>(SDB_BWD_ARGS);
         case 4: return launch_bwd_d32<128, 4, 8, 8>(SDB_BWD_ARGS);
         case 5: return launch_bwd_d32<128, 4, 8, 4>(SDB_BWD_ARGS);
-        case 7: return msda_backward_x8(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, Lq, grad_value,
-                                        grad_loc, grad_attn, nullptr, 0);
+        case 7:
+        case 8: return msda_backward_x8(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, Lq, grad_value,
+                                        grad_loc, grad_attn, nullptr, 0, v == 8);
         // experimental (not yet run on hardware): 2 / 4 points of corner loads in flight per warp
         case 10: return launch_bwd_d32<128, 4, 8, 4, false, float, 2>(SDB_BWD_ARGS);
         case 11: return launch_bwd_d32<128, 4, 8, 3, false, float, 2>(SDB_BWD_ARGS);
@@ -452,9 +454,10 @@ extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* gra
     case 3: return launch_bwd_d32<128, 4, 8, 3, true>(SDB_FBWD_ARGS);   // 143 registers, 12 warps / SM
     case 5: return launch_bwd_d32<128, 4, 8, 5, true>(SDB_FBWD_ARGS);   // 96 registers (spills 20 B), 20 warps / SM
     case 6: return launch_bwd_d32<128, 4, 8, 6, true>(SDB_FBWD_ARGS);   // 80 registers (spills 108 B), 24 warps / SM
-    case 7: return msda_backward_x8(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets,
+    case 7:   // experimental: 4 lanes x 8 channels per pair; 8 = the same with a rolled batch loop
+    case 8: return msda_backward_x8(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets,
                                     attn_logits, batch, S, L, Lq, grad_value, grad_offsets, grad_attn_logits,
-                                    reference_points, ref_dim);   // experimental: 4 lanes x 8 channels per pair
+                                    reference_points, ref_dim, g_bwd_variant == 8);
     // experimental (not yet run on hardware): 2 / 4 points of corner loads in flight per warp
     case 10: return launch_bwd_d32<128, 4, 8, 4, true, float, 2>(SDB_FBWD_ARGS);
     case 11: return launch_bwd_d32<128, 4, 8, 3, true, float, 2>(SDB_FBWD_ARGS);
