@@ -1,6 +1,7 @@
 """Experimental MSDA backward variants against the oracle and against the validated default kernel:
 
   7       4 lanes x 8 channels per (query, head) pair (csrc/msda_backward_x8.cu): 0.56x the instructions per pair
+  8       the same with the loop over a chunk's 4 batches kept rolled (29 KB of code instead of 60 KB)
   10, 11  the 8-lane kernel with the corner loads of 2 points in flight per warp (4 / 3 CTAs per SM)
   12      ... of 4 points in flight (3 CTAs per SM)
 
@@ -25,7 +26,7 @@ pytestmark = [pytest.mark.gpu,
                                  reason="experimental backward variants have not run on hardware yet "
                                         "(set SDB_RUN_UNVALIDATED=1)")]
 
-VARIANTS = [7, 10, 11, 12]
+VARIANTS = [7, 8, 10, 11, 12]
 
 
 def _relerr(a, b):

@@ -27,9 +27,9 @@ for name, Lq, refdim in (("enc", S, 2), ("dec", 1092, 4)):
     off = torch.randn(N, Lq, 8, 4, 4, 2, device="cuda", generator=g) * 2.0
     logits = torch.randn(N, Lq, 8, 16, device="cuda", generator=g)
     gout = torch.randn(N, Lq, 256, device="cuda", generator=g)
-    # 7 = experimental 4-lane x 8-channel mapping (msda_backward_x8.cu); 10 / 11 / 12 = 2 / 2 / 4 points of corner
+    # 7 / 8 = experimental 4-lane x 8-channel mapping (msda_backward_x8.cu), unrolled / rolled batch loop; 10 / 11 / 12 = 2 / 2 / 4 points of corner
     # loads in flight per warp at 4 / 3 / 3 CTAs per SM
-    for variant in (0, 6, 5, 3, 2, 7, 10, 11, 12):
+    for variant in (0, 6, 5, 3, 2, 7, 8, 10, 11, 12):
         _lib.lib().sdb_msda_set_variant(0, variant)
         ts = []
         for _ in range(33):
