@@ -123,3 +123,73 @@ def load_mean_teacher():
     sys.modules["detr_ssod_ref.utils.logger"] = lg
     sys.modules["detr_ssod_ref.utils"].logger = lg
     return _load("detr_ssod_ref.utils.hooks.mean_teacher", REF + "/detr_ssod/utils/hooks/mean_teacher.py")
+
+
+def load_dino_transformer():
+    """detr_od/models/utils/transformer.py (the DINO classes, :435-1406) and the reference's own ``MSDeformAttn`` module
+    (ops/modules/ms_deform_attn.py) from where they lie.  The file imports a long list of mmcv / timm / matplotlib
+    symbols for its Swin helpers (dead code for DINO): those get inert stand-ins.  The compiled extension is stubbed,
+    and ``MSDeformAttnFunction.apply`` is routed to the reference's own pure-PyTorch fallback
+    (``ms_deform_attn_core_pytorch``, ms_deform_attn_func.py:41-61) so the module runs on the CPU."""
+    import torch.nn as nn
+    _install_mmcv_stub()
+
+    class _Inert:
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, *a, **k):
+            return a[0] if a else None
+
+    def _decorator_factory(*a, **k):
+        if len(a) == 1 and callable(a[0]) and not k:
+            return a[0]
+        return lambda f: f
+
+    for name in ("matplotlib", "matplotlib.pyplot", "timm", "timm.models", "timm.models.layers"):
+        _pkg(name)
+    sys.modules["timm.models.layers"].DropPath = nn.Identity
+    sys.modules["timm.models.layers"].trunc_normal_ = nn.init.trunc_normal_
+    runner = _pkg("mmcv.runner")
+    runner.auto_fp16 = _decorator_factory
+    runner.force_fp32 = _decorator_factory
+    bm = _pkg("mmcv.runner.base_module")
+    bm.BaseModule, bm.ModuleList, bm.Sequential = nn.Module, nn.ModuleList, nn.Sequential
+    cnn = _pkg("mmcv.cnn")
+    for n in ("build_activation_layer", "build_conv_layer", "build_norm_layer", "xavier_init"):
+        setattr(cnn, n, _Inert())
+    _pkg("mmcv.cnn.bricks")
+    reg = _pkg("mmcv.cnn.bricks.registry")
+    reg.TRANSFORMER_LAYER, reg.TRANSFORMER_LAYER_SEQUENCE, reg.ATTENTION = (_Registry("tl"), _Registry("tls"),
+                                                                          _Registry("attn"))
+    tr = _pkg("mmcv.cnn.bricks.transformer")
+    for n in ("BaseTransformerLayer", "TransformerLayerSequence", "FFN", "MultiScaleDeformableAttention"):
+        setattr(tr, n, type(n, (nn.Module,), {}))
+    tr.build_transformer_layer_sequence = _Inert()
+    _pkg("mmcv.cnn.bricks.drop").build_dropout = _Inert()
+    utils = sys.modules["mmcv.utils"]
+    utils.to_2tuple = lambda x: (x, x)
+    utils.deprecated_api_warning = _decorator_factory
+    _pkg("mmcv.ops")
+    _pkg("mmcv.ops.multi_scale_deform_attn").MultiScaleDeformableAttention = tr.MultiScaleDeformableAttention
+    for p in ("mmdet", "mmdet.models", "mmdet.models.utils"):
+        _pkg(p)
+    _pkg("mmdet.models.utils.builder").TRANSFORMER = _Registry("transformer")
+
+    base = REF + "/detr_od/models/utils"
+    for p in ("detr_od_ref", "detr_od_ref.models", "detr_od_ref.models.utils", "detr_od_ref.models.utils.ops",
+              "detr_od_ref.models.utils.ops.functions", "detr_od_ref.models.utils.ops.modules"):
+        _pkg(p)
+    att = _pkg("detr_od_ref.models.utils.attention")
+    att.MultiheadAttention = type("MultiheadAttention", (nn.Module,), {})
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    fn = _load("detr_od_ref.models.utils.ops.functions.ms_deform_attn_func",
+               base + "/ops/functions/ms_deform_attn_func.py")
+    sys.modules["detr_od_ref.models.utils.ops.functions"].MSDeformAttnFunction = fn.MSDeformAttnFunction
+
+    def cpu_apply(value, shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
+        return fn.ms_deform_attn_core_pytorch(value, shapes, sampling_locations, attention_weights)
+    fn.MSDeformAttnFunction.apply = staticmethod(cpu_apply)
+    mod = _load("detr_od_ref.models.utils.ops.modules.ms_deform_attn", base + "/ops/modules/ms_deform_attn.py")
+    sys.modules["detr_od_ref.models.utils.ops.modules"].MSDeformAttn = mod.MSDeformAttn
+    return _load("detr_od_ref.models.utils.transformer", base + "/transformer.py"), mod

@@ -1,0 +1,70 @@
+"""Deterministic weights and inputs shared by the golden generator (reference side, make_golden.py) and the tests (our
+side): both models are filled parameter-by-parameter from a seed derived from the parameter's NAME, so the fixture
+needs no multi-megabyte state dict -- the reference's DINOTransformer and ours have the same 72 parameter names."""
+import zlib
+
+import torch
+
+TRANSFORMER_KW = dict(d_model=256, nhead=8, num_queries=30, num_encoder_layers=1, num_decoder_layers=2,
+                      dim_feedforward=64, num_feature_levels=4)
+LEVELS = [(12, 16), (6, 8), (3, 4), (2, 2)]
+NUM_CLASSES = 8
+N_DN = 6
+
+
+def fill_by_name(module, prefix=""):
+    """Every parameter <- N(0, s) drawn from a generator seeded by crc32(name); s by kind (weights ~ xavier scale,
+    LayerNorm gains around 1, sampling-offset biases a few pixels so taps sit off the pixel lattice)."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            full = prefix + name
+            g = torch.Generator().manual_seed(zlib.crc32(full.encode()))
+            r = torch.randn(p.shape, generator=g, dtype=torch.float32)
+            if "norm" in name and name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * r)
+            elif name.endswith("sampling_offsets.bias"):
+                p.copy_(1.7 * r)
+            elif name.endswith("bias"):
+                p.copy_(0.1 * r)
+            elif p.dim() >= 2:
+                p.copy_(r * (2.0 / (p.shape[0] + p.shape[-1])) ** 0.5)
+            else:
+                p.copy_(0.5 * r)
+    return module
+
+
+def inputs(seed=11):
+    """srcs / masks / pos_embeds per level (image 1 padded on the right and bottom), a denoising part of N_DN queries
+    and its (T, T) attention mask."""
+    g = torch.Generator().manual_seed(seed)
+    bs, C = 2, TRANSFORMER_KW["d_model"]
+    srcs, masks, poss = [], [], []
+    for (h, w) in LEVELS:
+        srcs.append(torch.randn(bs, C, h, w, generator=g))
+        poss.append(torch.randn(bs, C, h, w, generator=g) * 0.5)
+        m = torch.zeros(bs, h, w, dtype=torch.bool)
+        m[1, max(1, (3 * h) // 4):, :] = True
+        m[1, :, max(1, (2 * w) // 3):] = True
+        masks.append(m)
+    nq = TRANSFORMER_KW["num_queries"]
+    refpoint = torch.randn(bs, N_DN, 4, generator=g)               # unsigmoided boxes of the denoising queries
+    tgt = torch.randn(bs, N_DN, C, generator=g)
+    T = N_DN + nq
+    attn_mask = torch.zeros(T, T, dtype=torch.bool)
+    attn_mask[N_DN:, :N_DN] = True                                 # matching queries do not see the denoising part
+    attn_mask[:N_DN // 2, N_DN // 2:N_DN] = True                   # two denoising groups, isolated from each other
+    attn_mask[N_DN // 2:N_DN, :N_DN // 2] = True
+    return srcs, masks, poss, refpoint, tgt, attn_mask
+
+
+FULL_GRADS = ["level_embed", "enc_output_norm.weight", "decoder.layers.1.cross_attn.sampling_offsets.bias",
+              "encoder.layers.0.self_attn.attention_weights.bias", "decoder.ref_point_head.layers.1.bias",
+              "decoder.layers.0.self_attn.in_proj_bias", "encoder.layers.0.norm2.bias"]
+
+
+def scalar_loss(hs, references, hs_enc, ref_enc):
+    """A fixed smooth scalar of every differentiable output of DINOTransformer.forward."""
+    w = torch.linspace(0.5, 1.5, hs[0].shape[-1])
+    loss = sum((h * w).sin().mean() for h in hs) + (hs_enc * w).cos().mean()
+    loss = loss + sum((r * torch.tensor([1.0, -2.0, 0.5, 1.5])).sum(-1).square().mean() for r in references[1:])
+    return loss + (ref_enc * torch.tensor([0.3, 0.7, -1.1, 0.9])).sum(-1).square().mean()

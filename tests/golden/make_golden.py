@@ -14,6 +14,9 @@ Outputs (committed, small):
                         (scipy 1.18.1), incl. tie KATs
   ema_golden.npz        MeanTeacher.momentum_update / before_train_iter results
                         (detr_ssod/utils/hooks/mean_teacher.py:37-64)
+  dino_transformer_golden.npz  outputs of the reference's own DINOTransformer.forward (detr_od/models/utils/
+                        transformer.py:1047-1406, with its MSDeformAttn module on the pure-PyTorch op) on the
+                        deterministic weights / inputs of dino_fixture.py
 """
 import os
 import sys
@@ -206,9 +209,49 @@ def make_ema():
     print("ema_golden.npz: momenta", moms)
 
 
+def make_dino_transformer():
+    import dino_fixture as F
+    T, _ = R.load_dino_transformer()
+    torch.manual_seed(0)
+    model = F.fill_by_name(T.DINOTransformer(**F.TRANSFORMER_KW)).eval()
+    C, K = F.TRANSFORMER_KW["d_model"], F.NUM_CLASSES
+    n_dec = F.TRANSFORMER_KW["num_decoder_layers"]
+    heads = torch.nn.ModuleDict(dict(
+        fc_reg=torch.nn.ModuleList([T.MLP(C, C, 4, 3) for _ in range(n_dec)]),
+        fc_cls=torch.nn.ModuleList([torch.nn.Linear(C, K) for _ in range(n_dec)]),
+        fc_enc_reg=T.MLP(C, C, 4, 3), fc_enc_cls=torch.nn.Linear(C, K)))
+    F.fill_by_name(heads, "heads.")
+    srcs, masks, poss, refpoint, tgt, attn_mask = F.inputs()
+    srcs = [s_.requires_grad_(True) for s_ in srcs]
+    hs, references, hs_enc, ref_enc, init_box = model(srcs, masks, refpoint, poss, tgt, attn_mask,
+                                                      fc_reg=heads["fc_reg"], fc_cls=heads["fc_cls"],
+                                                      fc_enc_reg=heads["fc_enc_reg"], fc_enc_cls=heads["fc_enc_cls"])
+    out = {}
+    out["hs"] = torch.stack(list(hs)).detach().numpy()
+    out["references"] = torch.stack(list(references)).detach().numpy()
+    out["hs_enc"], out["ref_enc"] = hs_enc.detach().numpy(), ref_enc.detach().numpy()
+    out["init_box_proposal"] = init_box.detach().numpy()
+    # backward of a fixed scalar of every differentiable output (dino_fixture.scalar_loss): gradient norm of every
+    # parameter, full gradients of a few small ones and of the finest input level
+    F.scalar_loss(hs, references, hs_enc, ref_enc).backward()
+    names = sorted(n for n, _ in model.named_parameters())
+    params = dict(model.named_parameters())
+    out["grad_norms"] = np.array([float(params[n].grad.norm()) if params[n].grad is not None else -1.0 for n in names])
+    for n in F.FULL_GRADS:
+        out["grad/" + n] = params[n].grad.numpy()
+    out["grad_src3"] = srcs[3].grad.numpy()
+    out["grad_head_norms"] = np.array([float(p.grad.norm()) if p.grad is not None else -1.0
+                                       for _, p in sorted(heads.named_parameters())])
+    out["head_param_names"] = np.array(sorted(n for n, _ in heads.named_parameters()))
+    out["param_names"] = np.array(sorted(n for n, _ in model.named_parameters()))
+    np.savez_compressed(os.path.join(HERE, "dino_transformer_golden.npz"), **out)
+    print("dino_transformer_golden.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
     make_hungarian()
     make_lsap()
     make_ema()
+    make_dino_transformer()
