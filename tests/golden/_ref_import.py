@@ -193,3 +193,67 @@ def load_dino_transformer():
     mod = _load("detr_od_ref.models.utils.ops.modules.ms_deform_attn", base + "/ops/modules/ms_deform_attn.py")
     sys.modules["detr_od_ref.models.utils.ops.modules"].MSDeformAttn = mod.MSDeformAttn
     return _load("detr_od_ref.models.utils.transformer", base + "/transformer.py"), mod
+
+
+def load_dino_head():
+    """detr_od/models/dense_heads/dino_detr_head.py (``DINODETRHead.loss`` and everything under it: ``loss_single``,
+    ``get_targets``, ``_get_target_single`` / ``_get_target_single_dn``) with the REAL mmdet pieces it computes with --
+    HungarianAssigner + match costs, PseudoSampler, FocalLoss (python branch), L1Loss, GIoULoss, bbox transforms,
+    ``multi_apply`` -- loaded from thirdparty/mmdetection, and inert stand-ins for the rest (layer builders, the
+    AnchorFreeHead base, registries).  ``reduce_mean`` is the single-process identity, as in mmdet without
+    torch.distributed."""
+    import functools
+
+    import torch
+    import torch.nn as nn
+    ha, mc, iou = load_hungarian()
+    T, _ = load_dino_transformer()
+    mmcv = sys.modules["mmcv"]
+    mmcv.jit = lambda *a, **k: (lambda f: f)
+    ops = _pkg("mmcv.ops")
+    ops.sigmoid_focal_loss = None                      # CUDA op; the CPU tensors below take py_sigmoid_focal_loss
+    cnn = sys.modules["mmcv.cnn"]
+    cnn.Conv2d, cnn.Linear = nn.Conv2d, nn.Linear
+    cnn.bias_init_with_prob = lambda p: float(-__import__("math").log((1 - p) / p))
+    tr = sys.modules["mmcv.cnn.bricks.transformer"]
+    tr.build_positional_encoding = lambda cfg: None
+
+    # mmdet.core helpers the head imports by name
+    b = MMDET + "/core/bbox"
+    transforms = sys.modules["mmdet.core.bbox.transforms"]
+    _load("mmdet.core.bbox.samplers_sampling_result", b + "/samplers/sampling_result.py")
+    for p in ("mmdet.core.bbox.samplers",):
+        _pkg(p)
+    sys.modules["mmdet.core.bbox.samplers.sampling_result"] = sys.modules["mmdet.core.bbox.samplers_sampling_result"]
+    _pkg("mmdet.core.bbox.samplers").sampling_result = sys.modules["mmdet.core.bbox.samplers_sampling_result"]
+    _load("mmdet.core.bbox.samplers.base_sampler", b + "/samplers/base_sampler.py")
+    ps = _load("mmdet.core.bbox.samplers.pseudo_sampler", b + "/samplers/pseudo_sampler.py")
+
+    def multi_apply(func, *args, **kwargs):            # mmdet/core/utils/misc.py:11-29
+        pfunc = functools.partial(func, **kwargs) if kwargs else func
+        return tuple(map(list, zip(*map(pfunc, *args))))
+    core = _pkg("mmdet.core")
+    core.bbox_cxcywh_to_xyxy, core.bbox_xyxy_to_cxcywh = transforms.bbox_cxcywh_to_xyxy, transforms.bbox_xyxy_to_cxcywh
+    core.build_assigner = lambda cfg: None
+    core.build_sampler = lambda cfg, **k: None
+    core.multi_apply = multi_apply
+    core.reduce_mean = lambda t: t
+    core.bbox_overlaps = iou.bbox_overlaps
+    sys.modules["mmdet.models.utils"].build_transformer = lambda cfg: None
+    builder = _pkg("mmdet.models.builder")
+    builder.HEADS, builder.LOSSES = _Registry("heads"), _Registry("losses")
+    builder.build_loss = lambda cfg: None
+    _pkg("mmdet.models.utils.transformer").inverse_sigmoid = T.inverse_sigmoid
+    _pkg("mmdet.models.dense_heads")
+    afh = _pkg("mmdet.models.dense_heads.anchor_free_head")
+    afh.AnchorFreeHead = type("AnchorFreeHead", (nn.Module,), {})
+    _pkg("mmdet.models.losses")
+    _load("mmdet.models.losses.utils", MMDET + "/models/losses/utils.py")
+    fl = _load("mmdet.models.losses.focal_loss", MMDET + "/models/losses/focal_loss.py")
+    il = _load("mmdet.models.losses.iou_loss", MMDET + "/models/losses/iou_loss.py")
+    sl = _load("mmdet.models.losses.smooth_l1_loss", MMDET + "/models/losses/smooth_l1_loss.py")
+    for p in ("detr_od_ref.models.dense_heads",):
+        _pkg(p)
+    dn = _load("detr_od_ref.models.dense_heads.dn_components", REF + "/detr_od/models/dense_heads/dn_components.py")
+    head = _load("detr_od_ref.models.dense_heads.dino_detr_head", REF + "/detr_od/models/dense_heads/dino_detr_head.py")
+    return dict(head=head, dn=dn, focal=fl, iou=il, l1=sl, assigner=ha, sampler=ps, torch=torch)

@@ -68,3 +68,33 @@ def scalar_loss(hs, references, hs_enc, ref_enc):
     loss = sum((h * w).sin().mean() for h in hs) + (hs_enc * w).cos().mean()
     loss = loss + sum((r * torch.tensor([1.0, -2.0, 0.5, 1.5])).sum(-1).square().mean() for r in references[1:])
     return loss + (ref_enc * torch.tensor([0.3, 0.7, -1.1, 0.9])).sum(-1).square().mean()
+
+
+# ---- head loss fixture (reference: DINODETRHead.loss, dino_detr_head.py:506-980) ---------------------------------
+LOSS_KW = dict(num_classes=9, num_query=40, n_dec=3, dn_groups=2)
+LOSS_IMG_SHAPES = [(96, 128, 3), (80, 112, 3), (64, 64, 3)]
+LOSS_GT_COUNTS = [3, 0, 5]            # one image without boxes
+
+
+def loss_inputs(seed=23):
+    """Decoder / encoder / denoising predictions, GT boxes (xyxy pixels) and labels, img_metas, dn_meta."""
+    g = torch.Generator().manual_seed(seed)
+    K, Q, L, G = LOSS_KW["num_classes"], LOSS_KW["num_query"], LOSS_KW["n_dec"], LOSS_KW["dn_groups"]
+    bs = len(LOSS_IMG_SHAPES)
+    gt_bboxes, gt_labels = [], []
+    for (h, w, _), n in zip(LOSS_IMG_SHAPES, LOSS_GT_COUNTS):
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([w * 0.6, h * 0.6])
+        wh = torch.rand(n, 2, generator=g) * torch.tensor([w * 0.35, h * 0.35]) + 4.0
+        gt_bboxes.append(torch.cat([xy, xy + wh], 1))
+        gt_labels.append(torch.randint(0, K, (n,), generator=g))
+    pad = 2 * max(LOSS_GT_COUNTS) * G
+    rnd = lambda *shape: torch.randn(*shape, generator=g)
+    box = lambda *shape: torch.cat([torch.rand(*shape, 2, generator=g) * 0.8 + 0.1,
+                                    torch.rand(*shape, 2, generator=g) * 0.3 + 0.03], -1)
+    out = dict(all_cls_scores=rnd(L, bs, Q, K) - 2.0, all_bbox_preds=box(L, bs, Q),
+               enc_cls_scores=rnd(bs, Q, K) - 2.0, enc_bbox_preds=box(bs, Q),
+               dn_cls_scores=rnd(L, bs, pad, K) - 1.0, dn_bbox_preds=box(L, bs, pad),
+               gt_bboxes=gt_bboxes, gt_labels=gt_labels,
+               img_metas=[dict(img_shape=s, batch_input_shape=(96, 128)) for s in LOSS_IMG_SHAPES],
+               dn_meta=dict(pad_size=pad, num_dn_group=G))
+    return out

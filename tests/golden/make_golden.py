@@ -248,6 +248,43 @@ def make_dino_transformer():
     print("dino_transformer_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_dino_head_loss():
+    """The reference's own DINODETRHead.loss on CPU tensors (its `.to('cuda')` placeholders are not reached: the
+    fixture has a denoising part), with the DINO config's assigner / sampler / losses
+    (configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:30-60)."""
+    import dino_fixture as F
+    m = R.load_dino_head()
+    H = m["head"].DINODETRHead
+    head = H.__new__(H)
+    torch.nn.Module.__init__(head)
+    K = F.LOSS_KW["num_classes"]
+    head.num_classes, head.cls_out_channels, head.num_query = K, K, F.LOSS_KW["num_query"]
+    head.bg_cls_weight, head.sync_cls_avg_factor = 0.0, False
+    mc = sys.modules["mmdet.core.bbox.match_costs.match_cost"]
+    head.assigner = m["assigner"].HungarianAssigner(
+        cls_cost=dict(type="FocalLossCost", weight=2.0), reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+        iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0))
+    head.sampler = m["sampler"].PseudoSampler()
+    head.loss_cls = m["focal"].FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0)
+    head.loss_bbox = m["l1"].L1Loss(loss_weight=5.0)
+    head.loss_iou = m["iou"].GIoULoss(loss_weight=2.0)
+    x = F.loss_inputs()
+    # the denoising targets place their index tensors with `.cuda()` (dino_detr_head.py:774-790): device placement
+    # only, made a no-op here so the reference code runs on the CPU
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            losses = head.loss(x["all_cls_scores"], x["all_bbox_preds"], x["enc_cls_scores"], x["enc_bbox_preds"],
+                               x["dn_cls_scores"], x["dn_bbox_preds"], x["gt_bboxes"], x["gt_labels"],
+                               img_metas=x["img_metas"], dn_metas=x["dn_meta"])
+    finally:
+        torch.Tensor.cuda = saved
+    out = {"keys": np.array(list(losses.keys())), "values": np.array([float(v) for v in losses.values()], np.float64)}
+    np.savez_compressed(os.path.join(HERE, "dino_head_loss_golden.npz"), **out)
+    print("dino_head_loss_golden.npz:", len(losses), "losses;", dict(list(losses.items())[:6]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -255,3 +292,4 @@ if __name__ == "__main__":
     make_lsap()
     make_ema()
     make_dino_transformer()
+    make_dino_head_loss()
