@@ -98,3 +98,25 @@ def loss_inputs(seed=23):
                img_metas=[dict(img_shape=s, batch_input_shape=(96, 128)) for s in LOSS_IMG_SHAPES],
                dn_meta=dict(pad_size=pad, num_dn_group=G))
     return out
+
+
+# ---- contrastive denoising fixture (reference: prepare_for_cdn, dn_components.py:6-125) ---------------------------
+CDN_CASES = {
+    # name: (GT counts per image, dn_number, label_noise_ratio, box_noise_scale, num_queries, num_classes)
+    "config": ([3, 0, 5], 100, 0.5, 0.4, 30, 9),          # the shipped setting: dn_number 100 -> 20 groups
+    "few_groups": ([2, 4], 2, 0.5, 1.0, 12, 9),            # dn_number < 100 is taken literally (4 groups)
+    "no_noise": ([1, 2], 100, 0.0, 0.0, 10, 9),
+}
+
+
+def cdn_targets(counts, num_classes, seed=5):
+    g = torch.Generator().manual_seed(seed + sum(counts))
+    labels = [torch.randint(0, num_classes, (n,), generator=g) for n in counts]
+    boxes = [torch.cat([torch.rand(n, 2, generator=g) * 0.6 + 0.2, torch.rand(n, 2, generator=g) * 0.3 + 0.05], 1)
+             for n in counts]
+    return dict(labels=labels, boxes=boxes)
+
+
+def label_embedding(num_classes, hidden_dim=256):
+    emb = torch.nn.Embedding(num_classes + 1, hidden_dim)
+    return fill_by_name(emb, "label_enc.")

@@ -285,6 +285,50 @@ def make_dino_head_loss():
     print("dino_head_loss_golden.npz:", len(losses), "losses;", dict(list(losses.items())[:6]))
 
 
+def make_dino_cdn():
+    """The reference's own prepare_for_cdn on the CPU (`.cuda()` / `.to('cuda')` made no-ops), with every random draw
+    recorded so that the test can replay the same noise through our fixed-shape RNG entry points."""
+    import dino_fixture as F
+    m = R.load_dino_head()
+    dn = m["dn"]
+    out = {}
+    saved = torch.Tensor.cuda, torch.Tensor.to, torch.rand_like, torch.randint_like
+    draws = []
+
+    def to(self, *a, **k):
+        if a and isinstance(a[0], str) and a[0].startswith("cuda"):
+            return self
+        return saved[1](self, *a, **k)
+
+    def rec(fn):
+        def wrapped(*a, **k):
+            r = fn(*a, **k)
+            draws.append(r.clone())
+            return r
+        return wrapped
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = to
+    torch.rand_like, torch.randint_like = rec(saved[2]), rec(saved[3])
+    try:
+        for name, (counts, dn_number, lnr, bns, nq, K) in F.CDN_CASES.items():
+            torch.manual_seed(100 + len(name))
+            del draws[:]
+            tg = F.cdn_targets(counts, K)
+            emb = F.label_embedding(K)
+            with torch.no_grad():
+                ql, qb, mask, meta = dn.prepare_for_cdn((tg, dn_number, lnr, bns), True, nq, K, 256, emb)
+            out[name + "/query_label"], out[name + "/query_bbox"] = ql.numpy(), qb.numpy()
+            out[name + "/attn_mask"] = mask.numpy()
+            out[name + "/meta"] = np.array([meta["pad_size"], meta["num_dn_group"]])
+            for i, d in enumerate(draws):
+                out[f"{name}/draw{i}"] = d.numpy()
+            out[name + "/n_draws"] = np.array(len(draws))
+            print(name, "pad", meta, "draws", [tuple(d.shape) for d in draws])
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to, torch.rand_like, torch.randint_like = saved
+    np.savez_compressed(os.path.join(HERE, "dino_cdn_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -293,3 +337,4 @@ if __name__ == "__main__":
     make_ema()
     make_dino_transformer()
     make_dino_head_loss()
+    make_dino_cdn()
