@@ -257,3 +257,45 @@ def load_dino_head():
     dn = _load("detr_od_ref.models.dense_heads.dn_components", REF + "/detr_od/models/dense_heads/dn_components.py")
     head = _load("detr_od_ref.models.dense_heads.dino_detr_head", REF + "/detr_od/models/dense_heads/dino_detr_head.py")
     return dict(head=head, dn=dn, focal=fl, iou=il, l1=sl, assigner=ha, sampler=ps, torch=torch)
+
+
+def load_positional_encoding():
+    """detr_od/models/utils/positional_encoding.py (SinePositionalEncodingHW)."""
+    import torch.nn as nn
+    _install_mmcv_stub()
+    _pkg("mmcv.cnn")
+    _pkg("mmcv.cnn.bricks")
+    tr = _pkg("mmcv.cnn.bricks.transformer")
+    tr.POSITIONAL_ENCODING = _Registry("pe")
+    runner = _pkg("mmcv.runner")
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+    runner.BaseModule = BaseModule
+    for p in ("detr_od_ref", "detr_od_ref.models", "detr_od_ref.models.utils"):
+        _pkg(p)
+    return _load("detr_od_ref.models.utils.positional_encoding", REF + "/detr_od/models/utils/positional_encoding.py")
+
+
+def load_bbox_utils():
+    """detr_ssod/models/utils/bbox_utils.py (Transform2D.transform_bboxes and helpers)."""
+    for p in ("mmdet", "mmdet.core", "mmdet.core.mask"):
+        _pkg(p)
+    _pkg("mmdet.core.mask.structures").BitmapMasks = type("BitmapMasks", (), {})
+    for p in ("detr_ssod_ref", "detr_ssod_ref.models", "detr_ssod_ref.models.utils"):
+        _pkg(p)
+    return _load("detr_ssod_ref.models.utils.bbox_utils", REF + "/detr_ssod/models/utils/bbox_utils.py")
+
+
+def load_o2m_assigner():
+    """detr_od/core/bbox/assigners/o2m_assigner.py + o2m_assign_result.py on the real mmdet bbox pieces."""
+    load_hungarian()
+    ds = _pkg("detr_ssod")
+    _pkg("detr_ssod.utils").log_every_n = lambda *a, **k: None
+    sys.modules["detr_ssod.utils"].log_image_with_boxes = lambda *a, **k: None
+    for p in ("detr_od_ref", "detr_od_ref.core", "detr_od_ref.core.bbox", "detr_od_ref.core.bbox.assigners"):
+        _pkg(p)
+    base = REF + "/detr_od/core/bbox/assigners"
+    _load("detr_od_ref.core.bbox.assigners.o2m_assign_result", base + "/o2m_assign_result.py")
+    return _load("detr_od_ref.core.bbox.assigners.o2m_assigner", base + "/o2m_assigner.py")

@@ -329,6 +329,47 @@ def make_dino_cdn():
     np.savez_compressed(os.path.join(HERE, "dino_cdn_golden.npz"), **out)
 
 
+def make_ssod_pieces():
+    """Small reference-pinned pieces of rows a10 / a12 / a14: SinePositionalEncodingHW (positional_encoding.py),
+    Transform2D.transform_bboxes (bbox_utils.py:167-192) and O2MAssigner.assign (o2m_assigner.py:50-170)."""
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    # a14: the DINO setting (num_feats 128, temperature 20/20, normalize) on a padded batch
+    pe = R.load_positional_encoding().SinePositionalEncodingHW(128, temperatureH=20, temperatureW=20, normalize=True)
+    mask = torch.zeros(2, 7, 9, dtype=torch.bool)
+    mask[1, 5:, :] = True
+    mask[1, :, 6:] = True
+    out["pe/mask"], out["pe/out"] = mask.numpy(), pe(mask).numpy()
+    # a12: weak -> strong view warp (flip + scale + translate homographies, boxes with scores, clamp at the border)
+    bu = R.load_bbox_utils()
+    boxes = [torch.cat([torch.rand(6, 2, generator=g) * 200, torch.rand(6, 2, generator=g) * 200 + 210,
+                        torch.rand(6, 1, generator=g)], 1), torch.zeros(0, 5),
+             torch.cat([torch.rand(3, 2, generator=g) * 100, torch.rand(3, 2, generator=g) * 100 + 120], 1)]
+    Ms = [torch.tensor([[-1.3, 0.0, 400.0], [0.0, 1.3, -20.0], [0.0, 0.0, 1.0]]),
+          torch.eye(3), torch.tensor([[0.8, 0.1, 5.0], [-0.05, 0.9, 12.0], [0.0, 0.0, 1.0]])]
+    shapes = [(300, 380, 3), (200, 200, 3), (256, 256, 3)]
+    warped = bu.Transform2D.transform_bboxes(boxes, Ms, shapes)
+    for i in range(3):
+        out[f"warp/box{i}"], out[f"warp/M{i}"], out[f"warp/out{i}"] = boxes[i].numpy(), Ms[i].numpy(), warped[i].numpy()
+    out["warp/shapes"] = np.array(shapes)
+    # a10: O2M assignment (alpha 1, beta 6, top-13 candidates), predictions already sigmoid-ed
+    o2m = R.load_o2m_assigner().O2MAssigner(candidate_topk=13)
+    for ci, (Q, G, w, h) in enumerate([(200, 7, 640.0, 480.0), (60, 1, 320.0, 200.0), (150, 20, 500.0, 500.0)]):
+        bbox = torch.rand(Q, 4, generator=g) * torch.tensor([1, 1, 0.5, 0.5]) + 0.01
+        scores = torch.rand(Q, 80, generator=g)
+        xy = torch.rand(G, 2, generator=g) * 0.5
+        gtb = torch.cat([xy, xy + torch.rand(G, 2, generator=g) * 0.4 + 0.05], 1) * torch.tensor([w, h, w, h])
+        gtl = torch.randint(0, 80, (G,), generator=g)
+        res = o2m.assign(bbox, scores, gtb, gtl, dict(img_shape=(int(h), int(w), 3)))
+        out[f"o2m{ci}/bbox"], out[f"o2m{ci}/scores"] = bbox.numpy(), scores.numpy()
+        out[f"o2m{ci}/gtb"], out[f"o2m{ci}/gtl"], out[f"o2m{ci}/wh"] = gtb.numpy(), gtl.numpy(), np.array([w, h])
+        out[f"o2m{ci}/gt_inds"], out[f"o2m{ci}/labels"] = res.gt_inds.numpy(), res.labels.numpy()
+        out[f"o2m{ci}/max_overlaps"], out[f"o2m{ci}/assign_metrics"] = res.max_overlaps.numpy(), res.assign_metrics.numpy()
+    np.savez_compressed(os.path.join(HERE, "ssod_pieces_golden.npz"), **out)
+    print("ssod_pieces_golden.npz:", len(out), "arrays; O2M positives",
+          [int((out[f"o2m{c}/gt_inds"] > 0).sum()) for c in range(3)])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -338,3 +379,4 @@ if __name__ == "__main__":
     make_dino_transformer()
     make_dino_head_loss()
     make_dino_cdn()
+    make_ssod_pieces()
