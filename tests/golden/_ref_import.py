@@ -299,3 +299,20 @@ def load_o2m_assigner():
     base = REF + "/detr_od/core/bbox/assigners"
     _load("detr_od_ref.core.bbox.assigners.o2m_assign_result", base + "/o2m_assign_result.py")
     return _load("detr_od_ref.core.bbox.assigners.o2m_assigner", base + "/o2m_assigner.py")
+
+
+def load_dino_ssod_head():
+    """detr_od/models/dense_heads/dino_detr_ssod_head.py (``DINODETRSSODHead.loss`` with both assignment phases) plus
+    the reference's TaskAlignedFocalLoss and O2MAssigner, on the same stand-ins as ``load_dino_head``."""
+    m = load_dino_head()
+    o2m = load_o2m_assigner()
+    _pkg("mmcv.runner").get_dist_info = lambda: (0, 1)
+    sys.modules["mmdet.core"].multiclass_nms = None          # test-time only (get_bboxes), never called by loss()
+    for p in ("detr_od_ref.models.losses",):
+        _pkg(p)
+    tal = _load("detr_od_ref.models.losses.task_aligned_focal_loss",
+                REF + "/detr_od/models/losses/task_aligned_focal_loss.py")
+    head = _load("detr_od_ref.models.dense_heads.dino_detr_ssod_head",
+                 REF + "/detr_od/models/dense_heads/dino_detr_ssod_head.py")
+    m.update(ssod_head=head, o2m=o2m, tal=tal)
+    return m

@@ -370,6 +370,60 @@ def make_ssod_pieces():
           [int((out[f"o2m{c}/gt_inds"] > 0).sum()) for c in range(3)])
 
 
+def make_dino_ssod_head_loss():
+    """The reference's own DINODETRSSODHead.loss (dino_detr_ssod_head.py:508-1205) in its three regimes: warm-up on
+    labelled data (O2M assignment + TaskAlignedFocalLoss, denoising part on), warm-up on pseudo labels (no denoising
+    loss), and the Hungarian phase on pseudo labels (soft scores passed, second denoising block of the SSOD layout)."""
+    import dino_fixture as F
+    m = R.load_dino_ssod_head()
+    H = m["ssod_head"].DINODETRSSODHead
+    head = H.__new__(H)
+    torch.nn.Module.__init__(head)
+    K = F.LOSS_KW["num_classes"]
+    head.num_classes, head.cls_out_channels, head.num_query = K, K, F.LOSS_KW["num_query"]
+    head.bg_cls_weight, head.sync_cls_avg_factor = 0.0, False
+    head.assigner1 = m["o2m"].O2MAssigner(candidate_topk=13)
+    head.assigner2 = m["assigner"].HungarianAssigner(
+        cls_cost=dict(type="FocalLossCost", weight=2.0), reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+        iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0))
+    head.sampler = m["sampler"].PseudoSampler()
+    head.loss_cls1 = m["tal"].TaskAlignedFocalLoss(use_sigmoid=True, gamma=2.0, loss_weight=2.0)
+    head.loss_cls2 = m["focal"].FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0)
+    head.loss_bbox = m["l1"].L1Loss(loss_weight=5.0)
+    head.loss_iou = m["iou"].GIoULoss(loss_weight=2.0)
+    x = F.loss_inputs()
+    g = torch.Generator().manual_seed(9)
+    scores = [torch.rand(n, generator=g) * 0.5 + 0.4 for n in F.LOSS_GT_COUNTS]
+    ssod_meta = dict(pad_size_2=x["dn_meta"]["pad_size"], num_dn_group_2=x["dn_meta"]["num_dn_group"],
+                     pad_size=x["dn_meta"]["pad_size"], num_dn_group=x["dn_meta"]["num_dn_group"])
+    saved = torch.Tensor.cuda, torch.Tensor.to
+
+    def to(self, *a, **k):
+        if a and isinstance(a[0], str) and a[0].startswith("cuda"):
+            return self
+        return saved[1](self, *a, **k)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = to
+    out = {}
+    try:
+        for name, warm, pseudo, gts in (("warmup_sup", True, False, None), ("warmup_pseudo", True, True, scores),
+                                        ("hungarian_pseudo", False, True, scores)):
+            head.in_warm_up = warm
+            with torch.no_grad():
+                losses = head.loss(x["all_cls_scores"], x["all_bbox_preds"], x["enc_cls_scores"], x["enc_bbox_preds"],
+                                   x["dn_cls_scores"], x["dn_bbox_preds"], x["gt_bboxes"], x["gt_labels"],
+                                   gt_scores_list=gts, img_metas=x["img_metas"], dn_metas=ssod_meta,
+                                   is_pseudo_label=pseudo)
+            out[name + "/keys"] = np.array(list(losses.keys()))
+            out[name + "/values"] = np.array([float(v) for v in losses.values()], np.float64)
+            print(name, len(losses), [round(float(v), 4) for v in list(losses.values())[:7]])
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = saved
+    for i, s_ in enumerate(scores):
+        out[f"gt_scores{i}"] = s_.numpy()
+    np.savez_compressed(os.path.join(HERE, "dino_ssod_head_loss_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -380,3 +434,4 @@ if __name__ == "__main__":
     make_dino_head_loss()
     make_dino_cdn()
     make_ssod_pieces()
+    make_dino_ssod_head_loss()
