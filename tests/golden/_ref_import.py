@@ -316,3 +316,21 @@ def load_dino_ssod_head():
                  REF + "/detr_od/models/dense_heads/dino_detr_ssod_head.py")
     m.update(ssod_head=head, o2m=o2m, tal=tal)
     return m
+
+
+def load_methods(path, class_name, names, namespace):
+    """Compile individual methods of a reference class straight from its source file (for classes whose module pulls
+    in the whole mmdet detector stack): the function bodies are the reference's, only the surrounding module is not
+    executed.  -> {name: function}"""
+    import ast
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+    out = {}
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = dict(namespace)
+            exec(compile(mod, path, "exec"), ns)
+            out[node.name] = ns[node.name]
+    return out

@@ -424,6 +424,47 @@ def make_dino_ssod_head_loss():
     np.savez_compressed(os.path.join(HERE, "dino_ssod_head_loss_golden.npz"), **out)
 
 
+def make_ssod_gmm():
+    """The reference's own DinoDetrSSOD._fit_gmm (dino_detr_ssod.py:832-890; the method body compiled from the file,
+    sklearn underneath) on float32 cost pools, as the wrapper calls it.  A pool is flagged `tie` when the two best
+    log-likelihoods inside the chosen component differ by less than 1e-5: the reference then picks by float32 rounding
+    noise (e.g. a component holding two points symmetric about its mean)."""
+    import types
+    import sklearn.mixture as skm
+    fn = R.load_methods(R.REF + "/detr_ssod/models/dino_detr_ssod.py", "DinoDetrSSOD", ["_fit_gmm"],
+                        dict(np=np, torch=torch, skm=skm))["_fit_gmm"]
+    me = types.SimpleNamespace(covariance_type="diag")
+    rng = np.random.default_rng(0)
+    pools, thr, tie = [], [], []
+    for t in range(160):
+        k = int(rng.integers(1, 200)) if t > 5 else t            # sizes 0..5 first
+        if t % 3 == 0:
+            x = rng.normal(0, 1, k)
+        elif t % 3 == 1:
+            x = np.concatenate([rng.normal(-2, 0.5, k // 2 + 1), rng.normal(1.5, 0.8, k - k // 2)])[:max(k, 0)]
+        else:
+            x = np.concatenate([rng.normal(-1, 0.3, k // 3 + 1), rng.normal(3.0, 1.5, k)])
+        x = x.astype(np.float32)
+        r = fn(me, torch.from_numpy(x), device="cpu")
+        r = float(np.asarray(r).reshape(-1)[0])
+        is_tie = False
+        if x.size >= 2:
+            xs = np.sort(x).reshape(-1, 1)
+            gm = skm.GaussianMixture(2, weights_init=np.array([.5, .5]), means_init=np.array([xs.min(), xs.max()]).reshape(2, 1),
+                                     precisions_init=np.ones((2, 1)), covariance_type="diag", reg_covar=1e-5).fit(xs)
+            a, sc = gm.predict(xs), gm.score_samples(xs)
+            comp = 0 if (a == 0).any() else 1
+            top = np.sort(sc[a == comp])[::-1]
+            is_tie = top.size > 1 and (top[0] - top[1]) < 1e-5
+        pools.append(x)
+        thr.append(r)
+        tie.append(is_tie)
+    out = {f"pool{i}": p for i, p in enumerate(pools)}
+    out["thresholds"], out["tie"] = np.array(thr, np.float64), np.array(tie)
+    np.savez_compressed(os.path.join(HERE, "ssod_gmm_golden.npz"), **out)
+    print("ssod_gmm_golden.npz:", len(pools), "pools,", int(np.sum(tie)), "ties")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -435,3 +476,4 @@ if __name__ == "__main__":
     make_dino_cdn()
     make_ssod_pieces()
     make_dino_ssod_head_loss()
+    make_ssod_gmm()
