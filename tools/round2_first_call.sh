@@ -4,7 +4,8 @@
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
 #
 # 1. the validated suite (must stay green: the default kernels are SASS-identical, tests/test_abi.py checks that)
-# 2. the gated tests of the kernels that have never run: bf16 MSDA, backward variants 7 / 10 / 11 / 12
+# 2. the gated tests of what has never run: bf16 MSDA, backward variants 7 / 8 / 10 / 11 / 12, the device transformer
+#    against the reference's own DINOTransformer outputs
 # 3. timings that decide which variant becomes the default: tools/bwd_variants.py, tools/bf16_msda.py
 # 4. the TMA feed-rate microbenchmark behind the GEMM plan (docs/ROUND2_NOTES.md section 1)
 # Results land in gpurun_out/r2_first_*.txt; each step has its own timeout so one hang cannot eat the call.
@@ -14,6 +15,7 @@ run() { name=$1; shift; echo "== $name"; timeout "$1" "${@:2}" > "gpurun_out/r2_
 run validated      420 python -m pytest tests -m gpu -x -q
 SDB_RUN_UNVALIDATED=1 run bf16_tests     180 python -m pytest tests/test_msda_bf16_gpu.py -m gpu -q
 SDB_RUN_UNVALIDATED=1 run bwd_exp_tests  300 python -m pytest tests/test_msda_bwd_experimental_gpu.py -m gpu -q
+SDB_RUN_UNVALIDATED=1 run ref_golden_gpu 120 python -m pytest tests/test_dino_reference_golden.py -m gpu -q
 run bwd_variants   120 python tools/bwd_variants.py
 run bf16_timing    120 python tools/bf16_msda.py
 run tma_rate       120 python tools/tma_rate.py
