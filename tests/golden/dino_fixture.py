@@ -120,3 +120,36 @@ def cdn_targets(counts, num_classes, seed=5):
 def label_embedding(num_classes, hidden_dim=256):
     emb = torch.nn.Embedding(num_classes + 1, hidden_dim)
     return fill_by_name(emb, "label_enc.")
+
+
+# ---- SSOD query construction fixture (reference: DinoDetrSSOD.prepare_unsup_cdn, dino_detr_ssod.py:484-760) -------
+UNSUP_KW = dict(num_classes=80, num_queries=20, hidden_dim=256, dn_number=100, label_noise_ratio=0.5,
+                box_noise_scale=0.4)
+UNSUP_IMG_SHAPES = [(96, 128, 3), (80, 112, 3), (64, 64, 3)]
+UNSUP_PSEUDO_COUNTS = [2, 0, 3]        # high-recall pseudo boxes per image (consistency queries); image 1 has none
+UNSUP_RELIABLE_COUNTS = [1, 0, 2]      # reliable pseudo boxes per image (denoising part); image 1 gets the dummy box
+
+
+def unsup_inputs(seed=31):
+    g = torch.Generator().manual_seed(seed)
+    K = UNSUP_KW["num_classes"]
+
+    def boxes(n, h, w):
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([w * 0.6, h * 0.6])
+        return torch.cat([xy, xy + torch.rand(n, 2, generator=g) * torch.tensor([w * 0.3, h * 0.3]) + 3.0], 1)
+    pseudo = [boxes(n, h, w) for n, (h, w, _) in zip(UNSUP_PSEUDO_COUNTS, UNSUP_IMG_SHAPES)]
+    pseudo_labels = [torch.randint(0, K, (n,), generator=g) for n in UNSUP_PSEUDO_COUNTS]
+    det = [boxes(n, h, w) for n, (h, w, _) in zip(UNSUP_PSEUDO_COUNTS, UNSUP_IMG_SHAPES)]
+    rel = [boxes(n, h, w) for n, (h, w, _) in zip(UNSUP_RELIABLE_COUNTS, UNSUP_IMG_SHAPES)]
+    rel_labels = [torch.randint(0, K, (n,), generator=g) for n in UNSUP_RELIABLE_COUNTS]
+    rel_norm = []
+    for b, (h, w, _) in zip(rel, UNSUP_IMG_SHAPES):
+        cxcywh = torch.cat([(b[:, :2] + b[:, 2:]) / 2, b[:, 2:] - b[:, :2]], 1)
+        rel_norm.append(cxcywh / torch.tensor([w, h, w, h], dtype=torch.float32))
+    n_slots = 5 * max(max(UNSUP_PSEUDO_COUNTS), 1)
+    bs = len(UNSUP_IMG_SHAPES)
+    prior = dict(loss_weights=torch.rand(5 * sum(max(c, 1) for c in UNSUP_PSEUDO_COUNTS), 1, generator=g),
+                 input_query_label_1=torch.randn(bs, n_slots, UNSUP_KW["hidden_dim"], generator=g))
+    metas = [dict(img_shape=s) for s in UNSUP_IMG_SHAPES]
+    return dict(pseudo=pseudo, pseudo_labels=pseudo_labels, det=det, det_labels=pseudo_labels, prior=prior, metas=metas,
+                dn_targets=dict(labels=rel_labels, boxes=rel_norm), img=torch.zeros(bs, 3, 96, 128))

@@ -465,6 +465,62 @@ def make_ssod_gmm():
     print("ssod_gmm_golden.npz:", len(pools), "pools,", int(np.sum(tie)), "ties")
 
 
+def make_ssod_unsup_cdn():
+    """The reference's own DinoDetrSSOD.prepare_unsup_cdn (dino_detr_ssod.py:484-760; method body compiled from the
+    file) in its ``prior_info`` form -- the consistency content is given (the teacher pass re-uses the student's), so
+    neither RoIAlign nor the projector runs -- with every random draw of the denoising part recorded."""
+    import types
+    import dino_fixture as F
+    m = R.load_dino_head()
+    T = sys.modules["detr_od_ref.models.utils.transformer"]
+    tr = sys.modules["mmdet.core.bbox.transforms"]
+    fn = R.load_methods(R.REF + "/detr_ssod/models/dino_detr_ssod.py", "DinoDetrSSOD", ["prepare_unsup_cdn"],
+                        dict(torch=torch, np=np, inverse_sigmoid=T.inverse_sigmoid,
+                             bbox_xyxy_to_cxcywh=tr.bbox_xyxy_to_cxcywh))["prepare_unsup_cdn"]
+    kw = F.UNSUP_KW
+    emb = F.label_embedding(kw["num_classes"])
+    me = types.SimpleNamespace(curr_step=0, student=types.SimpleNamespace(
+        bbox_head=types.SimpleNamespace(label_enc=emb, warm_up_step=10)))
+    x = F.unsup_inputs()
+    info = dict(img_metas=x["metas"], img=x["img"])
+    saved = torch.Tensor.cuda, torch.Tensor.to, torch.rand_like, torch.randint_like, torch.randint
+    draws = []
+
+    def to(self, *a, **k):
+        if a and isinstance(a[0], str) and a[0].startswith("cuda"):
+            return self
+        return saved[1](self, *a, **k)
+
+    def rec(fn_):
+        def wrapped(*a, **k):
+            r = fn_(*a, **k)
+            draws.append(r.clone())
+            return r
+        return wrapped
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = to
+    torch.rand_like, torch.randint_like, torch.randint = rec(saved[2]), rec(saved[3]), rec(saved[4])
+    try:
+        torch.manual_seed(4)
+        with torch.no_grad():
+            q1l, q1b, q2l, q2b, mask, meta = fn(
+                me, info, info, x["pseudo"], x["pseudo_labels"], x["det"], x["det_labels"],
+                dn_args=(x["dn_targets"], kw["dn_number"], kw["label_noise_ratio"], kw["box_noise_scale"]),
+                hidden_dim=kw["hidden_dim"], num_queries=kw["num_queries"], num_classes=kw["num_classes"],
+                prior_info=x["prior"])
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to, torch.rand_like, torch.randint_like, torch.randint = saved
+    out = dict(q1_label=q1l.numpy(), q1_bbox=q1b.numpy(), q2_label=q2l.numpy(), q2_bbox=q2b.numpy(),
+               attn_mask=mask.numpy(),
+               meta=np.array([meta["pad_size_1"], meta["pad_size_2"], meta["num_dn_group_1"], meta["num_dn_group_2"]]),
+               known_bid_1=meta["known_bid_1"].long().numpy(), map_known_indice_1=meta["map_known_indice_1"].numpy(),
+               loss_weights=meta["loss_weights"].numpy(), n_draws=np.array(len(draws)))
+    for i, d in enumerate(draws):
+        out[f"draw{i}"] = d.numpy()
+    np.savez_compressed(os.path.join(HERE, "ssod_unsup_cdn_golden.npz"), **out)
+    print("ssod_unsup_cdn_golden.npz: meta", out["meta"], "draws", [tuple(d.shape) for d in draws])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -477,3 +533,4 @@ if __name__ == "__main__":
     make_ssod_pieces()
     make_dino_ssod_head_loss()
     make_ssod_gmm()
+    make_ssod_unsup_cdn()
