@@ -8,6 +8,8 @@ cores, TF32 arithmetic on fp32 storage.
 Reference call sites: ``ms_deform_attn.py:61-65, 94-112`` (value_proj with ``masked_fill``, sampling_offsets,
 attention_weights, output_proj) and the FFNs of ``transformer.py:626-630, 878-882``.  No CPU path: CPU tensors raise.
 """
+import os
+
 import torch
 
 from .. import _lib
@@ -76,6 +78,12 @@ def linear_grad_weight(g2d, x2d, with_bias_grad=False):
     n = x2d.shape[1]
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
     splits = max(1, min((k + 31) // 32, (2 * _sm_count(g2d.device)) // tiles))
+    min_kblocks = int(os.environ.get("SDB_GEMM_MIN_KBLOCKS_PER_SPLIT", "0"))
+    if min_kblocks > 1:
+        # EXPERIMENTAL (not yet run on hardware; docs/ROUND2_NOTES.md section 1): never fewer than this many k-blocks
+        # per split -- every split reduce-adds a full 64 KB output tile, which the decoder-sized products (69
+        # k-blocks) currently do once per k-block.  The MN-major kernel has not run with k_splits == 1 yet.
+        splits = max(1, min(splits, ((k + 31) // 32) // min_kblocks))
     if not with_bias_grad:
         return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits)
     buf = torch.zeros(m * n + m, dtype=torch.float32, device=g2d.device)      # one fill for both outputs
