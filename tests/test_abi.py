@@ -77,6 +77,27 @@ def test_argument_errors_without_gpu(libpath):
                                            None, None, None), "msda_backward")
 
 
+def test_bf16_entry_points_validate_before_any_cuda_call(libpath):
+    """sdb_msda_forward_bf16 / sdb_msda_backward_bf16: size, shape-support, null-pointer and alignment errors are
+    reported on the CPU box (codes of include/semidetr_b200.h: 1 = invalid argument, 3 = unsupported)."""
+    from semi_detr_b200 import _lib
+    l = _lib.lib()
+    fwd, bwd = l.sdb_msda_forward_bf16, l.sdb_msda_backward_bf16
+    assert fwd(None, None, None, None, None, None, 2, 10, 0, 32, 4, 5, 4, None) == 1 and b"bad sizes" in l.sdb_last_error()
+    # 4 heads x 64 channels: not built for bf16 storage
+    assert fwd(None, None, None, None, None, None, 2, 10, 4, 64, 4, 5, 4, None) == 3
+    assert b"heads=8" in l.sdb_last_error()
+    assert bwd(None, None, None, None, None, None, None, 2, 10, 8, 32, 4, 5, 3, None, None, None) == 3
+    # supported shape, no queries: nothing to do, no pointer is touched
+    assert fwd(None, None, None, None, None, None, 2, 10, 8, 32, 4, 0, 4, None) == 0
+    # supported shape with work but null / misaligned pointers
+    assert fwd(None, None, None, None, None, None, 2, 10, 8, 32, 4, 5, 4, None) == 1 and b"null" in l.sdb_last_error()
+    assert fwd(None, 0x1004, 0x2000, 0x3000, 0x4000, 0x5000, 2, 10, 8, 32, 4, 5, 4, 0x6000) == 1
+    assert b"aligned" in l.sdb_last_error()
+    assert bwd(None, 0x1000, 0x2000, 0x3000, 0x4000, 0x5000, 0x6000, 2, 10, 8, 32, 4, 5, 4, None, 0x8000, 0x9000) == 1
+    assert b"null grad_value" in l.sdb_last_error()
+
+
 def test_no_cpu_path():
     """CPU tensors are rejected like the reference does (src/ms_deform_attn.h:38: 'Not implemented on the CPU')."""
     import torch
