@@ -153,3 +153,64 @@ def unsup_inputs(seed=31):
     metas = [dict(img_shape=s) for s in UNSUP_IMG_SHAPES]
     return dict(pseudo=pseudo, pseudo_labels=pseudo_labels, det=det, det_labels=pseudo_labels, prior=prior, metas=metas,
                 dn_targets=dict(labels=rel_labels, boxes=rel_norm), img=torch.zeros(bs, 3, 96, 128))
+
+
+# ---- SSOD unsup_loss fixture (reference: DinoDetrSSOD.unsup_loss, dino_detr_ssod.py:204-482) -----------------------
+# The heavy collaborators (query construction, the two decoder passes, the head loss) are replaced on BOTH sides by the
+# same deterministic stand-ins below, so what is compared is the method's own logic: Hungarian costs of the student's
+# predictions against the pseudo boxes, the GMM threshold, the double filter, and the cross-view consistency loss.
+UNSUP_LOSS_KW = dict(num_query=40, num_classes=80, n_dec=3, score_thr=0.4)
+UNSUP_LOSS_IMG_SHAPES = [(96, 128, 3), (80, 112, 3), (64, 64, 3)]
+UNSUP_LOSS_COUNTS = [5, 0, 7]
+
+
+def unsup_loss_inputs(seed=41):
+    g = torch.Generator().manual_seed(seed)
+    Q, K, bs = UNSUP_LOSS_KW["num_query"], UNSUP_LOSS_KW["num_classes"], len(UNSUP_LOSS_IMG_SHAPES)
+    L = UNSUP_LOSS_KW["n_dec"]
+    cls = torch.randn(L, bs, Q, K, generator=g) - 2.0
+    box = torch.cat([torch.rand(L, bs, Q, 2, generator=g) * 0.8 + 0.1, torch.rand(L, bs, Q, 2, generator=g) * 0.3 + 0.03], -1)
+    pseudo, labels, scores, det = [], [], [], []
+    for n, (h, w, _) in zip(UNSUP_LOSS_COUNTS, UNSUP_LOSS_IMG_SHAPES):
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([w * 0.6, h * 0.6])
+        pseudo.append(torch.cat([xy, xy + torch.rand(n, 2, generator=g) * torch.tensor([w * 0.3, h * 0.3]) + 3.0], 1))
+        labels.append(torch.randint(0, K, (n,), generator=g))
+        scores.append(torch.rand(n, generator=g) * 0.7 + 0.05)            # some above, some below 0.4
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([w * 0.6, h * 0.6])
+        det.append(torch.cat([xy, xy + torch.rand(n, 2, generator=g) * torch.tensor([w * 0.3, h * 0.3]) + 3.0], 1))
+    metas = [dict(img_shape=s) for s in UNSUP_LOSS_IMG_SHAPES]
+    img = torch.zeros(bs, 3, 96, 128)
+    student = dict(img=img, img_metas=metas, backbone_feature="student-feat",
+                   outs=(cls, box, cls[-1], box[-1], None, None))
+    teacher = dict(img=img, img_metas=metas, backbone_feature="teacher-feat", det_bboxes=det, det_labels=labels,
+                   det_scores=scores)
+    return student, teacher, pseudo, labels, scores
+
+
+def fake_unsup_cdn(pseudo_bboxes, prior_info, hidden_dim=256, seed=0):
+    """Stand-in for prepare_unsup_cdn: the real layout of part 1 (5 groups, dummy slot for an empty image), random
+    content / weights (or the prior's), a 4-slot part 2."""
+    counts = [max(int(b.shape[0]), 1) for b in pseudo_bboxes]
+    bs, single = len(counts), max(counts)
+    pad1 = 5 * single
+    bid = torch.cat([torch.full((c,), i, dtype=torch.long) for i, c in enumerate(counts)]).repeat(5)
+    slot = torch.cat([torch.cat([torch.arange(c) for c in counts]) + single * g for g in range(5)]).long()
+    g = torch.Generator().manual_seed(1000 + seed + sum(counts))
+    if prior_info is None:
+        q1_label = torch.randn(bs, pad1, hidden_dim, generator=g)
+        weights = (torch.rand(bid.numel(), 1, generator=g) > 0.2).float()
+    else:
+        q1_label, weights = prior_info["input_query_label_1"], prior_info["loss_weights"]
+    meta = dict(pad_size_1=pad1, pad_size_2=4, num_dn_group_1=5, num_dn_group_2=1, known_bid_1=bid,
+                map_known_indice_1=slot, loss_weights=weights)
+    return (q1_label, torch.zeros(bs, pad1, 4), torch.zeros(bs, 4, hidden_dim), torch.zeros(bs, 4, 4),
+            torch.zeros(pad1 + 4 + UNSUP_LOSS_KW["num_query"], pad1 + 4 + UNSUP_LOSS_KW["num_query"], dtype=torch.bool),
+            meta)
+
+
+def fake_forward_dummy(tag, q_label, hidden_dim=256):
+    """Stand-in for bbox_head.forward_dummy: `n_dec` decoder states of the right shape, different per view."""
+    bs, T = q_label.shape[0], q_label.shape[1] + UNSUP_LOSS_KW["num_query"]
+    g = torch.Generator().manual_seed(77 if tag == "student" else 78)
+    hs = [torch.randn(bs, T, hidden_dim, generator=g) for _ in range(UNSUP_LOSS_KW["n_dec"])]
+    return (hs,) + (None,) * 8

@@ -521,6 +521,66 @@ def make_ssod_unsup_cdn():
     print("ssod_unsup_cdn_golden.npz: meta", out["meta"], "draws", [tuple(d.shape) for d in draws])
 
 
+def make_ssod_unsup_loss():
+    """The reference's own DinoDetrSSOD.unsup_loss (dino_detr_ssod.py:204-482; method body compiled from the file) with
+    its own _fit_gmm, the real mmdet match costs and scipy's solver; query construction, decoder passes and head loss
+    are the deterministic stand-ins of dino_fixture.py (the same ones the test gives our method)."""
+    import types
+    import scipy.optimize
+    import sklearn.mixture as skm
+    import torch.nn.functional as TF
+    import dino_fixture as F
+    m = R.load_dino_head()
+    tr = sys.modules["mmdet.core.bbox.transforms"]
+    ns = dict(torch=torch, np=np, F=TF, skm=skm, bbox_cxcywh_to_xyxy=tr.bbox_cxcywh_to_xyxy,
+              bbox_xyxy_to_cxcywh=tr.bbox_xyxy_to_cxcywh, linear_sum_assignment=scipy.optimize.linear_sum_assignment,
+              get_dist_info=lambda: (0, 1), concat_all_gather=lambda t: t)
+    fns = R.load_methods(R.REF + "/detr_ssod/models/dino_detr_ssod.py", "DinoDetrSSOD", ["unsup_loss", "_fit_gmm"], ns)
+    assigner = m["assigner"].HungarianAssigner(
+        cls_cost=dict(type="FocalLossCost", weight=2.0), reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+        iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0))
+    out = {}
+    for phase, curr_step in (("warmup", 0), ("after", 100)):
+        rec = {}
+
+        def cdn(teacher_info, student_info, pb, pl, db, dl, dn_args=None, prior_info=None, **kw):
+            key = "cdn2" if prior_info is not None else "cdn1"
+            rec[key] = dict(pseudo=[b.clone() for b in pb], labels=[l.clone() for l in pl], det=[b.clone() for b in db],
+                            det_labels=[l.clone() for l in dl], dn_boxes=[b.clone() for b in dn_args[0]["boxes"]],
+                            dn_labels=[l.clone() for l in dn_args[0]["labels"]])
+            return F.fake_unsup_cdn(pb, prior_info)
+
+        def loss(*a, **k):
+            rec["loss"] = dict(boxes=[b.clone() for b in k["gt_bboxes_list"]], labels=[l.clone() for l in k["gt_labels_list"]],
+                               scores=[s_.clone() for s_ in k["gt_scores_list"]], pseudo=k["is_pseudo_label"])
+            return dict(loss_cls=torch.tensor(1.0))
+        head_s = types.SimpleNamespace(assigner2=assigner, warm_up_step=50, in_warm_up=None, dn_number=100,
+                                       dn_label_noise_ratio=0.5, dn_box_noise_scale=0.4, loss=loss,
+                                       forward_dummy=lambda feat, metas, ql, qb, mask, meta: F.fake_forward_dummy("student", ql))
+        head_t = types.SimpleNamespace(forward_dummy=lambda feat, metas, ql, qb, mask, meta: F.fake_forward_dummy("teacher", ql))
+        me = types.SimpleNamespace(curr_step=curr_step, covariance_type="diag",
+                                   train_cfg=types.SimpleNamespace(pseudo_label_initial_score_thr=F.UNSUP_LOSS_KW["score_thr"]),
+                                   student=types.SimpleNamespace(bbox_head=head_s),
+                                   teacher=types.SimpleNamespace(bbox_head=head_t, extract_feat=lambda img: "teacher-feat"),
+                                   prepare_unsup_cdn=cdn)
+        me._fit_gmm = types.MethodType(fns["_fit_gmm"], me)
+        student, teacher, pseudo, labels, scores = F.unsup_loss_inputs()
+        losses = fns["unsup_loss"](me, student, teacher, pseudo, labels, scores)
+        out[phase + "/keys"] = np.array(list(losses.keys()))
+        out[phase + "/values"] = np.array([float(v) for v in losses.values()], np.float64)
+        out[phase + "/in_warm_up"] = np.array(bool(head_s.in_warm_up))
+        for key in ("cdn1", "cdn2"):
+            for field, lst in rec[key].items():
+                for i, t in enumerate(lst):
+                    out[f"{phase}/{key}/{field}{i}"] = t.numpy()
+        for field in ("boxes", "labels", "scores"):
+            for i, t in enumerate(rec["loss"][field]):
+                out[f"{phase}/loss/{field}{i}"] = t.numpy()
+        print(phase, dict(zip(losses.keys(), [round(float(v), 6) for v in losses.values()])),
+              "reliable", [len(b) for b in rec["loss"]["boxes"]], "high-recall", [len(b) for b in rec["cdn1"]["pseudo"]])
+    np.savez_compressed(os.path.join(HERE, "ssod_unsup_loss_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -534,3 +594,4 @@ if __name__ == "__main__":
     make_dino_ssod_head_loss()
     make_ssod_gmm()
     make_ssod_unsup_cdn()
+    make_ssod_unsup_loss()
