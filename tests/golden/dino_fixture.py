@@ -214,3 +214,19 @@ def fake_forward_dummy(tag, q_label, hidden_dim=256):
     g = torch.Generator().manual_seed(77 if tag == "student" else 78)
     hs = [torch.randn(bs, T, hidden_dim, generator=g) for _ in range(UNSUP_LOSS_KW["n_dec"])]
     return (hs,) + (None,) * 8
+
+
+# ---- teacher pseudo-label extraction fixture (reference: extract_teacher_info, dino_detr_ssod.py:893-951) ----------
+def teacher_proposals(seed=53):
+    """What ``simple_test_bboxes(..., for_pseudo_label=True)`` hands back per image: (n, 5) boxes with scores and (n,)
+    labels -- incl. an image without detections, one with a single detection, and degenerate (zero-width) boxes."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for n in (40, 0, 1, 25):
+        xy = torch.rand(n, 2, generator=g) * 200
+        wh = torch.rand(n, 2, generator=g) * 80
+        if n >= 25:
+            wh[::6, 0] = 0.0                                   # degenerate boxes that must be dropped
+        score = torch.rand(n, 1, generator=g) ** 2
+        out.append((torch.cat([xy, xy + wh, score], 1), torch.randint(0, 80, (n,), generator=g)))
+    return out

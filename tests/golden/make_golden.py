@@ -581,6 +581,27 @@ def make_ssod_unsup_loss():
     np.savez_compressed(os.path.join(HERE, "ssod_unsup_loss_golden.npz"), **out)
 
 
+def make_ssod_teacher_info():
+    """The reference's own extract_teacher_info (dino_detr_ssod.py:893-951; method body compiled from the file) on fixed
+    teacher detections: the per-image mean + std score filter and the removal of degenerate boxes."""
+    import types
+    import dino_fixture as F
+    fn = R.load_methods(R.REF + "/detr_ssod/models/dino_detr_ssod.py", "DinoDetrSSOD", ["extract_teacher_info"],
+                        dict(torch=torch, np=np))["extract_teacher_info"]
+    props = F.teacher_proposals()
+    feat = (torch.zeros(1, 1),)
+    head = types.SimpleNamespace(simple_test_bboxes=lambda *a, **k: props)
+    me = types.SimpleNamespace(curr_step=0, teacher=types.SimpleNamespace(extract_feat=lambda img: feat, bbox_head=head))
+    metas = [dict(transform_matrix=np.eye(3, dtype=np.float32) * (i + 1)) for i in range(len(props))]
+    info = fn(me, torch.zeros(len(props), 3, 8, 8), metas)
+    out = {}
+    for i in range(len(props)):
+        out[f"det_bboxes{i}"], out[f"det_labels{i}"] = info["det_bboxes"][i].numpy(), info["det_labels"][i].numpy()
+        out[f"det_scores{i}"], out[f"transform_matrix{i}"] = info["det_scores"][i].numpy(), info["transform_matrix"][i].numpy()
+    np.savez_compressed(os.path.join(HERE, "ssod_teacher_info_golden.npz"), **out)
+    print("ssod_teacher_info_golden.npz: kept", [len(b) for b in info["det_bboxes"]])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -595,3 +616,4 @@ if __name__ == "__main__":
     make_ssod_gmm()
     make_ssod_unsup_cdn()
     make_ssod_unsup_loss()
+    make_ssod_teacher_info()
