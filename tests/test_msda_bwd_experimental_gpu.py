@@ -4,6 +4,7 @@
   8       the same with the loop over a chunk's 4 batches kept rolled (29 KB of code instead of 60 KB)
   10, 11  the 8-lane kernel with the corner loads of 2 points in flight per warp (4 / 3 CTAs per SM)
   12      ... of 4 points in flight (3 CTAs per SM)
+  15, 16  8 x 8 pixel tiles (the forward's tile shape) with 256 threads, 1 / 2 points in flight
 
 Motivation (profiles/ncu_msda_stalls_r1.txt, ncu source view of the encoder backward): the default kernel has 4 loads
 in flight per warp and waits one L2 latency per point (32 % of the stall samples sit on the first FMUL after each
@@ -26,7 +27,7 @@ pytestmark = [pytest.mark.gpu,
                                  reason="experimental backward variants have not run on hardware yet "
                                         "(set SDB_RUN_UNVALIDATED=1)")]
 
-VARIANTS = [7, 8, 10, 11, 12]
+VARIANTS = [7, 8, 10, 11, 12, 15, 16]
 
 
 def _relerr(a, b):

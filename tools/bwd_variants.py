@@ -29,7 +29,8 @@ for name, Lq, refdim in (("enc", S, 2), ("dec", 1092, 4)):
     gout = torch.randn(N, Lq, 256, device="cuda", generator=g)
     # 7 / 8 = experimental 4-lane x 8-channel mapping (msda_backward_x8.cu), unrolled / rolled batch loop; 10 / 11 / 12 = 2 / 2 / 4 points of corner
     # loads in flight per warp at 4 / 3 / 3 CTAs per SM
-    for variant in (0, 6, 5, 3, 2, 7, 8, 10, 11, 12):
+    # 15 / 16 = 8 x 8 pixel tiles with 256 threads, 1 / 2 points in flight
+    for variant in (0, 6, 5, 3, 2, 7, 8, 10, 11, 12, 15, 16):
         _lib.lib().sdb_msda_set_variant(0, variant)
         ts = []
         for _ in range(33):
