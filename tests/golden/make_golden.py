@@ -365,6 +365,16 @@ def make_ssod_pieces():
         out[f"o2m{ci}/gtb"], out[f"o2m{ci}/gtl"], out[f"o2m{ci}/wh"] = gtb.numpy(), gtl.numpy(), np.array([w, h])
         out[f"o2m{ci}/gt_inds"], out[f"o2m{ci}/labels"] = res.gt_inds.numpy(), res.labels.numpy()
         out[f"o2m{ci}/max_overlaps"], out[f"o2m{ci}/assign_metrics"] = res.max_overlaps.numpy(), res.assign_metrics.numpy()
+    # a3: the reference MSDeformAttn's deterministic initialisation (ms_deform_attn.py:67-76): the sampling-offset
+    # bias grid (8 directions x point index), zero offset / attention weights and biases
+    _, msda_mod = R.load_dino_transformer()
+    for tag, (L, P) in (("l4p4", (4, 4)), ("l5p4", (5, 4))):
+        torch.manual_seed(0)
+        mref = msda_mod.MSDeformAttn(d_model=256, n_levels=L, n_heads=8, n_points=P)
+        out[f"msda_init/{tag}/sampling_offsets.bias"] = mref.sampling_offsets.bias.detach().numpy()
+        for n in ("sampling_offsets.weight", "attention_weights.weight", "attention_weights.bias", "value_proj.bias",
+                  "output_proj.bias"):
+            assert float(dict(mref.named_parameters())[n].abs().max()) == 0.0
     np.savez_compressed(os.path.join(HERE, "ssod_pieces_golden.npz"), **out)
     print("ssod_pieces_golden.npz:", len(out), "arrays; O2M positives",
           [int((out[f"o2m{c}/gt_inds"] > 0).sum()) for c in range(3)])
