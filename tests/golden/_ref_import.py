@@ -334,3 +334,32 @@ def load_methods(path, class_name, names, namespace):
             exec(compile(mod, path, "exec"), ns)
             out[node.name] = ns[node.name]
     return out
+
+
+def load_dino_head_buildable():
+    """``load_dino_head`` with the head module's builder names bound to the loaded reference / mmdet classes, so
+    ``DINODETRHead(**cfg)`` itself can be constructed (its ``__init__`` / ``_init_layers`` / ``forward`` run as written):
+    transformer -> the reference DINOTransformer, positional encoding -> the reference SinePositionalEncodingHW,
+    losses / assigner / sampler -> the real mmdet classes."""
+    import torch.nn as nn
+    m = load_dino_head()
+    T, _ = load_dino_transformer()
+    pe = load_positional_encoding()
+    head = m["head"]
+    strip = lambda cfg: {k: v for k, v in cfg.items() if k != "type"}
+    losses = {"FocalLoss": m["focal"].FocalLoss, "L1Loss": m["l1"].L1Loss, "GIoULoss": m["iou"].GIoULoss}
+    head.build_transformer = lambda cfg: T.DINOTransformer(**strip(cfg))
+    head.build_positional_encoding = lambda cfg: pe.SinePositionalEncodingHW(**strip(cfg))
+    head.build_loss = lambda cfg: losses[cfg["type"]](**strip(cfg))
+    head.build_assigner = lambda cfg: m["assigner"].HungarianAssigner(**strip(cfg))
+    head.build_sampler = lambda cfg, context=None: m["sampler"].PseudoSampler()
+    head.build_activation_layer = lambda cfg: nn.ReLU(inplace=True)
+
+    class BaseDenseHead(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+    if not issubclass(head.DINODETRHead, BaseDenseHead):
+        # re-base the stand-in AnchorFreeHead so that super(AnchorFreeHead, self).__init__(init_cfg) reaches nn.Module
+        afh = sys.modules["mmdet.models.dense_heads.anchor_free_head"].AnchorFreeHead
+        afh.__bases__ = (BaseDenseHead,)
+    return m

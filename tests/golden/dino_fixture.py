@@ -230,3 +230,40 @@ def teacher_proposals(seed=53):
         score = torch.rand(n, 1, generator=g) ** 2
         out.append((torch.cat([xy, xy + wh, score], 1), torch.randint(0, 80, (n,), generator=g)))
     return out
+
+
+# ---- full head fixture (reference: DINODETRHead.__init__/_init_layers/forward + loss, dino_detr_head.py:74-632) ------
+HEAD_CFG = dict(
+    num_classes=9, in_channels=2048, num_query=30, num_feature_levels=4, num_backbone_outs=3,
+    backbone_channels=[512, 1024, 2048], query_dim=4, dn_number=100, dn_box_noise_scale=0.4, dn_label_noise_ratio=0.5,
+    dn_labelbook_size=9,
+    transformer=dict(type="DINOTransformer", d_model=256, nhead=8, num_queries=30, num_encoder_layers=1,
+                     num_decoder_layers=2, dim_feedforward=64, num_feature_levels=4),
+    positional_encoding=dict(type="SinePositionalEncodingHW", num_feats=128, temperatureH=20, temperatureW=20,
+                             normalize=True),
+    loss_cls=dict(type="FocalLoss", use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+    loss_bbox=dict(type="L1Loss", loss_weight=5.0), loss_iou=dict(type="GIoULoss", loss_weight=2.0),
+    train_cfg=dict(assigner=dict(type="HungarianAssigner", cls_cost=dict(type="FocalLossCost", weight=2.0),
+                                 reg_cost=dict(type="BBoxL1Cost", weight=5.0, box_format="xywh"),
+                                 iou_cost=dict(type="IoUCost", iou_mode="giou", weight=2.0))),
+    test_cfg=dict(max_per_img=300))
+
+
+def head_inputs(seed=61):
+    """Backbone features of a 96 x 128 padded batch (image 1 is 80 x 112), a 6-query denoising part, GT."""
+    g = torch.Generator().manual_seed(seed)
+    bs = 2
+    feats = [torch.randn(bs, c, h, w, generator=g) * 0.5 for c, (h, w) in zip((512, 1024, 2048), LEVELS[:3])]
+    metas = [dict(img_shape=(96, 128, 3), batch_input_shape=(96, 128)),
+             dict(img_shape=(80, 112, 3), batch_input_shape=(96, 128))]
+    q_label = torch.randn(bs, N_DN, 256, generator=g)
+    q_bbox = torch.randn(bs, N_DN, 4, generator=g)
+    T = N_DN + HEAD_CFG["num_query"]
+    attn_mask = torch.zeros(T, T, dtype=torch.bool)
+    attn_mask[N_DN:, :N_DN] = True
+    dn_meta = dict(pad_size=N_DN, num_dn_group=1)
+    gt_bboxes = [torch.tensor([[10., 12., 60., 70.], [40., 30., 120., 90.], [5., 50., 30., 80.]]),
+                 torch.tensor([[20., 10., 100., 60.]])]
+    gt_labels = [torch.tensor([1, 4, 7]), torch.tensor([3])]
+    return dict(feats=feats, metas=metas, q_label=q_label, q_bbox=q_bbox, attn_mask=attn_mask, dn_meta=dn_meta,
+                gt_bboxes=gt_bboxes, gt_labels=gt_labels)

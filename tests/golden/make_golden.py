@@ -612,6 +612,33 @@ def make_ssod_teacher_info():
     print("ssod_teacher_info_golden.npz: kept", [len(b) for b in info["det_bboxes"]])
 
 
+def make_dino_head_forward():
+    """The reference's own DINODETRHead, constructed from a config like the shipped one (small transformer), by-name
+    weights: forward (masks, positional encodings, input projections incl. the extra stride-2 level, transformer,
+    shared heads, box refinement, denoising split) and the loss of its own outputs."""
+    import dino_fixture as F
+    m = R.load_dino_head_buildable()
+    torch.manual_seed(0)
+    head = m["head"].DINODETRHead(**F.HEAD_CFG)
+    F.fill_by_name(head, "head.")
+    head.eval()
+    x = F.head_inputs()
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            outs = head(x["feats"], x["metas"], x["q_label"], x["q_bbox"], x["attn_mask"], x["dn_meta"])
+            losses = head.loss(*outs, x["gt_bboxes"], x["gt_labels"], img_metas=x["metas"], dn_metas=x["dn_meta"])
+    finally:
+        torch.Tensor.cuda = saved
+    out = {f"out{i}": o.numpy() for i, o in enumerate(outs)}
+    out["loss_keys"] = np.array(list(losses.keys()))
+    out["loss_values"] = np.array([float(v) for v in losses.values()], np.float64)
+    out["param_names"] = np.array(sorted(n for n, _ in head.named_parameters()))
+    np.savez_compressed(os.path.join(HERE, "dino_head_forward_golden.npz"), **out)
+    print("dino_head_forward_golden.npz:", [tuple(o.shape) for o in outs], len(losses), "losses")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -627,3 +654,4 @@ if __name__ == "__main__":
     make_ssod_unsup_cdn()
     make_ssod_unsup_loss()
     make_ssod_teacher_info()
+    make_dino_head_forward()
