@@ -363,3 +363,44 @@ def load_dino_head_buildable():
         afh = sys.modules["mmdet.models.dense_heads.anchor_free_head"].AnchorFreeHead
         afh.__bases__ = (BaseDenseHead,)
     return m
+
+
+def load_mmdet_resnet():
+    """thirdparty/mmdetection/mmdet/models/backbones/resnet.py + models/utils/res_layer.py (the backbone the configs
+    name: ResNet-50, frozen_stages=1, BN frozen + norm_eval, style 'pytorch').  mmcv's layer builders are stood in by
+    what they return for the shipped config: ``nn.Conv2d`` and ``(name, nn.BatchNorm2d)`` with the ``requires_grad``
+    flag of ``norm_cfg`` applied (mmcv/cnn/bricks/norm.py)."""
+    import torch.nn as nn
+    _install_mmcv_stub()
+    cnn = _pkg("mmcv.cnn")
+
+    def build_conv_layer(cfg, *args, **kwargs):
+        assert cfg is None or cfg.get("type", "Conv2d") in ("Conv2d", "Conv"), cfg
+        return nn.Conv2d(*args, **kwargs)
+
+    def build_norm_layer(cfg, num_features, postfix=""):
+        assert cfg["type"] == "BN", cfg
+        layer = nn.BatchNorm2d(num_features, eps=cfg.get("eps", 1e-5))
+        for p in layer.parameters():
+            p.requires_grad = cfg.get("requires_grad", True)
+        return "bn" + str(postfix), layer
+    cnn.build_conv_layer, cnn.build_norm_layer = build_conv_layer, build_norm_layer
+    cnn.build_plugin_layer = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("plugins are not configured"))
+    runner = _pkg("mmcv.runner")
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+            self.init_cfg = init_cfg
+
+    class Sequential(BaseModule, nn.Sequential):
+        def __init__(self, *args, init_cfg=None):
+            BaseModule.__init__(self, init_cfg)
+            nn.Sequential.__init__(self, *args)
+    runner.BaseModule, runner.Sequential = BaseModule, Sequential
+    for p in ("mmdet", "mmdet.models", "mmdet.models.utils", "mmdet.models.backbones"):
+        _pkg(p)
+    _pkg("mmdet.models.builder").BACKBONES = _Registry("backbone")
+    rl = _load("mmdet.models.utils.res_layer", MMDET + "/models/utils/res_layer.py")
+    sys.modules["mmdet.models.utils"].ResLayer = rl.ResLayer
+    return _load("mmdet.models.backbones.resnet", MMDET + "/models/backbones/resnet.py")

@@ -267,3 +267,34 @@ def head_inputs(seed=61):
     gt_labels = [torch.tensor([1, 4, 7]), torch.tensor([3])]
     return dict(feats=feats, metas=metas, q_label=q_label, q_bbox=q_bbox, attn_mask=attn_mask, dn_meta=dn_meta,
                 gt_bboxes=gt_bboxes, gt_labels=gt_labels)
+
+
+# ---- backbone fixture (reference: mmdet ResNet-50 as the configs build it) ------------------------------------------
+RESNET_KW = dict(depth=50, num_stages=4, out_indices=(1, 2, 3), frozen_stages=1,
+                 norm_cfg=dict(type="BN", requires_grad=False), norm_eval=True, style="pytorch")
+
+
+def fill_backbone(net):
+    """By-name weights (He-like scale so activations neither vanish nor blow up over 50 layers) and non-trivial frozen
+    BatchNorm statistics."""
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            g = torch.Generator().manual_seed(zlib.crc32(("backbone." + name).encode()))
+            r = torch.randn(p.shape, generator=g)
+            if p.dim() == 4:
+                p.copy_(r * (2.0 / (p.shape[1] * p.shape[2] * p.shape[3])) ** 0.5)
+            elif name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * r)
+            else:
+                p.copy_(0.05 * r)
+        for name, b in net.named_buffers():
+            g = torch.Generator().manual_seed(zlib.crc32(("backbone." + name).encode()))
+            if name.endswith("running_mean"):
+                b.copy_(0.1 * torch.randn(b.shape, generator=g))
+            elif name.endswith("running_var"):
+                b.copy_(torch.rand(b.shape, generator=g) + 0.5)
+    return net
+
+
+def backbone_input(seed=71):
+    return torch.randn(2, 3, 96, 128, generator=torch.Generator().manual_seed(seed))

@@ -639,6 +639,28 @@ def make_dino_head_forward():
     print("dino_head_forward_golden.npz:", [tuple(o.shape) for o in outs], len(losses), "losses")
 
 
+def make_backbone():
+    """mmdet's own ResNet-50 (backbones/resnet.py) as the DINO configs build it, in train() mode (frozen stem + layer1,
+    BatchNorm in eval): the three output levels on by-name weights, and which parameters receive a gradient."""
+    import dino_fixture as F
+    rn = R.load_mmdet_resnet()
+    net = F.fill_backbone(rn.ResNet(**F.RESNET_KW))
+    net.train()                                   # mmdet's train() returns None
+    x = F.backbone_input()
+    outs = net(x)
+    sum(o.square().mean() for o in outs).backward()
+    out = {f"level{i}": o.detach()[:, ::8, ::2, ::2].numpy() for i, o in enumerate(outs)}
+    out["level2_full"] = outs[2].detach().numpy()
+    out["shapes"] = np.array([o.shape for o in outs])
+    names = [n for n, _ in net.named_parameters()]
+    params = dict(net.named_parameters())
+    out["param_names"] = np.array(names)
+    out["grad_norms"] = np.array([float(params[n].grad.norm()) if params[n].grad is not None else -1.0 for n in names])
+    out["bn_training"] = np.array([m.training for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)])
+    np.savez_compressed(os.path.join(HERE, "backbone_golden.npz"), **out)
+    print("backbone_golden.npz:", [tuple(o.shape) for o in outs], "params with grad", int((out["grad_norms"] >= 0).sum()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -655,3 +677,4 @@ if __name__ == "__main__":
     make_ssod_unsup_loss()
     make_ssod_teacher_info()
     make_dino_head_forward()
+    make_backbone()
