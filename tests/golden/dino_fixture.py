@@ -298,3 +298,18 @@ def fill_backbone(net):
 
 def backbone_input(seed=71):
     return torch.randn(2, 3, 96, 128, generator=torch.Generator().manual_seed(seed))
+
+
+# second transformer case: 5 feature levels (BASELINE configs[3]), no denoising part, no padding, no attention mask
+TRANSFORMER_KW5 = dict(d_model=256, nhead=8, num_queries=25, num_encoder_layers=2, num_decoder_layers=1,
+                       dim_feedforward=96, num_feature_levels=5)
+LEVELS5 = [(16, 20), (8, 10), (4, 5), (2, 3), (1, 2)]
+
+
+def inputs5(seed=13):
+    g = torch.Generator().manual_seed(seed)
+    bs, C = 2, 256
+    srcs = [torch.randn(bs, C, h, w, generator=g) for h, w in LEVELS5]
+    poss = [torch.randn(bs, C, h, w, generator=g) * 0.5 for h, w in LEVELS5]
+    masks = [torch.zeros(bs, h, w, dtype=torch.bool) for h, w in LEVELS5]
+    return srcs, masks, poss

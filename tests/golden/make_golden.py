@@ -244,6 +244,19 @@ def make_dino_transformer():
                                        for _, p in sorted(heads.named_parameters())])
     out["head_param_names"] = np.array(sorted(n for n, _ in heads.named_parameters()))
     out["param_names"] = np.array(sorted(n for n, _ in model.named_parameters()))
+    # second case: 5 levels, 2 encoder layers, inference-style call (no denoising part, no mask)
+    model5 = F.fill_by_name(T.DINOTransformer(**F.TRANSFORMER_KW5), "five.").eval()
+    heads5 = torch.nn.ModuleDict(dict(
+        fc_reg=torch.nn.ModuleList([T.MLP(C, C, 4, 3)]), fc_cls=torch.nn.ModuleList([torch.nn.Linear(C, K)]),
+        fc_enc_reg=T.MLP(C, C, 4, 3), fc_enc_cls=torch.nn.Linear(C, K)))
+    F.fill_by_name(heads5, "heads5.")
+    s5, m5, p5 = F.inputs5()
+    with torch.no_grad():
+        hs5, ref5, hs_enc5, ref_enc5, init5 = model5(s5, m5, None, p5, None, None, fc_reg=heads5["fc_reg"],
+                                                     fc_cls=heads5["fc_cls"], fc_enc_reg=heads5["fc_enc_reg"],
+                                                     fc_enc_cls=heads5["fc_enc_cls"])
+    out["five/hs"], out["five/references"] = torch.stack(list(hs5)).numpy(), torch.stack(list(ref5)).numpy()
+    out["five/hs_enc"], out["five/ref_enc"], out["five/init_box_proposal"] = hs_enc5.numpy(), ref_enc5.numpy(), init5.numpy()
     np.savez_compressed(os.path.join(HERE, "dino_transformer_golden.npz"), **out)
     print("dino_transformer_golden.npz:", {k: v.shape for k, v in out.items()})
 
