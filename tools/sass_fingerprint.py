@@ -5,7 +5,7 @@ longer produced by the current build.
     python tools/sass_fingerprint.py            # check the built objects against the committed fingerprints
     python tools/sass_fingerprint.py --write [--skip=REGEX ...]   # regenerate (only after the kernels ran green on a
         # B200); --skip leaves out kernels that have NOT run yet.  Round 1 was written with:
-        #   --skip=__nv_bfloat16 --skip=msda_bwd_x8 '--skip=msda_bwd_d32_kernel<.*\(int\)[24]>$' --skip=tma_rate_kernel
+        #   --skip=__nv_bfloat16 --skip=msda_bwd_x8 '--skip=msda_bwd_d32_kernel<.*.int.[24]>$' --skip=tma_rate_kernel
         # (the 8x8-tile backward variants 15 / 16 were added afterwards and are simply absent from the file)
 
 Why: work that happens without a GPU (new template parameters, shared headers, new variants) must not silently change
