@@ -648,7 +648,37 @@ def make_dino_head_forward():
     out["loss_keys"] = np.array(list(losses.keys()))
     out["loss_values"] = np.array([float(v) for v in losses.values()], np.float64)
     out["param_names"] = np.array(sorted(n for n, _ in head.named_parameters()))
+    # forward_train (:983-1046): GT normalisation -> prepare_for_cdn (noise recorded) -> forward -> loss, end to end
+    saved = torch.Tensor.cuda, torch.Tensor.to, torch.rand_like, torch.randint_like
+    draws = []
+
+    def to(self, *a, **k):
+        if a and isinstance(a[0], str) and a[0].startswith("cuda"):
+            return self
+        return saved[1](self, *a, **k)
+
+    def rec(fn_):
+        def wrapped(*a, **k):
+            r = fn_(*a, **k)
+            draws.append(r.clone())
+            return r
+        return wrapped
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.to = to
+    torch.rand_like, torch.randint_like = rec(saved[2]), rec(saved[3])
+    try:
+        torch.manual_seed(8)
+        with torch.no_grad():
+            tl = head.forward_train(x["feats"], x["metas"], x["gt_bboxes"], x["gt_labels"])
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to, torch.rand_like, torch.randint_like = saved
+    out["train_keys"] = np.array(list(tl.keys()))
+    out["train_values"] = np.array([float(v) for v in tl.values()], np.float64)
+    for i, d in enumerate(draws):
+        out[f"train_draw{i}"] = d.numpy()
+    out["train_n_draws"] = np.array(len(draws))
     np.savez_compressed(os.path.join(HERE, "dino_head_forward_golden.npz"), **out)
+    print("forward_train:", len(tl), "losses, draws", [tuple(d.shape) for d in draws])
     print("dino_head_forward_golden.npz:", [tuple(o.shape) for o in outs], len(losses), "losses")
 
 
