@@ -246,7 +246,12 @@ def load_dino_head():
     _pkg("mmdet.models.utils.transformer").inverse_sigmoid = T.inverse_sigmoid
     _pkg("mmdet.models.dense_heads")
     afh = _pkg("mmdet.models.dense_heads.anchor_free_head")
-    afh.AnchorFreeHead = type("AnchorFreeHead", (nn.Module,), {})
+    if not hasattr(afh, "AnchorFreeHead"):
+
+        class _BaseDenseHead(nn.Module):              # what super(AnchorFreeHead, self).__init__(init_cfg) reaches
+            def __init__(self, init_cfg=None):
+                super().__init__()
+        afh.AnchorFreeHead = type("AnchorFreeHead", (_BaseDenseHead,), {})
     _pkg("mmdet.models.losses")
     _load("mmdet.models.losses.utils", MMDET + "/models/losses/utils.py")
     fl = _load("mmdet.models.losses.focal_loss", MMDET + "/models/losses/focal_loss.py")
@@ -355,13 +360,6 @@ def load_dino_head_buildable():
     head.build_sampler = lambda cfg, context=None: m["sampler"].PseudoSampler()
     head.build_activation_layer = lambda cfg: nn.ReLU(inplace=True)
 
-    class BaseDenseHead(nn.Module):
-        def __init__(self, init_cfg=None):
-            super().__init__()
-    if not issubclass(head.DINODETRHead, BaseDenseHead):
-        # re-base the stand-in AnchorFreeHead so that super(AnchorFreeHead, self).__init__(init_cfg) reaches nn.Module
-        afh = sys.modules["mmdet.models.dense_heads.anchor_free_head"].AnchorFreeHead
-        afh.__bases__ = (BaseDenseHead,)
     return m
 
 
@@ -404,3 +402,26 @@ def load_mmdet_resnet():
     rl = _load("mmdet.models.utils.res_layer", MMDET + "/models/utils/res_layer.py")
     sys.modules["mmdet.models.utils"].ResLayer = rl.ResLayer
     return _load("mmdet.models.backbones.resnet", MMDET + "/models/backbones/resnet.py")
+
+
+def load_dino_ssod_head_buildable():
+    """``load_dino_ssod_head`` with the SSOD head module's builder names bound like ``load_dino_head_buildable`` does
+    for the supervised head (plus O2MAssigner and TaskAlignedFocalLoss), so ``DINODETRSSODHead(**cfg)`` is constructed
+    by its own ``__init__``."""
+    import torch.nn as nn
+    load_dino_head_buildable()
+    m = load_dino_ssod_head()
+    T, _ = load_dino_transformer()
+    pe = load_positional_encoding()
+    head = m["ssod_head"]
+    strip = lambda cfg: {k: v for k, v in cfg.items() if k != "type"}
+    losses = {"FocalLoss": m["focal"].FocalLoss, "L1Loss": m["l1"].L1Loss, "GIoULoss": m["iou"].GIoULoss,
+              "TaskAlignedFocalLoss": m["tal"].TaskAlignedFocalLoss}
+    assigners = {"HungarianAssigner": m["assigner"].HungarianAssigner, "O2MAssigner": m["o2m"].O2MAssigner}
+    head.build_transformer = lambda cfg: T.DINOTransformer(**strip(cfg))
+    head.build_positional_encoding = lambda cfg: pe.SinePositionalEncodingHW(**strip(cfg))
+    head.build_loss = lambda cfg: losses[cfg["type"]](**strip(cfg))
+    head.build_assigner = lambda cfg: assigners[cfg["type"]](**strip(cfg))
+    head.build_sampler = lambda cfg, context=None: m["sampler"].PseudoSampler()
+    head.build_activation_layer = lambda cfg: nn.ReLU(inplace=True)
+    return m

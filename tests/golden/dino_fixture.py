@@ -313,3 +313,31 @@ def inputs5(seed=13):
     poss = [torch.randn(bs, C, h, w, generator=g) * 0.5 for h, w in LEVELS5]
     masks = [torch.zeros(bs, h, w, dtype=torch.bool) for h, w in LEVELS5]
     return srcs, masks, poss
+
+
+# ---- SSOD head fixture (reference: DINODETRSSODHead.__init__ / forward_dummy, dino_detr_ssod_head.py:77-505) --------
+SSOD_HEAD_CFG = dict(
+    num_classes=9, in_channels=2048, num_query=30, num_feature_levels=4, num_backbone_outs=3,
+    backbone_channels=[512, 1024, 2048], query_dim=4, dn_number=100, dn_box_noise_scale=0.4, dn_label_noise_ratio=0.5,
+    dn_labelbook_size=9, transformer=HEAD_CFG["transformer"], positional_encoding=HEAD_CFG["positional_encoding"],
+    loss_cls1=dict(type="TaskAlignedFocalLoss", use_sigmoid=True, gamma=2.0, loss_weight=2.0),
+    loss_cls2=HEAD_CFG["loss_cls"], loss_bbox=HEAD_CFG["loss_bbox"], loss_iou=HEAD_CFG["loss_iou"],
+    train_cfg=dict(assigner1=dict(type="O2MAssigner"), assigner2=HEAD_CFG["train_cfg"]["assigner"], warm_up_step=50),
+    test_cfg=dict(max_per_img=300, warm_up_step=50))
+
+
+def ssod_head_inputs(seed=67):
+    """head_inputs with the SSOD three-part query layout: 5 consistency slots | 4 denoising slots | matching."""
+    x = head_inputs()
+    g = torch.Generator().manual_seed(seed)
+    p1, p2 = 5, 4
+    x["q_label"] = torch.randn(2, p1 + p2, 256, generator=g)
+    x["q_bbox"] = torch.randn(2, p1 + p2, 4, generator=g)
+    T = p1 + p2 + SSOD_HEAD_CFG["num_query"]
+    mask = torch.zeros(T, T, dtype=torch.bool)
+    mask[p1 + p2:, :p1 + p2] = True
+    mask[:p1, p1:p1 + p2] = True
+    mask[p1:p1 + p2, :p1] = True
+    x["attn_mask"] = mask
+    x["dn_meta"] = dict(pad_size_1=p1, pad_size_2=p2, num_dn_group_1=5, num_dn_group_2=1)
+    return x

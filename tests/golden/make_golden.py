@@ -704,6 +704,26 @@ def make_backbone():
     print("backbone_golden.npz:", [tuple(o.shape) for o in outs], "params with grad", int((out["grad_norms"] >= 0).sum()))
 
 
+def make_dino_ssod_head_forward():
+    """The reference's own DINODETRSSODHead built by its __init__ (both assigners, both classification losses), and its
+    forward_dummy on the three-part query layout of the unsupervised pass."""
+    import dino_fixture as F
+    m = R.load_dino_ssod_head_buildable()
+    torch.manual_seed(0)
+    head = m["ssod_head"].DINODETRSSODHead(**F.SSOD_HEAD_CFG)
+    F.fill_by_name(head, "head.")
+    head.eval()
+    x = F.ssod_head_inputs()
+    with torch.no_grad():
+        outs = head.forward_dummy(x["feats"], x["metas"], x["q_label"], x["q_bbox"], x["attn_mask"], x["dn_meta"])
+    out = {"hs": torch.stack(list(outs[0])).numpy(), "param_names": np.array(sorted(n for n, _ in head.named_parameters())),
+           "warm_up_step": np.array(head.warm_up_step), "in_warm_up": np.array(head.in_warm_up)}
+    for i, o in enumerate(outs[1:], 1):
+        out[f"out{i}"] = o.numpy()
+    np.savez_compressed(os.path.join(HERE, "dino_ssod_head_forward_golden.npz"), **out)
+    print("dino_ssod_head_forward_golden.npz:", [tuple(o.shape) for o in outs[1:]])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -721,3 +741,4 @@ if __name__ == "__main__":
     make_ssod_teacher_info()
     make_dino_head_forward()
     make_backbone()
+    make_dino_ssod_head_forward()
