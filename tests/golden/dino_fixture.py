@@ -341,3 +341,36 @@ def ssod_head_inputs(seed=67):
     x["attn_mask"] = mask
     x["dn_meta"] = dict(pad_size_1=p1, pad_size_2=p2, num_dn_group_1=5, num_dn_group_2=1)
     return x
+
+
+# ---- SSOD wiring fixture (reference: foward_unsup_train / compute_pseudo_label_loss, dino_detr_ssod.py:154-201) ------
+def unsup_wiring_inputs():
+    """Three weak / strong pairs whose order differs between the two views (the method pairs them by filename), each
+    with its own view matrices; teacher images are constant = their index so that the re-ordering is visible."""
+    import numpy as np
+    names = ["a.jpg", "b.jpg", "c.jpg"]
+    order_t, order_s = [2, 0, 1], [0, 1, 2]
+    flip = lambda w: np.array([[-1.0, 0.0, w], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]], dtype=np.float32)
+    scale = lambda s: np.array([[s, 0.0, 0.0], [0.0, s, 0.0], [0.0, 0.0, 1.0]], dtype=np.float32)
+    t_mats = {"a.jpg": scale(0.8), "b.jpg": flip(200.0), "c.jpg": np.eye(3, dtype=np.float32)}
+    s_mats = {"a.jpg": flip(160.0) @ scale(0.8), "b.jpg": scale(1.25), "c.jpg": flip(128.0)}
+    shapes = {"a.jpg": (120, 160, 3), "b.jpg": (150, 250, 3), "c.jpg": (96, 128, 3)}
+    t_metas = [dict(filename=names[i], transform_matrix=t_mats[names[i]], img_shape=(100, 200, 3)) for i in order_t]
+    s_metas = [dict(filename=names[i], transform_matrix=s_mats[names[i]], img_shape=shapes[names[i]]) for i in order_s]
+    t_img = torch.stack([torch.full((3, 4, 4), float(i)) for i in order_t])
+    s_img = torch.stack([torch.full((3, 4, 4), 10.0 + i) for i in order_s])
+    teacher = dict(img=t_img, img_metas=t_metas)
+    student = dict(img=s_img, img_metas=s_metas, gt_bboxes=[torch.zeros(0, 4)] * 3, gt_labels=[torch.zeros(0).long()] * 3)
+    return teacher, student
+
+
+def fake_teacher_detections(img_metas):
+    """Stand-in for simple_test_bboxes(for_pseudo_label=True): detections that depend on the image's filename."""
+    out = []
+    for m in img_metas:
+        g = torch.Generator().manual_seed(zlib.crc32(m["filename"].encode()))
+        n = 12
+        xy = torch.rand(n, 2, generator=g) * 150
+        out.append((torch.cat([xy, xy + torch.rand(n, 2, generator=g) * 40 + 2, torch.rand(n, 1, generator=g) ** 2], 1),
+                    torch.randint(0, 80, (n,), generator=g)))
+    return out

@@ -724,6 +724,45 @@ def make_dino_ssod_head_forward():
     print("dino_ssod_head_forward_golden.npz:", [tuple(o.shape) for o in outs[1:]])
 
 
+def make_ssod_wiring():
+    """The reference's own foward_unsup_train -> compute_pseudo_label_loss chain (dino_detr_ssod.py:154-201) with its
+    extract_teacher_info / extract_student_info / _get_trans_mat / _transform_bbox and the real Transform2D: pairing of
+    the two views by filename, the teacher->student view matrix, the warped pseudo boxes handed to unsup_loss."""
+    import types
+    import dino_fixture as F
+    bu = R.load_bbox_utils()
+    names = ["foward_unsup_train", "compute_pseudo_label_loss", "extract_teacher_info", "extract_student_info",
+             "_get_trans_mat", "_transform_bbox"]
+    fns = R.load_methods(R.REF + "/detr_ssod/models/dino_detr_ssod.py", "DinoDetrSSOD", names,
+                         dict(torch=torch, np=np, Transform2D=bu.Transform2D))
+    rec = {}
+
+    def unsup_loss(student_info, teacher_info, pseudo_bboxes, pseudo_labels, pseudo_scores):
+        rec.update(student=student_info, teacher=teacher_info, boxes=pseudo_bboxes, labels=pseudo_labels,
+                   scores=pseudo_scores)
+        return dict(loss_x=torch.tensor(2.0))
+    t_head = types.SimpleNamespace(simple_test_bboxes=lambda feat, metas, **k: F.fake_teacher_detections(metas))
+    s_head = types.SimpleNamespace(forward=lambda feat, metas: ("outs", [m["filename"] for m in metas]))
+    me = types.SimpleNamespace(curr_step=3, unsup_loss=unsup_loss,
+                               teacher=types.SimpleNamespace(extract_feat=lambda img: (img,), bbox_head=t_head),
+                               student=types.SimpleNamespace(extract_feat=lambda img: (img,), bbox_head=s_head))
+    for n in names:
+        setattr(me, n, types.MethodType(fns[n], me))
+    teacher, student = F.unsup_wiring_inputs()
+    loss = me.foward_unsup_train(teacher, student)
+    out = {"loss_keys": np.array(list(loss.keys())), "teacher_img": rec["teacher"]["img"].numpy(),
+           "teacher_names": np.array([m["filename"] for m in rec["teacher"]["img_metas"]]),
+           "student_outs": np.array(rec["student"]["outs"][1])}
+    for i in range(3):
+        out[f"boxes{i}"], out[f"labels{i}"], out[f"scores{i}"] = (rec["boxes"][i].numpy(), rec["labels"][i].numpy(),
+                                                                  rec["scores"][i].numpy())
+        out[f"det{i}"] = rec["teacher"]["det_bboxes"][i].numpy()
+        out[f"t_mat{i}"], out[f"s_mat{i}"] = (rec["teacher"]["transform_matrix"][i].numpy(),
+                                              rec["student"]["transform_matrix"][i].numpy())
+    np.savez_compressed(os.path.join(HERE, "ssod_wiring_golden.npz"), **out)
+    print("ssod_wiring_golden.npz: teacher order", list(out["teacher_names"]), "kept", [len(b) for b in rec["boxes"]])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -742,3 +781,4 @@ if __name__ == "__main__":
     make_dino_head_forward()
     make_backbone()
     make_dino_ssod_head_forward()
+    make_ssod_wiring()
