@@ -87,3 +87,16 @@ def test_bf16_variant_is_the_fp_op_on_rounded_inputs(msda_golden):
     wv, wl, wa = O.msda_backward(O.bf16_round(c["value"]), levels, c["start"], c["loc"], c["attn"],
                                  O.bf16_round(c["gout"]))
     assert np.array_equal(gv, wv) and np.array_equal(gl, wl) and np.array_equal(ga, wa)
+
+
+def test_bf16_widening_bit_logic_of_the_kernels():
+    """``Chan4<__nv_bfloat16>::widen`` (csrc/common.cuh): four bf16 channels arrive as two little-endian 32-bit words;
+    element 0 is the LOW half of word 0, and bf16 -> fp32 is a 16-bit left shift (x << 16, x & 0xffff0000)."""
+    import torch
+    v = torch.randn(64, 4).to(torch.bfloat16)
+    words = v.view(torch.int16).numpy().astype(np.uint16).reshape(-1, 2, 2)            # [.., word, half]
+    rx = words[:, 0, 0].astype(np.uint32) | (words[:, 0, 1].astype(np.uint32) << 16)
+    ry = words[:, 1, 0].astype(np.uint32) | (words[:, 1, 1].astype(np.uint32) << 16)
+    widened = np.stack([(rx << np.uint32(16)).view(np.float32), (rx & np.uint32(0xFFFF0000)).view(np.float32),
+                        (ry << np.uint32(16)).view(np.float32), (ry & np.uint32(0xFFFF0000)).view(np.float32)], 1)
+    assert np.array_equal(widened, v.float().numpy())
