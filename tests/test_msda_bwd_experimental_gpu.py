@@ -85,7 +85,7 @@ def test_unfused_vs_oracle_and_default_kernel(variant, levels, mode, Lq):
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_fused_vs_default_fused_kernel(variant, levels, Lq, ref_dim):
     from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
-    from tests_fused_inputs import fused_inputs
+    from fused_fixture import fused_inputs
     S = sum(h * w for h, w in levels)
     value, shapes, start, ref, off, logits, gout = fused_inputs(levels, 2, Lq or S, ref_dim, seed=len(levels) + ref_dim)
     with _variant(variant):
