@@ -269,6 +269,13 @@ int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const float* grad
                            float* exp_avg_sq, float* teacher, const float* clip_coef, const float* step_count,
                            const int64_t* seg_bounds, const float* seg_lr, const float* seg_weight_decay,
                            int num_segs, float beta1, float beta2, float eps, double ema_momentum);
+/* The same step with the per-group hyper-parameters in DEVICE memory: seg_hparams_dev = num_segs x (lr, weight_decay)
+ * floats.  A step captured in a CUDA graph then follows the learning-rate schedule of the config
+ * (lr_config step decay, dino_detr_r50_8x2_12e_coco.py:129) by rewriting that small buffer between replays. */
+int sdb_adamw_ema_step_sched_f32(sdb_stream_t stream, float* params, const float* grads, float* exp_avg,
+                                 float* exp_avg_sq, float* teacher, const float* clip_coef,
+                                 const float* step_count, const int64_t* seg_bounds, const float* seg_hparams_dev,
+                                 int num_segs, float beta1, float beta2, float eps, double ema_momentum);
 
 /* ------------------------------------------------------------------------------------------
  * Token-wise linear layers as tcgen05 (5th-generation tensor core) GEMMs, TF32 arithmetic on fp32 storage with

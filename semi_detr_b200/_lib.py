@@ -33,6 +33,7 @@ SIGNATURES = {
     "sdb_hungarian_assign_f32": [c_void_p] * 9 + [c_int] * 4 + [c_float] * 3 + [c_void_p] * 5,
     "sdb_ema_update_f32": [c_void_p, c_void_p, c_int, c_double],
     "sdb_adamw_ema_step_f32": [c_void_p] * 11 + [c_int] + [c_float] * 3 + [c_double],  # seg arrays are HOST pointers
+    "sdb_adamw_ema_step_sched_f32": [c_void_p] * 10 + [c_int] + [c_float] * 3 + [c_double],  # seg_bounds is a HOST pointer
     "sdb_colsum_f32": [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p],
     "sdb_relu_backward_colsum_f32": [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p],
     "sdb_gemm_tf32": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -33,13 +33,17 @@ struct AdamArgs {
 __global__ void __launch_bounds__(kOptThreads)
 adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  float* __restrict__ teacher, const float* __restrict__ clip_coef, const float* __restrict__ step,
-                 AdamArgs a) {
+                 const float* __restrict__ dev_hparams, AdamArgs a) {
   const float t = step[0] + 1.f;             // this update's 1-based step index
   const float bc1 = 1.f - powf(a.beta1, t);
   const float bc2_sqrt = sqrtf(1.f - powf(a.beta2, t));
   const float coef = clip_coef ? clip_coef[0] : 1.f;
   for (int s = 0; s < a.nseg; ++s) {
-    const AdamSeg sg = a.seg[s];
+    AdamSeg sg = a.seg[s];
+    if (dev_hparams) {   // (lr, weight_decay) per segment in device memory: a captured graph follows the schedule
+      sg.lr = dev_hparams[2 * s];
+      sg.weight_decay = dev_hparams[2 * s + 1];
+    }
     const float step_size = sg.lr / bc1;
     const float decay = 1.f - sg.lr * sg.weight_decay;
     // segments start 16-byte aligned (the host pads them), so the body is float4
@@ -79,16 +83,16 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 }  // namespace sdb
 
-extern "C" int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const float* grads, float* exp_avg,
-                                      float* exp_avg_sq, float* teacher, const float* clip_coef,
-                                      const float* step_count, const int64_t* seg_bounds, const float* seg_lr,
-                                      const float* seg_weight_decay, int num_segs, float beta1, float beta2, float eps,
-                                      double ema_momentum) {
+static int adamw_ema_step(sdb_stream_t stream, float* params, const float* grads, float* exp_avg,
+                          float* exp_avg_sq, float* teacher, const float* clip_coef, const float* step_count,
+                          const int64_t* seg_bounds, const float* seg_lr, const float* seg_weight_decay,
+                          const float* dev_hparams, int num_segs, float beta1, float beta2, float eps,
+                          double ema_momentum) {
   using namespace sdb;
   SDB_REQUIRE(num_segs >= 0 && num_segs <= kMaxSegs, "adamw_ema_step: num_segs=%d (max %d)", num_segs, kMaxSegs);
   if (num_segs == 0) return SDB_OK;
-  SDB_REQUIRE(params && grads && exp_avg && exp_avg_sq && step_count && seg_bounds && seg_lr && seg_weight_decay,
-              "adamw_ema_step: null pointer");
+  SDB_REQUIRE(params && grads && exp_avg && exp_avg_sq && step_count && seg_bounds &&
+              (dev_hparams || (seg_lr && seg_weight_decay)), "adamw_ema_step: null pointer");
   SDB_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
                 reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq) |
                 reinterpret_cast<uintptr_t>(teacher)) & 15) == 0, "adamw_ema_step: buffers must be 16-byte aligned");
@@ -100,8 +104,8 @@ extern "C" int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const 
   for (int s = 0; s < num_segs; ++s) {    // host arrays: a handful of scalars
     a.seg[s].begin = seg_bounds[2 * s];
     a.seg[s].end = seg_bounds[2 * s + 1];
-    a.seg[s].lr = seg_lr[s];
-    a.seg[s].weight_decay = seg_weight_decay[s];
+    a.seg[s].lr = dev_hparams ? 0.f : seg_lr[s];
+    a.seg[s].weight_decay = dev_hparams ? 0.f : seg_weight_decay[s];
     SDB_REQUIRE(a.seg[s].begin % 4 == 0 && a.seg[s].end % 4 == 0 && a.seg[s].end >= a.seg[s].begin,
                 "adamw_ema_step: segment %d [%lld, %lld) must be 4-element aligned", s, a.seg[s].begin, a.seg[s].end);
     total += a.seg[s].end - a.seg[s].begin;
@@ -111,7 +115,29 @@ extern "C" int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const 
   const long long cap = (long long)sm_count() * 8;
   if (grid > cap) grid = cap;
   adamw_ema_kernel<<<(unsigned)grid, kOptThreads, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq,
-                                                                            teacher, clip_coef, step_count, a);
+                                                                            teacher, clip_coef, step_count, dev_hparams, a);
   SDB_LAUNCH_CHECK("adamw_ema_kernel");
   return SDB_OK;
+}
+
+extern "C" int sdb_adamw_ema_step_f32(sdb_stream_t stream, float* params, const float* grads, float* exp_avg,
+                                      float* exp_avg_sq, float* teacher, const float* clip_coef,
+                                      const float* step_count, const int64_t* seg_bounds, const float* seg_lr,
+                                      const float* seg_weight_decay, int num_segs, float beta1, float beta2, float eps,
+                                      double ema_momentum) {
+  return adamw_ema_step(stream, params, grads, exp_avg, exp_avg_sq, teacher, clip_coef, step_count, seg_bounds, seg_lr,
+                        seg_weight_decay, nullptr, num_segs, beta1, beta2, eps, ema_momentum);
+}
+
+extern "C" int sdb_adamw_ema_step_sched_f32(sdb_stream_t stream, float* params, const float* grads, float* exp_avg,
+                                            float* exp_avg_sq, float* teacher, const float* clip_coef,
+                                            const float* step_count, const int64_t* seg_bounds,
+                                            const float* seg_hparams_dev, int num_segs, float beta1, float beta2,
+                                            float eps, double ema_momentum) {
+  if (!seg_hparams_dev) {
+    sdb::set_error("adamw_ema_step_sched: null seg_hparams_dev");
+    return SDB_ERR_INVALID_ARG;
+  }
+  return adamw_ema_step(stream, params, grads, exp_avg, exp_avg_sq, teacher, clip_coef, step_count, seg_bounds, nullptr,
+                        nullptr, seg_hparams_dev, num_segs, beta1, beta2, eps, ema_momentum);
 }

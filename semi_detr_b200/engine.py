@@ -5,8 +5,8 @@ configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:122-128 (AdamW lr 1e-4, wd 1e-4,
 max_norm 0.1; DDP wrap at detr_ssod/apis/train.py:84-93), laid out for one process per B200:
 
  * all trainable gradients live in ONE flat fp32 buffer (``p.grad`` are views), so the data-parallel exchange is a
-   single NCCL all-reduce over NVLink (~188 MB, well under a millisecond on NVSwitch -- <2% of the step, so it is
-   not split into overlap buckets), the grad-norm clip is one reduction + one scale over the flat buffer, and
+   single NCCL all-reduce (sum) over NVLink (~188 MB; the 1/world of the mean is folded into the clip coefficient),
+   the grad-norm clip is one reduction + one scale over the flat buffer, and
    zeroing is one memset;
  * the whole step (forward, loss with device-side Hungarian matching, backward, all-reduce, clip, AdamW) has no
    host synchronisation and no per-step host->device copies (``consts.device_const``), so it can be captured in a
@@ -32,6 +32,32 @@ def build_optimizer(model, lr=1e-4, weight_decay=1e-4, backbone_lr_mult=0.1, fus
         fused = all(p.is_cuda for p in rest + backbone)
     return torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, fused=fused,
                              capturable=capturable and fused)
+
+
+def train_step_options(cfg):
+    """What the train-step engines need from a loaded config (``semi_detr_b200.config.Config``): the optimizer /
+    grad-clip hook settings (dino_detr_r50_8x2_12e_coco.py:122-128) and, if present, the MeanTeacher hook's
+    (detr_ssod_dino_detr_r50_coco_120k.py:41-45).  ``FusedSupervisedTrainStep(model, **opts)`` /
+    ``FusedSSODTrainStep(model, **opts)`` take the result."""
+    opt = cfg.optimizer
+    if opt["type"] != "AdamW":
+        raise ValueError(f"optimizer type {opt['type']!r}: the fused step implements AdamW")
+    keys = (opt.get("paramwise_cfg") or {}).get("custom_keys") or {}
+    extra = set(keys) - {"backbone"}
+    if extra or any(v.get("decay_mult", 1.0) != 1.0 for v in keys.values()):
+        raise ValueError(f"paramwise_cfg beyond a backbone lr_mult is not supported: {dict(keys)}")
+    out = dict(lr=opt["lr"], weight_decay=opt.get("weight_decay", 0.0),
+               backbone_lr_mult=keys.get("backbone", {}).get("lr_mult", 1.0))
+    clip = (cfg.get("optimizer_config") or {}).get("grad_clip")
+    if clip is not None and clip.get("norm_type", 2) != 2:
+        raise ValueError("only 2-norm gradient clipping is implemented")
+    out["max_grad_norm"] = clip["max_norm"] if clip else None
+    for hook in cfg.get("custom_hooks") or []:
+        if hook.get("type") == "MeanTeacher":
+            if hook.get("interval", 1) != 1:
+                raise ValueError("MeanTeacher interval != 1 is not supported by the fused step")
+            out.update(momentum=hook.get("momentum", 0.999), warm_up=hook.get("warm_up", 100))
+    return out
 
 
 def _cache_student_bn_folds(model):
@@ -219,32 +245,86 @@ class FusedAdamW:
                 o += n
         import ctypes
         self._bounds = (ctypes.c_int64 * 4)(bounds[0][0], bounds[0][1], bounds[1][0], bounds[1][1])
-        self._lr = (ctypes.c_float * 2)(lr, lr * backbone_lr_mult)
-        self._wd = (ctypes.c_float * 2)(weight_decay, weight_decay)
         self.betas, self.eps = betas, eps
         self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.param_groups = [dict(params=groups[0], lr=lr), dict(params=groups[1], lr=lr * backbone_lr_mult)]
+        # the schedule lives in ``param_groups`` like a torch optimizer's (an lr scheduler / mmcv LrUpdaterHook writes
+        # ``group["lr"]``); the kernel reads (lr, weight_decay) per group from a small DEVICE buffer that ``step``
+        # refreshes whenever the host values changed, so a captured graph follows the schedule too (``sync_hparams``)
+        self.param_groups = [dict(params=groups[0], lr=lr, initial_lr=lr, weight_decay=weight_decay),
+                             dict(params=groups[1], lr=lr * backbone_lr_mult, initial_lr=lr * backbone_lr_mult,
+                                  weight_decay=weight_decay)]
+        self._hparams_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._hparams_host = None
+        self.sync_hparams()
+
+    def _host_hparams(self):
+        return tuple(float(g[k]) for g in self.param_groups for k in ("lr", "weight_decay"))
+
+    def sync_hparams(self):
+        """Copy the current ``param_groups`` lr / weight_decay to the device buffer the kernel reads.  ``step`` calls
+        it; with a captured graph call it between replays after changing ``param_groups`` (outside capture)."""
+        h = self._host_hparams()
+        if h != self._hparams_host:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FusedAdamW: param_groups changed during CUDA graph capture; call sync_hparams() "
+                                   "before capturing / between replays")
+            self._hparams_dev.copy_(torch.tensor(h, dtype=torch.float32), non_blocking=False)
+            self._hparams_host = h
+
+    def set_lr(self, lrs):
+        """lrs: one learning rate per param group (head/transformer, backbone)"""
+        for g, lr in zip(self.param_groups, lrs):
+            g["lr"] = float(lr)
+        self.sync_hparams()
+
+    def state_dict(self):
+        """Moments, step counter and the schedule state -- what torch.optim.AdamW.state_dict() carries, flat."""
+        return dict(exp_avg=self.flat_m.clone(), exp_avg_sq=self.flat_v.clone(), step=self.step_count.clone(),
+                    param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+                    param_names=list(self.param_names), betas=tuple(self.betas), eps=self.eps)
+
+    def load_state_dict(self, state):
+        if list(state["param_names"]) != list(self.param_names):
+            raise ValueError("FusedAdamW.load_state_dict: parameter list differs from the checkpoint's")
+        if state["exp_avg"].numel() != self.flat_m.numel():
+            raise ValueError("FusedAdamW.load_state_dict: flat buffer size differs from the checkpoint's")
+        self.flat_m.copy_(state["exp_avg"])
+        self.flat_v.copy_(state["exp_avg_sq"])
+        self.step_count.copy_(state["step"])
+        for g, sg in zip(self.param_groups, state["param_groups"]):
+            g.update(sg)
+        self.betas, self.eps = tuple(state["betas"]), state["eps"]
+        self.sync_hparams()
 
     def zero_grad(self):
         self.flat_g.zero_()
 
-    def all_reduce_mean(self, world_size):
+    def all_reduce_sum(self, world_size):
+        """One NCCL all-reduce (sum) of the flat gradient; the 1/world of the mean rides in the clip coefficient of
+        ``step`` (no separate pass over the 188 MB buffer)."""
         if world_size > 1:
             dist.all_reduce(self.flat_g)
-            self.flat_g.div_(world_size)
 
-    def step(self, max_grad_norm=None, ema_momentum=None):
+    def step(self, max_grad_norm=None, ema_momentum=None, grad_scale=1.0):
+        """``grad_scale``: factor applied to the gradient buffer before clipping (1/world after a summing all-reduce)."""
+        self.sync_hparams()
         coef = None
         if max_grad_norm is not None:
             total_norm = torch.linalg.vector_norm(self.flat_g, 2)
+            if grad_scale != 1.0:
+                total_norm = total_norm * grad_scale
             coef = torch.clamp(max_grad_norm / (total_norm + 1e-6), max=1.0).reshape(1)
+            if grad_scale != 1.0:
+                coef = coef * grad_scale
+        elif grad_scale != 1.0:
+            coef = torch.full((1,), grad_scale, dtype=torch.float32, device=self.flat_p.device)
         dev = self.flat_p.device
         teacher = self.flat_t if (self.flat_t is not None and ema_momentum is not None) else None
         with torch.cuda.device(dev):
-            rc = self._lib.lib().sdb_adamw_ema_step_f32(
+            rc = self._lib.lib().sdb_adamw_ema_step_sched_f32(
                 self._lib.current_stream(dev), self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
                 self.flat_v.data_ptr(), self._lib.ptr(teacher), self._lib.ptr(coef), self.step_count.data_ptr(),
-                self._bounds, self._lr, self._wd, 2, self.betas[0], self.betas[1], self.eps,
+                self._bounds, self._hparams_dev.data_ptr(), 2, self.betas[0], self.betas[1], self.eps,
                 float(ema_momentum) if ema_momentum is not None else 0.0)
         self._lib.check(rc, "adamw_ema_step")
         self._lib.LAUNCHES["adamw_ema_step"] += 1
@@ -292,8 +372,8 @@ class FusedSupervisedTrainStep:
             self._pack(torch.autograd.grad(loss, self.opt.params, allow_unused=True))
         else:
             loss.backward()
-        self.opt.all_reduce_mean(self.world_size)
-        self.opt.step(self.max_grad_norm)
+        self.opt.all_reduce_sum(self.world_size)
+        self.opt.step(self.max_grad_norm, grad_scale=1.0 / self.world_size)
         return loss.detach(), log_vars
 
 
@@ -305,7 +385,8 @@ class FusedSSODTrainStep:
     warm_up))`` (mean_teacher.py:37-50); here the blend with ``m_{i+1}`` rides on the optimizer kernel at the END of
     iteration i -- the same teacher for every forward pass.  Student parameters that are frozen (stem, layer1, BN
     affine) are still blended (the reference has no ``requires_grad`` filter, :60-64) by a second, small
-    ``sdb_ema_update_f32`` launch.  ``before_run``'s momentum-0 copy happens in the constructor."""
+    ``sdb_ema_update_f32`` launch.  ``before_run``'s momentum-0 copy happens in the constructor when ``start_iter == 0``
+    (a run resumed at ``start_iter > 0`` keeps the EMA teacher it loaded)."""
 
     def __init__(self, model, momentum=0.999, warm_up=0, max_grad_norm=0.1, world_size=None, start_iter=0, **opt_kw):
         from .teacher.mean_teacher import EmaPlan
@@ -316,9 +397,10 @@ class FusedSSODTrainStep:
         self.world_size = world_size
         student = dict(model.student.named_parameters())
         teacher = dict(model.teacher.named_parameters())
-        with torch.no_grad():
-            for n, t in teacher.items():            # before_run: teacher <- student
-                t.copy_(student[n])
+        if start_iter == 0:                         # before_run clones only at runner.iter == 0
+            with torch.no_grad():                   # (mean_teacher.py:26-35); a resumed run keeps the loaded teacher
+                for n, t in teacher.items():
+                    t.copy_(student[n])
         self.opt = FusedAdamW(model, teacher_params={"student." + n: t for n, t in teacher.items()}, **opt_kw)
         frozen = [n for n, p in student.items() if not p.requires_grad]
         self.frozen_plan = EmaPlan([teacher[n].data for n in frozen], [student[n].data for n in frozen])
@@ -335,9 +417,9 @@ class FusedSSODTrainStep:
         losses = self.model(**data)
         loss, log_vars = self.model._parse_losses(losses)
         self._pack(torch.autograd.grad(loss, self.opt.params, allow_unused=True))
-        self.opt.all_reduce_mean(self.world_size)
+        self.opt.all_reduce_sum(self.world_size)
         m = self.momentum_at(self.iter + 1)
-        self.opt.step(self.max_grad_norm, ema_momentum=m)
+        self.opt.step(self.max_grad_norm, ema_momentum=m, grad_scale=1.0 / self.world_size)
         self.frozen_plan.step(m)
         self.iter += 1
         log_vars["ema_momentum"] = m
