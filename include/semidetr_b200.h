@@ -304,20 +304,6 @@ int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const flo
                   int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu, int k_splits,
                   int round_mode, float* a_column_sums);
 
-/* Debug hook: device buffer of 64 x gridDim.x uint64 that subsequent sdb_gemm_tf32 launches fill with %globaltimer
- * stamps per warp role (tools/trace_gemm.py); NULL switches tracing off. */
-int sdb_gemm_tf32_set_trace(unsigned long long* device_buffer);
-
-/* Debug microbenchmark (csrc/umma_rate.cu): SM cycles for `iters` back-to-back tcgen05.mma kind::tf32 128 x n x 8 on
- * fixed operands; mode bit 0: A operand in tensor memory, bit 1: alternate between two accumulators. */
-int sdb_debug_umma_rate(sdb_stream_t stream, int n, int mode, int iters, int grid, long long* cycles_out);
-
-/* Debug microbenchmark (csrc/umma_rate.cu): streams a (rows, k) fp32 row-major matrix through every SM's shared memory
- * with TMA boxes of box_rows x 128 bytes x kblocks_per_box k-blocks, boxes_per_stage boxes per stage, a ring of `stages` stages and no consumer
- * work -- the feed rate the GEMM main loop can count on.  cycles_out: SM cycles of CTA 0. */
-int sdb_debug_tma_rate(sdb_stream_t stream, const float* x, int rows, int k, int box_rows, int boxes_per_stage,
-                       int kblocks_per_box, int stages, int grid, long long* cycles_out);
-
 #ifdef __cplusplus
 }
 #endif

@@ -37,15 +37,39 @@ SIGNATURES = {
     "sdb_colsum_f32": [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p],
     "sdb_relu_backward_colsum_f32": [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p],
     "sdb_gemm_tf32": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
-    "sdb_gemm_tf32_set_trace": [c_void_p],
-    "sdb_debug_umma_rate": [c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "sdb_debug_tma_rate": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_layernorm_bwd_workspace_floats": [],
     "sdb_layernorm_forward_f32": [c_void_p] * 4 + [ctypes.c_int64, c_int, c_float] + [c_void_p] * 3,
     "sdb_layernorm_backward_f32": [c_void_p] * 6 + [ctypes.c_int64, c_int] + [c_void_p] * 4,
 }
 
+# include/semidetr_b200_debug.h -> lib/libsemidetr_b200_debug.so (tools/ only; `python -m semi_detr_b200.build --debug`)
+DEBUG_LIB_PATH = os.path.join(_HERE, "lib", "libsemidetr_b200_debug.so")
+DEBUG_SIGNATURES = {
+    "sdb_gemm_tf32": SIGNATURES["sdb_gemm_tf32"],
+    "sdb_gemm_tf32_set_trace": [c_void_p],
+    "sdb_debug_umma_rate": [c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sdb_debug_tma_rate": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+}
+
 _lib = None
+_debug_lib = None
+
+
+def debug_lib():
+    """The instrumentation library (trace stamps, issue-rate microbenchmarks).  Never loaded by the package itself."""
+    global _debug_lib
+    if _debug_lib is None:
+        if not os.path.exists(DEBUG_LIB_PATH):
+            raise RuntimeError(f"{DEBUG_LIB_PATH} is missing: build it with `python -m semi_detr_b200.build --debug`")
+        l = ctypes.CDLL(DEBUG_LIB_PATH)
+        for name, argtypes in DEBUG_SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        l.sdb_last_error.restype = ctypes.c_char_p
+        _debug_lib = l
+    return _debug_lib
+
 
 # kernels of this library launched so far, by entry point (bench.py reports the per-step count)
 LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "msda_fused_forward": 0, "msda_fused_backward": 0, "msda_forward_tma": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,

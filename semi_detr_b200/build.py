@@ -22,7 +22,10 @@ EXTRA = {
     # the matching cost must round like torch's separately-rounded elementwise kernels
     "hungarian.cu": ["-fmad=false"],
 }
-SOURCES = ["abi.cu", "msda_forward.cu", "msda_forward_tma.cu", "msda_backward.cu", "msda_backward_x8.cu", "hungarian.cu", "ema.cu", "layernorm.cu", "optimizer.cu", "colsum.cu", "gemm_tf32.cu", "umma_rate.cu"]
+SOURCES = ["abi.cu", "msda_forward.cu", "msda_forward_tma.cu", "msda_backward.cu", "msda_backward_x8.cu", "hungarian.cu", "ema.cu", "layernorm.cu", "optimizer.cu", "colsum.cu", "gemm_tf32.cu"]
+# instrumentation library (include/semidetr_b200_debug.h): microbenchmarks + the GEMM with %globaltimer stamps
+DEBUG_LIB = os.path.join(LIBDIR, "libsemidetr_b200_debug.so")
+DEBUG_SOURCES = [("abi.cu", []), ("umma_rate.cu", []), ("gemm_tf32.cu", ["-DSDB_GEMM_TRACE=1"])]
 
 
 def _stale():
@@ -63,5 +66,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_debug(verbose=False):
+    """lib/libsemidetr_b200_debug.so -- only tools/ load it; never built by __graft_entry__.build()."""
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objdir = os.path.join(LIBDIR, "obj_debug")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src, extra in DEBUG_SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+    subprocess.run([nvcc, *ARCH, "-shared", "-o", DEBUG_LIB, *objs], check=True)
+    return DEBUG_LIB
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug(verbose="--verbose" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -62,13 +62,22 @@ constexpr int kTmemCols = 2 * kBN;
 constexpr size_t kDynSmem = (size_t)kStages * kStageBytes + 2 * kOutBufBytes + 1024;   // + alignment slack
 constexpr size_t kDynSmemRes = (size_t)(kResKB + kResStages) * kTileBytes + 2 * kOutBufBytes + 1024;
 
+// Per-role %globaltimer stamps exist only in the DEBUG build of this file (-DSDB_GEMM_TRACE=1 ->
+// lib/libsemidetr_b200_debug.so, include/semidetr_b200_debug.h); the product library compiles them out.
+#ifndef SDB_GEMM_TRACE
+#define SDB_GEMM_TRACE 0
+#endif
 __device__ __forceinline__ void stamp(unsigned long long* trace, int slot) {
+#if SDB_GEMM_TRACE
   if (trace) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     trace[(size_t)blockIdx.x * 64 + slot] = t;
     asm volatile("" ::: "memory");
   }
+#else
+  (void)trace; (void)slot;
+#endif
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1161,10 +1170,12 @@ static unsigned long long* g_gemm_trace = nullptr;
 
 // Debug hook (not part of the reference-facing surface): a device buffer of 64 x gridDim.x uint64 that the next launches
 // fill with %globaltimer stamps per warp role (tools/trace_gemm.py prints the timeline); NULL switches it off.
+#if SDB_GEMM_TRACE
 extern "C" int sdb_gemm_tf32_set_trace(unsigned long long* device_buffer) {
   g_gemm_trace = device_buffer;
   return SDB_OK;
 }
+#endif
 
 extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
                              float* y, int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu,

@@ -39,6 +39,15 @@ def test_library_exports_every_declared_symbol(libpath):
     assert lib.sdb_abi_version() == 1
 
 
+def test_product_library_exports_only_the_declared_surface(libpath):
+    """Instrumentation (trace stamps, issue-rate microbenchmarks) lives in include/semidetr_b200_debug.h /
+    libsemidetr_b200_debug.so; the product library exports exactly what its header declares."""
+    out = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r" T (sdb_[a-z0-9_]+)", out)))
+    assert exported == _declared()
+    assert not [n for n in exported if "debug" in n or "trace" in n]
+
+
 def test_ctypes_table_matches_header(libpath):
     from semi_detr_b200 import _lib
     assert sorted(list(_lib.SIGNATURES) + ["sdb_last_error"]) == _declared()

@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from semi_detr_b200 import _lib  # noqa: E402
 
-lib = _lib.lib()
+lib = _lib.debug_lib()
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for k in (256, 2048):

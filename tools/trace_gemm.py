@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from semi_detr_b200 import _lib  # noqa: E402
 from semi_detr_b200.layers import gemm as G  # noqa: E402
 
+# the traced GEMM is the debug library's build of the same source (-DSDB_GEMM_TRACE=1): route this tool's launches to it
+_lib.lib().sdb_gemm_tf32 = _lib.debug_lib().sdb_gemm_tf32
+
 NAMES = {0: "start", 1: "setup done", 2: "producer: B issued", 16: "mma: B ready", 48: "xform: B landed",
          49: "B rounded (smem variant) / weights in TMEM (wres)", 62: "epilogue: stores drained", 63: "end"}
 for t in range(6):
@@ -28,10 +31,10 @@ def run(m, n, k, round_mode):
         G.gemm_tf32(x, 0, w, 0, m, n, k, bias=b, round_mode=round_mode)
     torch.cuda.synchronize()
     trace = torch.zeros(148 * 64, dtype=torch.int64, device="cuda")
-    _lib.lib().sdb_gemm_tf32_set_trace(trace.data_ptr())
+    _lib.debug_lib().sdb_gemm_tf32_set_trace(trace.data_ptr())
     G.gemm_tf32(x, 0, w, 0, m, n, k, bias=b, round_mode=round_mode)
     torch.cuda.synchronize()
-    _lib.lib().sdb_gemm_tf32_set_trace(None)
+    _lib.debug_lib().sdb_gemm_tf32_set_trace(None)
     tr = trace.view(148, 64).cpu()
     t0 = int(tr[:, 0][tr[:, 0] > 0].min())
     print(f"== m={m} n={n} k={k} round_mode={round_mode}: CTA 0 and CTA 147 (us since the first CTA started)")

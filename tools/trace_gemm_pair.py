@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from semi_detr_b200 import _lib  # noqa: E402
 from semi_detr_b200.layers import gemm as G  # noqa: E402
 
+# the traced GEMM is the debug library's build of the same source (-DSDB_GEMM_TRACE=1): route this tool's launches to it
+_lib.lib().sdb_gemm_tf32 = _lib.debug_lib().sdb_gemm_tf32
+
 m, n, k = 44446, 256, 2048
 x = torch.randn(m, k, device="cuda")
 w = torch.randn(n, k, device="cuda") * 0.05
@@ -18,10 +21,10 @@ for rm in (3, 0):
         G.gemm_tf32(x, 0, w, 0, m, n, k, round_mode=rm)
     torch.cuda.synchronize()
     trace = torch.zeros(148 * 64, dtype=torch.int64, device="cuda")
-    _lib.lib().sdb_gemm_tf32_set_trace(trace.data_ptr())
+    _lib.debug_lib().sdb_gemm_tf32_set_trace(trace.data_ptr())
     G.gemm_tf32(x, 0, w, 0, m, n, k, round_mode=rm)
     torch.cuda.synchronize()
-    _lib.lib().sdb_gemm_tf32_set_trace(None)
+    _lib.debug_lib().sdb_gemm_tf32_set_trace(None)
     tr = trace.view(148, 64).cpu()
     t0 = int(tr[0, 0])
     us = lambda cta, slot: (int(tr[cta, slot]) - t0) / 1e3 if int(tr[cta, slot]) else float("nan")

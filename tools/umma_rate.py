@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from semi_detr_b200 import _lib  # noqa: E402
 
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
-lib = _lib.lib()
+lib = _lib.debug_lib()
 for grid in (1,):
     for n in (128, 256):
         for mode in (0, 1):
