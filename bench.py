@@ -1,6 +1,6 @@
 """bench.py -- the driver's measurement contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sup|ssod|msda]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -16,7 +16,16 @@ Prints ONE JSON line on rank 0 (see README / DESIGN.md for the keys):
             timed live with CUDA events around each launch inside the timed region
   cpu_baseline  (N=1 only) the reference's CPU path (oracle: python ms_deform_attn fallback + host Hungarian +
             torch-cpu) timed on this box's host cores on a bounded sample
-`--impl reference` times that CPU path alone (rank 0 only) and prints the same line with "impl": "reference".
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same line with "impl": "reference" -- on the
+SAME configuration (2 images 800x1333 per step), warm-up capped at one step so K steps end within a few minutes.
+
+`--workload` (default `sup`, the line above) selects the other BASELINE.json configurations:
+  ssod  configs[2] per-GPU batch: Semi-DETR teacher-student step, 1 labelled + 4 unlabelled (weak, strong) pairs
+        800x1333 per GPU, EMA + forward + backward + clip + AdamW; both phases (warm-up / Hungarian) are timed, `value`
+        is the Hungarian phase (the 120k-iteration schedule spends its second half there), images/s counts the 5
+        source images per GPU and step
+  msda  configs[4] microbenchmark: MSDeformAttn forward + backward at N=2, S=Lq=17 821 (and the decoder shape
+        Lq=1100), fp32 and bf16 storage, L2 flushed before every launch, algorithmic HBM GB/s against the measured peak
 """
 import argparse
 import copy
@@ -35,6 +44,15 @@ UNIT = "images/s"
 IMG_H, IMG_W, PER_GPU_BATCH = 800, 1333, 2
 WORKLOAD = ("configs[1]: DINO-4scale R50 supervised train step (fwd + CDN + 13x Hungarian-matched loss + bwd + "
             "clip 0.1 + AdamW), bs=2/GPU, synthetic COCO-shape 800x1333")
+
+
+SSOD_METRIC = "images/sec (train step) Semi-DETR teacher-student DINO-4scale R50"
+SSOD_WORKLOAD = ("configs[2] per-GPU batch: Semi-DETR teacher-student step (detr_ssod_dino_detr_r50_coco_120k), 1 labelled + 4 "
+                 "unlabelled (weak, strong) pairs 800x1333 per GPU, teacher EMA + fwd + pseudo-label filter + bwd + clip 0.1 + "
+                 "AdamW; images/s counts the 5 source images per GPU and step")
+MSDA_METRIC = "MSDeformAttn fwd+bwd HBM GB/s"
+MSDA_WORKLOAD = ("configs[4]: MSDeformAttn microbench, 4 levels, sum HW = 17821, C=256, 8 heads, 4 points, N=2, encoder shape "
+                 "(Lq = S), fp32; one step = one forward + one backward launch")
 
 
 def measured_peak():
@@ -118,29 +136,94 @@ def cpu_reference_step_time(n_images, height, width, steps, warmup, threads):
     return times
 
 
+def cpu_reference_ssod_step_time(steps, warmup, threads):
+    """The teacher-student step (1 labelled + 4 unlabelled pairs 800x1333) on the reference's CPU path."""
+    import torch
+    from oracle.cpu_path import reference_cpu_ops
+    from semi_detr_b200 import dino, ssod  # noqa: F401
+    from semi_detr_b200.engine import FlatGrads, build_optimizer
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import ssod_batch, ssod_model_cfg
+    from semi_detr_b200.teacher import MeanTeacher
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = DETECTORS.build(ssod_model_cfg()).train()
+    model.curr_step = 60000
+    data = ssod_batch(1, 4, IMG_H, IMG_W, seed=0)
+    opt = build_optimizer(model, fused=False)
+    grads = FlatGrads([p for g in opt.param_groups for p in g["params"]])
+    runner = type("R", (), dict(model=model, iter=60000, log_buffer=type("B", (), {"output": {}})()))()
+    hook = MeanTeacher(momentum=0.999, interval=1, warm_up=0)
+    times = []
+    with reference_cpu_ops():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            hook.before_train_iter(runner)
+            grads.zero()
+            loss, _ = model._parse_losses(model(**data))
+            loss.backward()
+            grads.clip_(0.1)
+            opt.step()
+            float(loss)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_reference_msda_time(steps, warmup, threads):
+    """The reference's pure-PyTorch MSDA fallback (ms_deform_attn_core_pytorch: grid_sample) forward + backward at the
+    microbench shape -> seconds per (fwd + bwd)."""
+    import torch
+    from oracle import msda_oracle
+    from semi_detr_b200.synthetic import MICROBENCH_LEVELS, msda_inputs
+    torch.set_num_threads(threads)
+    x = msda_inputs(MICROBENCH_LEVELS, N=2, mode="encoder", seed=0, device="cpu")
+    times = []
+    for i in range(warmup + steps):
+        leaves = [x[k].clone().requires_grad_(True) for k in ("value", "loc", "attn")]
+        t0 = time.perf_counter()
+        out = msda_oracle.msda_forward_torch(leaves[0], MICROBENCH_LEVELS, leaves[1], leaves[2])
+        out.backward(x["gout"])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # bounded sample: ONE full-size image per step unless K+W steps of that would not end within a few minutes,
-    # then a half-resolution image counted in full-size-image equivalents (pixel ratio)
-    total_steps = args.steps + args.warmup
-    h, w, scale_note = IMG_H, IMG_W, ""
-    if total_steps > 16:
-        h, w = IMG_H // 2, (IMG_W + 1) // 2
-        scale_note = " (half resolution; images/s in 800x1333-pixel equivalents)"
-    times = cpu_reference_step_time(1, h, w, args.steps, args.warmup, threads)
-    sec = sum(times) / len(times)
-    equiv = (h * w) / float(IMG_H * IMG_W)
-    value = equiv / sec
-    sample = f"{args.steps} steps of 1 synthetic image {h}x{w} per step{scale_note}, {threads} host threads"
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    # The reference's CPU path on the SAME configuration as our arm (no shrunken images); the only bound applied is on
+    # the warm-up (one step -- a CPU run has nothing to autotune), so that K timed steps end within a few minutes.
+    warm = min(args.warmup, 1)
+    if args.workload == "sup":
+        times = cpu_reference_step_time(PER_GPU_BATCH, IMG_H, IMG_W, args.steps, warm, threads)
+        sec = sum(times) / len(times)
+        value, metric, unit, workload = PER_GPU_BATCH / sec, METRIC, UNIT, WORKLOAD
+        sample = (f"{args.steps} full train steps of {PER_GPU_BATCH} synthetic images {IMG_H}x{IMG_W} (the configuration "
+                  f"of our arm), {warm} warm-up, reference CPU path (python ms_deform_attn fallback + host LSAP + "
+                  f"torch-cpu), {threads} host threads")
+    elif args.workload == "ssod":
+        times = cpu_reference_ssod_step_time(args.steps, warm, threads)
+        sec = sum(times) / len(times)
+        value, metric, unit, workload = 5 / sec, SSOD_METRIC, UNIT, SSOD_WORKLOAD
+        sample = (f"{args.steps} teacher-student steps (Hungarian phase) of 1 + 4 pairs {IMG_H}x{IMG_W}, {warm} warm-up, "
+                  f"reference CPU path, {threads} host threads")
+    else:
+        from semi_detr_b200.synthetic import msda_bytes
+        times = cpu_reference_msda_time(args.steps, warm, threads)
+        sec = sum(times) / len(times)
+        fb, bb = msda_bytes(2, 17821, 17821)
+        value, metric, unit, workload = (fb + bb) / sec / 1e9, MSDA_METRIC, "GB/s", MSDA_WORKLOAD
+        sample = (f"{args.steps} x (forward + backward) of the reference's ms_deform_attn_core_pytorch (grid_sample) at "
+                  f"N=2, S=Lq=17821, {warm} warm-up, {threads} host threads")
+    line = dict(metric=metric, value=value, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=warm,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, sample=sample, parallelism="cpu"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
-                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                config=dict(workload=workload, sample=sample, parallelism="cpu"),
+                cpu_baseline=dict(value=value, unit=unit, cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
 
@@ -148,14 +231,11 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
-def run_ours(args):
+def _init_ours():
+    """One process per GPU; NCCL when launched by torchrun.  -> (world, rank, local_rank, device)"""
     import torch
     import torch.distributed as dist
     from semi_detr_b200 import _lib
-    from semi_detr_b200.engine import FusedSupervisedTrainStep, GraphedTrainStep, SupervisedTrainStep, build_optimizer
-    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
-    from semi_detr_b200.synthetic import coco_like_batch, msda_bytes
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,6 +258,36 @@ def run_ours(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     _lib.lib()  # fail loudly if the extension is missing
+    return world, rank, local_rank, device
+
+
+def _sync_tools(world, device):
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    return barrier, max_over_ranks
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.engine import FusedSupervisedTrainStep, GraphedTrainStep, SupervisedTrainStep, build_optimizer
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import coco_like_batch, msda_bytes
+
+    world, rank, local_rank, device = _init_ours()
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
@@ -201,17 +311,7 @@ def run_ours(args):
     h2d_bytes = host["img"].numel() * 4 + sum(x.numel() * 4 for x in host["gt_bboxes"]) + \
         sum(x.numel() * 8 for x in host["gt_labels"])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+    barrier, max_over_ranks = _sync_tools(world, device)
 
     if args.ncu:
         step(resident)
@@ -325,14 +425,7 @@ def run_ours(args):
         d = kernels[dom_name]
         # DRAM bytes per launch of the same kernel at the same shape, from the committed `ncu --set full` capture of
         # `bench.py --ncu` (profiles/ncu_msda_step_r1.txt); ncu cannot run inside the timed region.
-        traffic, traffic_src = None, None
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_msda_traffic_r1.json")) as f:
-                tj = json.load(f)
-            traffic = tj["kernels"][dom_name]["dram_bytes_per_launch"]
-            traffic_src = tj["source"]
-        except (OSError, KeyError, ValueError):
-            pass
+        traffic, traffic_src = _committed_traffic(dom_name)
         roofline = dict(bound="hbm", kernel=dom_name, achieved=d["gbs"], peak=peak, unit="GB/s",
                         frac=d["gbs"] / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                         avg_launch_us=d["avg_us"],
@@ -368,6 +461,227 @@ def run_ours(args):
     _leave(world)
 
 
+# ----------------------------------------------------------------------------------------------------
+# workload msda: BASELINE.json configs[4], the MSDeformAttn microbenchmark
+# ----------------------------------------------------------------------------------------------------
+def run_msda(args):
+    import torch
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.msda import MSDeformAttnFunction
+    from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA
+    from semi_detr_b200.synthetic import MICROBENCH_LEVELS, msda_bytes, msda_inputs
+
+    world, rank, local_rank, device = _init_ours()
+    barrier, max_over_ranks = _sync_tools(world, device)
+    peak, peak_src = measured_peak()
+    N = 2
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)     # 2x the 126 MB L2
+
+    def time_launches(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return ts
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    results, launches = {}, 0
+    enc_fp32 = None
+    for shape, mode, Lq in (("enc", "encoder", None), ("dec", "uniform", 1100)):
+        x = msda_inputs(MICROBENCH_LEVELS, N=N, mode=mode, Lq=Lq, seed=0, device=device)
+        S, q = x["value"].shape[1], x["loc"].shape[1]
+        for dt_name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+            v, go = x["value"].to(dt), x["gout"].to(dt)
+            a = (v, x["shapes"], x["start"], x["loc"], x["attn"])
+            elt = 4 if dt == torch.float32 else 2
+            fb32, bb32 = msda_bytes(N, S, q)
+            vq = N * S * 256 + N * q * 256                                   # value + out (fwd) elements
+            fb = fb32 - (4 - elt) * vq                                       # bf16 storage halves value / out
+            bb = bb32 - (4 - elt) * vq                                       # and grad_out / value (grad_value stays fp32)
+            tf = time_launches(lambda: MSDA.ms_deform_attn_forward(*a, 64), args.steps, warm)
+            tb = time_launches(lambda: MSDA.ms_deform_attn_backward(*a, go, 64), args.steps, warm)
+            launches += 2 * (args.steps + warm)
+            for kind, ts, nb in (("fwd", tf, fb), ("bwd", tb, bb)):
+                med = statistics.median(ts)
+                results[f"msda_{kind}_{shape}_{dt_name}"] = dict(
+                    median_us=round(med * 1e6, 2), min_us=round(min(ts) * 1e6, 2), algorithmic_bytes=nb,
+                    gbs=round(nb / med / 1e9, 1), frac=round(nb / med / 1e9 / peak, 4), launches=len(ts))
+            if shape == "enc" and dt_name == "f32":
+                enc_fp32 = (x, tf, tb, fb, bb)
+    # ---- end to end through the reference-facing operator: host tensors in, gradients' checksum out ----------
+    x, tf, tb, fb, bb = enc_fp32
+    host = {k: x[k].cpu().pin_memory() for k in ("value", "loc", "attn", "gout")}
+    h2d = sum(t.numel() * 4 for t in host.values())
+
+    def e2e_step():
+        leaves = [host[k].to(device, non_blocking=True).requires_grad_(True) for k in ("value", "loc", "attn")]
+        out = MSDeformAttnFunction.apply(leaves[0], x["shapes"], x["start"], leaves[1], leaves[2], 64)
+        out.backward(host["gout"].to(device, non_blocking=True))
+        return float(leaves[0].grad.sum() + out.detach().sum())
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    sec_step = max_over_ranks((statistics.median(tf) + statistics.median(tb)) * 1e3) * 1e-3
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        _leave(world)
+        return
+    value = world * (fb + bb) / sec_step / 1e9
+    dom = results["msda_bwd_enc_f32"]
+    traffic, traffic_src = _committed_traffic("msda_bwd_micro_enc")
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t = cpu_reference_msda_time(2, 1, threads)
+        sec = sum(t) / len(t)
+        cpu_baseline = dict(value=(fb + bb) / sec / 1e9, unit="GB/s", cores=threads, kind="port",
+                            sample=f"2 x (forward + backward) of the reference's ms_deform_attn_core_pytorch at the same "
+                                   f"shape, {threads} host threads")
+    line = dict(metric=MSDA_METRIC, value=value, unit="GB/s", n_gpus=world, steps=args.steps, warmup=warm,
+                ms_per_step=sec_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32 (bf16-storage variants listed under kernels)", data="synthetic",
+                config=dict(workload=MSDA_WORKLOAD, parallelism=f"replicas x{world}",
+                            l2="256 MB buffer written before every timed launch (L2 is 126 MB)",
+                            timing="CUDA events around each launch; step = median fwd + median bwd"),
+                clocks=clocks,
+                e2e=dict(value=world * (fb + bb) / (ms_e2e / args.steps / 1e3) / 1e9, unit="GB/s",
+                         h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
+                         note="MSDeformAttnFunction.apply + backward on pinned host tensors; PCIe-bound"),
+                gpu_launches=launches, gpu_launches_per_step=2,
+                roofline=dict(bound="hbm", kernel="msda_bwd_enc_f32", achieved=dom["gbs"], peak=peak, unit="GB/s",
+                              frac=dom["frac"], traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
+                              avg_launch_us=dom["median_us"], algorithmic_bytes_per_launch=dom["algorithmic_bytes"]),
+                kernels=results, cpu_baseline=cpu_baseline)
+    print(json.dumps(line), flush=True)
+    _leave(world)
+
+
+def _committed_traffic(key):
+    """DRAM bytes per launch from the newest committed `ncu --set full` extract that has this kernel (ncu cannot run
+    inside a timed region)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_msda_traffic_r*.json")), reverse=True):
+        try:
+            with open(path) as f:
+                tj = json.load(f)
+            return tj["kernels"][key]["dram_bytes_per_launch"], tj["source"]
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload ssod: BASELINE.json configs[2], the teacher-student step
+# ----------------------------------------------------------------------------------------------------
+def run_ssod(args):
+    import torch
+    import torch.distributed as dist
+    from semi_detr_b200 import _lib, dino, ssod  # noqa: F401
+    from semi_detr_b200.engine import FusedSSODTrainStep
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import ssod_batch, ssod_model_cfg
+
+    world, rank, local_rank, device = _init_ours()
+    barrier, max_over_ranks = _sync_tools(world, device)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    model = DETECTORS.build(ssod_model_cfg()).to(device).train()
+    if world > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+    fused = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, world_size=world)
+    host = ssod_batch(1, 4, IMG_H, IMG_W, seed=rank)
+    host["img"] = host["img"].pin_memory()
+    h2d = host["img"].numel() * 4 + sum(x.numel() * 4 for x in host["gt_bboxes"]) + \
+        sum(x.numel() * 8 for x in host["gt_labels"])
+
+    def to_device():
+        return dict(img=host["img"].to(device, non_blocking=True), img_metas=[dict(m) for m in host["img_metas"]],
+                    gt_bboxes=[x.to(device, non_blocking=True) for x in host["gt_bboxes"]],
+                    gt_labels=[x.to(device, non_blocking=True) for x in host["gt_labels"]])
+
+    resident = to_device()
+    warm = max(args.warmup, 3)
+    phases = {}
+    sampler = None
+    for phase, it0 in (("warm-up (O2M assigner, consistency loss on)", 0), ("Hungarian", 60000)):
+        def step(batch):
+            fused.iter = it0                     # stay inside the phase being timed
+            return fused(batch)
+        for _ in range(warm):
+            step(resident)
+        barrier()
+        if phase == "Hungarian" and rank == 0:
+            sampler = ClockSampler(local_rank)
+        l0 = sum(_lib.LAUNCHES.values())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step(resident)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = sum(_lib.LAUNCHES.values()) - l0
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e2.record()
+        last = 0.0
+        for _ in range(args.steps):
+            loss, _ = step(to_device())
+            last = float(loss)
+        e3.record()
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+        phases[phase] = dict(ms_per_step=ms / args.steps, images_per_s=5 * world * args.steps / (ms / 1e3),
+                             e2e_ms_per_step=ms_e2e / args.steps, e2e_images_per_s=5 * world * args.steps / (ms_e2e / 1e3),
+                             last_loss=last, launches=launches)
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        _leave(world)
+        return
+    h = phases["Hungarian"]
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t = cpu_reference_ssod_step_time(1, 0, threads)
+        cpu_baseline = dict(value=5 / t[0], unit=UNIT, cores=threads, kind="port",
+                            sample=f"1 teacher-student step (Hungarian phase), 1 + 4 pairs {IMG_H}x{IMG_W}, reference CPU "
+                                   f"path, {threads} host threads")
+    line = dict(metric=SSOD_METRIC, value=h["images_per_s"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
+                ms_per_step=h["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32 (tf32 tensor-core matmul/conv; MSDA, matching and losses in f32)", data="synthetic",
+                config=dict(workload=SSOD_WORKLOAD, global_batch=5 * world, parallelism=f"dp{world}",
+                            execution="eager", phase="Hungarian (curr_step = 60000); warm-up phase under `phases`",
+                            l2="per-step working set exceeds the 126 MB L2"),
+                clocks=clocks,
+                e2e=dict(value=h["e2e_images_per_s"], unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                         ms_per_step=h["e2e_ms_per_step"], last_loss=h["last_loss"]),
+                gpu_launches=h["launches"], gpu_launches_per_step=h["launches"] / args.steps, phases=phases,
+                roofline=None, cpu_baseline=cpu_baseline)
+    print(json.dumps(line), flush=True)
+    _leave(world)
+
+
 def _leave(world):
     """End a multi-rank run without NCCL teardown: destroying a communicator that a live CUDA graph still references
     was observed to block (N=2, round 1), so every rank drains its device, meets the others at a host-side barrier
@@ -390,6 +704,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sup", choices=["sup", "ssod", "msda"],
+                    help="sup = configs[1] (default, the contract line); ssod = configs[2] per-GPU batch; msda = configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--torch-optimizer", action="store_true",
@@ -400,6 +716,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "msda":
+        run_msda(args)
+    elif args.workload == "ssod":
+        run_ssod(args)
     else:
         run_ours(args)
 

@@ -22,11 +22,10 @@ namespace sdb {
 
 extern int g_bwd_variant;
 
-// experimental 4-lanes-per-pair mapping (msda_backward_x8.cu), backward variant 7
-int msda_backward_x8(cudaStream_t st, const float* grad_out, const float* value, const int64_t* shapes,
-                     const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int L, int Lq,
-                     float* grad_value, float* grad_loc, float* grad_attn, const float* ref, int ref_dim,
-                     bool rolled);
+// encoder self-attention (num_query == spatial_size): tile-combined grad_value (msda_backward_tile.cu), the default
+int msda_backward_tile(cudaStream_t st, const float* grad_out, const float* value, const int64_t* shapes,
+                       const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int L,
+                       float* grad_value, float* grad_loc, float* grad_attn, const float* ref);
 
 // ------------------------------------------------------------------------------------------------
 // generic kernel: any channel count, float or double.  One warp per (n, q, m).
@@ -129,8 +128,7 @@ constexpr unsigned kFull = 0xffffffffu;
 // kFused: `loc` / `attn` are the RAW sampling offsets / attention logits, (ref, ref_dim) the reference points, and
 // the outputs are the gradients w.r.t. those raw tensors (location arithmetic and softmax differentiated here).
 // V: storage type of `grad_out` and `value` (float or __nv_bfloat16); every gradient is accumulated and written in fp32.
-// kDepth: points whose corner loads are in flight before the first use (1 = the validated default; 2 / 4 experimental).
-template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float, int kDepth = 1>
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -197,7 +195,6 @@ msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
           const int ws = lt.wstr[lvl];
           float d[4][4];
           float klh = 0.f, klw = 0.f, ka = 0.f;   // the point this lane finalises: batch index j >> 1
-          if constexpr (kDepth == 1) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int sl = 2 * b + (r >> 1);
@@ -230,49 +227,6 @@ msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
             d[r][1] = q01 ? dot4(g, v01) : 0.f;
             d[r][2] = q10 ? dot4(g, v10) : 0.f;
             d[r][3] = q11 ? dot4(g, v11) : 0.f;
-          }
-          } else {
-            // kDepth points in flight: the corner loads (and reductions) of kDepth points are issued before the first
-            // dot product waits for data.  In the kDepth == 1 form every point exposes one full load latency (ncu
-            // source view: 32 % of the stall samples sit on the first FMUL after each point's loads, 4 loads in
-            // flight per warp -- profiles/ncu_msda_stalls_r1.txt).
-            static_assert(4 % kDepth == 0, "kDepth must divide the batch of 4 points");
-#pragma unroll
-            for (int r0 = 0; r0 < 4; r0 += kDepth) {
-              float4 v[kDepth][4];
-              int okm[kDepth];
-#pragma unroll
-              for (int u = 0; u < kDepth; ++u) {
-                const int r = r0 + u;
-                const int sl = 2 * b + (r >> 1);
-                const BwdPrep& src = (r & 1) ? p1 : p0;
-                const int offm = __shfl_sync(kFull, src.offm, sl, 8);
-                const float lh = __shfl_sync(kFull, src.lh, sl, 8);
-                const float lw = __shfl_sync(kFull, src.lw, sl, 8);
-                const float a = __shfl_sync(kFull, src.a, sl, 8);
-                if ((j >> 1) == r) { klh = lh; klw = lw; ka = a; }
-                const float hh = 1.f - lh, hw = 1.f - lw;
-                const float4 tg = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
-                const int off = offm & ~15;
-                const V* pv = vhead + off;
-                float* pg = gvhead + off;
-                okm[u] = offm;
-                const bool q00 = offm & 1, q01 = offm & 2, q10 = offm & 4, q11 = offm & 8;
-                if (q00) v[u][0] = Chan4<V>::gather(pv);
-                if (q01) v[u][1] = Chan4<V>::gather(pv + px_stride);
-                if (q10) v[u][2] = Chan4<V>::gather(pv + ws);
-                if (q11) v[u][3] = Chan4<V>::gather(pv + ws + px_stride);
-                const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
-                red_add_f4_if(q00, pg, w00 * tg.x, w00 * tg.y, w00 * tg.z, w00 * tg.w);
-                red_add_f4_if(q01, pg + px_stride, w01 * tg.x, w01 * tg.y, w01 * tg.z, w01 * tg.w);
-                red_add_f4_if(q10, pg + ws, w10 * tg.x, w10 * tg.y, w10 * tg.z, w10 * tg.w);
-                red_add_f4_if(q11, pg + ws + px_stride, w11 * tg.x, w11 * tg.y, w11 * tg.z, w11 * tg.w);
-              }
-#pragma unroll
-              for (int u = 0; u < kDepth; ++u)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) d[r0 + u][k] = (okm[u] >> k) & 1 ? dot4(g, v[u][k]) : 0.f;
-            }
           }
           // reduce-scatter over the 8 lanes: afterwards lanes (j, j^1) hold the sums of point j >> 1
           float e[2][4], f[4];
@@ -329,12 +283,12 @@ msda_bwd_d32_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
   }
 }
 
-template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float, int kDepth = 1>
+template <int kThreads, int TH, int TW, int kMinBlocks, bool kFused = false, typename V = float>
 static int launch_bwd_d32(cudaStream_t st, const V* grad_out, const V* value, const int64_t* shapes,
                           const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int M,
                           int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn,
                           const float* ref = nullptr, int ref_dim = 0) {
-  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kFused, V, kDepth>;
+  auto kern = msda_bwd_d32_kernel<kThreads, TH, TW, kMinBlocks, kFused, V>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -380,24 +334,18 @@ static int msda_backward(cudaStream_t st, const T* grad_out, const T* value, con
     const bool fast_ok = D == 32 && M == 8 && P == 4 && L <= kMaxLevels && fits32 && (al & 15) == 0;
     int v = g_bwd_variant;
     if (v != 9 && fast_ok) {
-      if (v == 0) v = 1;  // measured best on B200 (profiles/)
+      // default: the tile-combining kernel for encoder self-attention (one reduction line per touched pixel and tile
+      // instead of one per sampled corner), the 8-lane kernel for everything else (profiles/msda_bwd_variants_r2.txt)
+      if ((v == 0 || v == 20) && Lq == S && L <= 8 && Lq > 0)
+        return msda_backward_tile(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value, grad_loc,
+                                  grad_attn, nullptr);
+      if (v == 0 || v == 20) v = 5;   // spill-free 115-register build
       switch (v) {
         case 1: return launch_bwd_d32<128, 4, 8, 6>(SDB_BWD_ARGS);
         case 2: return launch_bwd_d32<256, 4, 8, 3>(SDB_BWD_ARGS);
         case 3: return launch_bwd_d32<256, 4, 8, 2>(SDB_BWD_ARGS);
         case 4: return launch_bwd_d32<128, 4, 8, 8>(SDB_BWD_ARGS);
         case 5: return launch_bwd_d32<128, 4, 8, 4>(SDB_BWD_ARGS);
-        case 7:
-        case 8: return msda_backward_x8(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, Lq, grad_value,
-                                        grad_loc, grad_attn, nullptr, 0, v == 8);
-        // experimental (not yet run on hardware): 2 / 4 points of corner loads in flight per warp
-        case 10: return launch_bwd_d32<128, 4, 8, 4, false, float, 2>(SDB_BWD_ARGS);
-        case 11: return launch_bwd_d32<128, 4, 8, 3, false, float, 2>(SDB_BWD_ARGS);
-        case 12: return launch_bwd_d32<128, 4, 8, 3, false, float, 4>(SDB_BWD_ARGS);
-        // experimental: 8 x 8 pixel tiles (the forward's tile: more corner-line reuse in L1 per CTA; in the ncu capture
-        // 77.9 % of the load sectors hit L1 and every miss exposes an L2 latency), 1 / 2 points in flight
-        case 15: return launch_bwd_d32<256, 8, 8, 2, false, float, 1>(SDB_BWD_ARGS);
-        case 16: return launch_bwd_d32<256, 8, 8, 2, false, float, 2>(SDB_BWD_ARGS);
         default: return launch_bwd_d32<512, 8, 8, 1>(SDB_BWD_ARGS);
       }
     }
@@ -451,6 +399,9 @@ extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* gra
               attn_logits && grad_offsets && grad_attn_logits, "msda_fused_backward: null pointer");
 #define SDB_FBWD_ARGS st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, batch, S, M, L, \
                       Lq, P, grad_value, grad_offsets, grad_attn_logits, reference_points, ref_dim
+  if ((g_bwd_variant == 0 || g_bwd_variant == 20) && Lq == S && ref_dim == 2)
+    return msda_backward_tile(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                              batch, S, L, grad_value, grad_offsets, grad_attn_logits, reference_points);
   switch (g_bwd_variant) {     // sdb_msda_set_variant: register budget / occupancy trade-off (tools/microbench.py)
     // measured at the train-step shapes (profiles/msda_bwd_variants_r1.txt): 582 / 536 / 527 / 534 / 546 us (encoder)
     // for 6 / 5 / 4 / 3 CTAs of 128 threads and 2 of 256 per SM -- the spill-free 115-register build wins
@@ -458,17 +409,6 @@ extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* gra
     case 3: return launch_bwd_d32<128, 4, 8, 3, true>(SDB_FBWD_ARGS);   // 143 registers, 12 warps / SM
     case 5: return launch_bwd_d32<128, 4, 8, 5, true>(SDB_FBWD_ARGS);   // 96 registers (spills 20 B), 20 warps / SM
     case 6: return launch_bwd_d32<128, 4, 8, 6, true>(SDB_FBWD_ARGS);   // 80 registers (spills 108 B), 24 warps / SM
-    case 7:   // experimental: 4 lanes x 8 channels per pair; 8 = the same with a rolled batch loop
-    case 8: return msda_backward_x8(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets,
-                                    attn_logits, batch, S, L, Lq, grad_value, grad_offsets, grad_attn_logits,
-                                    reference_points, ref_dim, g_bwd_variant == 8);
-    // experimental (not yet run on hardware): 2 / 4 points of corner loads in flight per warp
-    case 10: return launch_bwd_d32<128, 4, 8, 4, true, float, 2>(SDB_FBWD_ARGS);
-    case 11: return launch_bwd_d32<128, 4, 8, 3, true, float, 2>(SDB_FBWD_ARGS);
-    case 12: return launch_bwd_d32<128, 4, 8, 3, true, float, 4>(SDB_FBWD_ARGS);
-    // experimental: 8 x 8 pixel tiles (more corner-line reuse in L1 per CTA), 1 / 2 points in flight
-    case 15: return launch_bwd_d32<256, 8, 8, 2, true, float, 1>(SDB_FBWD_ARGS);
-    case 16: return launch_bwd_d32<256, 8, 8, 2, true, float, 2>(SDB_FBWD_ARGS);
     default: return launch_bwd_d32<128, 4, 8, 4, true>(SDB_FBWD_ARGS);  // 115 registers, no spills, 16 warps / SM
   }
 #undef SDB_FBWD_ARGS

@@ -9,6 +9,13 @@ from oracle.cpu_path import reference_cpu_ops
 
 pytestmark = pytest.mark.gpu
 
+# Bounds (relative).  fp32 products: the north star's 1e-3 on every loss; per-parameter gradient norms within
+# GRAD_TOL_FP32 (fp32 atomics / summation order through 12 layers).  TF32 products: see the TF32 test's docstring.
+GRAD_TOL_FP32 = 2e-2
+LOSS_TOL_TF32 = 2e-2
+TOTAL_TOL_TF32 = 5e-3
+GRAD_TOL_TF32 = 1e-1
+
 
 @pytest.fixture
 def cpu_noise(monkeypatch):
@@ -68,16 +75,78 @@ def test_train_step_matches_cpu_reference_path(cpu_noise, fp32_products, scales)
         a, b = float(out["log_vars"][k]), float(ref["log_vars"][k])
         assert abs(a - b) <= 1e-3 * abs(b) + 1e-5, (k, a, b)
     # gradients: compare the big, well-conditioned ones by relative norm
-    checked = 0
+    checked, worst = 0, (0.0, "")
     for (n, pg), (_, pc) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
         if pc.grad is None:
             assert pg.grad is None
             continue
         g, c = pg.grad.cpu().double(), pc.grad.double()
         if c.norm() > 1e-4:
-            rel = (g - c).norm() / c.norm()
-            assert rel < 2e-2, (n, float(rel))
+            rel = float((g - c).norm() / c.norm())
+            worst = max(worst, (rel, n))
+            assert rel < GRAD_TOL_FP32, (n, rel)
             checked += 1
+    print(f"[fp32 step, {scales} scales] worst gradient deviation {worst[0]:.2e} ({worst[1]}) over {checked} tensors")
+    assert checked > 150
+
+
+def test_train_step_with_tf32_products_stays_close_to_the_fp32_reference_path(cpu_noise):
+    """The configuration bench.py times: TF32 tensor-core products ON (tcgen05 linears by the `auto` policy, cuDNN
+    TF32 convolutions).  TF32 rounds every GEMM / convolution operand to 10 mantissa bits (2^-11 relative per
+    operand), so the step cannot reproduce the fp32 CPU path to 1e-3 per tensor; what must hold is that every loss
+    value stays within the TF32 error budget of it -- asserted on LOSS VALUES, never on match indices: with TF32 a
+    near-tied Hungarian match may go to an equally good query, which changes indices but not (beyond the budget) the
+    losses."""
+    from semi_detr_b200 import dino  # noqa: F401
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        torch.manual_seed(0)
+        cpu_model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE)).train()
+        with torch.no_grad():
+            for name, p in cpu_model.named_parameters():
+                if name.endswith("sampling_offsets.bias"):
+                    p.add_(torch.randn_like(p) * 0.37)
+        gpu_model = copy.deepcopy(cpu_model).cuda().train()
+        data = coco_like_batch(2, 288, 352, seed=5)
+        gdata = dict(img=data["img"].cuda(), img_metas=[dict(m) for m in data["img_metas"]],
+                     gt_bboxes=[b.cuda() for b in data["gt_bboxes"]], gt_labels=[l.cuda() for l in data["gt_labels"]])
+        cpu_noise()
+        with reference_cpu_ops():
+            ref = cpu_model.train_step(data)
+            ref["loss"].backward()
+        cpu_noise()
+        from semi_detr_b200 import _lib
+        before = _lib.LAUNCHES["gemm_tf32"]
+        out = gpu_model.train_step(gdata)
+        out["loss"].backward()
+        assert _lib.LAUNCHES["gemm_tf32"] > before, "the TF32 step must run the tcgen05 linears"
+        gpu_model.bbox_head.assigner.check_status()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    assert list(out["log_vars"]) == list(ref["log_vars"])
+    worst = (0.0, "")
+    for k in ref["log_vars"]:
+        a, b = float(out["log_vars"][k]), float(ref["log_vars"][k])
+        worst = max(worst, (abs(a - b) / max(abs(b), 1e-6), k))
+        assert abs(a - b) <= LOSS_TOL_TF32 * abs(b) + 1e-4, (k, a, b)
+    total = abs(float(out["loss"]) - float(ref["loss"])) / abs(float(ref["loss"]))
+    assert total <= TOTAL_TOL_TF32, total
+    gworst, checked = (0.0, ""), 0
+    for (n, pg), (_, pc) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
+        if pc.grad is None:
+            continue
+        g, c = pg.grad.cpu().double(), pc.grad.double()
+        if c.norm() > 1e-4:
+            rel = float((g - c).norm() / c.norm())
+            gworst = max(gworst, (rel, n))
+            assert rel < GRAD_TOL_TF32, (n, rel)
+            checked += 1
+    print(f"[tf32 step] worst loss deviation {worst[0]:.2e} ({worst[1]}), total loss {total:.2e}, "
+          f"worst gradient deviation {gworst[0]:.2e} ({gworst[1]}) over {checked} tensors")
     assert checked > 150
 
 

@@ -1,27 +1,19 @@
 """bf16-storage MSDA kernels (BASELINE.json configs[3]: bf16 value / output, fp32 sampling math) against the oracle.
 
-NOT YET RUN ON HARDWARE: the kernels were added after this round's GPU budget was spent (they compile for sm_100a, and
-the fp32 kernels they share their source with are SASS-identical to the validated build), so these tests only run with
-SDB_RUN_UNVALIDATED=1 -- the first thing to do with a GPU in the next round:
-
-    SDB_RUN_UNVALIDATED=1 python -m pytest tests/test_msda_bf16_gpu.py -m gpu -q
+First hardware run: round 2 (11 passed on a B200); part of the default `pytest -m gpu` suite since.
 
 Tolerances: the output is the exact sum rounded to bf16 once (device: fp32 accumulation), so it must sit within one
 bf16 ulp (2^-8 relative) of the float64 oracle value plus the fp32 accumulation error; gradients are produced in fp32
 from bf16-exact inputs, so they keep the fp32 bound of the north star (1e-3 relative), grad_value after its final
 narrowing to bf16 one bf16 ulp.
 """
-import os
-
 import numpy as np
 import pytest
 import torch
 
 from oracle import msda_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SDB_RUN_UNVALIDATED") != "1",
-                                 reason="bf16 MSDA kernels have not run on hardware yet (set SDB_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 BF16_ULP = 2.0 ** -8
 LEVELS4 = [(19, 27), (10, 14), (5, 7), (3, 4)]

@@ -1,5 +1,7 @@
-"""Lane-level emulation of the experimental 4-lanes x 8-channels MSDA backward (csrc/msda_backward_x8.cu) in numpy,
-against the oracle.  The CUDA kernel has not run on hardware yet; this pins its ALGORITHM -- which lane prepares which
+"""Lane-level emulation in numpy of the 4-lanes x 8-channels gather the encoder backward uses (step C of
+csrc/msda_backward_tile.cu; first written for the stand-alone x8 kernel, which measured 2x slower than the 8-lane one
+because it split every reduction line into half-sector requests and was removed -- profiles/msda_bwd_variants_r2.txt),
+against the oracle.  It pins the ALGORITHM -- which lane prepares which
 level, what each broadcast carries, the two-stage reduce-scatter that leaves lane j with the corner sums of point j,
 the closed forms of grad_x / grad_y / grad_attn from the four corner dot products, and (fused form) the chain through
 the location arithmetic and the softmax -- so that a first hardware run only has the transcription left to get wrong.

@@ -3,14 +3,13 @@
 ``semi_detr_b200.install_as_reference_extension()`` puts the C-ABI-backed module under the name the reference imports
 (``import MultiScaleDeformableAttention as MSDA``, functions/ms_deform_attn_func.py:18).  The reference's
 ``MSDeformAttnFunction`` (ms_deform_attn_func.py:21-38) and its own test file (ops/test.py:31-86) are then executed
-from the bytecode `make -C oracle ref` compiled out of /root/reference (oracle/_ref/*.pyc -- no reference source in
+from the bytecode `make -C oracle ref` compiled out of /root/reference (oracle/_ref/*.bin, marshalled code objects -- no reference source in
 the repository, and /root/reference does not exist on the GPU box).  What must hold is exactly what the reference's
 test prints: ``* True check_forward_equal_with_pytorch_double``, ``..._float`` and ``check_gradient_numerical(D=...)``.
 """
 import contextlib
-import importlib.machinery
-import importlib.util
 import io
+import marshal
 import os
 import sys
 import types
@@ -22,22 +21,23 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-FUNC_PYC = os.path.join(REF_DIR, "ref_ms_deform_attn_func.pyc")
-TEST_PYC = os.path.join(REF_DIR, "ref_ops_test.pyc")
+FUNC_PYC = os.path.join(REF_DIR, "ref_ms_deform_attn_func.bin")
+TEST_PYC = os.path.join(REF_DIR, "ref_ops_test.bin")
 
 
 def _load_pyc(name, path):
-    loader = importlib.machinery.SourcelessFileLoader(name, path)
-    spec = importlib.util.spec_from_loader(name, loader)
-    mod = importlib.util.module_from_spec(spec)
-    loader.exec_module(mod)
+    with open(path, "rb") as f:
+        code = marshal.loads(f.read())
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    exec(code, mod.__dict__)
     return mod
 
 
 @pytest.fixture(scope="module")
 def reference_ops():
     if not (os.path.exists(FUNC_PYC) and os.path.exists(TEST_PYC)):
-        pytest.fail("oracle/_ref/ref_*.pyc missing: run `make -C oracle ref` where /root/reference exists "
+        pytest.fail("oracle/_ref/ref_*.bin missing: run `make -C oracle ref` where /root/reference exists "
                     "(__graft_entry__.build() does) -- the prebuilt files travel to the GPU box")
     import semi_detr_b200
     saved = {k: sys.modules.get(k) for k in ("MultiScaleDeformableAttention", "functions",

@@ -6,9 +6,11 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clocks / throttle reasons sampled while the timings run)
 from semi_detr_b200 import _lib  # noqa: E402
 from semi_detr_b200.msda import MultiScaleDeformableAttention as MSDA  # noqa: E402
 
+_clocks = ClockSampler(0)
 levels = [(100, 167), (50, 84), (25, 42), (13, 21)]
 S = sum(h * w for h, w in levels)
 shapes = torch.tensor(levels, dtype=torch.int64, device="cuda")
@@ -30,7 +32,9 @@ for name, Lq, refdim in (("enc", S, 2), ("dec", 1092, 4)):
     # 7 / 8 = experimental 4-lane x 8-channel mapping (msda_backward_x8.cu), unrolled / rolled batch loop; 10 / 11 / 12 = 2 / 2 / 4 points of corner
     # loads in flight per warp at 4 / 3 / 3 CTAs per SM
     # 15 / 16 = 8 x 8 pixel tiles with 256 threads, 1 / 2 points in flight
-    for variant in (0, 6, 5, 3, 2, 7, 8, 10, 11, 12, 15, 16):
+    # 0 / 20 = default: tile-combining kernel for the encoder shape (msda_backward_tile.cu), 8-lane kernel otherwise
+    variants = (0, 5, 6, 3, 2, 7, 8, 10, 11, 12, 15, 16) if "--all" in sys.argv else (0, 5, 7, 12)
+    for variant in variants:
         _lib.lib().sdb_msda_set_variant(0, variant)
         ts = []
         for _ in range(33):
@@ -59,3 +63,5 @@ for name, Lq, refdim in (("enc", S, 2), ("dec", 1092, 4)):
         ts = sorted(ts[3:])
         print(f"{name} Lq={Lq} forward variant {variant}: median {ts[len(ts) // 2]:.1f} us  min {ts[0]:.1f}")
 _lib.lib().sdb_msda_set_variant(0, 0)
+import json  # noqa: E402
+print("clocks:", json.dumps(_clocks.stop()))
