@@ -278,6 +278,32 @@ int sdb_adamw_ema_step_sched_f32(sdb_stream_t stream, float* params, const float
                                  int num_segs, float beta1, float beta2, float eps, double ema_momentum);
 
 /* ------------------------------------------------------------------------------------------
+ * Classification + box losses of the DINO head for all (decoder layer, image) problems in one launch, targets
+ * gathered from the assignment inside the kernel.
+ *
+ * Replaces the 13 x loss_single / get_targets chain of detr_od/models/dense_heads/dino_detr_head.py:634-736, 895-980
+ * (FocalLoss mmdet losses/focal_loss.py:12-57, L1Loss smooth_l1_loss.py:34-46, GIoULoss iou_loss.py:101-116).
+ *   cls_scores (P, Q, C) logits; bbox_preds (P, Q, 4) normalised cxcywh
+ *   gt_inds (P, Q) int64: 0 = background, k + 1 = GT k of the problem's segment (HungarianAssigner output)
+ *   prob_seg (P,) int32 segment of each problem; seg_offsets (nseg + 1,) int32; gt_bboxes (G, 4) pixel xyxy;
+ *   gt_labels (G,) int64; img_wh (nseg, 2); cls_weight (P,) or NULL
+ *   sums (P, 5) = { focal, l1, l1_xy, l1_hw, 1 - giou } summed over the problem's queries in a fixed order
+ *   (un-normalised, un-weighted: the normalisers involve a cross-rank mean, dino_detr_head.py:698-723).
+ * backward: grad_sums (P, 5) -> grad_cls_scores (P, Q, C), grad_bbox_preds (P, Q, 4), every element written.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_detr_loss_forward_f32(sdb_stream_t stream, const float* cls_scores, const float* bbox_preds,
+                              const int64_t* gt_inds, const int32_t* prob_seg, const int32_t* seg_offsets,
+                              const float* gt_bboxes, const int64_t* gt_labels, const float* img_wh,
+                              const float* cls_weight, int num_problems, int num_query, int num_classes, float alpha,
+                              float gamma, float giou_eps, float* sums);
+int sdb_detr_loss_backward_f32(sdb_stream_t stream, const float* cls_scores, const float* bbox_preds,
+                               const int64_t* gt_inds, const int32_t* prob_seg, const int32_t* seg_offsets,
+                               const float* gt_bboxes, const int64_t* gt_labels, const float* img_wh,
+                               const float* cls_weight, const float* grad_sums, int num_problems, int num_query,
+                               int num_classes, float alpha, float gamma, float giou_eps, float* grad_cls_scores,
+                               float* grad_bbox_preds);
+
+/* ------------------------------------------------------------------------------------------
  * Token-wise linear layers as tcgen05 (5th-generation tensor core) GEMMs, TF32 arithmetic on fp32 storage with
  * fp32 accumulation in tensor memory -- the three products of the nn.Linear layers on the path
  * (ms_deform_attn.py:61-65, 94-112 value_proj / sampling_offsets / attention_weights / output_proj;

@@ -9,22 +9,26 @@
 // whatever its occupancy, loads in flight or instruction count; the one that split each line into half-sector
 // requests took exactly twice as long: profiles/msda_bwd_variants_r2.txt).  In encoder self-attention query i sits on
 // pixel i, so the 64 queries of an 8 x 8 pixel tile sample the SAME few hundred value pixels of each level over and
-// over (a level-0 tile: 4096 corner updates onto ~250 distinct pixels).  This kernel combines them on chip:
+// over (a level-0 tile: 4096 corner updates onto 200-550 distinct pixels).  This kernel turns the scatter into an
+// on-chip gather: the VALUE PIXEL owns the work, not the query.
 //
-//   A  one thread per sampling point: bilinear tap -> record {pixel offset | corner bits, lh, lw, attention weight} in
-//      shared memory; the point is counted into the bucket of its top-left pixel inside a per-level WINDOW around the
-//      tile's footprint (integer shared-memory atomics, which are native; fp32 shared atomics are CAS loops);
-//   B  prefix sum over the buckets + index scatter = the tile's points sorted by pixel;
-//   C  gather: 4 lanes x 8 channels per (query, head) read the records (broadcast LDS), fetch the four corner lines,
-//      reduce to the four corner dot products and finish grad_sampling_loc / grad_attn_weight exactly like the d32
-//      kernel (closed forms of the corner dot products, two-stage reduce-scatter) -- but issue NO reductions;
-//   D  scatter turned into a gather: each window pixel is owned by 4 lanes x 8 channels, which walk the (at most
-//      four) buckets whose points touch it, accumulate weight x grad_out from shared memory in registers in a fixed
-//      order, and issue ONE 128-byte reduction line per touched pixel.
+//   A  one thread per (query, level): bilinear taps of its 4 points -> record {pixel offset | corner bits, lh, lw, a};
+//      the four corner coefficients a*w_k go to the point's result slots; every valid corner ("visit") is counted into
+//      the bucket of the pixel it touches inside a per-level WINDOW around the tile's footprint (integer shared-memory
+//      atomics, which are native -- fp32 shared atomics are CAS loops);
+//   B  prefix sum over the buckets, each padded to whole TASKS of kT visits, and scatter of the visit codes: the tile's
+//      visits sorted by pixel, cut into equal-sized tasks (a warp's 8 tasks run in lock step, no divergence);
+//   D  one task per 4 lanes x 8 channels: load the task's value pixel ONCE, then for each visit read grad_out of the
+//      visiting query from shared memory, accumulate coefficient x grad_out (grad_value) and reduce <grad_out, value>
+//      (the corner dot product, which replaces the coefficient in the point's result slot); one reduction line per task;
+//   X  points whose top-left pixel falls outside the window (offsets beyond +-kHalo pixels, levels finer than the
+//      tile's own, or a tile whose visits overflow the tables) are handled the direct way: corner loads, dot
+//      products, one reduction line per corner -- any input is handled, only the speed depends on locality;
+//   F  one thread per point: grad_sampling_loc / grad_attn_weight from the four corner dot products (closed forms,
+//      like the d32 kernel), in the fused form followed by the location chain rule and the softmax backward.
 //
-// Points whose top-left pixel falls outside the window (sampling offsets beyond +-kHalo pixels, or a level whose
-// footprint would not fit the bucket table) take the direct `red` path inside step C, so any input is handled; only
-// the speed depends on locality.  grad_value is still accumulated with reductions because neighbouring tiles overlap.
+// grad_value is still accumulated with reductions (neighbouring tiles overlap), but ~4-5x fewer of them; no query ever
+// gathers a corner line from global memory in the common case.
 #include "msda_common.cuh"
 
 namespace sdb {
@@ -35,25 +39,17 @@ constexpr int kTT = 256;          // threads per CTA
 constexpr int kTH = 8, kTW = 8;   // query tile (pixels of the query's own level)
 constexpr int kTQ = kTH * kTW;
 constexpr int kHalo = 5;          // sampling offsets up to +-kHalo pixels stay inside the window
-constexpr int kMaxBuckets = 2040; // bucket table (ints); + guard entries = 2048
-constexpr int kTableInts = 2048;
+constexpr int kT = 4;             // visits per task
+constexpr int kTableInts = 2048;  // bucket table incl. guard entries
+constexpr int kMaxBuckets = kTableInts - 8;
+constexpr int kVisitCap = 8192;   // visit slots (padded)
 constexpr int kMaxWinLevels = 8;
 constexpr unsigned kAllLanes = 0xffffffffu;
 
 struct Windows {
   int y0[kMaxWinLevels], x0[kMaxWinLevels], h[kMaxWinLevels], w[kMaxWinLevels], base[kMaxWinLevels];
+  int magic[kMaxWinLevels];   // floor(p / w) == (p * magic) >> 16 for p < 2048, w <= 32
 };
-
-__device__ __forceinline__ float dot8(const float4& a0, const float4& a1, const float4& b0, const float4& b1) {
-  float s = a0.x * b0.x;
-  s = fmaf(a0.y, b0.y, s);
-  s = fmaf(a0.z, b0.z, s);
-  s = fmaf(a0.w, b0.w, s);
-  s = fmaf(a1.x, b1.x, s);
-  s = fmaf(a1.y, b1.y, s);
-  s = fmaf(a1.z, b1.z, s);
-  return fmaf(a1.w, b1.w, s);
-}
 
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   acc.x = fmaf(w, v.x, acc.x);
@@ -61,34 +57,34 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   acc.z = fmaf(w, v.z, acc.z);
   acc.w = fmaf(w, v.w, acc.w);
 }
-
-template <int kWidth>
-__device__ __forceinline__ float seg_max(float v) {
-#pragma unroll
-  for (int o = kWidth / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kAllLanes, v, o, kWidth));
-  return v;
+__device__ __forceinline__ float dot4acc(const float4& a, const float4& b, float s) {
+  s = fmaf(a.x, b.x, s);
+  s = fmaf(a.y, b.y, s);
+  s = fmaf(a.z, b.z, s);
+  return fmaf(a.w, b.w, s);
 }
-template <int kWidth>
-__device__ __forceinline__ float seg_sum(float v) {
-#pragma unroll
-  for (int o = kWidth / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kAllLanes, v, o, kWidth);
-  return v;
+__device__ __forceinline__ float group4_sum(float v) {
+  v += __shfl_xor_sync(kAllLanes, v, 2, 4);
+  return v + __shfl_xor_sync(kAllLanes, v, 1, 4);
 }
-
-// Shared-memory layout (dynamic): records | grad_out tile | bucket table | sorted point ids
+// Shared-memory layout (dynamic).  kSlots = point slots per (query, head): 16 (L <= 4) or 32 (L <= 8).
 template <int kSlots>
 struct TileSmem {
-  static constexpr int kRecStride = kSlots + 1;                 // records per query row (+1: bank spread)
-  static constexpr int kRecBytes = kTQ * kRecStride * 16;
-  static constexpr int kGBytes = kTQ * 32 * 4;
+  static constexpr int kRecBytes = kTQ * kSlots * 16;            // {offm, lh, lw, a} per point
+  static constexpr int kResFloats = kTQ * kSlots * 4 + 4;        // 4 result slots per point (+ 1 dummy, padded)
+  static constexpr int kResBytes = kResFloats * 4;
+  static constexpr int kGBytes = (kTQ + 1) * 32 * 4;             // grad_out rows of the tile (+ 1 zero row)
   static constexpr int kTableBytes = kTableInts * 4;
-  static constexpr int kIdxBytes = kTQ * kSlots * 2;
-  static constexpr int kTotal = kRecBytes + kGBytes + kTableBytes + kIdxBytes;
+  static constexpr int kVisBytes = kVisitCap * 2;
+  static constexpr int kKeyBytes = (kVisitCap / kT) * 2;
+  static constexpr int kDirectBytes = kTQ * kSlots * 2;
+  static constexpr int oRes = kRecBytes, oG = oRes + kResBytes, oTable = oG + kGBytes, oVis = oTable + kTableBytes,
+                       oKey = oVis + kVisBytes, oDirect = oKey + kKeyBytes;
+  static constexpr int kTotal = oDirect + kDirectBytes;
 };
 
-// kSlots: point slots per (query, head) -- 16 (L <= 4) or 32 (L <= 8); P == 4, 8 heads x 32 channels.
 // kFused: `loc` / `attn` are the RAW sampling offsets / attention logits, `ref` the (N, Lq, L, 2) reference points and
-// the outputs are the gradients of the raw tensors (ms_deform_attn.py:98-105 differentiated here); kSlots == 16 only.
+// the outputs are the gradients of the raw tensors (ms_deform_attn.py:98-105 differentiated here).
 template <int kSlots, bool kFused>
 __global__ void __launch_bounds__(kTT, 2)
 msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
@@ -98,17 +94,23 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
                      const float* __restrict__ ref) {
   constexpr int M = 8, P = 4;
   constexpr int px_stride = M * 32;
+  constexpr int kLv = kSlots / P;                        // level slots per query
+  constexpr int kQLPasses = kTQ * kLv / kTT;             // (query, level) pairs per thread: 1 or 2
+  constexpr int kCodeShift = kSlots == 16 ? 6 : 7;       // visit code = ql << shift | pt << 2 | corner
+  constexpr int kNullCode = kTQ * kSlots * 4;            // dummy result slot, zero grad_out row
   using SM = TileSmem<kSlots>;
-  constexpr int RS = SM::kRecStride;
-  constexpr int kPtsPerThread = kTQ * kSlots / kTT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* rec = reinterpret_cast<float4*>(smem_raw);
-  float* gtile = reinterpret_cast<float*>(smem_raw + SM::kRecBytes);
-  int* table = reinterpret_cast<int*>(smem_raw + SM::kRecBytes + SM::kGBytes);
-  unsigned short* sidx = reinterpret_cast<unsigned short*>(smem_raw + SM::kRecBytes + SM::kGBytes + SM::kTableBytes);
+  float* res = reinterpret_cast<float*>(smem_raw + SM::oRes);
+  float* gtile = reinterpret_cast<float*>(smem_raw + SM::oG);
+  int* table = reinterpret_cast<int*>(smem_raw + SM::oTable);
+  unsigned short* vis = reinterpret_cast<unsigned short*>(smem_raw + SM::oVis);
+  unsigned short* tkey = reinterpret_cast<unsigned short*>(smem_raw + SM::oKey);
+  unsigned short* direct = reinterpret_cast<unsigned short*>(smem_raw + SM::oDirect);
   __shared__ LevelTable lt;
   __shared__ Windows win;
   __shared__ int warp_tot[kTT / 32];
+  __shared__ int n_direct, n_slots, overflow;
 
   load_levels<kTH, kTW>(lt, shapes, lsi, L, px_stride);
   const int Lq = S;
@@ -116,6 +118,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
   const long long total = (long long)batch * n_tiles * M;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int LP = L * P;
+  if (tid < 32) gtile[kTQ * 32 + tid] = 0.f;   // the null visit's grad_out row
 
   for (long long item = blockIdx.x; item < total; item += gridDim.x) {
     const int m = (int)(item % M);
@@ -124,15 +127,32 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
     const int n = (int)(t2 / n_tiles);
     TileCursor<kTH, kTW> cur;
     cur.seek(lt, L, tile, true, Lq);
+    const long long img = (long long)n * S * px_stride + m * 32;
 
-    // ---- window geometry (thread 0) + cleared bucket table ------------------------------------------------------
-    __syncthreads();   // previous item's phase D has finished with the table / records
+    // ---- window geometry (thread 0), cleared tables, grad_out tile ------------------------------------------------
+    __syncthreads();   // the previous item is finished with shared memory
     {
       int4* t4 = reinterpret_cast<int4*>(table);
       for (int i = tid; i < kTableInts / 4; i += kTT) t4[i] = make_int4(0, 0, 0, 0);
+      // every visit slot starts as the null visit (padding of the last task of a pixel)
+      const unsigned nn = (unsigned)kNullCode | ((unsigned)kNullCode << 16);
+      uint4* v4 = reinterpret_cast<uint4*>(vis);
+      for (int i = tid; i < kVisitCap / 8; i += kTT) v4[i] = make_uint4(nn, nn, nn, nn);
+      const int ql = tid >> 2, j = tid & 3;    // grad_out rows: 4 lanes x 8 channels per query
+      const int q = cur.query(ql, Lq);
+      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+      if (q >= 0) {
+        const float* gp = grad_out + (((long long)n * Lq + q) * M + m) * 32 + 8 * j;
+        g0 = ld_stream_f4(reinterpret_cast<const float4*>(gp));
+        g1 = ld_stream_f4(reinterpret_cast<const float4*>(gp + 4));
+      }
+      *reinterpret_cast<float4*>(gtile + ql * 32 + 8 * j) = g0;
+      *reinterpret_cast<float4*>(gtile + ql * 32 + 8 * j + 4) = g1;
     }
     if (tid == 0) {
-      int acc = 1;   // bucket 0 is a guard (always empty)
+      int acc = 1;   // bucket 0 is a guard
+      n_direct = 0;
+      res[kNullCode] = 0.f;
       for (int l = L - 1; l >= 0; --l) {   // coarse levels first: smallest windows, most reuse
         const float sy = (float)lt.H[l] / (float)cur.Hl, sx = (float)lt.W[l] / (float)cur.Wl;
         const int wy0 = (int)floorf((float)cur.y0 * sy) - kHalo - 1;
@@ -140,78 +160,112 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
         const int wy1 = (int)ceilf((float)(cur.y0 + kTH) * sy) + kHalo + 1;
         const int wx1 = (int)ceilf((float)(cur.x0 + kTW) * sx) + kHalo + 1;
         const int wh = wy1 - wy0 + 1, ww = wx1 - wx0 + 1;
-        const bool use = l < kMaxWinLevels && acc + wh * ww <= kMaxBuckets;
+        // windows only where the tile's footprint is at most its own size (own level and coarser): finer levels
+        // spread 64 queries over >= 256 pixels -- little to combine -- and take the direct path
+        const bool use = l >= cur.lvl && l < kMaxWinLevels && ww <= 32 && acc + wh * ww <= kMaxBuckets;
         win.y0[l] = wy0;
         win.x0[l] = wx0;
         win.h[l] = use ? wh : 0;
         win.w[l] = use ? ww : 0;
         win.base[l] = acc;
+        win.magic[l] = use ? 65536 / ww + 1 : 0;
         if (use) acc += wh * ww;
       }
     }
     __syncthreads();
 
-    // ---- A: records + bucket counts ------------------------------------------------------------------------------
-    int key[kPtsPerThread], rank[kPtsPerThread];
+    // ---- A: records, coefficients, visit counts --------------------------------------------------------------------
+    unsigned short vkey[kQLPasses][P][4], vrank[kQLPasses][P][4];   // bucket / rank of every visit (0xffff: none)
 #pragma unroll
-    for (int i = 0; i < kPtsPerThread; ++i) {
-      const int e = tid + i * kTT;
-      const int ql = e / kSlots, pt = e % kSlots;
+    for (int ps = 0; ps < kQLPasses; ++ps) {
+      const int u = tid + ps * kTT;
+      const int ql = u / kLv, lv = u % kLv;
       const int q = cur.query(ql, Lq);
-      const bool live = q >= 0;
-      const bool on = live && pt < LP;
-      const int lvl = min(pt / P, L - 1);
-      const long long nq = (long long)n * Lq + (live ? q : 0);
+      const bool on = q >= 0 && lv < L;
+      const int lvl = min(lv, L - 1);
+      const long long nq = (long long)n * Lq + (q >= 0 ? q : 0);
       const long long pair = nq * M + m;
-      float x = 0.f, y = 0.f, a = 0.f;
+      float xs[P], ys[P], as[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) { xs[p] = 0.f; ys[p] = 0.f; as[p] = 0.f; }
+      const int H = lt.H[lvl], W = lt.W[lvl];
       if (kFused) {
-        float2 off = make_float2(0.f, 0.f);
-        float lg = live ? -INFINITY : 0.f;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        const float dead = q >= 0 ? -INFINITY : 0.f;
+        float4 lg = make_float4(dead, dead, dead, dead);
         if (on) {
-          off = ld_stream_f2(reinterpret_cast<const float2*>(loc + pair * LP * 2 + 2 * pt));
-          lg = __ldg(attn + pair * LP + pt);
+          o0 = ld_stream_f4(reinterpret_cast<const float4*>(loc + pair * LP * 2 + 8 * lv));
+          o1 = ld_stream_f4(reinterpret_cast<const float4*>(loc + pair * LP * 2 + 8 * lv + 4));
+          lg = ld_stream_f4(reinterpret_cast<const float4*>(attn + pair * LP + 4 * lv));
         }
-        const float mx = seg_max<kSlots>(lg);
-        const float ex = expf(lg - mx);
-        const float inv = 1.f / seg_sum<kSlots>(ex);
+        // softmax over the query's L*P logits: the kLv threads of a query are adjacent lanes
+        float mx = fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w));
+#pragma unroll
+        for (int o = kLv / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kAllLanes, mx, o, kLv));
+        const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx), e2 = expf(lg.z - mx), e3 = expf(lg.w - mx);
+        float sum = (e0 + e1) + (e2 + e3);
+#pragma unroll
+        for (int o = kLv / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(kAllLanes, sum, o, kLv);
+        const float inv = 1.f / sum;
         if (on) {
-          a = ex * inv;
+          as[0] = e0 * inv; as[1] = e1 * inv; as[2] = e2 * inv; as[3] = e3 * inv;
           const float2 rp = __ldg(reinterpret_cast<const float2*>(ref + (nq * L + lvl) * 2));
-          x = rp.x + off.x / (float)lt.W[lvl];
-          y = rp.y + off.y / (float)lt.H[lvl];
+          const float Wf = (float)W, Hf = (float)H;
+          xs[0] = rp.x + o0.x / Wf; ys[0] = rp.y + o0.y / Hf;
+          xs[1] = rp.x + o0.z / Wf; ys[1] = rp.y + o0.w / Hf;
+          xs[2] = rp.x + o1.x / Wf; ys[2] = rp.y + o1.y / Hf;
+          xs[3] = rp.x + o1.z / Wf; ys[3] = rp.y + o1.w / Hf;
         }
       } else if (on) {
-        const float2 xy = ld_stream_f2(reinterpret_cast<const float2*>(loc + pair * LP * 2 + 2 * pt));
-        x = xy.x;
-        y = xy.y;
-        a = __ldg(attn + pair * LP + pt);
+        const float4 o0 = ld_stream_f4(reinterpret_cast<const float4*>(loc + pair * LP * 2 + 8 * lv));
+        const float4 o1 = ld_stream_f4(reinterpret_cast<const float4*>(loc + pair * LP * 2 + 8 * lv + 4));
+        const float4 aw = ld_stream_f4(reinterpret_cast<const float4*>(attn + pair * LP + 4 * lv));
+        xs[0] = o0.x; ys[0] = o0.y; xs[1] = o0.z; ys[1] = o0.w;
+        xs[2] = o1.x; ys[2] = o1.y; xs[3] = o1.z; ys[3] = o1.w;
+        as[0] = aw.x; as[1] = aw.y; as[2] = aw.z; as[3] = aw.w;
       }
-      const int H = lt.H[lvl], W = lt.W[lvl];
-      const Tap<float> t = make_tap<float>(x, y, H, W);
-      int mask = on ? ((t.c00 ? 1 : 0) | (t.c01 ? 2 : 0) | (t.c10 ? 4 : 0) | (t.c11 ? 8 : 0)) : 0;
-      key[i] = -1;
-      rank[i] = 0;
-      if (mask) {
-        const int ww = win.w[lvl];
-        const int wy = t.h0 - win.y0[lvl], wx = t.w0 - win.x0[lvl];
-        if (ww > 0 && wy >= 0 && wy < win.h[lvl] - 1 && wx >= 0 && wx < ww - 1) {
-          key[i] = win.base[lvl] + wy * ww + wx;
-          rank[i] = atomicAdd(&table[key[i] + 1], 1);
-        } else {
-          mask |= 16;   // outside the window: step C reduces this point directly
+      const int ww = win.w[lvl], wh = win.h[lvl], wy0 = win.y0[lvl], wx0 = win.x0[lvl], wbase = win.base[lvl];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const Tap<float> t = make_tap<float>(xs[p], ys[p], H, W);
+        int mask = on ? ((t.c00 ? 1 : 0) | (t.c01 ? 2 : 0) | (t.c10 ? 4 : 0) | (t.c11 ? 8 : 0)) : 0;
+        const float a = as[p];
+        const float hh = 1.f - t.lh, hw = 1.f - t.lw;
+        const int e = ql * kSlots + lv * P + p;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { vkey[ps][p][r] = 0xffff; vrank[ps][p][r] = 0; }
+        if (mask) {
+          const int wy = t.h0 - wy0, wx = t.w0 - wx0;
+          if (ww > 0 && wy >= 0 && wy < wh - 1 && wx >= 0 && wx < ww - 1) {
+            const int k00 = wbase + wy * ww + wx;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (mask & (1 << r)) {
+                const int k = k00 + (r & 1) + (r >> 1) * ww;
+                vkey[ps][p][r] = (unsigned short)k;
+                vrank[ps][p][r] = (unsigned short)atomicAdd(&table[k + 1], 1);
+              }
+          } else {
+            mask |= 16;   // outside the window: step X handles this point
+            direct[atomicAdd(&n_direct, 1)] = (unsigned short)e;
+          }
         }
+        const int offm = ((lt.start[lvl] + t.h0 * W + t.w0) * px_stride) | mask;
+        rec[e] = make_float4(__int_as_float(offm), t.lh, t.lw, a);
+        *reinterpret_cast<float4*>(res + 4 * e) =
+            make_float4((mask & 1) ? hh * hw * a : 0.f, (mask & 2) ? hh * t.lw * a : 0.f,
+                        (mask & 4) ? t.lh * hw * a : 0.f, (mask & 8) ? t.lh * t.lw * a : 0.f);
       }
-      const int offm = ((lt.start[lvl] + t.h0 * W + t.w0) * px_stride) | mask;
-      rec[ql * RS + pt] = make_float4(__int_as_float(offm), t.lh, t.lw, a);
     }
     __syncthreads();
 
-    // ---- B: inclusive scan of table[1..] in place: bucket k = [table[k], table[k+1]) ------------------------------
+    // ---- B: counts -> padded to whole tasks -> inclusive scan in place: bucket k = [table[k], table[k+1]) ---------
     {
       int4* t4 = reinterpret_cast<int4*>(table);
       int4 v0 = t4[2 * tid], v1 = t4[2 * tid + 1];
-      v0.y += v0.x; v0.z += v0.y; v0.w += v0.z;
-      v1.x += v0.w; v1.y += v1.x; v1.z += v1.y; v1.w += v1.z;
+      auto pad = [](int c) { return (c + kT - 1) & ~(kT - 1); };
+      v0.x = pad(v0.x); v0.y = pad(v0.y) + v0.x; v0.z = pad(v0.z) + v0.y; v0.w = pad(v0.w) + v0.z;
+      v1.x = pad(v1.x) + v0.w; v1.y = pad(v1.y) + v1.x; v1.z = pad(v1.z) + v1.y; v1.w = pad(v1.w) + v1.z;
       int incl = v1.w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -228,173 +282,159 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
       v1.x += before; v1.y += before; v1.z += before; v1.w += before;
       t4[2 * tid] = v0;
       t4[2 * tid + 1] = v1;
+      if (tid == kTT - 1) {
+        n_slots = v1.w;
+        overflow = v1.w > kVisitCap ? 1 : 0;
+      }
     }
     __syncthreads();
+    const bool all_direct = overflow != 0;
+    if (!all_direct) {
 #pragma unroll
-    for (int i = 0; i < kPtsPerThread; ++i)
-      if (key[i] >= 0) sidx[table[key[i]] + rank[i]] = (unsigned short)(tid + i * kTT);
-
-    // ---- C: gather; grad_sampling_loc, grad_attn_weight -----------------------------------------------------------
-    {
-      const int grp = tid >> 2, j = tid & 3;   // query slot of the tile, channel octet
-      const bool hi2 = (j & 2) != 0, hi1 = (j & 1) != 0;
-      const int q = cur.query(grp, Lq);
-      const bool live = q >= 0;
-      const long long nq = (long long)n * Lq + (live ? q : 0);
-      const long long pair = nq * M + m;
-      const long long img = (long long)n * S * px_stride + m * 32 + 8 * j;
-      const float* vhead = value + img;
-      float* gvhead = grad_value + img;
-      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-      if (live) {
-        g0 = ld_stream_f4(reinterpret_cast<const float4*>(grad_out + pair * 32 + 8 * j));
-        g1 = ld_stream_f4(reinterpret_cast<const float4*>(grad_out + pair * 32 + 8 * j + 4));
+      for (int ps = 0; ps < kQLPasses; ++ps) {
+        const int u = tid + ps * kTT;
+        const int ql = u / kLv, lv = u % kLv;
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int k = vkey[ps][p][r];
+            if (k != 0xffff) {
+              const int pos = table[k] + vrank[ps][p][r];
+              vis[pos] = (unsigned short)((ql << kCodeShift) | ((lv * P + p) << 2) | r);
+              tkey[pos / kT] = (unsigned short)(k | (min(lv, L - 1) << 12));   // same value from every visit of the task
+            }
+          }
       }
-      *reinterpret_cast<float4*>(gtile + grp * 32 + 8 * j) = g0;
-      *reinterpret_cast<float4*>(gtile + grp * 32 + 8 * j + 4) = g1;
-      const float4* myrec = rec + grp * RS;
-      float sm_a[kSlots / 4], sm_g[kSlots / 4];   // fused: softmax backward state (point j of every batch)
+    }
+    __syncthreads();
+
+    const int j = tid & 3;   // 4 lanes x 8 channels per task: lane j owns channels 4j..4j+3 and 16+4j..16+4j+3
+    const float* vimg = value + img + 4 * j;
+    float* gvimg = grad_value + img + 4 * j;
+
+    // ---- D: one task (pixel, <= kT visits) per 4 lanes ---------------------------------------------------------------
+    // Loop bounds are warp-uniform (every lane takes part in the width-4 shuffles); a group past the end re-runs the
+    // last task with its writes switched off.
+    if (!all_direct) {
+      const int n_tasks = n_slots / kT;
+      for (int i0 = warp * 8; i0 < n_tasks; i0 += kTT / 4) {
+        const bool valid = i0 + (lane >> 2) < n_tasks;
+        const int i = valid ? i0 + (lane >> 2) : n_tasks - 1;
+        const int tk = tkey[i];
+        const int l = tk >> 12;
+        const int pidx = (tk & 4095) - win.base[l];
+        const int ww = win.w[l];
+        const int wy = (pidx * win.magic[l]) >> 16;
+        const int wx = pidx - wy * ww;
+        const int pix = lt.start[l] + (win.y0[l] + wy) * lt.W[l] + (win.x0[l] + wx);   // in range: it has a valid visit
+        const float* pv = vimg + (long long)pix * px_stride;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(pv));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(pv + 16));
+        const uint2 codes = *reinterpret_cast<const uint2*>(vis + kT * i);
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
 #pragma unroll
-      for (int b = 0; b < kSlots / 4; ++b) { sm_a[b] = 0.f; sm_g[b] = 0.f; }
-#pragma unroll
-      for (int b = 0; b < kSlots / 4; ++b) {   // batch b = the 4 points of level b
-        if (b >= L) break;                     // warp-uniform
-        const int ws = lt.wstr[b];
-        float d[4][4];
+        for (int s = 0; s < kT; ++s) {
+          const int code = (int)(((s & 2) ? codes.y : codes.x) >> ((s & 1) * 16)) & 0xffff;
+          const float c = res[code];
+          const float* gr = gtile + (code >> kCodeShift) * 32 + 4 * j;
+          const float4 g0 = *reinterpret_cast<const float4*>(gr);
+          const float4 g1 = *reinterpret_cast<const float4*>(gr + 16);
+          fma4(acc0, c, g0);
+          fma4(acc1, c, g1);
+          const float d = group4_sum(dot4acc(g1, v1, dot4acc(g0, v0, 0.f)));
+          if (valid && j == 0) res[code] = d;   // coefficient consumed: the slot now holds <grad_out, value_corner>
+        }
+        if (valid) {
+          float* pg = gvimg + (long long)pix * px_stride;
+          red_add_f4(pg, acc0);
+          red_add_f4(pg + 16, acc1);
+        }
+      }
+    }
+
+    // ---- X: points outside the windows -- corner loads, dot products, one reduction line per corner ----------------
+    {
+      const int nd = all_direct ? kTQ * kSlots : n_direct;
+      for (int i0 = warp * 8; i0 < nd; i0 += kTT / 4) {
+        const bool valid = i0 + (lane >> 2) < nd;
+        const int i = valid ? i0 + (lane >> 2) : nd - 1;
+        const int e = all_direct ? i : direct[i];
+        const float4 R = rec[e];
+        const int offm = valid ? __float_as_int(R.x) : 0;
+        const int ql = e / kSlots;
+        const int lvl = (e % kSlots) / P;
+        const int ws = lt.wstr[lvl];
+        const int off = offm & ~31;
+        const float* pv = vimg + off;
+        float* pg = gvimg + off;
+        const float4 g0 = *reinterpret_cast<const float4*>(gtile + ql * 32 + 4 * j);
+        const float4 g1 = *reinterpret_cast<const float4*>(gtile + ql * 32 + 16 + 4 * j);
+        const float4 C = *reinterpret_cast<const float4*>(res + 4 * e);
+        float d[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const float4 R = myrec[4 * b + r];
-          const int offm = __float_as_int(R.x);
-          const int off = offm & ~31;
-          const float* pv = vhead + off;
-          const bool q00 = offm & 1, q01 = offm & 2, q10 = offm & 4, q11 = offm & 8;
-          float4 a00, b00, a01, b01, a10, b10, a11, b11;   // corner k: channels 8j..8j+3 | 8j+4..8j+7
-          if (q00) { a00 = __ldg(reinterpret_cast<const float4*>(pv)); b00 = __ldg(reinterpret_cast<const float4*>(pv + 4)); }
-          if (q01) { a01 = __ldg(reinterpret_cast<const float4*>(pv + px_stride)); b01 = __ldg(reinterpret_cast<const float4*>(pv + px_stride + 4)); }
-          if (q10) { a10 = __ldg(reinterpret_cast<const float4*>(pv + ws)); b10 = __ldg(reinterpret_cast<const float4*>(pv + ws + 4)); }
-          if (q11) { a11 = __ldg(reinterpret_cast<const float4*>(pv + ws + px_stride)); b11 = __ldg(reinterpret_cast<const float4*>(pv + ws + px_stride + 4)); }
-          if (offm & 16) {   // outside the window (rare): reduce directly, like the d32 kernel
-            const float lh = R.y, lw = R.z, a = R.w;
-            const float hh = 1.f - lh, hw = 1.f - lw;
-            float* pg = gvhead + off;
-            const float w00 = hh * hw * a, w01 = hh * lw * a, w10 = lh * hw * a, w11 = lh * lw * a;
-            if (q00) { red_add_f4(pg, make_float4(w00 * g0.x, w00 * g0.y, w00 * g0.z, w00 * g0.w)); red_add_f4(pg + 4, make_float4(w00 * g1.x, w00 * g1.y, w00 * g1.z, w00 * g1.w)); }
-            if (q01) { red_add_f4(pg + px_stride, make_float4(w01 * g0.x, w01 * g0.y, w01 * g0.z, w01 * g0.w)); red_add_f4(pg + px_stride + 4, make_float4(w01 * g1.x, w01 * g1.y, w01 * g1.z, w01 * g1.w)); }
-            if (q10) { red_add_f4(pg + ws, make_float4(w10 * g0.x, w10 * g0.y, w10 * g0.z, w10 * g0.w)); red_add_f4(pg + ws + 4, make_float4(w10 * g1.x, w10 * g1.y, w10 * g1.z, w10 * g1.w)); }
-            if (q11) { red_add_f4(pg + ws + px_stride, make_float4(w11 * g0.x, w11 * g0.y, w11 * g0.z, w11 * g0.w)); red_add_f4(pg + ws + px_stride + 4, make_float4(w11 * g1.x, w11 * g1.y, w11 * g1.z, w11 * g1.w)); }
+          d[r] = 0.f;
+          if (offm & (1 << r)) {
+            const int o = (r & 1) * px_stride + (r >> 1) * ws;
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(pv + o));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(pv + o + 16));
+            const float c = r == 0 ? C.x : (r == 1 ? C.y : (r == 2 ? C.z : C.w));
+            red_add_f4(pg + o, make_float4(c * g0.x, c * g0.y, c * g0.z, c * g0.w));
+            red_add_f4(pg + o + 16, make_float4(c * g1.x, c * g1.y, c * g1.z, c * g1.w));
+            d[r] = dot4acc(g1, v1, dot4acc(g0, v0, 0.f));
           }
-          d[r][0] = q00 ? dot8(g0, g1, a00, b00) : 0.f;
-          d[r][1] = q01 ? dot8(g0, g1, a01, b01) : 0.f;
-          d[r][2] = q10 ? dot8(g0, g1, a10, b10) : 0.f;
-          d[r][3] = q11 ? dot8(g0, g1, a11, b11) : 0.f;
         }
-        // reduce-scatter over the 4 lanes: afterwards lane j holds the four corner sums of point j of the batch
-        float e2[2][4], f[4];
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < 4; ++r) d[r] = group4_sum(d[r]);
+        if (valid && (offm & 15) && j == 0) *reinterpret_cast<float4*>(res + 4 * e) = make_float4(d[0], d[1], d[2], d[3]);
+      }
+    }
+    __syncthreads();
+
+    // ---- F: grad_sampling_loc, grad_attn_weight from the corner dot products ----------------------------------------
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float keep = hi2 ? d[r + 2][k] : d[r][k];
-            const float send = hi2 ? d[r][k] : d[r + 2][k];
-            e2[r][k] = keep + __shfl_xor_sync(kAllLanes, send, 2, 4);
-          }
+    for (int ps = 0; ps < kQLPasses; ++ps) {
+      const int u = tid + ps * kTT;
+      const int ql = u / kLv, lv = u % kLv;
+      const int q = cur.query(ql, Lq);
+      const bool on = q >= 0 && lv < L;
+      const int lvl = min(lv, L - 1);
+      const long long pair = ((long long)n * Lq + (q >= 0 ? q : 0)) * M + m;
+      const float Wf = (float)lt.W[lvl], Hf = (float)lt.H[lvl];
+      float gx[P], gy[P], ga[P], aa[P];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float keep = hi1 ? e2[1][k] : e2[0][k];
-          const float send = hi1 ? e2[0][k] : e2[1][k];
-          f[k] = keep + __shfl_xor_sync(kAllLanes, send, 1, 4);
-        }
-        const float4 K = myrec[4 * b + j];   // the point this lane finalises
-        const float klh = K.y, klw = K.z, ka = K.w;
-        const float hh = 1.f - klh, hw = 1.f - klw;
-        const int point = 4 * b + j;
-        float gx = (float)lt.W[b] * ka * (hh * (f[1] - f[0]) + klh * (f[3] - f[2]));
-        float gy = (float)lt.H[b] * ka * (hw * (f[2] - f[0]) + klw * (f[3] - f[1]));
-        const float ga = hh * (hw * f[0] + klw * f[1]) + klh * (hw * f[2] + klw * f[3]);
-        if (kFused) {   // loc = ref + off / (W, H)
-          gx *= 1.f / (float)lt.W[b];
-          gy *= 1.f / (float)lt.H[b];
-          sm_a[b] = ka;
-          sm_g[b] = ga;
-        }
-        if (live) {
-          st_stream_f2(reinterpret_cast<float2*>(grad_loc + (pair * LP + point) * 2), make_float2(gx, gy));
-          if (!kFused) grad_attn[pair * LP + point] = ga;
-        }
+      for (int p = 0; p < P; ++p) {
+        const int e = ql * kSlots + lv * P + p;
+        const float4 R = rec[e];
+        const float4 D = *reinterpret_cast<const float4*>(res + 4 * e);
+        const int offm = __float_as_int(R.x);
+        const float f0 = (offm & 1) ? D.x : 0.f, f1 = (offm & 2) ? D.y : 0.f;
+        const float f2 = (offm & 4) ? D.z : 0.f, f3 = (offm & 8) ? D.w : 0.f;
+        const float lh = R.y, lw = R.z, a = R.w;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        gx[p] = Wf * a * (hh * (f1 - f0) + lh * (f3 - f2));
+        gy[p] = Hf * a * (hw * (f2 - f0) + lw * (f3 - f1));
+        ga[p] = hh * (hw * f0 + lw * f1) + lh * (hw * f2 + lw * f3);
+        aa[p] = a;
       }
       if (kFused) {
-        // softmax backward over the pair's L*P points: dlogit_i = a_i * (ga_i - sum_k a_k ga_k)
-        float part = 0.f;
+        // loc = ref + off / (W, H); softmax backward: dlogit_i = a_i * (ga_i - sum_k a_k ga_k)
+        float part = (aa[0] * ga[0] + aa[1] * ga[1]) + (aa[2] * ga[2] + aa[3] * ga[3]);
 #pragma unroll
-        for (int b = 0; b < kSlots / 4; ++b) part = fmaf(sm_a[b], sm_g[b], part);
-        const float dotp = seg_sum<4>(part);
-        if (live) {
+        for (int o = kLv / 2; o > 0; o >>= 1) part += __shfl_xor_sync(kAllLanes, part, o, kLv);
 #pragma unroll
-          for (int b = 0; b < kSlots / 4; ++b)
-            if (b < L) grad_attn[pair * LP + 4 * b + j] = sm_a[b] * (sm_g[b] - dotp);
+        for (int p = 0; p < P; ++p) {
+          gx[p] *= 1.f / Wf;
+          gy[p] *= 1.f / Hf;
+          ga[p] = aa[p] * (ga[p] - part);
         }
       }
-    }
-    __syncthreads();
-
-    // ---- C': records -> the four corner coefficients a * w_k (0 for corners that do not contribute) ---------------
-#pragma unroll
-    for (int i = 0; i < kPtsPerThread; ++i) {
-      const int e = tid + i * kTT;
-      const int ri = (e / kSlots) * RS + (e % kSlots);
-      const float4 R = rec[ri];
-      const int offm = __float_as_int(R.x);
-      const float lh = R.y, lw = R.z, a = R.w;
-      const float hh = 1.f - lh, hw = 1.f - lw;
-      rec[ri] = make_float4((offm & 1) ? hh * hw * a : 0.f, (offm & 2) ? hh * lw * a : 0.f,
-                            (offm & 4) ? lh * hw * a : 0.f, (offm & 8) ? lh * lw * a : 0.f);
-    }
-    __syncthreads();
-
-    // ---- D: every window pixel gathers its contributions; one reduction line per touched pixel --------------------
-    {
-      const int grp = tid >> 2, j = tid & 3;   // pixel owner group; lane j owns channels 4j..4j+3 and 16+4j..16+4j+3
-      const float* recf = reinterpret_cast<const float*>(rec);
-      float* gvimg = grad_value + (long long)n * S * px_stride + m * 32 + 4 * j;
-      for (int l = 0; l < L; ++l) {
-        const int ww = win.w[l];
-        if (ww == 0) continue;
-        const int npx = win.h[l] * ww, wb = win.base[l];
-        const int H = lt.H[l], W = lt.W[l];
-        int wy = grp / ww, wx = grp - wy * ww;
-        for (int p = grp; p < npx; p += kTT / 4) {
-          const int k = wb + p;
-          // same-row buckets (wx-1 -> this pixel is their corner 01, wx -> corner 00)
-          const int b0 = table[k - 1], b1 = table[k], b2 = table[k + 1];
-          // previous-row buckets (wx-1 -> corner 11, wx -> corner 10); row 0 has none
-          int a0 = 0, a1 = 0, a2 = 0;
-          if (wy > 0) { a0 = table[k - ww - 1]; a1 = table[k - ww]; a2 = table[k - ww + 1]; }
-          if (b2 > b0 || a2 > a0) {
-            float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-            for (int i = a0; i < a2; ++i) {
-              const int e = sidx[i];
-              const int ql = e / kSlots;
-              const float c = recf[(ql * RS + (e % kSlots)) * 4 + (i < a1 ? 3 : 2)];
-              fma4(acc0, c, *reinterpret_cast<const float4*>(gtile + ql * 32 + 4 * j));
-              fma4(acc1, c, *reinterpret_cast<const float4*>(gtile + ql * 32 + 16 + 4 * j));
-            }
-            for (int i = b0; i < b2; ++i) {
-              const int e = sidx[i];
-              const int ql = e / kSlots;
-              const float c = recf[(ql * RS + (e % kSlots)) * 4 + (i < b1 ? 1 : 0)];
-              fma4(acc0, c, *reinterpret_cast<const float4*>(gtile + ql * 32 + 4 * j));
-              fma4(acc1, c, *reinterpret_cast<const float4*>(gtile + ql * 32 + 16 + 4 * j));
-            }
-            const int y = win.y0[l] + wy, x = win.x0[l] + wx;
-            if (y >= 0 && y < H && x >= 0 && x < W) {   // an out-of-level pixel only ever collects zero coefficients
-              float* pg = gvimg + (long long)(lt.start[l] + y * W + x) * px_stride;
-              red_add_f4(pg, acc0);
-              red_add_f4(pg + 16, acc1);
-            }
-          }
-          wx += kTT / 4;
-          while (wx >= ww) { wx -= ww; ++wy; }
-        }
+      if (on) {
+        float* gl = grad_loc + (pair * LP + lv * P) * 2;
+        st_stream_f4(reinterpret_cast<float4*>(gl), make_float4(gx[0], gy[0], gx[1], gy[1]));
+        st_stream_f4(reinterpret_cast<float4*>(gl + 4), make_float4(gx[2], gy[2], gx[3], gy[3]));
+        st_stream_f4(reinterpret_cast<float4*>(grad_attn + pair * LP + lv * P), make_float4(ga[0], ga[1], ga[2], ga[3]));
       }
     }
   }
@@ -409,8 +449,9 @@ int launch_tile(cudaStream_t st, const float* grad_out, const float* value, cons
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // shared memory for two CTAs, the rest of the 228 KB stays L1 for the corner gathers
-    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (2 * (smem + 2048) * 100 + 233471) / 233472));
+    // shared memory for two CTAs; what is left of the 228 KB stays L1 for the value-pixel loads
+    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)((2LL * (smem + 1024) * 100 + 233471) / 233472)));
     int b = 0;
     SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kTT, smem));
     blocks_per_sm = b > 0 ? b : 1;

@@ -30,7 +30,7 @@ from ..registry import BBOX_ASSIGNERS, HEADS, LOSSES, POSITIONAL_ENCODING, TRANS
 from . import losses as _losses  # noqa: F401  (registers the losses)
 from . import positional_encoding as _pe  # noqa: F401
 from .dn_components import dn_post_process, prepare_for_cdn
-from .losses import giou_aligned, sigmoid_focal_elementwise
+from . import fused_loss
 from .transformer import MLP, inverse_sigmoid
 
 LOSS_PARTS = ("loss_cls", "loss_bbox", "loss_iou", "loss_bbox_xy", "loss_bbox_hw")
@@ -204,17 +204,16 @@ class DINODETRHead(nn.Module):
         return outputs_class, outputs_coord, interm_class, interm_coord, dn_class, dn_coord
 
     # ------------------------------------------------------------------------------------------------
-    def _batched_terms(self, cls, box, labels, box_t, pos, factor, cls_weight=None):
-        """Element-wise loss terms summed per problem.  cls (P,Q,C), box/box_t (P,Q,4), labels/pos (P,Q),
-        factor (P,1,4), cls_weight (P,) or None -> dict of (P,) sums (un-normalised, un-weighted)."""
-        w = pos.unsqueeze(-1).to(box.dtype)
-        focal = sigmoid_focal_elementwise(cls, labels, self.num_classes, self.loss_cls.gamma, self.loss_cls.alpha)
-        if cls_weight is not None:
-            focal = focal * cls_weight[:, None, None]
-        l1 = (box - box_t).abs() * w
-        giou = giou_aligned(bbox_cxcywh_to_xyxy(box) * factor, bbox_cxcywh_to_xyxy(box_t) * factor, self.loss_iou.eps)
-        return dict(loss_cls=focal.sum((1, 2)), loss_bbox=l1.sum((1, 2)), loss_bbox_xy=l1[..., :2].sum((1, 2)),
-                    loss_bbox_hw=l1[..., 2:].sum((1, 2)), loss_iou=((1 - giou) * w.squeeze(-1)).sum(1))
+    def _loss_sums(self, cls, box, gt_inds, prob_seg, targets, cls_weight=None):
+        """Per-problem loss sums by the fused kernel (``fused_loss.detr_loss_sums``): targets gathered from the
+        assignment, focal / L1 (+ xy, hw) / GIoU terms, one launch.  cls (P,Q,C), box (P,Q,4), gt_inds (P,Q), prob_seg
+        (P,) int32 -> dict of (P,) sums (un-normalised, un-weighted)."""
+        has_gt = targets.offsets_host[-1] > 0
+        sums = fused_loss.detr_loss_sums(cls, box, gt_inds, prob_seg, targets.seg_offsets,
+                                         targets.gt_bboxes if has_gt else None, targets.gt_labels if has_gt else None,
+                                         targets.img_wh, cls_weight, self.loss_cls.alpha, self.loss_cls.gamma,
+                                         self.loss_iou.eps)
+        return {name: sums[:, i] for i, name in enumerate(fused_loss.LOSS_SUM_NAMES)}
 
     def _finish(self, sums, layers, bs, cls_avg, reg_avg):
         """(P,) per-problem sums -> per-layer losses with the reference's normalisers and weights."""
@@ -254,22 +253,9 @@ class DINODETRHead(nn.Module):
         prob_seg = [(bs if (has_enc and l == L) else 0) + i for l in range(layers) for i in range(bs)]
         gt_inds, labels = self.assigner.assign_batch(box_stack.view(P, Q, 4), cls_stack.view(P, Q, C), targets,
                                                      prob_img=prob_seg)
-        # per-GT normalised cxcywh targets (dino_detr_head.py:969-976) and per-problem geometry
-        seg_counts = tuple(targets.counts)
-        seg_of_gt_d = device_const(dev, "seg_of_gt", seg_counts, lambda: np.concatenate(
-            [np.full(c, s, dtype=np.int64) for s, c in enumerate(seg_counts)] + [np.zeros(0, dtype=np.int64)]))
-        prob_seg_d = device_const(dev, "prob_seg64", tuple(prob_seg), lambda: np.asarray(prob_seg, dtype=np.int64))
-        wh4 = torch.cat([targets.img_wh, targets.img_wh], 1)                                     # (nseg, 4)
-        if sum(seg_counts):
-            gt_norm = bbox_xyxy_to_cxcywh(targets.gt_bboxes / wh4[seg_of_gt_d])
-        else:
-            gt_norm = torch.zeros((1, 4), device=dev)
-        pos = gt_inds > 0
-        gidx = (targets.seg_offsets.long()[prob_seg_d][:, None] + gt_inds - 1).clamp(min=0)
-        box_t = gt_norm[gidx] * pos.unsqueeze(-1)
-        labels_t = torch.where(pos, labels, torch.full_like(labels, self.num_classes))
-        factor = wh4[prob_seg_d][:, None, :]
-        sums = self._batched_terms(cls_stack.view(P, Q, C), box_stack.view(P, Q, 4), labels_t, box_t, pos, factor)
+        # targets (labels, normalised cxcywh boxes: dino_detr_head.py:969-976) are gathered inside the loss kernel
+        prob_seg_d = device_const(dev, "prob_seg32", tuple(prob_seg), lambda: np.asarray(prob_seg, dtype=np.int32))
+        sums = self._loss_sums(cls_stack.reshape(P, Q, C), box_stack.reshape(P, Q, 4), gt_inds, prob_seg_d, targets)
         num_pos = sum(min(c, Q) for c in counts)
         reg_avg = _clamp_min1(reduce_mean_scalar(num_pos, dev))
         main = self._finish(sums, layers, bs, max(num_pos * 1.0, 1), reg_avg)
@@ -277,56 +263,43 @@ class DINODETRHead(nn.Module):
         # --- denoising part: targets follow from the CDN layout, no matcher (:739-819) -------------------------
         if dn_cls_scores is not None and dn_bbox_preds is not None:
             dn = self._dn_terms(dn_cls_scores, dn_bbox_preds, gt_bboxes_list, gt_labels_list, img_metas, dn_metas,
-                                zero_weight_empty_dn)
+                                zero_weight_empty_dn, targets=targets)
         else:
             dn = {k: torch.zeros(L, device=dev) for k in LOSS_PARTS}
         return self._assemble(main, dn, L, has_enc)
 
     def _dn_terms(self, dn_cls_scores, dn_bbox_preds, gt_bboxes_list, gt_labels_list, img_metas, dn_metas,
-                  zero_weight_empty_dn=False):
+                  zero_weight_empty_dn=False, targets=None):
         """Per-layer denoising losses.  Slot of GT k of image b in group g is g*single_pad + k (positives first,
-        negatives ``single_pad // 2`` later); everything else is background (dino_detr_head.py:739-819).  With
+        negatives ``single_pad // 2`` later); everything else is background (dino_detr_head.py:739-819) -- i.e. the
+        "assignment" is a constant of the batch geometry, so the same fused loss kernel serves.  With
         ``zero_weight_empty_dn`` an image without boxes contributes no classification loss
-        (dino_detr_ssod_head.py:921-924)."""
+        (dino_detr_ssod_head.py:921-924).  ``targets``: a MatchTargets whose first ``bs`` segments are these images."""
         dev = dn_cls_scores.device
         Ld, bs, pad, C = dn_cls_scores.shape
         counts = [int(b.shape[0]) for b in gt_bboxes_list]
         groups = dn_metas["num_dn_group"]
         single_pad = pad // groups            # = 2 * max_gt: positives then negatives of one group
         total = sum(counts)
+        if targets is None:
+            img_wh = [(m["img_shape"][1], m["img_shape"][0]) for m in img_metas]
+            targets = MatchTargets(list(gt_bboxes_list), list(gt_labels_list), img_wh, dev)
 
-        def build_ix():
-            z = [np.zeros(0, np.int64)]
-            bid = np.concatenate([np.full(c, i, dtype=np.int64) for i, c in enumerate(counts)] + z)
-            within = np.concatenate([np.arange(c, dtype=np.int64) for c in counts] + z)
-            return np.stack([np.tile(bid, groups),
-                             np.concatenate([within + single_pad * g for g in range(groups)] + z),
-                             np.tile(np.arange(total, dtype=np.int64), groups)])
-        ix = device_const(dev, "dn_loss_ix", (tuple(counts), groups, single_pad), build_ix)
-        img_wh = tuple((float(m["img_shape"][1]), float(m["img_shape"][0])) for m in img_metas)
-        wh = device_const(dev, "img_wh", img_wh, lambda: torch.tensor(img_wh, dtype=torch.float32).reshape(-1, 2))
-        wh4 = torch.cat([wh, wh], 1)
-        dn_labels = torch.full((bs, pad), self.num_classes, dtype=torch.long, device=dev)
-        dn_pos = torch.zeros((bs, pad), dtype=torch.bool, device=dev)
-        dn_box_t = torch.zeros((bs, pad, 4), device=dev)
-        if total > 0:
-            seg_of_gt = device_const(dev, "seg_of_gt", tuple(counts), lambda: np.concatenate(
-                [np.full(c, s_, dtype=np.int64) for s_, c in enumerate(counts)]))
-            gt_all = torch.cat([b.reshape(-1, 4) for b in gt_bboxes_list]).to(dev, torch.float32)
-            lab_all = torch.cat([l.reshape(-1) for l in gt_labels_list]).to(dev, torch.long)
-            gt_norm = bbox_xyxy_to_cxcywh(gt_all / wh4[seg_of_gt])
-            dn_labels[ix[0], ix[1]] = lab_all[ix[2]]
-            dn_pos[ix[0], ix[1]] = torch.ones(ix.shape[1], dtype=torch.bool, device=dev)   # device value: graph-safe
-            dn_box_t[ix[0], ix[1]] = gt_norm[ix[2]]
+        def build_gt_inds():
+            gi = np.zeros((bs, pad), dtype=np.int64)
+            for b, c in enumerate(counts):
+                for g in range(groups):
+                    gi[b, g * single_pad:g * single_pad + c] = np.arange(1, c + 1)
+            return np.tile(gi[None], (Ld, 1, 1)).reshape(Ld * bs, pad)
+        gt_inds = device_const(dev, "dn_gt_inds", (tuple(counts), groups, single_pad, pad, Ld), build_gt_inds)
         Pd = Ld * bs
-        rep = lambda t: t[None].expand(Ld, *t.shape).reshape(Pd, *t.shape[1:])
+        prob_seg = device_const(dev, "dn_prob_seg32", (Ld, bs), lambda: np.tile(np.arange(bs, dtype=np.int32), Ld))
         cls_w = None
         if zero_weight_empty_dn and any(c == 0 for c in counts):
-            cw = tuple(0.0 if c == 0 else 1.0 for c in counts)
-            cls_w = rep(device_const(dev, "dn_cls_w", cw, lambda: torch.tensor(cw, dtype=torch.float32)))
-        dsums = self._batched_terms(dn_cls_scores.float().reshape(Pd, pad, C),
-                                    dn_bbox_preds.float().reshape(Pd, pad, 4), rep(dn_labels), rep(dn_box_t),
-                                    rep(dn_pos), rep(wh4[:, None, :]), cls_w)
+            cw = tuple(0.0 if c == 0 else 1.0 for c in counts) * Ld
+            cls_w = device_const(dev, "dn_cls_w", cw, lambda: torch.tensor(cw, dtype=torch.float32))
+        dsums = self._loss_sums(dn_cls_scores.float().reshape(Pd, pad, C), dn_bbox_preds.float().reshape(Pd, pad, 4),
+                                gt_inds, prob_seg, targets, cls_w)
         dn_num_pos = total * groups
         return self._finish(dsums, Ld, bs, max(dn_num_pos * 1.0, 1), _clamp_min1(reduce_mean_scalar(dn_num_pos, dev)))
 

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 # Bounds (relative).  fp32 products: the north star's 1e-3 on every loss; per-parameter gradient norms within
 # GRAD_TOL_FP32 (fp32 atomics / summation order through 12 layers).  TF32 products: see the TF32 test's docstring.
 GRAD_TOL_FP32 = 2e-2
-LOSS_TOL_TF32 = 2e-2
+DN_LOSS_TOL_TF32 = 1e-2       # a denoising loss value (no matcher involved)
+LAYER_LOSS_TOL_TF32 = 2e-2    # loss_cls + loss_bbox + loss_iou of one decoder layer / the encoder proposals
 TOTAL_TOL_TF32 = 5e-3
 GRAD_TOL_TF32 = 1e-1
 
@@ -128,11 +129,28 @@ def test_train_step_with_tf32_products_stays_close_to_the_fp32_reference_path(cp
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
     assert list(out["log_vars"]) == list(ref["log_vars"])
-    worst = (0.0, "")
-    for k in ref["log_vars"]:
-        a, b = float(out["log_vars"][k]), float(ref["log_vars"][k])
-        worst = max(worst, (abs(a - b) / max(abs(b), 1e-6), k))
-        assert abs(a - b) <= LOSS_TOL_TF32 * abs(b) + 1e-4, (k, a, b)
+    # (1) denoising losses have no matcher in them: each value individually
+    # (2) matched losses: a near-tied match that TF32 flips trades loss_cls / loss_bbox / loss_iou of that layer against
+    #     each other at (nearly) constant matching cost -- the cost weights equal the loss weights
+    #     (dino_detr_r50_8x2_12e_coco.py:29-44) -- so the per-layer SUM of the three is what stays put
+    # (3) the total loss
+    got, want = out["log_vars"], ref["log_vars"]
+    worst_dn, worst_layer = (0.0, ""), (0.0, "")
+    prefixes = sorted({k[:-len("loss_cls")] for k in want if k.endswith("loss_cls")})
+    for pre in prefixes:
+        if "dn_" in pre:
+            for part in ("loss_cls", "loss_bbox", "loss_iou"):
+                a, b = float(got[pre + part]), float(want[pre + part])
+                worst_dn = max(worst_dn, (abs(a - b) / max(abs(b), 1e-6), pre + part))
+                assert abs(a - b) <= DN_LOSS_TOL_TF32 * abs(b) + 1e-4, (pre + part, a, b)
+        else:
+            a = sum(float(got[pre + part]) for part in ("loss_cls", "loss_bbox", "loss_iou"))
+            b = sum(float(want[pre + part]) for part in ("loss_cls", "loss_bbox", "loss_iou"))
+            worst_layer = max(worst_layer, (abs(a - b) / abs(b), pre))
+            assert abs(a - b) <= LAYER_LOSS_TOL_TF32 * abs(b), (pre, a, b)
+    for k in want:
+        print(f"    {k:24s} {float(got[k]):12.6f} {float(want[k]):12.6f} {abs(float(got[k]) - float(want[k])) / max(abs(float(want[k])), 1e-6):.2e}")
+    worst = max(worst_dn, worst_layer)
     total = abs(float(out["loss"]) - float(ref["loss"])) / abs(float(ref["loss"]))
     assert total <= TOTAL_TOL_TF32, total
     gworst, checked = (0.0, ""), 0
@@ -145,7 +163,8 @@ def test_train_step_with_tf32_products_stays_close_to_the_fp32_reference_path(cp
             gworst = max(gworst, (rel, n))
             assert rel < GRAD_TOL_TF32, (n, rel)
             checked += 1
-    print(f"[tf32 step] worst loss deviation {worst[0]:.2e} ({worst[1]}), total loss {total:.2e}, "
+    print(f"[tf32 step] worst denoising loss deviation {worst_dn[0]:.2e} ({worst_dn[1]}), worst per-layer matched-loss "
+          f"deviation {worst_layer[0]:.2e} ({worst_layer[1]}), total loss {total:.2e}, "
           f"worst gradient deviation {gworst[0]:.2e} ({gworst[1]}) over {checked} tensors")
     assert checked > 150
 

@@ -129,9 +129,10 @@ def test_fused_ssod_engine_keeps_the_hook_semantics():
     with torch.no_grad():                      # make the teacher differ from the student before the engine copies
         for p in model.teacher.parameters():
             p.add_(1.0)
-    step = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, start_iter=70000, lr=1e-3)
+    step = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, start_iter=0, lr=1e-3)   # iteration 0: before_run copies
     for (n, s), (_, t) in zip(model.student.named_parameters(), model.teacher.named_parameters()):
         assert torch.equal(s, t), n
+    step.iter = 70000                           # continue in the Hungarian phase
     data = ssod_batch(1, 2, 256, 320, seed=3, device="cuda")
     for it in range(2):
         t_prev = {n: p.detach().clone() for n, p in model.teacher.named_parameters()}
