@@ -70,13 +70,16 @@ __device__ __forceinline__ float group4_sum(float v) {
 // Shared-memory layout (dynamic).  kSlots = point slots per (query, head): 16 (L <= 4) or 32 (L <= 8).
 template <int kSlots>
 struct TileSmem {
-  static constexpr int kRecBytes = kTQ * kSlots * 16;            // {offm, lh, lw, a} per point
-  static constexpr int kResFloats = kTQ * kSlots * 4 + 4;        // 4 result slots per point (+ 1 dummy, padded)
+  // point e lives at slot e + (e >> 3): a thread's 4 records are 64 contiguous bytes and the extra 16 bytes per 8
+  // points spread a quarter-warp's 16-byte stores over all 32 banks
+  static constexpr int kPointSlots = kTQ * kSlots + kTQ * kSlots / 8;
+  static constexpr int kRecBytes = kPointSlots * 16;             // {offm, lh, lw, a} per point
+  static constexpr int kResFloats = kPointSlots * 4 + 4;         // 4 result slots per point (+ 1 dummy, padded)
   static constexpr int kResBytes = kResFloats * 4;
   static constexpr int kGBytes = (kTQ + 1) * 32 * 4;             // grad_out rows of the tile (+ 1 zero row)
   static constexpr int kTableBytes = kTableInts * 4;
   static constexpr int kVisBytes = kVisitCap * 2;
-  static constexpr int kKeyBytes = (kVisitCap / kT) * 2;
+  static constexpr int kKeyBytes = (kVisitCap / kT) * 4;         // value-pixel index of every task
   static constexpr int kDirectBytes = kTQ * kSlots * 2;
   static constexpr int oRes = kRecBytes, oG = oRes + kResBytes, oTable = oG + kGBytes, oVis = oTable + kTableBytes,
                        oKey = oVis + kVisBytes, oDirect = oKey + kKeyBytes;
@@ -99,13 +102,15 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
   constexpr int kCodeShift = kSlots == 16 ? 6 : 7;       // visit code = ql << shift | pt << 2 | corner
   constexpr int kNullCode = kTQ * kSlots * 4;            // dummy result slot, zero grad_out row
   using SM = TileSmem<kSlots>;
+  constexpr int kNullRes = SM::kPointSlots * 4;          // where the dummy result slot lives
+  auto slot = [](int e) { return e + (e >> 3); };        // padded point index
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* rec = reinterpret_cast<float4*>(smem_raw);
   float* res = reinterpret_cast<float*>(smem_raw + SM::oRes);
   float* gtile = reinterpret_cast<float*>(smem_raw + SM::oG);
   int* table = reinterpret_cast<int*>(smem_raw + SM::oTable);
   unsigned short* vis = reinterpret_cast<unsigned short*>(smem_raw + SM::oVis);
-  unsigned short* tkey = reinterpret_cast<unsigned short*>(smem_raw + SM::oKey);
+  int* tpix = reinterpret_cast<int*>(smem_raw + SM::oKey);
   unsigned short* direct = reinterpret_cast<unsigned short*>(smem_raw + SM::oDirect);
   __shared__ LevelTable lt;
   __shared__ Windows win;
@@ -152,7 +157,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
     if (tid == 0) {
       int acc = 1;   // bucket 0 is a guard
       n_direct = 0;
-      res[kNullCode] = 0.f;
+      res[kNullRes] = 0.f;
       for (int l = L - 1; l >= 0; --l) {   // coarse levels first: smallest windows, most reuse
         const float sy = (float)lt.H[l] / (float)cur.Hl, sx = (float)lt.W[l] / (float)cur.Wl;
         const int wy0 = (int)floorf((float)cur.y0 * sy) - kHalo - 1;
@@ -251,8 +256,8 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
           }
         }
         const int offm = ((lt.start[lvl] + t.h0 * W + t.w0) * px_stride) | mask;
-        rec[e] = make_float4(__int_as_float(offm), t.lh, t.lw, a);
-        *reinterpret_cast<float4*>(res + 4 * e) =
+        rec[slot(e)] = make_float4(__int_as_float(offm), t.lh, t.lw, a);
+        *reinterpret_cast<float4*>(res + 4 * slot(e)) =
             make_float4((mask & 1) ? hh * hw * a : 0.f, (mask & 2) ? hh * t.lw * a : 0.f,
                         (mask & 4) ? t.lh * hw * a : 0.f, (mask & 8) ? t.lh * t.lw * a : 0.f);
       }
@@ -294,6 +299,9 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
       for (int ps = 0; ps < kQLPasses; ++ps) {
         const int u = tid + ps * kTT;
         const int ql = u / kLv, lv = u % kLv;
+        const int lvl = min(lv, L - 1);
+        const int ww = win.w[lvl], wbase = win.base[lvl], magic = win.magic[lvl];
+        const int pix0 = lt.start[lvl] + win.y0[lvl] * lt.W[lvl] + win.x0[lvl], Wl = lt.W[lvl];
 #pragma unroll
         for (int p = 0; p < P; ++p)
 #pragma unroll
@@ -302,53 +310,74 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
             if (k != 0xffff) {
               const int pos = table[k] + vrank[ps][p][r];
               vis[pos] = (unsigned short)((ql << kCodeShift) | ((lv * P + p) << 2) | r);
-              tkey[pos / kT] = (unsigned short)(k | (min(lv, L - 1) << 12));   // same value from every visit of the task
+              const int pidx = k - wbase;
+              const int wy = (pidx * magic) >> 16;
+              tpix[pos / kT] = pix0 + wy * Wl + (pidx - wy * ww);   // same value from every visit of the task
             }
           }
       }
     }
     __syncthreads();
 
-    const int j = tid & 3;   // 4 lanes x 8 channels per task: lane j owns channels 4j..4j+3 and 16+4j..16+4j+3
-    const float* vimg = value + img + 4 * j;
-    float* gvimg = grad_value + img + 4 * j;
+    // 4 lanes x 8 channels per task.  Lane j owns channels 4j..4j+3 and 16+4j..16+4j+3; the two 16-byte halves are
+    // touched in opposite order by even and odd groups, so the two groups of a quarter-warp always read different
+    // halves (banks 0-15 / 16-31) of their grad_out rows: no shared-memory bank conflicts whatever the rows.
+    const int j = tid & 3;
+    const int c0 = 4 * j + 16 * ((lane >> 2) & 1), c1 = 4 * j + 16 * (1 - ((lane >> 2) & 1));
+    const float* vimg = value + img;
+    float* gvimg = grad_value + img;
 
     // ---- D: one task (pixel, <= kT visits) per 4 lanes ---------------------------------------------------------------
     // Loop bounds are warp-uniform (every lane takes part in the width-4 shuffles); a group past the end re-runs the
-    // last task with its writes switched off.
+    // last task with its writes switched off.  The next task's pixel index, visit codes and value line are fetched
+    // while the current one is processed.
     if (!all_direct) {
       const int n_tasks = n_slots / kT;
-      for (int i0 = warp * 8; i0 < n_tasks; i0 += kTT / 4) {
-        const bool valid = i0 + (lane >> 2) < n_tasks;
-        const int i = valid ? i0 + (lane >> 2) : n_tasks - 1;
-        const int tk = tkey[i];
-        const int l = tk >> 12;
-        const int pidx = (tk & 4095) - win.base[l];
-        const int ww = win.w[l];
-        const int wy = (pidx * win.magic[l]) >> 16;
-        const int wx = pidx - wy * ww;
-        const int pix = lt.start[l] + (win.y0[l] + wy) * lt.W[l] + (win.x0[l] + wx);   // in range: it has a valid visit
+      auto task_of = [&](int i0) { return min(i0 + (lane >> 2), n_tasks - 1); };
+      int i0 = warp * 8;
+      int pix = 0;
+      uint2 codes = make_uint2(0u, 0u);
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (i0 < n_tasks) {
+        const int i = task_of(i0);
+        pix = tpix[i];
+        codes = *reinterpret_cast<const uint2*>(vis + kT * i);
         const float* pv = vimg + (long long)pix * px_stride;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(pv));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(pv + 16));
-        const uint2 codes = *reinterpret_cast<const uint2*>(vis + kT * i);
+        v0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
+        v1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
+      }
+      for (; i0 < n_tasks; i0 += kTT / 4) {
+        const bool valid = i0 + (lane >> 2) < n_tasks;
+        const int cur_pix = pix;
+        const uint2 cur_codes = codes;
+        const float4 w0 = v0, w1 = v1;
+        if (i0 + kTT / 4 < n_tasks) {   // warp-uniform
+          const int i = task_of(i0 + kTT / 4);
+          pix = tpix[i];
+          codes = *reinterpret_cast<const uint2*>(vis + kT * i);
+          const float* pv = vimg + (long long)pix * px_stride;
+          v0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
+          v1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
+        }
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
 #pragma unroll
         for (int s = 0; s < kT; ++s) {
-          const int code = (int)(((s & 2) ? codes.y : codes.x) >> ((s & 1) * 16)) & 0xffff;
-          const float c = res[code];
-          const float* gr = gtile + (code >> kCodeShift) * 32 + 4 * j;
-          const float4 g0 = *reinterpret_cast<const float4*>(gr);
-          const float4 g1 = *reinterpret_cast<const float4*>(gr + 16);
+          const int code = (int)(((s & 2) ? cur_codes.y : cur_codes.x) >> ((s & 1) * 16)) & 0xffff;
+          const int e = code >> 2;
+          const int ri = code == kNullCode ? kNullRes : ((slot(e) << 2) | (code & 3));
+          const float c = res[ri];
+          const float* gr = gtile + (code >> kCodeShift) * 32;
+          const float4 g0 = *reinterpret_cast<const float4*>(gr + c0);
+          const float4 g1 = *reinterpret_cast<const float4*>(gr + c1);
           fma4(acc0, c, g0);
           fma4(acc1, c, g1);
-          const float d = group4_sum(dot4acc(g1, v1, dot4acc(g0, v0, 0.f)));
-          if (valid && j == 0) res[code] = d;   // coefficient consumed: the slot now holds <grad_out, value_corner>
+          const float d = group4_sum(dot4acc(g1, w1, dot4acc(g0, w0, 0.f)));
+          if (valid && j == 0) res[ri] = d;   // coefficient consumed: the slot now holds <grad_out, value_corner>
         }
         if (valid) {
-          float* pg = gvimg + (long long)pix * px_stride;
-          red_add_f4(pg, acc0);
-          red_add_f4(pg + 16, acc1);
+          float* pg = gvimg + (long long)cur_pix * px_stride;
+          red_add_f4(pg + c0, acc0);
+          red_add_f4(pg + c1, acc1);
         }
       }
     }
@@ -360,7 +389,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
         const bool valid = i0 + (lane >> 2) < nd;
         const int i = valid ? i0 + (lane >> 2) : nd - 1;
         const int e = all_direct ? i : direct[i];
-        const float4 R = rec[e];
+        const float4 R = rec[slot(e)];
         const int offm = valid ? __float_as_int(R.x) : 0;
         const int ql = e / kSlots;
         const int lvl = (e % kSlots) / P;
@@ -368,26 +397,27 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
         const int off = offm & ~31;
         const float* pv = vimg + off;
         float* pg = gvimg + off;
-        const float4 g0 = *reinterpret_cast<const float4*>(gtile + ql * 32 + 4 * j);
-        const float4 g1 = *reinterpret_cast<const float4*>(gtile + ql * 32 + 16 + 4 * j);
-        const float4 C = *reinterpret_cast<const float4*>(res + 4 * e);
+        const float4 g0 = *reinterpret_cast<const float4*>(gtile + ql * 32 + c0);
+        const float4 g1 = *reinterpret_cast<const float4*>(gtile + ql * 32 + c1);
+        const float4 C = *reinterpret_cast<const float4*>(res + 4 * slot(e));
         float d[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           d[r] = 0.f;
           if (offm & (1 << r)) {
             const int o = (r & 1) * px_stride + (r >> 1) * ws;
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(pv + o));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(pv + o + 16));
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(pv + o + c0));
+            const float4 x1 = __ldg(reinterpret_cast<const float4*>(pv + o + c1));
             const float c = r == 0 ? C.x : (r == 1 ? C.y : (r == 2 ? C.z : C.w));
-            red_add_f4(pg + o, make_float4(c * g0.x, c * g0.y, c * g0.z, c * g0.w));
-            red_add_f4(pg + o + 16, make_float4(c * g1.x, c * g1.y, c * g1.z, c * g1.w));
-            d[r] = dot4acc(g1, v1, dot4acc(g0, v0, 0.f));
+            red_add_f4(pg + o + c0, make_float4(c * g0.x, c * g0.y, c * g0.z, c * g0.w));
+            red_add_f4(pg + o + c1, make_float4(c * g1.x, c * g1.y, c * g1.z, c * g1.w));
+            d[r] = dot4acc(g1, x1, dot4acc(g0, x0, 0.f));
           }
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) d[r] = group4_sum(d[r]);
-        if (valid && (offm & 15) && j == 0) *reinterpret_cast<float4*>(res + 4 * e) = make_float4(d[0], d[1], d[2], d[3]);
+        if (valid && (offm & 15) && j == 0)
+          *reinterpret_cast<float4*>(res + 4 * slot(e)) = make_float4(d[0], d[1], d[2], d[3]);
       }
     }
     __syncthreads();
@@ -406,8 +436,8 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         const int e = ql * kSlots + lv * P + p;
-        const float4 R = rec[e];
-        const float4 D = *reinterpret_cast<const float4*>(res + 4 * e);
+        const float4 R = rec[slot(e)];
+        const float4 D = *reinterpret_cast<const float4*>(res + 4 * slot(e));
         const int offm = __float_as_int(R.x);
         const float f0 = (offm & 1) ? D.x : 0.f, f1 = (offm & 2) ? D.y : 0.f;
         const float f2 = (offm & 4) ? D.z : 0.f, f3 = (offm & 8) ? D.w : 0.f;
