@@ -29,6 +29,8 @@
 //
 // grad_value is still accumulated with reductions (neighbouring tiles overlap), but ~4-5x fewer of them; no query ever
 // gathers a corner line from global memory in the common case.
+#include <algorithm>
+
 #include "msda_common.cuh"
 
 namespace sdb {
@@ -78,7 +80,7 @@ struct TileSmem {
   static constexpr int kResBytes = kResFloats * 4;
   static constexpr int kGBytes = (kTQ + 1) * 32 * 4;             // grad_out rows of the tile (+ 1 zero row)
   static constexpr int kTableBytes = kTableInts * 4;
-  static constexpr int kVisBytes = kVisitCap * 2;
+  static constexpr int kVisBytes = kVisitCap * 4;                // visit word: result slot | grad_out row << 16
   static constexpr int kKeyBytes = (kVisitCap / kT) * 4;         // value-pixel index of every task
   static constexpr int kDirectBytes = kTQ * kSlots * 2;
   static constexpr int oRes = kRecBytes, oG = oRes + kResBytes, oTable = oG + kGBytes, oVis = oTable + kTableBytes,
@@ -99,17 +101,16 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
   constexpr int px_stride = M * 32;
   constexpr int kLv = kSlots / P;                        // level slots per query
   constexpr int kQLPasses = kTQ * kLv / kTT;             // (query, level) pairs per thread: 1 or 2
-  constexpr int kCodeShift = kSlots == 16 ? 6 : 7;       // visit code = ql << shift | pt << 2 | corner
-  constexpr int kNullCode = kTQ * kSlots * 4;            // dummy result slot, zero grad_out row
   using SM = TileSmem<kSlots>;
-  constexpr int kNullRes = SM::kPointSlots * 4;          // where the dummy result slot lives
+  constexpr int kNullRes = SM::kPointSlots * 4;          // the null visit: a zero coefficient slot ...
+  constexpr unsigned kNullVisit = (unsigned)kNullRes | ((unsigned)kTQ << 16);   // ... and the zero grad_out row
   auto slot = [](int e) { return e + (e >> 3); };        // padded point index
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* rec = reinterpret_cast<float4*>(smem_raw);
   float* res = reinterpret_cast<float*>(smem_raw + SM::oRes);
   float* gtile = reinterpret_cast<float*>(smem_raw + SM::oG);
   int* table = reinterpret_cast<int*>(smem_raw + SM::oTable);
-  unsigned short* vis = reinterpret_cast<unsigned short*>(smem_raw + SM::oVis);
+  unsigned* vis = reinterpret_cast<unsigned*>(smem_raw + SM::oVis);
   int* tpix = reinterpret_cast<int*>(smem_raw + SM::oKey);
   unsigned short* direct = reinterpret_cast<unsigned short*>(smem_raw + SM::oDirect);
   __shared__ LevelTable lt;
@@ -140,9 +141,8 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
       int4* t4 = reinterpret_cast<int4*>(table);
       for (int i = tid; i < kTableInts / 4; i += kTT) t4[i] = make_int4(0, 0, 0, 0);
       // every visit slot starts as the null visit (padding of the last task of a pixel)
-      const unsigned nn = (unsigned)kNullCode | ((unsigned)kNullCode << 16);
       uint4* v4 = reinterpret_cast<uint4*>(vis);
-      for (int i = tid; i < kVisitCap / 8; i += kTT) v4[i] = make_uint4(nn, nn, nn, nn);
+      for (int i = tid; i < kVisitCap / 4; i += kTT) v4[i] = make_uint4(kNullVisit, kNullVisit, kNullVisit, kNullVisit);
       const int ql = tid >> 2, j = tid & 3;    // grad_out rows: 4 lanes x 8 channels per query
       const int q = cur.query(ql, Lq);
       float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
@@ -309,7 +309,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
             const int k = vkey[ps][p][r];
             if (k != 0xffff) {
               const int pos = table[k] + vrank[ps][p][r];
-              vis[pos] = (unsigned short)((ql << kCodeShift) | ((lv * P + p) << 2) | r);
+              vis[pos] = (unsigned)((slot(ql * kSlots + lv * P + p) << 2) | r) | ((unsigned)ql << 16);
               const int pidx = k - wbase;
               const int wy = (pidx * magic) >> 16;
               tpix[pos / kT] = pix0 + wy * Wl + (pidx - wy * ww);   // same value from every visit of the task
@@ -336,45 +336,54 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
       auto task_of = [&](int i0) { return min(i0 + (lane >> 2), n_tasks - 1); };
       int i0 = warp * 8;
       int pix = 0;
-      uint2 codes = make_uint2(0u, 0u);
+      uint4 codes = make_uint4(0u, 0u, 0u, 0u);
       float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
       if (i0 < n_tasks) {
         const int i = task_of(i0);
         pix = tpix[i];
-        codes = *reinterpret_cast<const uint2*>(vis + kT * i);
+        codes = *reinterpret_cast<const uint4*>(vis + kT * i);
         const float* pv = vimg + (long long)pix * px_stride;
         v0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
         v1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
       }
+      const bool hi2 = (j & 2) != 0, hi1 = (j & 1) != 0;
       for (; i0 < n_tasks; i0 += kTT / 4) {
         const bool valid = i0 + (lane >> 2) < n_tasks;
         const int cur_pix = pix;
-        const uint2 cur_codes = codes;
+        const unsigned cur_codes[kT] = {codes.x, codes.y, codes.z, codes.w};
+        const unsigned my_code = j == 0 ? codes.x : (j == 1 ? codes.y : (j == 2 ? codes.z : codes.w));
         const float4 w0 = v0, w1 = v1;
         if (i0 + kTT / 4 < n_tasks) {   // warp-uniform
           const int i = task_of(i0 + kTT / 4);
           pix = tpix[i];
-          codes = *reinterpret_cast<const uint2*>(vis + kT * i);
+          codes = *reinterpret_cast<const uint4*>(vis + kT * i);
           const float* pv = vimg + (long long)pix * px_stride;
           v0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
           v1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
         }
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        float d[kT];
 #pragma unroll
         for (int s = 0; s < kT; ++s) {
-          const int code = (int)(((s & 2) ? cur_codes.y : cur_codes.x) >> ((s & 1) * 16)) & 0xffff;
-          const int e = code >> 2;
-          const int ri = code == kNullCode ? kNullRes : ((slot(e) << 2) | (code & 3));
-          const float c = res[ri];
-          const float* gr = gtile + (code >> kCodeShift) * 32;
+          const float c = res[cur_codes[s] & 0xffffu];
+          const float* gr = gtile + (cur_codes[s] >> 16) * 32;
           const float4 g0 = *reinterpret_cast<const float4*>(gr + c0);
           const float4 g1 = *reinterpret_cast<const float4*>(gr + c1);
           fma4(acc0, c, g0);
           fma4(acc1, c, g1);
-          const float d = group4_sum(dot4acc(g1, w1, dot4acc(g0, w0, 0.f)));
-          if (valid && j == 0) res[ri] = d;   // coefficient consumed: the slot now holds <grad_out, value_corner>
+          d[s] = dot4acc(g1, w1, dot4acc(g0, w0, 0.f));
         }
+        // reduce-scatter of the 4 partial dot products over the 4 lanes: lane j ends with the full sum of visit j
+        // (3 shuffles instead of 8) and stores it; the coefficient in that slot has been consumed above
+        static_assert(kT == 4, "the reduce-scatter below is written for 4 visits per task");
+        const float k0 = hi2 ? d[2] : d[0], k1 = hi2 ? d[3] : d[1];
+        const float s0 = hi2 ? d[0] : d[2], s1 = hi2 ? d[1] : d[3];
+        const float e0 = k0 + __shfl_xor_sync(kAllLanes, s0, 2, 4);   // visit (hi2 ? 2 : 0), over lane pairs
+        const float e1 = k1 + __shfl_xor_sync(kAllLanes, s1, 2, 4);   // visit (hi2 ? 3 : 1)
+        const float keep = hi1 ? e1 : e0, send = hi1 ? e0 : e1;
+        const float full = keep + __shfl_xor_sync(kAllLanes, send, 1, 4);   // visit j
         if (valid) {
+          res[my_code & 0xffffu] = full;   // <grad_out, value_corner> (the null visit's slot just gets its 0 back)
           float* pg = gvimg + (long long)cur_pix * px_stride;
           red_add_f4(pg + c0, acc0);
           red_add_f4(pg + c1, acc1);
@@ -481,7 +490,7 @@ int launch_tile(cudaStream_t st, const float* grad_out, const float* value, cons
     SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // shared memory for two CTAs; what is left of the 228 KB stays L1 for the value-pixel loads
     SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  (int)((2LL * (smem + 1024) * 100 + 233471) / 233472)));
+                                  (int)std::min(100LL, (2LL * (smem + 1024) * 100 + 233471) / 233472)));
     int b = 0;
     SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kTT, smem));
     blocks_per_sm = b > 0 ? b : 1;
