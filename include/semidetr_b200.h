@@ -304,6 +304,36 @@ int sdb_detr_loss_backward_f32(sdb_stream_t stream, const float* cls_scores, con
                                float* grad_bbox_preds);
 
 /* ------------------------------------------------------------------------------------------
+ * Pseudo-label side path of the teacher-student step on the device.
+ *
+ * sdb_pseudo_label_nms_f32: the teacher's detections -> pseudo boxes, one CTA per image, no host round trip.
+ *   Class-wise greedy NMS (mmdet multiclass_nms / mmcv batched_nms as called by
+ *   detr_od/models/dense_heads/dino_detr_ssod_head.py:1371-1395: score > score_thr, IoU > iou_thr suppresses within a
+ *   class, the first max_per_img survivors in descending score order), then -- if apply_mean_std_filter -- keep
+ *   score >= mean + std (unbiased; NaN for a single detection keeps nothing) and w > 0, h > 0
+ *   (detr_ssod/models/dino_detr_ssod.py:921-939).
+ *     scores_sorted / index_sorted (batch, num_candidates): every image's candidates in DESCENDING score order,
+ *         index = query * num_classes + class (e.g. torch.sort of the flattened sigmoid scores)
+ *     boxes_xyxy (batch, num_query, 4) pixels
+ *     out_boxes (batch, max_per_img, 4), out_scores / out_labels (batch, max_per_img): survivors in score order,
+ *         zero past out_count[b]; nms_count (optional): survivors of the NMS before the filter
+ *
+ * sdb_gmm_threshold_f32: cost threshold from a two-component 1-D Gaussian mixture on the pooled matched costs
+ *   (dino_detr_ssod.py:832-890; sklearn GaussianMixture(2, 'diag', reg_covar, means_init [min, max], weights .5/.5,
+ *   precisions 1, one init), EM in float64): threshold[0] = cost of the most likely sample assigned to component 0
+ *   (else component 1; a single cost -> itself; none -> 0), threshold[1] = number of pooled costs.
+ *     costs: num_segs segments of seg_stride floats, segment s holding seg_counts[s] (device int32) values -- the
+ *     padded all-gather buffer of the ranks, or one segment.  At most 4096 costs are pooled.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_pseudo_label_nms_f32(sdb_stream_t stream, const float* scores_sorted, const int64_t* index_sorted,
+                             const float* boxes_xyxy, int batch, int num_candidates, int num_query, int num_classes,
+                             float score_thr, float iou_thr, int max_per_img, int apply_mean_std_filter,
+                             float* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_count,
+                             int32_t* nms_count);
+int sdb_gmm_threshold_f32(sdb_stream_t stream, const float* costs, const int32_t* seg_counts, int num_segs,
+                          int seg_stride, float tol, int max_iter, double reg_covar, float* threshold);
+
+/* ------------------------------------------------------------------------------------------
  * Token-wise linear layers as tcgen05 (5th-generation tensor core) GEMMs, TF32 arithmetic on fp32 storage with
  * fp32 accumulation in tensor memory -- the three products of the nn.Linear layers on the path
  * (ms_deform_attn.py:61-65, 94-112 value_proj / sampling_offsets / attention_weights / output_proj;

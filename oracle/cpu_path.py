@@ -7,6 +7,8 @@
 * Hungarian       -> per-problem cost on torch-CPU + ``cost.cpu()`` + LSAP on the host
                      (hungarian_assigner.py:115-148), i.e. the reference's actual control flow
 * EMA             -> python loop of ``mul_`` / ``add_`` (mean_teacher.py:60-64)
+* teacher decode  -> ``ssod_oracle.pseudo_label_nms`` (torchvision batched_nms per image + the mean / std filter)
+* GMM threshold   -> ``ssod_oracle.gmm_threshold`` (float64 numpy EM, ``gmm_oracle``)
 * head loss sums  -> ``loss_oracle.detr_loss_sums`` (mmdet's focal / L1 / GIoU expressions in plain torch, targets
                      gathered from the assignment like ``_get_target_single``, dino_detr_head.py:895-980)
 
@@ -18,7 +20,7 @@ import contextlib
 
 import torch
 
-from . import hungarian_oracle, loss_oracle, msda_oracle
+from . import hungarian_oracle, loss_oracle, msda_oracle, ssod_oracle
 from .ema_oracle import ema_update
 
 
@@ -64,15 +66,18 @@ def reference_cpu_ops():
     from semi_detr_b200.matching import hungarian_assigner as ha
     from semi_detr_b200.msda import modules as msda_modules
     from semi_detr_b200.dino import fused_loss
+    from semi_detr_b200.ssod import device_ops
     from semi_detr_b200.teacher import mean_teacher as mt
     saved = (msda_modules.MSDeformAttnFunction, ha.HungarianAssigner.assign_batch, mt.EmaPlan.step,
-             fused_loss.detr_loss_sums)
+             fused_loss.detr_loss_sums, device_ops.pseudo_label_nms, device_ops.gmm_threshold)
     msda_modules.MSDeformAttnFunction = _CpuMSDeformAttnFunction
     ha.HungarianAssigner.assign_batch = _cpu_assign_batch
     mt.EmaPlan.step = _cpu_plan_step
     fused_loss.detr_loss_sums = loss_oracle.detr_loss_sums
+    device_ops.pseudo_label_nms = ssod_oracle.pseudo_label_nms
+    device_ops.gmm_threshold = ssod_oracle.gmm_threshold
     try:
         yield
     finally:
         (msda_modules.MSDeformAttnFunction, ha.HungarianAssigner.assign_batch, mt.EmaPlan.step,
-         fused_loss.detr_loss_sums) = saved
+         fused_loss.detr_loss_sums, device_ops.pseudo_label_nms, device_ops.gmm_threshold) = saved

@@ -1,13 +1,14 @@
-"""Cost threshold from a 1-D two-component Gaussian mixture -- host-side mirror of
-``DinoDetrSSOD._fit_gmm`` (detr_ssod/models/dino_detr_ssod.py:832-890).
+"""Oracle: cost threshold from a 1-D two-component Gaussian mixture -- CPU restatement of
+``DinoDetrSSOD._fit_gmm`` (detr_ssod/models/dino_detr_ssod.py:832-890).  TEST INFRASTRUCTURE ONLY: the product runs
+``sdb_gmm_threshold_f32`` (csrc/ssod.cu) and is checked against this file.
 
 The reference fits ``sklearn.mixture.GaussianMixture(2, covariance_type='diag', reg_covar=1e-5)`` initialised
 with means [min, max], weights [.5, .5], precisions [1, 1] on the matched Hungarian costs pooled over images and
 ranks (a few dozen to a few hundred scalars), and returns the cost of the most likely sample of component 0
 (falling back to component 1).  sklearn is an un-vendored, unpinned dependency of the reference
 (thirdparty/mmdetection/requirements/optional.txt:5); this is its EM loop (tol 1e-3, max_iter 100, one init)
-restated in float64 numpy for that 1-D case, pinned against sklearn 1.9 in tests/test_ssod_host.py.  The data
-is tiny and already on the host (the matched costs decide tensor shapes downstream), so this stays host code.
+restated in float64 numpy for that 1-D case, pinned against sklearn 1.9 in tests/test_ssod_host.py and against the
+reference method itself in tests/test_dino_reference_golden.py (tests/golden/ssod_gmm_golden.npz).
 """
 import numpy as np
 

@@ -15,7 +15,9 @@ What is different from the reference is where the work runs:
    in ONE device->host copy together with the per-image counts;
  * the teacher backbone runs once per step -- the reference recomputes ``teacher.extract_feat`` on the same weak
    images three times (:364, :598, :897);
- * GMM fit: float64 numpy EM on the host (``gmm.py``) instead of sklearn.
+ * the teacher's detections are decoded, NMS-ed and mean+std-filtered in one launch and the GMM cost threshold is
+   fitted by a float64 EM kernel (``device_ops``, csrc/ssod.cu): two device->host reads per step remain -- the counts
+   of pseudo boxes and of reliable / high-recall boxes, which decide tensor shapes.
 """
 import numpy as np
 import torch
@@ -31,7 +33,7 @@ from ..matching.match_cost import bbox_xyxy_to_cxcywh
 from ..registry import DETECTORS
 from . import ssod_head as _ssod_head  # noqa: F401  (registers DINODETRSSODHead)
 from .bbox_utils import Transform2D
-from .gmm import fit_gmm_threshold
+from . import device_ops
 
 
 class Projector(nn.Module):
@@ -72,18 +74,32 @@ def single_level_roi_extract(feats, rois, strides=(8, 16, 32, 64), out=7, finest
     return res
 
 
-def concat_all_gather_1d(t, max_len=4096):
-    """``concat_all_gather`` (detr_ssod/models/utils/dist_utils.py:5-30) for a 1-D tensor: one fixed-size padded
-    all_gather carrying the length in slot 0 (no separate shape exchange)."""
+def pooled_cost_segments(t, max_len=4096):
+    """``concat_all_gather`` (detr_ssod/models/utils/dist_utils.py:5-30) of a 1-D tensor without a shape exchange and
+    without reading anything back: ONE fixed-size padded all-gather with each rank's length in slot 0.
+    -> (costs, seg_counts, seg_stride) as ``device_ops.gmm_threshold`` takes them: rank r's values sit at
+    ``costs[r * seg_stride : r * seg_stride + seg_counts[r]]`` (single process: ``(t, None, None)``).
+    A rank with more than ``max_len`` values is an error, not a silent truncation."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return t
+        return t, None, None
+    if t.numel() > max_len:
+        raise ValueError(f"{t.numel()} matched costs on this rank exceed the all-gather buffer ({max_len})")
+    world = dist.get_world_size()
     buf = t.new_zeros(max_len + 1)
-    n = min(t.numel(), max_len)
-    buf[0] = n
-    buf[1:1 + n] = t[:n]
-    out = [torch.zeros_like(buf) for _ in range(dist.get_world_size())]
-    dist.all_gather(out, buf)
-    return torch.cat([o[1:1 + int(o[0])] for o in out])
+    buf[0] = t.numel()
+    buf[1:1 + t.numel()] = t
+    out = t.new_zeros(world * (max_len + 1))
+    dist.all_gather_into_tensor(out, buf)
+    counts = out.view(world, max_len + 1)[:, 0].to(torch.int32)
+    return out[1:], counts, max_len + 1
+
+
+def concat_all_gather_1d(t, max_len=4096):
+    """The pooled values as one compact tensor (reads the per-rank counts back: diagnostics and tests only)."""
+    costs, counts, stride = pooled_cost_segments(t, max_len)
+    if counts is None:
+        return costs
+    return torch.cat([costs[r * stride:r * stride + n] for r, n in enumerate(counts.tolist())])
 
 
 def dict_split(data, tags):
@@ -190,18 +206,28 @@ class DinoDetrSSOD(nn.Module):
         info = dict(img=img, img_metas=img_metas)
         feat = self.teacher.extract_feat(img)
         info["backbone_feature"] = feat
-        proposals = self.teacher.bbox_head.simple_test_bboxes(feat, img_metas, rescale=False,
-                                                              curr_step=self.curr_step, for_pseudo_label=True)
+        head = self.teacher.bbox_head
         det_bboxes, det_labels, det_scores = [], [], []
-        for boxes, labels in proposals:
-            if boxes.shape[0] == 0:
-                boxes = boxes.new_zeros(0, 5)
-            s = boxes[:, -1]
-            thr = s.mean() + s.std()
-            keep = (s >= thr) & (boxes[:, 2] - boxes[:, 0] > 0) & (boxes[:, 3] - boxes[:, 1] > 0)
-            det_bboxes.append(boxes[keep, :4])
-            det_labels.append(labels[keep])
-            det_scores.append(boxes[keep, 4])
+        if hasattr(head, "pseudo_label_detections"):
+            # decode + class-wise NMS + mean/std filter for the whole batch in one launch; the per-image counts decide
+            # tensor shapes from here on: ONE device->host read
+            boxes, scores, labels, counts = head.pseudo_label_detections(feat, img_metas, curr_step=self.curr_step)
+            for i, n in enumerate(counts.tolist()):
+                det_bboxes.append(boxes[i, :n])
+                det_labels.append(labels[i, :n])
+                det_scores.append(scores[i, :n])
+        else:   # any head that only offers the reference's list interface
+            proposals = head.simple_test_bboxes(feat, img_metas, rescale=False, curr_step=self.curr_step,
+                                                for_pseudo_label=True)
+            for boxes, labels in proposals:
+                if boxes.shape[0] == 0:
+                    boxes = boxes.new_zeros(0, 5)
+                s = boxes[:, -1]
+                thr = s.mean() + s.std()
+                keep = (s >= thr) & (boxes[:, 2] - boxes[:, 0] > 0) & (boxes[:, 3] - boxes[:, 1] > 0)
+                det_bboxes.append(boxes[keep, :4])
+                det_labels.append(labels[keep])
+                det_scores.append(boxes[keep, 4])
         info.update(det_bboxes=det_bboxes, det_labels=det_labels, det_scores=det_scores)
         info["transform_matrix"] = [torch.as_tensor(np.asarray(m["transform_matrix"]), dtype=torch.float32,
                                                     device=img.device) for m in img_metas]
@@ -218,8 +244,9 @@ class DinoDetrSSOD(nn.Module):
                                                     device=img.device) for m in img_metas]
         return info
 
-    def _fit_gmm(self, costs):
-        return fit_gmm_threshold(costs)
+    def _fit_gmm(self, costs, seg_counts=None, seg_stride=None):
+        """Cost threshold of dino_detr_ssod.py:832-890 as a 0-d DEVICE tensor (``sdb_gmm_threshold_f32``)."""
+        return device_ops.gmm_threshold(costs, seg_counts, seg_stride)[0]
 
     # ------------------------------------------------------------------------------------------------
     def unsup_loss(self, student_info, teacher_info, pseudo_bboxes, pseudo_labels, pseudo_scores):
@@ -239,7 +266,10 @@ class DinoDetrSSOD(nn.Module):
                                                                 return_cost=True)
                 matched_cost, matched_gt = [], []
                 for i in range(bs):
-                    rows = torch.nonzero(gt_inds[i] > 0).reshape(-1)         # ascending, like scipy's row_ind
+                    # the min(count, Q) matched rows in ascending order, like scipy's row_ind -- their number is known
+                    # on the host, so a stable sort of the mask replaces nonzero() (no synchronisation)
+                    k = min(counts[i], gt_inds.shape[1])
+                    rows = torch.sort((gt_inds[i] > 0).to(torch.uint8), descending=True, stable=True).indices[:k]
                     cols = gt_inds[i][rows] - 1
                     matched_gt.append(cols)
                     matched_cost.append(costs[i][rows, cols] if counts[i] else box_last.new_zeros(0))
@@ -248,22 +278,33 @@ class DinoDetrSSOD(nn.Module):
                 matched_cost = [box_last.new_zeros(0) for _ in range(bs)]
                 matched_gt = [box_last.new_zeros(0, dtype=torch.long) for _ in range(bs)]
                 cost_all = box_last.new_zeros(0)
-            thr = self._fit_gmm(concat_all_gather_1d(cost_all).detach().cpu().numpy())
+            thr = self._fit_gmm(*pooled_cost_segments(cost_all.detach()))
 
         # 2. double filter (:324-353): reliable = score >= 0.4; high-recall = reliable U {matched cost <= thr}
         base_thr = self.train_cfg["pseudo_label_initial_score_thr"]
         assert isinstance(base_thr, float), "Dynamic Threshold is not implemented yet."
         gt_b, gt_l, gt_s, hr_b, hr_l, det_b, det_l = [], [], [], [], [], [], []
+        rel_masks, keep_masks = [], []
         for i in range(bs):
             reliable = pseudo_scores[i] >= base_thr
             low_cost = torch.zeros_like(reliable)
             if matched_gt[i].numel():
-                low_cost[matched_gt[i][matched_cost[i] <= thr]] = True
-            keep = reliable | low_cost
-            gt_b.append(pseudo_bboxes[i][reliable, :4]); gt_l.append(pseudo_labels[i][reliable])
-            gt_s.append(pseudo_scores[i][reliable])
-            hr_b.append(pseudo_bboxes[i][keep, :4]); hr_l.append(pseudo_labels[i][keep])
-            det_b.append(teacher_info["det_bboxes"][i][keep, :4]); det_l.append(teacher_info["det_labels"][i][keep])
+                low_cost[matched_gt[i]] = matched_cost[i] <= thr          # distinct indices: a plain scatter
+            rel_masks.append(reliable)
+            keep_masks.append(reliable | low_cost)
+        # the sizes of the two sets decide tensor shapes: ONE device->host read for all images, then order-preserving
+        # compaction with a stable sort instead of boolean indexing (which would synchronise per use)
+        sizes = torch.stack([m.sum() for m in rel_masks + keep_masks]).tolist() if bs else []
+
+        def take(mask, k, *tensors):
+            idx = torch.sort(mask.to(torch.uint8), descending=True, stable=True).indices[:k]
+            return [t[idx] for t in tensors]
+        for i in range(bs):
+            b, l, sc = take(rel_masks[i], int(sizes[i]), pseudo_bboxes[i][:, :4], pseudo_labels[i], pseudo_scores[i])
+            gt_b.append(b); gt_l.append(l); gt_s.append(sc)
+            b, l, tb, tl = take(keep_masks[i], int(sizes[bs + i]), pseudo_bboxes[i][:, :4], pseudo_labels[i],
+                                teacher_info["det_bboxes"][i][:, :4], teacher_info["det_labels"][i])
+            hr_b.append(b); hr_l.append(l); det_b.append(tb); det_l.append(tl)
 
         head.in_warm_up = self.curr_step < head.warm_up_step
         self.teacher.bbox_head.in_warm_up = head.in_warm_up

@@ -10,28 +10,13 @@ Also here: ``forward_dummy`` (returns the decoder states and splits off the cons
 :1332-1395), and the CDN variant that tolerates images without boxes (dn_components.py:128-274).
 """
 import torch
-from torchvision.ops import nms
-from torchvision.ops.boxes import _batched_nms_vanilla
-
-
-def class_aware_nms(boxes, scores, classes, iou_threshold, max_coordinate):
-    """Per-class NMS, kept indices sorted by descending score (mmdet ``multiclass_nms`` -> mmcv ``batched_nms``,
-    dino_detr_ssod_head.py:1373-1393).  Few candidates (a trained teacher): ONE suppression pass over boxes shifted by
-    class * (max_coordinate + 1) -- no data-dependent round trip per class.  Many candidates (an untrained teacher
-    puts ~36 000 (query, class) pairs above 0.01): the per-class loop, because the single pass costs n^2 / 64 mask
-    words however few pairs can overlap (measured: 250 ms for one 36 000-box pass).  Same keep set either way."""
-    if boxes.numel() == 0:
-        return torch.zeros(0, dtype=torch.long, device=boxes.device)
-    if boxes.shape[0] > 4000:
-        return _batched_nms_vanilla(boxes, scores, classes, iou_threshold)
-    shifted = boxes + (classes.to(boxes.dtype) * (max_coordinate + 1.0))[:, None]
-    return nms(shifted, scores, iou_threshold)
 
 from ..consts import device_const
 from ..dino.dn_components import prepare_for_cdn
 from ..dino.head import LOSS_PARTS, DINODETRHead, _clamp_min1, reduce_mean_scalar
 from ..dino.losses import giou_aligned
 from ..matching.match_cost import bbox_cxcywh_to_xyxy, bbox_xyxy_to_cxcywh
+from . import device_ops
 from ..registry import BBOX_ASSIGNERS, HEADS, LOSSES
 from . import o2m_assigner as _o2m  # noqa: F401  (registers O2MAssigner)
 from . import task_aligned_focal_loss as _tal  # noqa: F401
@@ -173,32 +158,50 @@ class DINODETRSSODHead(DINODETRHead):
                          gt_bboxes_ignore=gt_bboxes_ignore, is_pseudo_label=is_pseudo_label)
 
     # ---------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def simple_test_bboxes(self, feats, img_metas, rescale=False, curr_step=None, for_pseudo_label=False):
-        """Teacher decoding for pseudo labels (:1281-1400): last decoder layer, sigmoid, class-wise NMS.
-        -> list of (det_bboxes (n, 5) [x1 y1 x2 y2 score], det_labels (n,))"""
-        if curr_step is not None:
-            self.in_warm_up = curr_step < self.warm_up_step
+    def _decode_last_layer(self, feats, img_metas, rescale=False):
+        """Last decoder layer -> (sigmoid scores (B, Q, C), xyxy boxes in pixels clamped to the image (B, Q, 4))
+        (dino_detr_ssod_head.py:1332-1370)."""
         cls_all, coord_all = self.forward(feats, img_metas)[:2]
         cls, box = cls_all[-1], coord_all[-1]
+        dev = cls.device
+        whs = tuple((float(m["img_shape"][1]), float(m["img_shape"][0])) for m in img_metas)
+        wh = device_const(dev, "img_wh", whs, lambda: torch.tensor(whs, dtype=torch.float32).reshape(-1, 2))
+        whwh = torch.cat([wh, wh], 1)[:, None, :]                                  # (B, 1, 4)
+        b = torch.minimum((bbox_cxcywh_to_xyxy(box) * whwh).clamp(min=0), whwh)
+        if rescale:
+            sf = tuple(tuple(float(v) for v in m["scale_factor"]) for m in img_metas)
+            b = b / device_const(dev, "scale_factor", sf, lambda: torch.tensor(sf, dtype=torch.float32))[:, None, :]
+        return cls.sigmoid(), b
+
+    @torch.no_grad()
+    def pseudo_label_detections(self, feats, img_metas, curr_step=None, mean_std_filter=True):
+        """The teacher's pseudo boxes without leaving the device: class-wise NMS (score > 0.01, IoU 0.6, top
+        ``max_per_img``; :1371-1395) and, by default, the ``score >= mean + std`` / non-degenerate filter of
+        detr_ssod/models/dino_detr_ssod.py:921-939, in ONE launch for the whole batch (``sdb_pseudo_label_nms_f32``).
+        -> boxes (B, max_per_img, 4), scores (B, max_per_img), labels (B, max_per_img), count (B,) int32 on the device."""
+        if curr_step is not None:
+            self.in_warm_up = curr_step < self.warm_up_step
+        scores, b = self._decode_last_layer(feats, img_metas)
+        max_per_img = (self.test_cfg or {}).get("max_per_img", self.num_query)
+        ob, os_, ol, cnt, _ = device_ops.pseudo_label_nms(scores, b, 0.01, 0.6, max_per_img, mean_std_filter)
+        return ob, os_, ol, cnt
+
+    @torch.no_grad()
+    def simple_test_bboxes(self, feats, img_metas, rescale=False, curr_step=None, for_pseudo_label=False):
+        """Teacher decoding (:1281-1400): last decoder layer, sigmoid, class-wise NMS (warm-up / pseudo labels) or plain
+        top-k.  -> list of (det_bboxes (n, 5) [x1 y1 x2 y2 score], det_labels (n,)); the list form costs one
+        device->host read of the per-image counts."""
+        if curr_step is not None:
+            self.in_warm_up = curr_step < self.warm_up_step
+        scores, b = self._decode_last_layer(feats, img_metas, rescale)
         max_per_img = (self.test_cfg or {}).get("max_per_img", self.num_query)
         results = []
-        for i, meta in enumerate(img_metas):
-            h, w = meta["img_shape"][:2]
-            scores = cls[i].sigmoid()
-            b = bbox_cxcywh_to_xyxy(box[i])
-            b = torch.stack([(b[:, 0] * w).clamp(0, w), (b[:, 1] * h).clamp(0, h),
-                             (b[:, 2] * w).clamp(0, w), (b[:, 3] * h).clamp(0, h)], -1)
-            if rescale:
-                b = b / b.new_tensor(meta["scale_factor"])
-            if self.in_warm_up or for_pseudo_label:
-                # mmdet multiclass_nms: every (query, class) pair above the score threshold competes
-                keep_mask = scores > 0.01
-                q_idx, c_idx = keep_mask.nonzero(as_tuple=True)
-                bb, ss = b[q_idx], scores[q_idx, c_idx]
-                keep = class_aware_nms(bb, ss, c_idx, 0.6, float(max(h, w)))[:max_per_img]
-                results.append((torch.cat([bb[keep], ss[keep, None]], 1), c_idx[keep]))
-            else:
-                s, idx = scores.reshape(-1).topk(max_per_img)
-                results.append((torch.cat([b[idx // self.num_classes], s[:, None]], 1), idx % self.num_classes))
+        if self.in_warm_up or for_pseudo_label:
+            ob, os_, ol, cnt, _ = device_ops.pseudo_label_nms(scores, b, 0.01, 0.6, max_per_img, False)
+            for i, n in enumerate(cnt.tolist()):
+                results.append((torch.cat([ob[i, :n], os_[i, :n, None]], 1), ol[i, :n]))
+        else:
+            for i in range(scores.shape[0]):
+                s, idx = scores[i].reshape(-1).topk(max_per_img)
+                results.append((torch.cat([b[i][idx // self.num_classes], s[:, None]], 1), idx % self.num_classes))
         return results

