@@ -1,0 +1,51 @@
+"""Two-rank check of the overlapped gradient exchange (engine.FusedSupervisedTrainStep._overlapped_backward):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_overlap.py
+
+Each rank builds the same model twice, runs 2 steps on its own batch with the single post-backward all-reduce and with the
+two-bucket overlapped one, and compares gradients and parameters (same sums in the same order per element: equal up to
+NCCL's reduction order, 1e-6).  Prints one JSON line on rank 0."""
+import copy
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from semi_detr_b200 import dino  # noqa: E402,F401
+from semi_detr_b200.engine import FusedSupervisedTrainStep  # noqa: E402
+from semi_detr_b200.registry import DETECTORS  # noqa: E402
+from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch  # noqa: E402
+
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+torch.manual_seed(0)
+cfg = copy.deepcopy(DINO_R50_4SCALE)
+cfg["bbox_head"]["transformer"] = dict(type="DINOTransformer", num_encoder_layers=2, num_decoder_layers=2)
+base = DETECTORS.build(cfg).to(dev).train()
+data = coco_like_batch(2, 320, 416, seed=10 + rank, device=dev)
+out = {}
+for mode in (False, True):
+    model = copy.deepcopy(base)
+    step = FusedSupervisedTrainStep(model, world_size=2, overlap=mode)
+    torch.manual_seed(123)                      # same CDN noise in both runs
+    losses = [float(step(dict(data, img_metas=[dict(m) for m in data["img_metas"]]))[0]) for _ in range(2)]
+    out[mode] = (losses, step.opt.flat_g.clone(), step.opt.flat_p.clone())
+g0, g1 = out[False][1], out[True][1]
+p0, p1 = out[False][2], out[True][2]
+res = dict(losses_single=out[False][0], losses_overlapped=out[True][0],
+           grad_rel=float((g0 - g1).norm() / g0.norm()), param_rel=float((p0 - p1).norm() / p0.norm()))
+ok = res["grad_rel"] < 1e-5 and res["param_rel"] < 1e-6 and all(
+    abs(a - b) <= 1e-5 * abs(a) for a, b in zip(*[out[m][0] for m in (False, True)]))
+res["ok"] = bool(ok)
+if rank == 0:
+    print(json.dumps(res), flush=True)
+torch.cuda.synchronize()
+dist.barrier()
+os._exit(0 if ok else 1)
