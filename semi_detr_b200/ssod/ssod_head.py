@@ -20,7 +20,7 @@ from . import device_ops
 from ..registry import BBOX_ASSIGNERS, HEADS, LOSSES
 from . import o2m_assigner as _o2m  # noqa: F401  (registers O2MAssigner)
 from . import task_aligned_focal_loss as _tal  # noqa: F401
-from .o2m_assigner import normalized_alignment_metrics
+from .o2m_assigner import assign_layers, normalized_alignment_metrics
 
 
 def _reduce_mean_tensor(t):
@@ -66,46 +66,49 @@ class DINODETRSSODHead(DINODETRHead):
 
     # ---------------------------------------------------------------------------------------------
     def _warmup_terms(self, cls_stack, box_stack, gt_bboxes_list, gt_labels_list, img_metas, labels_override=None):
-        """O2M phase (:665-738): per (layer, image) assignment with the one-to-many assigner; returns per-layer
-        losses.  cls_stack (layers, bs, Q, C), box_stack (layers, bs, Q, 4)."""
+        """O2M phase (:665-738): one-to-many assignment of every (layer, image) problem, TaskAlignedFocalLoss and box
+        losses weighted by the normalised alignment metric; returns per-layer losses.  cls_stack (layers, bs, Q, C),
+        box_stack (layers, bs, Q, 4).  All layers of an image are assigned in one vectorised pass and the losses of
+        all layers are formed together (the reference: layers x images python-level calls, ~60 launches each)."""
         layers, bs, Q, C = cls_stack.shape
         dev = cls_stack.device
-        out = {k: [] for k in LOSS_PARTS}
-        for l in range(layers):
-            labels, box_t, box_w, metrics, facs = [], [], [], [], []
-            for i in range(bs):
-                gl = gt_labels_list[i] if labels_override is None or l < layers - 1 else labels_override[i]
-                h, w, _ = img_metas[i]["img_shape"]
-                fac = device_const(dev, "whwh", (w, h), lambda: torch.tensor([w, h, w, h], dtype=torch.float32))
-                res = self.assigner1.assign(box_stack[l, i].detach(), cls_stack[l, i].detach().sigmoid(),
-                                            gt_bboxes_list[i], gl, img_metas[i])
-                pos = res.gt_inds > 0
-                g = (res.gt_inds - 1).clamp(min=0)
-                if gt_bboxes_list[i].shape[0] > 0:
-                    lab = torch.where(pos, gl.long()[g], torch.full_like(g, self.num_classes))
-                    bt = bbox_xyxy_to_cxcywh(gt_bboxes_list[i][g] / fac) * pos[:, None]
-                    nm = normalized_alignment_metrics(res)
-                else:
-                    lab = torch.full((Q,), self.num_classes, dtype=torch.long, device=dev)
-                    bt = torch.zeros((Q, 4), device=dev)
-                    nm = torch.zeros((Q,), device=dev)
-                labels.append(lab); box_t.append(bt); metrics.append(nm)
-                box_w.append(nm[:, None].expand(-1, 4))
-                facs.append(fac[None].expand(Q, 4))
-            labels, box_t, box_w = torch.cat(labels), torch.cat(box_t), torch.cat(box_w)
-            metrics, facs = torch.cat(metrics), torch.cat(facs)
-            cls = cls_stack[l].reshape(-1, C)
-            box = box_stack[l].reshape(-1, 4)
-            sum_metrics = _reduce_mean_tensor(metrics.sum().reshape(1)).clamp(min=1.0)
-            out["loss_cls"].append(self.loss_cls1(cls.sigmoid(), labels, metrics, avg_factor=sum_metrics))
-            reg_avg = _reduce_mean_tensor(box_w[:, 0].sum().reshape(1)).clamp(min=1.0)
-            giou = giou_aligned(bbox_cxcywh_to_xyxy(box) * facs, bbox_cxcywh_to_xyxy(box_t) * facs, self.loss_iou.eps)
-            out["loss_iou"].append(((1 - giou) * box_w[:, 0]).sum() / reg_avg[0] * self.loss_iou.loss_weight)
-            l1 = (box - box_t).abs() * box_w
-            out["loss_bbox"].append(l1.sum() / reg_avg[0] * self.loss_bbox.loss_weight)
-            out["loss_bbox_xy"].append(l1[:, :2].sum() / reg_avg[0] * self.loss_bbox.loss_weight)
-            out["loss_bbox_hw"].append(l1[:, 2:].sum() / reg_avg[0] * self.loss_bbox.loss_weight)
-        return {k: torch.stack([x.reshape(()) for x in v]) for k, v in out.items()}
+        prob = cls_stack.sigmoid()
+        labels, box_t, metrics, facs = [], [], [], []
+        for i in range(bs):
+            gl = gt_labels_list[i].long()
+            G = gt_bboxes_list[i].shape[0]
+            h, w, _ = img_metas[i]["img_shape"]
+            fac = device_const(dev, "whwh", (w, h), lambda: torch.tensor([w, h, w, h], dtype=torch.float32))
+            if G > 0:
+                gl_layers = gl[None].expand(layers, G)
+                if labels_override is not None:      # the last row (encoder proposals) is matched against class 0
+                    gl_layers = torch.cat([gl_layers[:-1], labels_override[i].long()[None]])
+                gt_inds, _, _, nm = assign_layers(self.assigner1, box_stack[:, i].detach(), prob[:, i].detach(),
+                                                  gt_bboxes_list[i], gl_layers, img_metas[i])
+                pos = gt_inds > 0
+                g = (gt_inds - 1).clamp(min=0)
+                lab = torch.where(pos, gl_layers.gather(1, g), torch.full_like(g, self.num_classes))
+                bt = bbox_xyxy_to_cxcywh(gt_bboxes_list[i] / fac)[g] * pos[..., None]
+            else:
+                lab = torch.full((layers, Q), self.num_classes, dtype=torch.long, device=dev)
+                bt = torch.zeros((layers, Q, 4), device=dev)
+                nm = torch.zeros((layers, Q), device=dev)
+            labels.append(lab); box_t.append(bt); metrics.append(nm)
+            facs.append(fac[None, None].expand(layers, Q, 4))
+        labels, box_t = torch.stack(labels, 1), torch.stack(box_t, 1)            # (layers, bs, Q[, 4])
+        metrics, facs = torch.stack(metrics, 1), torch.stack(facs, 1)
+        sum_metrics = _reduce_mean_tensor(metrics.sum((1, 2))).clamp(min=1.0)    # (layers,): one all-reduce
+        tal = self.loss_cls1(prob.reshape(layers, bs * Q, C), labels.reshape(layers, bs * Q),
+                             metrics.reshape(layers, bs * Q), reduction_override="none")
+        w = metrics[..., None]
+        giou = giou_aligned(bbox_cxcywh_to_xyxy(box_stack) * facs, bbox_cxcywh_to_xyxy(box_t) * facs, self.loss_iou.eps)
+        l1 = (box_stack - box_t).abs() * w
+        reg_avg = sum_metrics                                                     # the same sum, the same clamp
+        return dict(loss_cls=tal.sum((1, 2)) / sum_metrics,
+                    loss_iou=((1 - giou) * metrics).sum((1, 2)) / reg_avg * self.loss_iou.loss_weight,
+                    loss_bbox=l1.sum((1, 2, 3)) / reg_avg * self.loss_bbox.loss_weight,
+                    loss_bbox_xy=l1[..., :2].sum((1, 2, 3)) / reg_avg * self.loss_bbox.loss_weight,
+                    loss_bbox_hw=l1[..., 2:].sum((1, 2, 3)) / reg_avg * self.loss_bbox.loss_weight)
 
     def loss(self, all_cls_scores, all_bbox_preds, enc_cls_scores, enc_bbox_preds, dn_cls_scores, dn_bbox_preds,
              gt_bboxes_list, gt_labels_list, gt_scores_list=None, img_metas=None, dn_metas=None,
