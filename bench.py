@@ -299,7 +299,7 @@ def run_ours(args):
     if args.torch_optimizer:
         step = SupervisedTrainStep(model, build_optimizer(model, capturable=True), world_size=world)
     else:   # clip + AdamW as one kernel over flat buffers (sdb_adamw_ema_step_f32)
-        step = FusedSupervisedTrainStep(model, world_size=world)
+        step = FusedSupervisedTrainStep(model, world_size=world, overlap=os.environ.get("SDB_OVERLAP", "1") != "0")
     host = coco_like_batch(PER_GPU_BATCH, IMG_H, IMG_W, seed=rank, pin=True)
 
     def to_device(b):

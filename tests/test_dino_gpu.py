@@ -181,3 +181,4 @@ def test_full_size_step_runs_and_is_finite():
     assert n["msda_forward"] + n["msda_fused_forward"] == 24 and n["msda_backward"] + n["msda_fused_backward"] == 24
     assert n["msda_fused_forward"] == 24, "the shipped config takes the fused-prologue kernels"
     assert n["lsap_solve"] == 2 and n["match_cost"] == 2 and n["layernorm_forward"] == 2 * 37
+    assert n["detr_loss_forward"] == 4, "matched + denoising losses of each step go through the fused loss kernel"
