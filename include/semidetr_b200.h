@@ -238,6 +238,18 @@ int sdb_layernorm_forward_f32(sdb_stream_t stream, const float* x, const float* 
 int sdb_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float* x, const float* gamma,
                                const float* mean, const float* rstd, int64_t rows, int cols, float* dx,
                                float* dgamma, float* dbeta, float* workspace);
+/* The post-norm blocks of the DINO layers, `x = norm(x + dropout(sublayer(x)))` (transformer.py:606-642, 762-791), with
+ * the residual add inside the LayerNorm pass: y = LN(x + residual) (residual may be NULL).  Optionally the kernel also
+ * writes y_plus_pos = y + pos -- the next encoder layer's query (`with_pos_embed`, transformer.py:635) -- from the
+ * registers that hold y.  backward: dx = d(x + residual) from dy (+ dy_plus_pos, may be NULL); the caller hands the same
+ * dx to both addends.  x / residual are re-read and re-added, so no (rows, 256) sum is kept between the passes. */
+int sdb_add_layernorm_forward_f32(sdb_stream_t stream, const float* x, const float* residual, const float* gamma,
+                                  const float* beta, int64_t rows, int cols, float eps, float* y, float* mean,
+                                  float* rstd, const float* pos, float* y_plus_pos);
+int sdb_add_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float* dy_plus_pos, const float* x,
+                                   const float* residual, const float* gamma, const float* mean, const float* rstd,
+                                   int64_t rows, int cols, float* dx, float* dgamma, float* dbeta, float* workspace);
+
 
 /* ------------------------------------------------------------------------------------------
  * Column sums of a row-major (rows, cols) fp32 matrix into out[cols] (zero-filled by the call): the bias gradient

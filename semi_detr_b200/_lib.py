@@ -43,6 +43,8 @@ SIGNATURES = {
     "sdb_gemm_tf32": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "sdb_layernorm_bwd_workspace_floats": [],
     "sdb_layernorm_forward_f32": [c_void_p] * 4 + [ctypes.c_int64, c_int, c_float] + [c_void_p] * 3,
+    "sdb_add_layernorm_forward_f32": [c_void_p] * 5 + [ctypes.c_int64, c_int, c_float] + [c_void_p] * 5,
+    "sdb_add_layernorm_backward_f32": [c_void_p] * 8 + [ctypes.c_int64, c_int] + [c_void_p] * 4,
     "sdb_layernorm_backward_f32": [c_void_p] * 6 + [ctypes.c_int64, c_int] + [c_void_p] * 4,
 }
 

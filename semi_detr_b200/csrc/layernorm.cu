@@ -24,9 +24,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __global__ void __launch_bounds__(kLnThreads)
-layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     long long rows, float eps, float* __restrict__ y, float* __restrict__ mean,
-                     float* __restrict__ rstd) {
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, long long rows, float eps, float* __restrict__ y,
+                     float* __restrict__ mean, float* __restrict__ rstd, const float* __restrict__ pos,
+                     float* __restrict__ y_plus_pos) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * kLnThreads + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * kLnThreads) >> 5;
@@ -34,7 +35,13 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   const float4 b0 = reinterpret_cast<const float4*>(beta)[lane], b1 = reinterpret_cast<const float4*>(beta)[32 + lane];
   for (long long r = warp; r < rows; r += nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + r * kLnCols);
-    const float4 a = ld_stream_f4(xr + lane), b = ld_stream_f4(xr + 32 + lane);
+    float4 a = ld_stream_f4(xr + lane), b = ld_stream_f4(xr + 32 + lane);
+    if (residual) {   // y = LN(x + residual): the post-norm residual add of the layer rides in this pass
+      const float4* rr = reinterpret_cast<const float4*>(residual + r * kLnCols);
+      const float4 ra = ld_stream_f4(rr + lane), rb = ld_stream_f4(rr + 32 + lane);
+      a = make_float4(a.x + ra.x, a.y + ra.y, a.z + ra.z, a.w + ra.w);
+      b = make_float4(b.x + rb.x, b.y + rb.y, b.z + rb.z, b.w + rb.w);
+    }
     const float mu = warp_sum(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w) * (1.f / kLnCols);
     const float4 da = make_float4(a.x - mu, a.y - mu, a.z - mu, a.w - mu);
     const float4 db = make_float4(b.x - mu, b.y - mu, b.z - mu, b.w - mu);
@@ -42,16 +49,26 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
                                db.z * db.z + db.w * db.w) * (1.f / kLnCols);
     const float rs = rsqrtf(var + eps);
     float4* yr = reinterpret_cast<float4*>(y + r * kLnCols);
-    st_stream_f4(yr + lane, make_float4(da.x * rs * g0.x + b0.x, da.y * rs * g0.y + b0.y, da.z * rs * g0.z + b0.z,
-                                        da.w * rs * g0.w + b0.w));
-    st_stream_f4(yr + 32 + lane, make_float4(db.x * rs * g1.x + b1.x, db.y * rs * g1.y + b1.y,
-                                             db.z * rs * g1.z + b1.z, db.w * rs * g1.w + b1.w));
+    const float4 ya = make_float4(da.x * rs * g0.x + b0.x, da.y * rs * g0.y + b0.y, da.z * rs * g0.z + b0.z,
+                                  da.w * rs * g0.w + b0.w);
+    const float4 yb = make_float4(db.x * rs * g1.x + b1.x, db.y * rs * g1.y + b1.y, db.z * rs * g1.z + b1.z,
+                                  db.w * rs * g1.w + b1.w);
+    st_stream_f4(yr + lane, ya);
+    st_stream_f4(yr + 32 + lane, yb);
+    if (y_plus_pos) {   // the next layer's query = output + positional embedding, written from registers
+      const float4* pr = reinterpret_cast<const float4*>(pos + r * kLnCols);
+      const float4 pa = ld_stream_f4(pr + lane), pb = ld_stream_f4(pr + 32 + lane);
+      float4* qr = reinterpret_cast<float4*>(y_plus_pos + r * kLnCols);
+      st_stream_f4(qr + lane, make_float4(ya.x + pa.x, ya.y + pa.y, ya.z + pa.z, ya.w + pa.w));
+      st_stream_f4(qr + 32 + lane, make_float4(yb.x + pb.x, yb.y + pb.y, yb.z + pb.z, yb.w + pb.w));
+    }
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
   }
 }
 
 __global__ void __launch_bounds__(kLnThreads)
-layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ x,
+                     const float* __restrict__ residual, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, long long rows,
                      float* __restrict__ dx, float* __restrict__ partial /* [grid][2][256] */) {
   __shared__ float s_acc[kLnThreads / 32][2][kLnCols];
@@ -63,8 +80,20 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   for (long long r = warp; r < rows; r += nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + r * kLnCols);
     const float4* dr = reinterpret_cast<const float4*>(dy + r * kLnCols);
-    const float4 xa = ld_stream_f4(xr + lane), xb = ld_stream_f4(xr + 32 + lane);
-    const float4 da = ld_stream_f4(dr + lane), db = ld_stream_f4(dr + 32 + lane);
+    float4 xa = ld_stream_f4(xr + lane), xb = ld_stream_f4(xr + 32 + lane);
+    float4 da = ld_stream_f4(dr + lane), db = ld_stream_f4(dr + 32 + lane);
+    if (residual) {   // the normalised input was x + residual
+      const float4* rr = reinterpret_cast<const float4*>(residual + r * kLnCols);
+      const float4 ra = ld_stream_f4(rr + lane), rb = ld_stream_f4(rr + 32 + lane);
+      xa = make_float4(xa.x + ra.x, xa.y + ra.y, xa.z + ra.z, xa.w + ra.w);
+      xb = make_float4(xb.x + rb.x, xb.y + rb.y, xb.z + rb.z, xb.w + rb.w);
+    }
+    if (dy2) {        // gradient of the second output (y + pos) adds to the gradient of y
+      const float4* d2 = reinterpret_cast<const float4*>(dy2 + r * kLnCols);
+      const float4 ea = ld_stream_f4(d2 + lane), eb = ld_stream_f4(d2 + 32 + lane);
+      da = make_float4(da.x + ea.x, da.y + ea.y, da.z + ea.z, da.w + ea.w);
+      db = make_float4(db.x + eb.x, db.y + eb.y, db.z + eb.z, db.w + eb.w);
+    }
     const float mu = mean[r], rs = rstd[r];
     const float xh[8] = {(xa.x - mu) * rs, (xa.y - mu) * rs, (xa.z - mu) * rs, (xa.w - mu) * rs,
                          (xb.x - mu) * rs, (xb.y - mu) * rs, (xb.z - mu) * rs, (xb.w - mu) * rs};
@@ -141,15 +170,36 @@ extern "C" int sdb_layernorm_forward_f32(sdb_stream_t stream, const float* x, co
   SDB_REQUIRE(x && gamma && beta && y && mean && rstd, "layernorm_forward: null pointer");
   SDB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
                 reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "layernorm_forward: pointers must be 16-byte aligned");
-  sdb::layernorm_fwd_kernel<<<sdb::ln_grid(rows), sdb::kLnThreads, 0, (cudaStream_t)stream>>>(x, gamma, beta, rows,
-                                                                                             eps, y, mean, rstd);
+  sdb::layernorm_fwd_kernel<<<sdb::ln_grid(rows), sdb::kLnThreads, 0, (cudaStream_t)stream>>>(
+      x, nullptr, gamma, beta, rows, eps, y, mean, rstd, nullptr, nullptr);
   SDB_LAUNCH_CHECK("layernorm_fwd_kernel");
   return SDB_OK;
 }
 
-extern "C" int sdb_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float* x, const float* gamma,
-                                          const float* mean, const float* rstd, int64_t rows, int cols, float* dx,
-                                          float* dgamma, float* dbeta, float* workspace) {
+extern "C" int sdb_add_layernorm_forward_f32(sdb_stream_t stream, const float* x, const float* residual,
+                                             const float* gamma, const float* beta, int64_t rows, int cols, float eps,
+                                             float* y, float* mean, float* rstd, const float* pos, float* y_plus_pos) {
+  SDB_REQUIRE(rows >= 0 && cols > 0, "add_layernorm_forward: bad sizes rows=%lld cols=%d", (long long)rows, cols);
+  if (cols != sdb::kLnCols) {
+    sdb::set_error("add_layernorm_forward: cols=%d (only d_model=%d is built)", cols, sdb::kLnCols);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  if (rows == 0) return SDB_OK;
+  SDB_REQUIRE(x && gamma && beta && y && mean && rstd, "add_layernorm_forward: null pointer");
+  SDB_REQUIRE((pos == nullptr) == (y_plus_pos == nullptr), "add_layernorm_forward: pos and y_plus_pos go together");
+  SDB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(residual) |
+                reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(y_plus_pos)) & 15) == 0,
+              "add_layernorm_forward: pointers must be 16-byte aligned");
+  sdb::layernorm_fwd_kernel<<<sdb::ln_grid(rows), sdb::kLnThreads, 0, (cudaStream_t)stream>>>(
+      x, residual, gamma, beta, rows, eps, y, mean, rstd, pos, y_plus_pos);
+  SDB_LAUNCH_CHECK("layernorm_fwd_kernel");
+  return SDB_OK;
+}
+
+static int layernorm_backward(sdb_stream_t stream, const float* dy, const float* dy2, const float* x,
+                              const float* residual, const float* gamma, const float* mean, const float* rstd,
+                              int64_t rows, int cols, float* dx, float* dgamma, float* dbeta, float* workspace) {
   SDB_REQUIRE(rows >= 0 && cols > 0, "layernorm_backward: bad sizes rows=%lld cols=%d", (long long)rows, cols);
   if (cols != sdb::kLnCols) {
     sdb::set_error("layernorm_backward: cols=%d (only d_model=%d is built)", cols, sdb::kLnCols);
@@ -158,13 +208,28 @@ extern "C" int sdb_layernorm_backward_f32(sdb_stream_t stream, const float* dy, 
   SDB_REQUIRE(dgamma && dbeta && workspace, "layernorm_backward: null pointer");
   SDB_REQUIRE(rows == 0 || (dy && x && gamma && mean && rstd && dx), "layernorm_backward: null pointer");
   SDB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
-                reinterpret_cast<uintptr_t>(gamma)) & 15) == 0, "layernorm_backward: pointers must be 16-byte aligned");
+                reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(dy2) |
+                reinterpret_cast<uintptr_t>(residual)) & 15) == 0, "layernorm_backward: pointers must be 16-byte aligned");
   const int grid = sdb::ln_grid(rows);
-  sdb::layernorm_bwd_kernel<<<grid, sdb::kLnThreads, 0, (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, rows, dx,
-                                                                                workspace);
+  sdb::layernorm_bwd_kernel<<<grid, sdb::kLnThreads, 0, (cudaStream_t)stream>>>(dy, dy2, x, residual, gamma, mean, rstd,
+                                                                                rows, dx, workspace);
   SDB_LAUNCH_CHECK("layernorm_bwd_kernel");
   sdb::layernorm_bwd_finish_kernel<<<2 * sdb::kLnCols / 8, 256, 0, (cudaStream_t)stream>>>(workspace, grid, dgamma,
                                                                                           dbeta);
   SDB_LAUNCH_CHECK("layernorm_bwd_finish_kernel");
   return SDB_OK;
+}
+
+extern "C" int sdb_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float* x, const float* gamma,
+                                          const float* mean, const float* rstd, int64_t rows, int cols, float* dx,
+                                          float* dgamma, float* dbeta, float* workspace) {
+  return layernorm_backward(stream, dy, nullptr, x, nullptr, gamma, mean, rstd, rows, cols, dx, dgamma, dbeta, workspace);
+}
+
+extern "C" int sdb_add_layernorm_backward_f32(sdb_stream_t stream, const float* dy, const float* dy_plus_pos,
+                                              const float* x, const float* residual, const float* gamma,
+                                              const float* mean, const float* rstd, int64_t rows, int cols, float* dx,
+                                              float* dgamma, float* dbeta, float* workspace) {
+  return layernorm_backward(stream, dy, dy_plus_pos, x, residual, gamma, mean, rstd, rows, cols, dx, dgamma, dbeta,
+                            workspace);
 }

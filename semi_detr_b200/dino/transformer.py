@@ -129,12 +129,15 @@ class DINOTransformerEncoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = LayerNorm(d_model)
 
-    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
-        q = src if pos is None else src + pos
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None,
+                query=None, next_pos=None):
+        """``query``: ``src + pos`` if the caller already has it (the previous layer's second output); ``next_pos``: also
+        return ``out + next_pos`` -- both additions then ride in the LayerNorm kernels (``LayerNorm.add_norm``)."""
+        q = query if query is not None else (src if pos is None else src + pos)
         src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, key_padding_mask)
-        src = self.norm1(src + self.dropout1(src2))
+        src = self.norm1.add_norm(src, self.dropout1(src2))
         src2 = self.linear2(self.dropout2(self.linear1(src, relu=True)))
-        return self.norm2(src + self.dropout3(src2))
+        return self.norm2.add_norm(src, self.dropout3(src2), next_pos)
 
 
 class DINOTransformerEncoder(nn.Module):
@@ -169,8 +172,13 @@ class DINOTransformerEncoder(nn.Module):
         out = src
         if reference_points is None:
             reference_points = self.get_reference_points(spatial_shapes_list, valid_ratios, src.device)
-        for layer in self.layers:
-            out = layer(out, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask)
+        query = None
+        for i, layer in enumerate(self.layers):
+            # every layer but the last also emits the next layer's query (out + pos) from its final LayerNorm pass
+            nxt = pos if (pos is not None and i + 1 < len(self.layers)) else None
+            res = layer(out, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask, query=query,
+                        next_pos=nxt)
+            out, query = res if nxt is not None else (res, None)
         if self.norm is not None:
             out = self.norm(out)
         return out
@@ -230,15 +238,15 @@ class DINOTransformerDecoderLayer(nn.Module):
         for name in self.module_seq:
             if name == "sa":
                 tgt2 = self._self_attention(tgt + query_pos, tgt, self_attn_mask)
-                tgt = self.norm2(tgt + self.dropout2(tgt2))
+                tgt = self.norm2.add_norm(tgt, self.dropout2(tgt2))
             elif name == "ca":
                 tgt2 = self.cross_attn((tgt + query_pos).transpose(0, 1), reference_points.transpose(0, 1).contiguous(),
                                        memory, spatial_shapes, level_start_index,
                                        memory_key_padding_mask).transpose(0, 1)
-                tgt = self.norm1(tgt + self.dropout1(tgt2))
+                tgt = self.norm1.add_norm(tgt, self.dropout1(tgt2))
             else:
                 tgt2 = self.linear2(self.dropout3(self.linear1(tgt, relu=True)))
-                tgt = self.norm3(tgt + self.dropout4(tgt2))
+                tgt = self.norm3.add_norm(tgt, self.dropout4(tgt2))
         return tgt
 
 

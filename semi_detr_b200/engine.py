@@ -378,11 +378,17 @@ class FusedSupervisedTrainStep:
         for m in data["img_metas"]:
             m["batch_input_shape"] = batch_input_shape
         feats = model.extract_feat(data["img"])
+        # the head sees detached copies of the backbone features: segment 1 then stops exactly at the cut (the feature
+        # levels are nested outputs of one convolution chain, so a cut on the live tensors would run -- and free --
+        # part of the backbone graph already in segment 1)
+        cut_in = [f.detach().requires_grad_(f.requires_grad) for f in feats]
         rest = {k: v for k, v in data.items() if k not in ("img", "img_metas", "gt_bboxes", "gt_labels")}
-        losses = model.bbox_head.forward_train(feats, data["img_metas"], data["gt_bboxes"], data["gt_labels"], **rest)
+        losses = model.bbox_head.forward_train(tuple(cut_in), data["img_metas"], data["gt_bboxes"], data["gt_labels"],
+                                               **rest)
         loss, log_vars = model._parse_losses(losses)
-        cut = [f for f in feats if f.requires_grad]
-        g = torch.autograd.grad(loss, head_params + cut, allow_unused=True)
+        live = [i for i, f in enumerate(feats) if f.requires_grad]
+        cut = [feats[i] for i in live]
+        g = torch.autograd.grad(loss, head_params + [cut_in[i] for i in live], allow_unused=True)
         self._pack(g[:n_head], head_params)
         b = opt._bounds
         work1 = dist.all_reduce(opt.flat_g[b[0]:b[1]], async_op=True)

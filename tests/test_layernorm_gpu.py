@@ -62,3 +62,32 @@ def test_linear_backward_matches_nn_linear():
     rel = lambda u, v: ((u - v).norm() / v.norm()).item()
     assert rel(x.grad, x2.grad) < 1e-5 and rel(a.weight.grad, b.weight.grad) < 1e-5
     assert rel(a.bias.grad, b.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("with_pos", [False, True])
+def test_add_norm_matches_layer_norm_of_the_sum(with_pos):
+    """``LayerNorm.add_norm(x, r[, pos])`` = LN(x + r) [and LN(x + r) + pos] in one kernel: values and every gradient
+    (x, r, gamma, beta, pos) against the library expression; fp32 summation-order differences only."""
+    from semi_detr_b200.layers.layernorm import LayerNorm
+    torch.manual_seed(3)
+    ln = LayerNorm(256).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(2, 1301, 256, device="cuda", requires_grad=True)
+    r = (torch.randn(2, 1301, 256, device="cuda") * 0.7).requires_grad_(True)
+    pos = torch.randn(2, 1301, 256, device="cuda", requires_grad=True) if with_pos else None
+    gy, gq = torch.randn(2, 1301, 256, device="cuda"), torch.randn(2, 1301, 256, device="cuda")
+    out = ln.add_norm(x, r, pos)
+    loss = ((out[0] * gy).sum() + (out[1] * gq).sum()) if with_pos else (out * gy).sum()
+    got = torch.autograd.grad(loss, [x, r, ln.weight, ln.bias] + ([pos] if with_pos else []))
+    want_y = torch.nn.functional.layer_norm(x + r, (256,), ln.weight, ln.bias, ln.eps)
+    want_loss = ((want_y * gy).sum() + ((want_y + pos) * gq).sum()) if with_pos else (want_y * gy).sum()
+    want = torch.autograd.grad(want_loss, [x, r, ln.weight, ln.bias] + ([pos] if with_pos else []))
+    y = out[0] if with_pos else out
+    assert torch.allclose(y, want_y, rtol=1e-5, atol=1e-5)
+    if with_pos:
+        assert torch.allclose(out[1], want_y + pos, rtol=1e-5, atol=1e-5)
+    for g, w, name in zip(got, want, ("x", "residual", "gamma", "beta", "pos")):
+        assert float((g - w).abs().max()) <= 2e-5 * float(w.abs().max()) + 1e-6, name
+    assert got[0].data_ptr() == got[1].data_ptr() or torch.equal(got[0], got[1])
