@@ -1,6 +1,6 @@
 """bench.py -- the driver's measurement contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sup|ssod|msda]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sup|ssod|sup5|msda]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -24,6 +24,8 @@ SAME configuration (2 images 800x1333 per step), warm-up capped at one step so K
         800x1333 per GPU, EMA + forward + backward + clip + AdamW; both phases (warm-up / Hungarian) are timed, `value`
         is the Hungarian phase (the 120k-iteration schedule spends its second half there), images/s counts the 5
         source images per GPU and step
+  sup5  configs[3] per-GPU batch: the 5-scale model (all four ResNet stages + one extra level, S = 89 000 pixels) under
+        bf16 autocast, bs=2/GPU
   msda  configs[4] microbenchmark: MSDeformAttn forward + backward at N=2, S=Lq=17 821 (and the decoder shape
         Lq=1100), fp32 and bf16 storage, L2 flushed before every launch, algorithmic HBM GB/s against the measured peak
 """
@@ -103,13 +105,20 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def build_model(device):
+SUP5_METRIC = "images/sec (train step) DINO-5scale R50 bf16"
+SUP5_WORKLOAD = ("configs[3] per-GPU batch: DINO-5scale R50 (900 queries + CDN groups) supervised train step under bf16 "
+                 "autocast (bf16 GEMMs / convolutions / MSDA value+output storage, fp32 sampling arithmetic, "
+                 "normalisations, matching, losses, master weights and optimizer), bs=2/GPU (16 over an 8-GPU box), "
+                 "synthetic COCO-shape 800x1333")
+
+
+def build_model(device, five_scale=False):
     import torch
     from semi_detr_b200 import dino  # noqa: F401
     from semi_detr_b200.registry import DETECTORS
-    from semi_detr_b200.synthetic import DINO_R50_4SCALE
+    from semi_detr_b200.synthetic import DINO_R50_4SCALE, dino_r50_5scale
     torch.manual_seed(0)
-    model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE))
+    model = DETECTORS.build(dino_r50_5scale() if five_scale else copy.deepcopy(DINO_R50_4SCALE))
     return model.to(device).train()
 
 
@@ -292,14 +301,16 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
 
-    model = build_model(device)
+    five = args.workload == "sup5"
+    model = build_model(device, five_scale=five)
     if world > 1:   # identical seeds give identical weights; broadcast anyway so the ranks cannot drift
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
     if args.torch_optimizer:
         step = SupervisedTrainStep(model, build_optimizer(model, capturable=True), world_size=world)
     else:   # clip + AdamW as one kernel over flat buffers (sdb_adamw_ema_step_f32)
-        step = FusedSupervisedTrainStep(model, world_size=world, overlap=os.environ.get("SDB_OVERLAP", "1") != "0")
+        step = FusedSupervisedTrainStep(model, world_size=world, overlap=os.environ.get("SDB_OVERLAP", "1") != "0",
+                                        autocast=torch.bfloat16 if five else None)
     host = coco_like_batch(PER_GPU_BATCH, IMG_H, IMG_W, seed=rank, pin=True)
 
     def to_device(b):
@@ -413,7 +424,10 @@ def run_ours(args):
         by.setdefault((kind, "enc" if q == s else "dec", b, s, q), []).append(a.elapsed_time(z) * 1e-3)
     kernels = {}
     for (kind, shape, b, s, q), ts in by.items():
-        fb, bb = msda_bytes(b, s, q)
+        fb, bb = msda_bytes(b, s, q, L=5 if five else 4)
+        if five:   # bf16 storage of value / output / grad_out; locations, weights and all gradients stay fp32
+            vq = 2 * (b * s * 256 + b * q * 256)
+            fb, bb = fb - vq, bb - vq
         nbytes = fb if kind == "fwd" else bb
         avg = sum(ts) / len(ts)
         kernels[f"msda_{kind}_{shape}"] = dict(launches=len(ts), avg_us=avg * 1e6, bytes=nbytes,
@@ -439,17 +453,19 @@ def run_ours(args):
                                   for k, v in kernels.items()})
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not five:
         threads = os.cpu_count() or 1
         times = cpu_reference_step_time(PER_GPU_BATCH, IMG_H, IMG_W, 1, 0, threads)
         cpu_baseline = dict(value=PER_GPU_BATCH / times[0], unit=UNIT, cores=threads, kind="port",
                             sample=f"1 full train step, {PER_GPU_BATCH} images {IMG_H}x{IMG_W}, reference CPU path "
                                    f"(python ms_deform_attn fallback + host LSAP + torch-cpu), {threads} threads")
 
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
-                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32 (tf32 tensor-core matmul/conv; MSDA, matching and losses in f32)", data="synthetic",
-                config=dict(workload=WORKLOAD, global_batch=PER_GPU_BATCH * world, parallelism=f"dp{world}",
+    line = dict(metric=SUP5_METRIC if five else METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=warm, ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=("bf16 (autocast: bf16 matmul/conv and MSDA storage; sampling arithmetic, norms, matching, losses, "
+                       "master weights in f32)" if five else
+                       "f32 (tf32 tensor-core matmul/conv; MSDA, matching and losses in f32)"), data="synthetic",
+                config=dict(workload=SUP5_WORKLOAD if five else WORKLOAD, global_batch=PER_GPU_BATCH * world, parallelism=f"dp{world}",
                             execution=graph_note,
                             l2="per-step working set (activations + 25.6 MB input) exceeds the 126 MB L2"),
                 clocks=clocks,
@@ -547,7 +563,7 @@ def run_msda(args):
     dom = results["msda_bwd_enc_f32"]
     traffic, traffic_src = _committed_traffic("msda_bwd_micro_enc")
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not five:
         threads = os.cpu_count() or 1
         t = cpu_reference_msda_time(2, 1, threads)
         sec = sum(t) / len(t)
@@ -661,7 +677,7 @@ def run_ssod(args):
         return
     h = phases["Hungarian"]
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not five:
         threads = os.cpu_count() or 1
         t = cpu_reference_ssod_step_time(1, 0, threads)
         cpu_baseline = dict(value=5 / t[0], unit=UNIT, cores=threads, kind="port",
@@ -704,8 +720,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sup", choices=["sup", "ssod", "msda"],
-                    help="sup = configs[1] (default, the contract line); ssod = configs[2] per-GPU batch; msda = configs[4]")
+    ap.add_argument("--workload", default="sup", choices=["sup", "ssod", "msda", "sup5"],
+                    help="sup = configs[1] (default, the contract line); ssod = configs[2] per-GPU batch; "
+                         "sup5 = configs[3] per-GPU batch (5-scale, bf16 autocast); msda = configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--torch-optimizer", action="store_true",

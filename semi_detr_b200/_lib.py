@@ -80,7 +80,7 @@ def debug_lib():
 # kernels of this library launched so far, by entry point (bench.py reports the per-step count)
 LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "msda_fused_forward": 0, "msda_fused_backward": 0, "msda_forward_tma": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,
             "layernorm_forward": 0, "layernorm_backward": 0, "adamw_ema_step": 0, "colsum": 0, "gemm_tf32": 0, "relu_backward_colsum": 0, "detr_loss_forward": 0, "detr_loss_backward": 0, "pseudo_label_nms": 0,
-            "gmm_threshold": 0}
+            "gmm_threshold": 0, "msda_forward_bf16": 0, "msda_backward_bf16": 0}
 
 
 class EmaChunk(ctypes.Structure):

@@ -107,8 +107,8 @@ def folded_conv(conv, bn):
 
 def conv_bn_relu(conv, bn, x, identity=None):
     """relu(BN(conv(x)) [+ identity]) -- with frozen statistics on the device: one fused cuDNN call."""
-    if bn.training or not x.is_cuda or not fused_conv_enabled():
-        out = conv_bn(conv, bn, x)
+    if bn.training or not x.is_cuda or not fused_conv_enabled() or torch.is_autocast_enabled():
+        out = conv_bn(conv, bn, x)      # (under autocast the library casts per op; the fused call takes one dtype)
         return F.relu(out if identity is None else out + identity, inplace=True)
     w, t = folded_conv(conv, bn)
     args = (tuple(conv.stride), tuple(conv.padding), tuple(conv.dilation), conv.groups)

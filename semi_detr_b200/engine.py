@@ -339,8 +339,12 @@ class FusedSupervisedTrainStep:
     read-modify-write kernel per parameter (~430 launches and a 188 MB memset per step) for sums that have a single
     term.  Same numbers either way (``tests/test_optimizer_gpu.py``)."""
 
-    def __init__(self, model, max_grad_norm=0.1, world_size=None, gather_grads=True, overlap=True, **opt_kw):
-        self.model, self.max_grad_norm, self.overlap = model, max_grad_norm, overlap
+    def __init__(self, model, max_grad_norm=0.1, world_size=None, gather_grads=True, overlap=True, autocast=None,
+                 **opt_kw):
+        """``autocast``: None (fp32 storage, TF32 products) or ``torch.bfloat16`` -- forward and loss run under
+        ``torch.autocast``: library bf16 GEMMs / convolutions, bf16-storage MSDA kernels with fp32 sampling arithmetic,
+        fp32 normalisations, matching, losses, master weights and optimizer (BASELINE.json configs[3])."""
+        self.model, self.max_grad_norm, self.overlap, self.autocast = model, max_grad_norm, overlap, autocast
         if world_size is None:
             world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.world_size = world_size
@@ -401,15 +405,17 @@ class FusedSupervisedTrainStep:
         return loss, log_vars
 
     def __call__(self, data):
-        if self.world_size > 1 and self.gather_grads and self.overlap and hasattr(self.model, "extract_feat") \
+        if self.world_size > 1 and self.gather_grads and self.overlap and self.autocast is None \
+                and hasattr(self.model, "extract_feat") \
                 and hasattr(self.model, "bbox_head"):
             loss, log_vars = self._overlapped_backward(data)
             self.opt.step(self.max_grad_norm, grad_scale=1.0 / self.world_size)
             return loss.detach(), log_vars
         if not self.gather_grads:
             self.opt.zero_grad()
-        losses = self.model(**data)
-        loss, log_vars = self.model._parse_losses(losses)
+        with torch.autocast("cuda", dtype=self.autocast, enabled=self.autocast is not None):
+            losses = self.model(**data)
+            loss, log_vars = self.model._parse_losses(losses)
         if self.gather_grads:
             self._pack(torch.autograd.grad(loss, self.opt.params, allow_unused=True))
         else:

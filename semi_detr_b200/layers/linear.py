@@ -168,11 +168,13 @@ class Linear(nn.Linear):
     def forward(self, x, relu=False, row_mask=None):
         """relu / row_mask (bool, one entry per row of x): applied to the output, inside the GEMM epilogue when the
         forward product runs on the tcgen05 kernel."""
-        plan = self._plan(x, relu or row_mask is not None)
+        # bf16 autocast (BASELINE.json configs[3]): the product is a library bf16 GEMM managed by torch.autocast -- the
+        # hand-written GEMM of this package is TF32 on fp32 storage
+        plan = None if torch.is_autocast_enabled() else self._plan(x, relu or row_mask is not None)
         if plan is not None:
             return _TensorCoreLinearFn.apply(x, self.weight, self.bias, relu, row_mask, plan)
         if (x.is_cuda and x.dtype == torch.float32 and self.bias is not None and self.out_features % 4 == 0
-                and x.numel() >= (1 << 16) and torch.is_grad_enabled()):
+                and x.numel() >= (1 << 16) and torch.is_grad_enabled() and not torch.is_autocast_enabled()):
             y = _LinearFn.apply(x, self.weight, self.bias)
         else:
             y = F.linear(x, self.weight, self.bias)

@@ -185,7 +185,7 @@ def _forward_bf16(value, spatial_shapes, level_start_index, sampling_loc, attn_w
             level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
             b, s, m, d, l, q, p, out.data_ptr()))
     _lib.check(rc, "ms_deform_attn_forward (bf16)")
-    _lib.LAUNCHES["msda_forward"] += 1
+    _lib.LAUNCHES["msda_forward_bf16"] += 1
     return out
 
 
@@ -205,7 +205,7 @@ def _backward_bf16(value, spatial_shapes, level_start_index, sampling_loc, attn_
             attn_weight.data_ptr(), b, s, m, d, l, q, p, grad_value.data_ptr(), grad_loc.data_ptr(),
             grad_attn.data_ptr()))
     _lib.check(rc, "ms_deform_attn_backward (bf16)")
-    _lib.LAUNCHES["msda_backward"] += 1
+    _lib.LAUNCHES["msda_backward_bf16"] += 1
     return [grad_value.to(_BF16), grad_loc, grad_attn]
 
 

@@ -105,7 +105,13 @@ class MSDeformAttn(nn.Module):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
                 reference_points.shape[-1]))
 
-        if value.dtype in (torch.float16, torch.bfloat16):
+        if value.dtype == torch.bfloat16 and M == 8 and self.d_model // M == 32 and P == 4:
+            # bf16 storage for value / output, fp32 sampling arithmetic (BASELINE.json configs[3]): the bf16 kernels
+            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                             locations.float().contiguous(), weights.float().contiguous(),
+                                             self.im2col_step)
+        elif value.dtype in (torch.float16, torch.bfloat16):
+            # the reference's own handling of half inputs: compute in fp32 (ms_deform_attn.py:114-121)
             out = MSDeformAttnFunction.apply(value.float(), input_spatial_shapes, input_level_start_index,
                                              locations.float(), weights.float(), self.im2col_step)
             out = out.to(value.dtype)

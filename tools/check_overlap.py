@@ -3,8 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_overlap.py
 
 Each rank builds the same model twice, runs 2 steps on its own batch with the single post-backward all-reduce and with the
-two-bucket overlapped one, and compares gradients and parameters (same sums in the same order per element: equal up to
-NCCL's reduction order, 1e-6).  Prints one JSON line on rank 0."""
+two-bucket overlapped one, and compares the first step's gradients (1e-5) and the parameters / losses after the second (1e-4).  Prints one JSON line on rank 0."""
 import copy
 import json
 import os
@@ -35,14 +34,20 @@ for mode in (False, True):
     model = copy.deepcopy(base)
     step = FusedSupervisedTrainStep(model, world_size=2, overlap=mode)
     torch.manual_seed(123)                      # same CDN noise in both runs
-    losses = [float(step(dict(data, img_metas=[dict(m) for m in data["img_metas"]]))[0]) for _ in range(2)]
-    out[mode] = (losses, step.opt.flat_g.clone(), step.opt.flat_p.clone())
+    losses, g_first = [], None
+    for it in range(2):
+        losses.append(float(step(dict(data, img_metas=[dict(m) for m in data["img_metas"]]))[0]))
+        if it == 0:
+            g_first = step.opt.flat_g.clone()   # same parameters in both modes: only the summation order differs
+    out[mode] = (losses, g_first, step.opt.flat_p.clone())
 g0, g1 = out[False][1], out[True][1]
 p0, p1 = out[False][2], out[True][2]
 res = dict(losses_single=out[False][0], losses_overlapped=out[True][0],
            grad_rel=float((g0 - g1).norm() / g0.norm()), param_rel=float((p0 - p1).norm() / p0.norm()))
-ok = res["grad_rel"] < 1e-5 and res["param_rel"] < 1e-6 and all(
-    abs(a - b) <= 1e-5 * abs(a) for a, b in zip(*[out[m][0] for m in (False, True)]))
+# first-step gradients: the same sums up to the order of the fp32 reductions (MSDA grad_value, NCCL); after the
+# second step AdamW's normalised update has amplified those last-bit differences, hence the looser bounds there
+ok = res["grad_rel"] < 1e-5 and res["param_rel"] < 1e-4 and all(
+    abs(a - b) <= 1e-4 * abs(a) for a, b in zip(*[out[m][0] for m in (False, True)]))
 res["ok"] = bool(ok)
 if rank == 0:
     print(json.dumps(res), flush=True)
