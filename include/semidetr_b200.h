@@ -265,6 +265,30 @@ int sdb_relu_backward_colsum_f32(sdb_stream_t stream, const float* dy, const flo
                                  float* g, float* colsum);
 
 /* ------------------------------------------------------------------------------------------
+ * Decoder self-attention core (the softmax(q k^T / sqrt(d) + mask) v inside nn.MultiheadAttention as the DINO decoder
+ * layer calls it: transformer.py:765, 795-812; mask from dn_components.py:97-113), scores kept on chip.
+ *
+ * Operands are (T, B, H*D) tensors addressed through strides: element (t, b, h, c) of q lives at
+ * q[t * q_tok + b * q_bat + h * D + c] (so q and k may be the two halves of one in-projection output); all pointers
+ * 16-byte aligned, strides multiples of 4 floats.  D must be 32 (else SDB_ERR_UNSUPPORTED).  `mask_add` is the additive
+ * (T, T) float mask (0 / -inf, row = query) or NULL; `scale` multiplies q before the product (torch's order).
+ *   forward : out (T, B, H*D) contiguous, lse (B*H, T) = log-sum-exp of every score row (saved for the backward)
+ *   backward: dq / dk / dv through the same kind of strided views; needs the transposed mask too (`mask_add_t`, (T, T),
+ *             row = key; NULL iff mask_add is NULL) and a (B*H, T) float scratch `delta`.
+ * The four products are TF32 tensor-core contractions with fp32 accumulation (the rounding of torch's TF32 matmul
+ * mode, which is when the host layer uses this path); softmax statistics and all sums are fp32.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_mha_forward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int64_t q_bat, const float* k,
+                        int64_t k_tok, int64_t k_bat, const float* v, int64_t v_tok, int64_t v_bat,
+                        const float* mask_add, int T, int B, int H, int D, float scale, float* out, float* lse);
+int sdb_mha_backward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int64_t q_bat, const float* k,
+                         int64_t k_tok, int64_t k_bat, const float* v, int64_t v_tok, int64_t v_bat,
+                         const float* mask_add, const float* mask_add_t, const float* out, const float* dout,
+                         const float* lse, int T, int B, int H, int D, float scale, float* dq, int64_t dq_tok,
+                         int64_t dq_bat, float* dk, int64_t dk_tok, int64_t dk_bat, float* dv, int64_t dv_tok,
+                         int64_t dv_bat, float* delta);
+
+/* ------------------------------------------------------------------------------------------
  * Gradient clip + AdamW (+ mean-teacher EMA) in one pass over flat fp32 buffers.
  *
  * Replaces mmcv's OptimizerHook for configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:122-128 (clip_grad_norm_ 0.1,

@@ -38,6 +38,10 @@ SIGNATURES = {
     "sdb_detr_loss_backward_f32": [c_void_p] * 11 + [c_int] * 3 + [c_float] * 3 + [c_void_p] * 2,
     "sdb_pseudo_label_nms_f32": [c_void_p] * 4 + [c_int] * 4 + [c_float] * 2 + [c_int] * 2 + [c_void_p] * 5,
     "sdb_gmm_threshold_f32": [c_void_p] * 3 + [c_int] * 2 + [c_float, c_int, c_double, c_void_p],
+    "sdb_mha_forward_f32": [c_void_p] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p] + [c_int] * 4 +
+                           [c_float, c_void_p, c_void_p],
+    "sdb_mha_backward_f32": [c_void_p] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p] * 5 + [c_int] * 4 +
+                            [c_float] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p],
     "sdb_colsum_f32": [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p],
     "sdb_relu_backward_colsum_f32": [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p],
     "sdb_gemm_tf32": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
@@ -80,7 +84,8 @@ def debug_lib():
 # kernels of this library launched so far, by entry point (bench.py reports the per-step count)
 LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "msda_fused_forward": 0, "msda_fused_backward": 0, "msda_forward_tma": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,
             "layernorm_forward": 0, "layernorm_backward": 0, "adamw_ema_step": 0, "colsum": 0, "gemm_tf32": 0, "relu_backward_colsum": 0, "detr_loss_forward": 0, "detr_loss_backward": 0, "pseudo_label_nms": 0,
-            "gmm_threshold": 0, "msda_forward_bf16": 0, "msda_backward_bf16": 0}
+            "gmm_threshold": 0, "msda_forward_bf16": 0, "msda_backward_bf16": 0,
+            "mha_forward": 0, "mha_backward": 0}
 
 
 class EmaChunk(ctypes.Structure):

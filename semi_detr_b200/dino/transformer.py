@@ -23,6 +23,7 @@ from ..consts import device_const
 from ..msda import MSDeformAttn
 from ..registry import TRANSFORMER
 from ..layers import LayerNorm, Linear
+from ..layers.attention import attention_enabled, fused_self_attention
 
 
 def inverse_sigmoid(x, eps=1e-5):
@@ -205,7 +206,7 @@ class DINOTransformerDecoderLayer(nn.Module):
         self.dropout4 = nn.Dropout(dropout)
         self.norm3 = LayerNorm(d_model)
 
-    def _self_attention(self, qk, value, attn_mask):
+    def _self_attention(self, qk, value, attn_mask, attn_mask_t=None):
         """``self.self_attn(qk, qk, value, attn_mask=attn_mask)[0]`` (nn.MultiheadAttention, transformer.py:795-803)
         written out on the module's own parameters: q and k share one projection GEMM, the (T, T) mask is added by
         the ``baddbmm`` that forms the scores instead of a separate pass over the (N*H, T, T) tensor, and the
@@ -216,6 +217,15 @@ class DINOTransformerDecoderLayer(nn.Module):
         H = mha.num_heads
         d = C // H
         w, b = mha.in_proj_weight, mha.in_proj_bias
+        if (attention_enabled(qk, d) and not (self.training and mha.dropout > 0)
+                and (attn_mask is None or (attn_mask.dtype == torch.float32 and attn_mask.dim() == 2))):
+            # scores, mask, softmax and the value product in one kernel each way (csrc/attention.cu): q and k are read
+            # in place from the shared projection's output, no (N*H, T, T) tensor exists
+            if attn_mask is not None and attn_mask_t is None:
+                attn_mask_t = attn_mask.t().contiguous()
+            out = fused_self_attention(F.linear(qk, w[:2 * C], b[:2 * C]), F.linear(value, w[2 * C:], b[2 * C:]),
+                                       attn_mask, attn_mask_t, H)
+            return F.linear(out, mha.out_proj.weight, mha.out_proj.bias)
         q, k = F.linear(qk, w[:2 * C], b[:2 * C]).split(C, -1)
         v = F.linear(value, w[2 * C:], b[2 * C:])
         q = (q * (float(d) ** -0.5)).reshape(T, N * H, d).transpose(0, 1)
@@ -233,11 +243,11 @@ class DINOTransformerDecoderLayer(nn.Module):
         return F.linear(out, mha.out_proj.weight, mha.out_proj.bias)
 
     def forward(self, tgt, query_pos, reference_points, memory, memory_key_padding_mask, level_start_index,
-                spatial_shapes, self_attn_mask=None):
+                spatial_shapes, self_attn_mask=None, self_attn_mask_t=None):
         """tgt / query_pos (nq, bs, C); reference_points (nq, bs, L, 4); memory (bs, S, C) batch-first."""
         for name in self.module_seq:
             if name == "sa":
-                tgt2 = self._self_attention(tgt + query_pos, tgt, self_attn_mask)
+                tgt2 = self._self_attention(tgt + query_pos, tgt, self_attn_mask, self_attn_mask_t)
                 tgt = self.norm2.add_norm(tgt, self.dropout2(tgt2))
             elif name == "ca":
                 tgt2 = self.cross_attn((tgt + query_pos).transpose(0, 1), reference_points.transpose(0, 1).contiguous(),
@@ -277,11 +287,13 @@ class DINOTransformerDecoder(nn.Module):
             # the additive form every layer's score product needs: built once per pass, not once per layer
             tgt_mask = torch.zeros(tgt_mask.shape, dtype=tgt.dtype, device=tgt.device).masked_fill_(tgt_mask,
                                                                                                   float("-inf"))
+        # the key-major copy the attention backward reads (csrc/attention.cu), also once per pass
+        tgt_mask_t = tgt_mask.t().contiguous() if (tgt_mask is not None and tgt_mask.dim() == 2) else None
         for lid, layer in enumerate(self.layers):
             ref_in = reference_points[:, :, None] * vr4                   # (nq, bs, L, 4)
             query_pos = self.ref_point_head(gen_sineembed_for_position(ref_in[:, :, 0, :]))
             output = layer(output, query_pos, ref_in, memory, memory_key_padding_mask, level_start_index,
-                           spatial_shapes, self_attn_mask=tgt_mask)
+                           spatial_shapes, self_attn_mask=tgt_mask, self_attn_mask_t=tgt_mask_t)
             if fc_reg is not None:
                 new_ref = (fc_reg[lid](output) + inverse_sigmoid(reference_points)).sigmoid()
                 reference_points = new_ref.detach()

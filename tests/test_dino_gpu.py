@@ -224,8 +224,10 @@ def test_five_scale_bf16_autocast_step_stays_close_to_the_fp32_reference_path(cp
             assert abs(a - b) <= 3e-2 * abs(b) + 1e-4, (k, a, b)
     assert abs(float(loss) - float(ref["loss"])) <= 5e-2 * abs(float(ref["loss"]))
     dot = gg = cc = 0.0
-    for p, (n, _) in zip(step.opt.params, [(n, q) for n, q in gpu_model.named_parameters() if q.requires_grad]):
-        g = p.grad.detach().float().cpu().double()
+    for n, p in gpu_model.named_parameters():
+        if not p.requires_grad:
+            continue
+        g = p.grad.detach().float().cpu().double()       # a view of the flat gradient buffer
         assert torch.isfinite(g).all(), n
         if n in want_grads:
             c = want_grads[n].double()
