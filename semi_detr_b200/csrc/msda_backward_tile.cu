@@ -65,6 +65,36 @@ __device__ __forceinline__ float dot4acc(const float4& a, const float4& b, float
   s = fmaf(a.z, b.z, s);
   return fmaf(a.w, b.w, s);
 }
+// shared-memory accesses through 32-bit shared-space addresses (no generic-to-shared conversion in the loop)
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ float lds_f(unsigned a) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ int lds_i(unsigned a) {
+  int r;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void sts_f(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+// two fp32 lanes per instruction (FFMA2)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ void ffma2(f32x2& d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
 __device__ __forceinline__ float group4_sum(float v) {
   v += __shfl_xor_sync(kAllLanes, v, 2, 4);
   return v + __shfl_xor_sync(kAllLanes, v, 1, 4);
@@ -80,7 +110,7 @@ struct TileSmem {
   static constexpr int kResBytes = kResFloats * 4;
   static constexpr int kGBytes = (kTQ + 1) * 32 * 4;             // grad_out rows of the tile (+ 1 zero row)
   static constexpr int kTableBytes = kTableInts * 4;
-  static constexpr int kVisBytes = kVisitCap * 4;                // visit word: result slot | grad_out row << 16
+  static constexpr int kVisBytes = kVisitCap * 4;                // visit word: result slot byte offset | grad_out row byte offset << 16
   static constexpr int kKeyBytes = (kVisitCap / kT) * 4;         // value-pixel index of every task
   static constexpr int kDirectBytes = kTQ * kSlots * 2;
   static constexpr int oRes = kRecBytes, oG = oRes + kResBytes, oTable = oG + kGBytes, oVis = oTable + kTableBytes,
@@ -103,7 +133,8 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
   constexpr int kQLPasses = kTQ * kLv / kTT;             // (query, level) pairs per thread: 1 or 2
   using SM = TileSmem<kSlots>;
   constexpr int kNullRes = SM::kPointSlots * 4;          // the null visit: a zero coefficient slot ...
-  constexpr unsigned kNullVisit = (unsigned)kNullRes | ((unsigned)kTQ << 16);   // ... and the zero grad_out row
+  constexpr unsigned kNullVisit = (unsigned)(kNullRes * 4) | ((unsigned)(kTQ * 128) << 16);   // ... and the zero grad_out row
+  static_assert(kNullRes * 4 + 4 <= 65536 && kTQ * 128 < 65536, "visit words hold 16-bit byte offsets");
   auto slot = [](int e) { return e + (e >> 3); };        // padded point index
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* rec = reinterpret_cast<float4*>(smem_raw);
@@ -309,7 +340,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
             const int k = vkey[ps][p][r];
             if (k != 0xffff) {
               const int pos = table[k] + vrank[ps][p][r];
-              vis[pos] = (unsigned)((slot(ql * kSlots + lv * P + p) << 2) | r) | ((unsigned)ql << 16);
+              vis[pos] = (unsigned)(((slot(ql * kSlots + lv * P + p) << 2) | r) << 2) | ((unsigned)(ql * 128) << 16);
               const int pidx = k - wbase;
               const int wy = (pidx * magic) >> 16;
               tpix[pos / kT] = pix0 + wy * Wl + (pidx - wy * ww);   // same value from every visit of the task
@@ -327,51 +358,84 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
     const float* vimg = value + img;
     float* gvimg = grad_value + img;
 
-    // ---- D: one task (pixel, <= kT visits) per 4 lanes ---------------------------------------------------------------
-    // Loop bounds are warp-uniform (every lane takes part in the width-4 shuffles); a group past the end re-runs the
-    // last task with its writes switched off.  The next task's pixel index, visit codes and value line are fetched
-    // while the current one is processed.
+    // ---- D: tasks (pixel, <= kT visits) in contiguous runs, one run per 4 lanes ------------------------------------
+    // Group G (4 lanes) owns tasks [G * per, G * per + per): consecutive tasks of one pixel -- every pixel with more than
+    // kT visits -- meet in the same group, which keeps the value line and the accumulated grad_value line in
+    // registers across them: one line load and one reduction line per PIXEL RUN instead of per task.  Loop bounds are
+    // warp-uniform (every lane takes part in the width-4 shuffles); a group past its range runs null visits.  The next
+    // distinct pixel's value line is fetched while the current task is processed.
     if (!all_direct) {
       const int n_tasks = n_slots / kT;
-      auto task_of = [&](int i0) { return min(i0 + (lane >> 2), n_tasks - 1); };
-      int i0 = warp * 8;
-      int pix = 0;
-      uint4 codes = make_uint4(0u, 0u, 0u, 0u);
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (i0 < n_tasks) {
-        const int i = task_of(i0);
-        pix = tpix[i];
-        codes = *reinterpret_cast<const uint4*>(vis + kT * i);
-        const float* pv = vimg + (long long)pix * px_stride;
-        v0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
-        v1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
-      }
+      const int per = (n_tasks + kTT / 4 - 1) / (kTT / 4);
+      int i = (tid >> 2) * per;
+      const int i_end = min(i + per, n_tasks);
+      const unsigned res_s = (unsigned)__cvta_generic_to_shared(res);
+      const unsigned g_s = (unsigned)__cvta_generic_to_shared(gtile) + 4u * (unsigned)c0;
+      const int g_d = 4 * (c1 - c0);                       // second half of the row: +-64 bytes
+      const unsigned vis_s = (unsigned)__cvta_generic_to_shared(vis);
+      const unsigned pix_s = (unsigned)__cvta_generic_to_shared(tpix);
       const bool hi2 = (j & 2) != 0, hi1 = (j & 1) != 0;
-      for (; i0 < n_tasks; i0 += kTT / 4) {
-        const bool valid = i0 + (lane >> 2) < n_tasks;
-        const int cur_pix = pix;
-        const unsigned cur_codes[kT] = {codes.x, codes.y, codes.z, codes.w};
-        const unsigned my_code = j == 0 ? codes.x : (j == 1 ? codes.y : (j == 2 ? codes.z : codes.w));
-        const float4 w0 = v0, w1 = v1;
-        if (i0 + kTT / 4 < n_tasks) {   // warp-uniform
-          const int i = task_of(i0 + kTT / 4);
-          pix = tpix[i];
-          codes = *reinterpret_cast<const uint4*>(vis + kT * i);
-          const float* pv = vimg + (long long)pix * px_stride;
-          v0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
-          v1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
+      int cur_pix = -1;
+      int nxt_pix = i < i_end ? lds_i(pix_s + 4u * (unsigned)i) : -1;
+      float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
+      if (nxt_pix >= 0) {
+        const float* pv = vimg + (long long)nxt_pix * px_stride;
+        n0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
+        n1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
+      }
+      f32x2 w[4] = {0ull, 0ull, 0ull, 0ull};               // value line of cur_pix: channels c0..c0+3, c1..c1+3
+      f32x2 acc[4] = {0ull, 0ull, 0ull, 0ull};             // grad_value line of cur_pix
+      auto flush = [&]() {
+        float* pg = gvimg + (long long)cur_pix * px_stride;
+        const float2 a0 = unpack2(acc[0]), a1 = unpack2(acc[1]), a2 = unpack2(acc[2]), a3 = unpack2(acc[3]);
+        red_add_f4(pg + c0, make_float4(a0.x, a0.y, a1.x, a1.y));
+        red_add_f4(pg + c1, make_float4(a2.x, a2.y, a3.x, a3.y));
+      };
+      for (int it = 0; it < per; ++it, ++i) {
+        const bool valid = i < i_end;
+        const int pix = nxt_pix;
+        uint4 codes = make_uint4(kNullVisit, kNullVisit, kNullVisit, kNullVisit);
+        unsigned my_code = kNullVisit;
+        if (valid) {
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(codes.x), "=r"(codes.y), "=r"(codes.z), "=r"(codes.w)
+                       : "r"(vis_s + 16u * (unsigned)i));
+          my_code = (unsigned)lds_i(vis_s + 16u * (unsigned)i + 4u * (unsigned)j);
         }
-        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        nxt_pix = i + 1 < i_end ? lds_i(pix_s + 4u * (unsigned)i + 4u) : -1;
+        if (valid && pix != cur_pix) {                     // a new pixel run: hand over the finished line
+          if (cur_pix >= 0) flush();
+          acc[0] = acc[1] = acc[2] = acc[3] = 0ull;
+          w[0] = pack2(n0.x, n0.y); w[1] = pack2(n0.z, n0.w);
+          w[2] = pack2(n1.x, n1.y); w[3] = pack2(n1.z, n1.w);
+          cur_pix = pix;
+        }
+        if (nxt_pix >= 0 && nxt_pix != pix) {
+          const float* pv = vimg + (long long)nxt_pix * px_stride;
+          n0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
+          n1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
+        }
+        const unsigned cur_codes[kT] = {codes.x, codes.y, codes.z, codes.w};
         float d[kT];
 #pragma unroll
         for (int s = 0; s < kT; ++s) {
-          const float c = res[cur_codes[s] & 0xffffu];
-          const float* gr = gtile + (cur_codes[s] >> 16) * 32;
-          const float4 g0 = *reinterpret_cast<const float4*>(gr + c0);
-          const float4 g1 = *reinterpret_cast<const float4*>(gr + c1);
-          fma4(acc0, c, g0);
-          fma4(acc1, c, g1);
-          d[s] = dot4acc(g1, w1, dot4acc(g0, w0, 0.f));
+          const float c = lds_f(res_s + (cur_codes[s] & 0xffffu));
+          const unsigned ga = g_s + (cur_codes[s] >> 16);
+          const float4 g0 = lds_f4(ga);
+          const float4 g1 = lds_f4(ga + g_d);
+          const f32x2 cc = pack2(c, c);
+          const f32x2 p0 = pack2(g0.x, g0.y), p1 = pack2(g0.z, g0.w), p2 = pack2(g1.x, g1.y), p3 = pack2(g1.z, g1.w);
+          ffma2(acc[0], cc, p0);
+          ffma2(acc[1], cc, p1);
+          ffma2(acc[2], cc, p2);
+          ffma2(acc[3], cc, p3);
+          f32x2 da = 0ull, db = 0ull;
+          ffma2(da, p0, w[0]);
+          ffma2(db, p1, w[1]);
+          ffma2(da, p2, w[2]);
+          ffma2(db, p3, w[3]);
+          const float2 xa = unpack2(da), xb = unpack2(db);
+          d[s] = (xa.x + xa.y) + (xb.x + xb.y);
         }
         // reduce-scatter of the 4 partial dot products over the 4 lanes: lane j ends with the full sum of visit j
         // (3 shuffles instead of 8) and stores it; the coefficient in that slot has been consumed above
@@ -382,13 +446,9 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
         const float e1 = k1 + __shfl_xor_sync(kAllLanes, s1, 2, 4);   // visit (hi2 ? 3 : 1)
         const float keep = hi1 ? e1 : e0, send = hi1 ? e0 : e1;
         const float full = keep + __shfl_xor_sync(kAllLanes, send, 1, 4);   // visit j
-        if (valid) {
-          res[my_code & 0xffffu] = full;   // <grad_out, value_corner> (the null visit's slot just gets its 0 back)
-          float* pg = gvimg + (long long)cur_pix * px_stride;
-          red_add_f4(pg + c0, acc0);
-          red_add_f4(pg + c1, acc1);
-        }
+        sts_f(res_s + (my_code & 0xffffu), full);   // <grad_out, value_corner> (the null visit's slot just gets its 0 back)
       }
+      if (cur_pix >= 0) flush();
     }
 
     // ---- X: points outside the windows -- corner loads, dot products, one reduction line per corner ----------------

@@ -203,10 +203,17 @@ class ResNet(nn.Module):
                     m.eval()
         return self
 
-    def forward(self, x):
+    def forward(self, x, cut_before_last_stage=None):
+        """``cut_before_last_stage`` (a list, optional): layer4 then runs on a detached copy of layer3's output and the
+        pair (layer3 output, detached copy) is appended -- the engine's segmented backward differentiates the two halves
+        of the backbone separately so that layer4's gradients can be exchanged while layer2 / layer3 still compute."""
         x = self.maxpool(conv_bn_relu(self.conv1, self.bn1, x))
         outs = []
         for i in range(4):
+            if i == 3 and cut_before_last_stage is not None and x.requires_grad:
+                leaf = x.detach().requires_grad_(True)
+                cut_before_last_stage.append((x, leaf))
+                x = leaf
             x = getattr(self, f"layer{i + 1}")(x)
             if i in self.out_indices:
                 outs.append(x)

@@ -30,12 +30,14 @@ class DINODETR(nn.Module):
         self.backbone.to(memory_format=torch.channels_last)
         self.bbox_head.input_proj.to(memory_format=torch.channels_last)
 
-    def extract_feat(self, img):
+    def extract_feat(self, img, cut_before_last_stage=None):
         # NHWC end to end through the convolutional backbone: cuDNN's tensor-core kernels are channels-last, so this
         # removes the NCHW<->NHWC transposes around every convolution, and (N, C, H, W) channels-last flattens to the
         # transformer's (N, HW, C) token layout for free
         if img.is_cuda:
             img = img.contiguous(memory_format=torch.channels_last)
+        if cut_before_last_stage is not None:
+            return self.backbone(img, cut_before_last_stage=cut_before_last_stage)
         return self.backbone(img)
 
     def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore=None, **kwargs):

@@ -368,20 +368,23 @@ class FusedSupervisedTrainStep:
             torch._foreach_copy_(fast_dst, fast_src)
 
     def _overlapped_backward(self, data):
-        """Backward in two segments so that the gradient exchange overlaps it (world_size > 1, DINODETR).
+        """Backward in three segments so that the gradient exchange overlaps it (world_size > 1, DINODETR).
 
-        The flat gradient buffer is laid out [head + transformer | backbone] (``FusedAdamW``).  Segment 1 differentiates
-        the loss down to the backbone's output features and packs the head / transformer gradients; their all-reduce
-        (half of the 188 MB) is issued asynchronously on NCCL's stream and runs while segment 2 -- the backbone
-        backward, ~4 ms of convolutions -- is still computing on the main stream.  Only the backbone bucket's reduction
-        is left exposed.  Same numbers as one ``autograd.grad`` over all parameters."""
+        The flat gradient buffer is laid out [head + transformer | backbone layer2, layer3, layer4] (``FusedAdamW``
+        keeps ``named_parameters`` order inside each group).  Segment 1 differentiates the loss down to the backbone's
+        output features and packs the head / transformer gradients, whose all-reduce (half of the 188 MB) is issued
+        asynchronously on NCCL's stream; segment 2 is layer4's backward (two thirds of the backbone's parameters), its
+        bucket is exchanged while segment 3 -- layer3 and layer2, most of the backbone's backward time -- computes.
+        Only the last, smallest bucket (layer2 + layer3, 34 MB) is left exposed.  Same sums as one ``autograd.grad``
+        over all parameters."""
         model, opt = self.model, self.opt
         n_head = len(opt.param_groups[0]["params"])
         head_params, bb_params = opt.params[:n_head], opt.params[n_head:]
         batch_input_shape = tuple(data["img"].shape[-2:])
         for m in data["img_metas"]:
             m["batch_input_shape"] = batch_input_shape
-        feats = model.extract_feat(data["img"])
+        stage_cut = []
+        feats = model.extract_feat(data["img"], cut_before_last_stage=stage_cut)
         # the head sees detached copies of the backbone features: segment 1 then stops exactly at the cut (the feature
         # levels are nested outputs of one convolution chain, so a cut on the live tensors would run -- and free --
         # part of the backbone graph already in segment 1)
@@ -391,18 +394,50 @@ class FusedSupervisedTrainStep:
                                                **rest)
         loss, log_vars = model._parse_losses(losses)
         live = [i for i, f in enumerate(feats) if f.requires_grad]
-        cut = [feats[i] for i in live]
         g = torch.autograd.grad(loss, head_params + [cut_in[i] for i in live], allow_unused=True)
         self._pack(g[:n_head], head_params)
         b = opt._bounds
-        work1 = dist.all_reduce(opt.flat_g[b[0]:b[1]], async_op=True)
+        works = [dist.all_reduce(opt.flat_g[b[0]:b[1]], async_op=True)]
         if bb_params:
-            g_cut = [gc if gc is not None else torch.zeros_like(c) for gc, c in zip(g[n_head:], cut)]
-            self._pack(torch.autograd.grad(cut, bb_params, grad_outputs=g_cut, allow_unused=True), bb_params)
-            work2 = dist.all_reduce(opt.flat_g[b[2]:b[3]], async_op=True)
-            work2.wait()
-        work1.wait()
+            g_feat = {i: (gc if gc is not None else torch.zeros_like(feats[i])) for i, gc in zip(live, g[n_head:])}
+            split = self._last_stage_split(bb_params) if stage_cut else None
+            if split is not None and (len(feats) - 1) in g_feat:
+                # segment 2: layer4 (its output is the last feature level) down to the detached copy of layer3's output
+                n_early, off_late = split
+                late = bb_params[n_early:]
+                (x3, leaf3), last = stage_cut[0], len(feats) - 1
+                g2 = torch.autograd.grad([feats[last]], late + [leaf3], grad_outputs=[g_feat.pop(last)],
+                                         allow_unused=True)
+                self._pack(g2[:-1], late)
+                works.append(dist.all_reduce(opt.flat_g[off_late:b[3]], async_op=True))
+                # segment 3: the remaining feature levels plus layer4's input gradient, through layer3 / layer2
+                outs = [feats[i] for i in g_feat] + [x3]
+                gouts = [g_feat[i] for i in g_feat] + [g2[-1] if g2[-1] is not None else torch.zeros_like(x3)]
+                early = bb_params[:n_early]
+                self._pack(torch.autograd.grad(outs, early, grad_outputs=gouts, allow_unused=True), early)
+                works.append(dist.all_reduce(opt.flat_g[b[2]:off_late], async_op=True))
+            else:
+                outs = [feats[i] for i in g_feat]
+                self._pack(torch.autograd.grad(outs, bb_params, grad_outputs=[g_feat[i] for i in g_feat],
+                                               allow_unused=True), bb_params)
+                works.append(dist.all_reduce(opt.flat_g[b[2]:b[3]], async_op=True))
+        for w in reversed(works):
+            w.wait()
         return loss, log_vars
+
+    def _last_stage_split(self, bb_params):
+        """-> (number of backbone parameters before layer4, offset of layer4's first gradient in the flat buffer), or
+        None when the backbone group is not laid out [..., layer4] with a 4-aligned boundary."""
+        if getattr(self, "_stage_split", "unset") != "unset":
+            return self._stage_split
+        opt = self.opt
+        names = opt.param_names[len(opt.params) - len(bb_params):]
+        late = [".layer4." in n or n.startswith("backbone.layer4.") for n in names]
+        n_early = late.index(True) if True in late else len(late)
+        ok = 0 < n_early < len(late) and all(late[n_early:]) and not any(late[:n_early])
+        off = int(opt._bounds[2]) + sum(p.numel() for p in bb_params[:n_early])
+        self._stage_split = (n_early, off) if ok and off % 4 == 0 else None
+        return self._stage_split
 
     def __call__(self, data):
         if self.world_size > 1 and self.gather_grads and self.overlap and self.autocast is None \
