@@ -467,6 +467,10 @@ def run_ours(args):
                        "f32 (tf32 tensor-core matmul/conv; MSDA, matching and losses in f32)"), data="synthetic",
                 config=dict(workload=SUP5_WORKLOAD if five else WORKLOAD, global_batch=PER_GPU_BATCH * world, parallelism=f"dp{world}",
                             execution=graph_note,
+                            exchange=(None if world == 1 else
+                                      ("gradient sum + clip + AdamW + parameter broadcast fused over NVLink multicast "
+                                       "(sdb_dp_adamw_exchange_f32)" if getattr(step, "exchange", "") == "peer" else
+                                       "NCCL all-reduce of the flat gradient, bucketed under the backward")),
                             l2="per-step working set (activations + 25.6 MB input) exceeds the 126 MB L2"),
                 clocks=clocks,
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,

@@ -314,6 +314,34 @@ int sdb_adamw_ema_step_sched_f32(sdb_stream_t stream, float* params, const float
                                  int num_segs, float beta1, float beta2, float eps, double ema_momentum);
 
 /* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange fused with clip + AdamW over NVLink peer memory.
+ *
+ * Replaces DistributedDataParallel's gradient all-reduce followed by mmcv's OptimizerHook (detr_ssod/apis/train.py:84-93;
+ * configs/dino_detr/dino_detr_r50_8x2_12e_coco.py:122-128) for one process per GPU on an NVSwitch node.  `grads` and
+ * `params` are this rank's SYMMETRIC flat buffers (same size and offset on every rank, bound to a multicast object);
+ * `grads_mc` / `params_mc` are the multicast addresses of the same buffers.  Rank r sums shard r of every rank's
+ * gradients with `multimem.ld_reduce` (the switch adds), exchanges the shard's squared norm, clips by the norm of the
+ * MEAN gradient (`grad_scale` = 1/world, `max_grad_norm` <= 0: no clipping), applies AdamW to shard r only (its slice of
+ * exp_avg / exp_avg_sq) and broadcasts the new parameters into every rank's `params` with `multimem.st`.  The call
+ * returns (in stream order) when every rank's parameter buffer is complete.  `ctrl_ptrs`: HOST array of `world` device
+ * pointers, entry r = rank r's control block (sdb_dp_ctrl_bytes() bytes, symmetric, zero-filled once) as mapped in THIS
+ * process.  `seg_bounds` (host) / `seg_hparams_dev` (device: lr, weight_decay per segment) as in
+ * sdb_adamw_ema_step_sched_f32.  All launches are CUDA-graph replayable; a peer that never arrives sets the word at
+ * sdb_dp_error_word_offset() of the control block instead of hanging the device.
+ * sdb_dp_small_allreduce_f32: in-place sum over ranks of n <= 2 floats (the loss normalisers, dino_detr_head.py:698-723)
+ * through the same control blocks; `slot` (0..3) separates independent call sites.
+ * ------------------------------------------------------------------------------------------ */
+int sdb_dp_ctrl_bytes(void);
+int sdb_dp_error_word_offset(void);
+int sdb_dp_adamw_exchange_f32(sdb_stream_t stream, int rank, int world, const void* const* ctrl_ptrs, float* grads,
+                              const float* grads_mc, float* params, float* params_mc, float* exp_avg,
+                              float* exp_avg_sq, const float* step_count, const int64_t* seg_bounds,
+                              const float* seg_hparams_dev, int num_segs, float beta1, float beta2, float eps,
+                              float max_grad_norm, float grad_scale, int64_t total);
+int sdb_dp_small_allreduce_f32(sdb_stream_t stream, int rank, int world, const void* const* ctrl_ptrs, int slot,
+                               float* values, int n);
+
+/* ------------------------------------------------------------------------------------------
  * Classification + box losses of the DINO head for all (decoder layer, image) problems in one launch, targets
  * gathered from the assignment inside the kernel.
  *

@@ -42,6 +42,10 @@ SIGNATURES = {
                            [c_float, c_void_p, c_void_p],
     "sdb_mha_backward_f32": [c_void_p] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p] * 5 + [c_int] * 4 +
                             [c_float] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p],
+    "sdb_dp_ctrl_bytes": [],
+    "sdb_dp_error_word_offset": [],
+    "sdb_dp_adamw_exchange_f32": [c_void_p, c_int, c_int] + [c_void_p] * 10 + [c_int] + [c_float] * 5 + [ctypes.c_int64],
+    "sdb_dp_small_allreduce_f32": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int],
     "sdb_colsum_f32": [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p],
     "sdb_relu_backward_colsum_f32": [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p],
     "sdb_gemm_tf32": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
@@ -85,7 +89,7 @@ def debug_lib():
 LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "msda_fused_forward": 0, "msda_fused_backward": 0, "msda_forward_tma": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,
             "layernorm_forward": 0, "layernorm_backward": 0, "adamw_ema_step": 0, "colsum": 0, "gemm_tf32": 0, "relu_backward_colsum": 0, "detr_loss_forward": 0, "detr_loss_backward": 0, "pseudo_label_nms": 0,
             "gmm_threshold": 0, "msda_forward_bf16": 0, "msda_backward_bf16": 0,
-            "mha_forward": 0, "mha_backward": 0}
+            "mha_forward": 0, "mha_backward": 0, "dp_adamw_exchange": 0, "dp_small_allreduce": 0}
 
 
 class EmaChunk(ctypes.Structure):

@@ -51,13 +51,28 @@ class LossDict(dict):
         super().update(*args, **kwargs)
 
 
-def reduce_mean_scalar(value, device):
-    """mmdet core/utils/dist_utils.py:67-73 for a host scalar: mean over ranks, kept on the device (no .item())."""
+_SCALAR_ALLREDUCE = None
+
+
+def set_scalar_allreduce(fn):
+    """``fn(tensor, slot) -> tensor`` (in-place sum over ranks of a 1-element device tensor) replaces the NCCL call of
+    ``reduce_mean_scalar`` -- the engine installs the peer-memory kernel (``sdb_dp_small_allreduce_f32``) when the
+    gradient exchange runs over NVLink multicast; ``None`` restores NCCL."""
+    global _SCALAR_ALLREDUCE
+    _SCALAR_ALLREDUCE = fn
+
+
+def reduce_mean_scalar(value, device, slot=0):
+    """mmdet core/utils/dist_utils.py:67-73 for a host scalar: mean over ranks, kept on the device (no .item()).
+    ``slot`` tells independent call sites of one step apart (they may be in flight on different ranks at once)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)
     v = float(value)
     t = device_const(device, "scalar", v, lambda: torch.tensor([v], dtype=torch.float32)).clone()   # graph-safe
-    dist.all_reduce(t.div_(dist.get_world_size()), op=dist.ReduceOp.SUM)
+    t.div_(dist.get_world_size())
+    if _SCALAR_ALLREDUCE is not None:
+        return _SCALAR_ALLREDUCE(t, slot)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
 
@@ -301,7 +316,7 @@ class DINODETRHead(nn.Module):
         dsums = self._loss_sums(dn_cls_scores.float().reshape(Pd, pad, C), dn_bbox_preds.float().reshape(Pd, pad, 4),
                                 gt_inds, prob_seg, targets, cls_w)
         dn_num_pos = total * groups
-        return self._finish(dsums, Ld, bs, max(dn_num_pos * 1.0, 1), _clamp_min1(reduce_mean_scalar(dn_num_pos, dev)))
+        return self._finish(dsums, Ld, bs, max(dn_num_pos * 1.0, 1), _clamp_min1(reduce_mean_scalar(dn_num_pos, dev, slot=1)))
 
     @staticmethod
     def _assemble(main, dn, L, has_enc):

@@ -16,6 +16,9 @@ max_norm 0.1; DDP wrap at detr_ssod/apis/train.py:84-93), laid out for one proce
 torch's fused AdamW is library plumbing here; fusing clip+AdamW+EMA over the flat buffers is a "next" row
 (SURVEY.md section 8f, rank 3).
 """
+import os
+import sys
+
 import torch
 import torch.distributed as dist
 
@@ -305,6 +308,92 @@ class FusedAdamW:
         if world_size > 1:
             dist.all_reduce(self.flat_g)
 
+    # ---- gradient exchange fused with the update, over NVLink peer memory (csrc/exchange.cu) ---------------------------
+    def enable_peer_exchange(self, group=None):
+        """Move the flat parameter / gradient buffers into SYMMETRIC memory (torch's symmetric-memory allocator: the same
+        allocation on every rank of ``group``, mapped peer-to-peer and bound to an NVLS multicast object) so that
+        ``step_exchange`` can sum the gradients and broadcast the parameters through the NVSwitch.  Returns False --
+        leaving everything as it was -- when the node has no multicast support; raises when the ranks disagree."""
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+        if self.flat_t is not None:
+            raise RuntimeError("FusedAdamW.enable_peer_exchange: not combined with the EMA teacher blend")
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = self.flat_p.device
+        lib = self._lib.lib()
+        total = self.flat_p.numel()
+        new_p = symm.empty(total, dtype=torch.float32, device=dev)
+        new_g = symm.empty(total, dtype=torch.float32, device=dev)
+        ctrl = symm.empty(lib.sdb_dp_ctrl_bytes() // 4, dtype=torch.int32, device=dev)
+        ctrl.zero_()
+        handles = [symm.rendezvous(t, group.group_name) for t in (new_p, new_g, ctrl)]
+        ok = torch.tensor([1 if all(h.multicast_ptr != 0 for h in handles[:2]) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok) == 0:
+            return False
+        new_p.copy_(self.flat_p)
+        new_g.copy_(self.flat_g)
+        off = 0
+        for gi, g in enumerate(self.param_groups):
+            off = int(self._bounds[2 * gi])
+            for p in g["params"]:
+                n = p.numel()
+                p.data = new_p[off:off + n].as_strided(p.shape, p.stride())
+                p.grad = new_g[off:off + n].as_strided(p.shape, p.stride())
+                off += n
+        self.flat_p, self.flat_g = new_p, new_g
+
+        def local_offset(t, h):
+            return t.data_ptr() - int(h.buffer_ptrs[h.rank])
+        hp, hg, hc = handles
+        self._peer = dict(
+            rank=rank, world=world, group=group, handles=handles, ctrl=ctrl,
+            p_mc=int(hp.multicast_ptr) + local_offset(new_p, hp), g_mc=int(hg.multicast_ptr) + local_offset(new_g, hg),
+            ctrl_ptrs=(ctypes.c_void_p * world)(*[int(ptr) + local_offset(ctrl, hc) for ptr in hc.buffer_ptrs]))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        return True
+
+    @property
+    def peer_exchange(self):
+        return getattr(self, "_peer", None) is not None
+
+    def step_exchange(self, max_grad_norm=None):
+        """Gradient mean over the ranks + clip + AdamW + parameter broadcast as one fused exchange
+        (``sdb_dp_adamw_exchange_f32``): no NCCL call, no separate norm pass, optimizer state touched once per node."""
+        x = self._peer
+        self.sync_hparams()
+        dev = self.flat_p.device
+        with torch.cuda.device(dev):
+            rc = self._lib.lib().sdb_dp_adamw_exchange_f32(
+                self._lib.current_stream(dev), x["rank"], x["world"], x["ctrl_ptrs"], self.flat_g.data_ptr(), x["g_mc"],
+                self.flat_p.data_ptr(), x["p_mc"], self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                self.step_count.data_ptr(), self._bounds, self._hparams_dev.data_ptr(), 2, self.betas[0], self.betas[1],
+                self.eps, float(max_grad_norm) if max_grad_norm is not None else 0.0, 1.0 / x["world"],
+                self.flat_p.numel())
+        self._lib.check(rc, "dp_adamw_exchange")
+        self._lib.LAUNCHES["dp_adamw_exchange"] += 3
+        self.step_count.add_(1.0)
+
+    def peer_error(self):
+        """True if a bounded wait of the exchange kernels ran out (a peer never arrived); reads the control block."""
+        x = self._peer
+        word = self._lib.lib().sdb_dp_error_word_offset() // 4
+        return bool(int(x["ctrl"][word]) != 0)
+
+    def small_allreduce(self, values, slot=0):
+        """In-place sum over the ranks of a 1- or 2-element fp32 device tensor through the peer control blocks."""
+        x = self._peer
+        dev = values.device
+        with torch.cuda.device(dev):
+            rc = self._lib.lib().sdb_dp_small_allreduce_f32(self._lib.current_stream(dev), x["rank"], x["world"],
+                                                            x["ctrl_ptrs"], slot, values.data_ptr(), values.numel())
+        self._lib.check(rc, "dp_small_allreduce")
+        self._lib.LAUNCHES["dp_small_allreduce"] += 1
+        return values
+
     def step(self, max_grad_norm=None, ema_momentum=None, grad_scale=1.0):
         """``grad_scale``: factor applied to the gradient buffer before clipping (1/world after a summing all-reduce)."""
         self.sync_hparams()
@@ -340,7 +429,7 @@ class FusedSupervisedTrainStep:
     term.  Same numbers either way (``tests/test_optimizer_gpu.py``)."""
 
     def __init__(self, model, max_grad_norm=0.1, world_size=None, gather_grads=True, overlap=True, autocast=None,
-                 **opt_kw):
+                 exchange=None, **opt_kw):
         """``autocast``: None (fp32 storage, TF32 products) or ``torch.bfloat16`` -- forward and loss run under
         ``torch.autocast``: library bf16 GEMMs / convolutions, bf16-storage MSDA kernels with fp32 sampling arithmetic,
         fp32 normalisations, matching, losses, master weights and optimizer (BASELINE.json configs[3])."""
@@ -350,6 +439,22 @@ class FusedSupervisedTrainStep:
         self.world_size = world_size
         self.opt = FusedAdamW(model, **opt_kw)
         self.gather_grads = gather_grads
+        # how the ranks exchange gradients: "peer" = fused with the optimizer over NVLink multicast (csrc/exchange.cu,
+        # the default when the node supports it), "nccl" = bucketed all-reduce overlapped with the backward
+        exchange = exchange or os.environ.get("SDB_EXCHANGE", "auto")
+        self.exchange = "nccl"
+        if (world_size > 1 and gather_grads and exchange in ("auto", "peer") and dist.is_available()
+                and dist.is_initialized() and dist.get_world_size() == world_size):
+            try:
+                if self.opt.enable_peer_exchange():
+                    self.exchange = "peer"
+            except Exception as e:   # no symmetric memory on this box: keep NCCL, loudly if peer was demanded
+                if exchange == "peer":
+                    raise
+                print(f"FusedSupervisedTrainStep: peer exchange unavailable ({type(e).__name__}: {e}); using NCCL",
+                      file=sys.stderr)
+        if exchange == "peer" and self.exchange != "peer" and world_size > 1:
+            raise RuntimeError("FusedSupervisedTrainStep: exchange='peer' needs NVLink multicast (NVLS) on this node")
         _cache_student_bn_folds(model)
 
     def _pack(self, grads, params=None):
@@ -440,6 +545,19 @@ class FusedSupervisedTrainStep:
         return self._stage_split
 
     def __call__(self, data):
+        if self.exchange == "peer":
+            from .dino import head as _head
+            # the two loss normalisers go through the peer control blocks too (one 32-thread kernel each, no NCCL launch)
+            _head.set_scalar_allreduce(lambda t, slot: self.opt.small_allreduce(t, slot))
+            try:
+                with torch.autocast("cuda", dtype=self.autocast, enabled=self.autocast is not None):
+                    losses = self.model(**data)
+                    loss, log_vars = self.model._parse_losses(losses)
+            finally:
+                _head.set_scalar_allreduce(None)
+            self._pack(torch.autograd.grad(loss, self.opt.params, allow_unused=True))
+            self.opt.step_exchange(self.max_grad_norm)
+            return loss.detach(), log_vars
         if self.world_size > 1 and self.gather_grads and self.overlap and self.autocast is None \
                 and hasattr(self.model, "extract_feat") \
                 and hasattr(self.model, "bbox_head"):

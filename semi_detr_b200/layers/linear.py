@@ -137,7 +137,9 @@ class _TensorCoreLinearFn(torch.autograd.Function):
             else:
                 g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)
         elif mask is not None:
-            g2 = g2.masked_fill(mask.view(torch.bool)[:, None], 0.0)
+            # in place: the incoming gradient is the MSDA backward's own grad_value buffer (this layer's output has one
+            # consumer), so the out-of-place form's 45 MB copy per call buys nothing
+            g2 = (g2 if g2.is_contiguous() else g2.contiguous()).masked_fill_(mask.view(torch.bool)[:, None], 0.0)
         elif not g2.is_contiguous():
             g2 = g2.contiguous()
         gx = gw = gb = None

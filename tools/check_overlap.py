@@ -2,8 +2,8 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_overlap.py
 
-Each rank builds the same model twice, runs 2 steps on its own batch with the single post-backward all-reduce and with the
-two-bucket overlapped one, and compares the first step's gradients (1e-5) and the parameters / losses after the second (1e-4).  Prints one JSON line on rank 0."""
+Each rank builds the same model three times, runs 2 steps on its own batch with the single post-backward all-reduce, with
+the bucketed overlapped one and with the exchange fused into the optimizer over NVLink multicast (csrc/exchange.cu), and compares the first step's gradients (1e-5) and the parameters / losses after the second (1e-4).  Prints one JSON line on rank 0."""
 import copy
 import json
 import os
@@ -30,9 +30,11 @@ cfg["bbox_head"]["transformer"] = dict(type="DINOTransformer", num_encoder_layer
 base = DETECTORS.build(cfg).to(dev).train()
 data = coco_like_batch(2, 320, 416, seed=10 + rank, device=dev)
 out = {}
-for mode in (False, True):
+MODES = {False: dict(overlap=False, exchange="nccl"), True: dict(overlap=True, exchange="nccl"),
+         "peer": dict(exchange="peer")}
+for mode, kw in MODES.items():
     model = copy.deepcopy(base)
-    step = FusedSupervisedTrainStep(model, world_size=2, overlap=mode)
+    step = FusedSupervisedTrainStep(model, world_size=2, **kw)
     torch.manual_seed(123)                      # same CDN noise in both runs
     losses, g_first = [], None
     for it in range(2):
@@ -48,6 +50,20 @@ res = dict(losses_single=out[False][0], losses_overlapped=out[True][0],
 # second step AdamW's normalised update has amplified those last-bit differences, hence the looser bounds there
 ok = res["grad_rel"] < 1e-5 and res["param_rel"] < 1e-4 and all(
     abs(a - b) <= 1e-4 * abs(a) for a, b in zip(*[out[m][0] for m in (False, True)]))
+# the exchange fused with the optimizer over NVLink multicast (csrc/exchange.cu) against the same single all-reduce
+gp, pp = out["peer"][1], out["peer"][2]
+# after the fused exchange every rank's buffer holds the SUM on its own shard only: compare through the parameters
+# (first step: same gradients -> same update) and the second-step loss
+p_first_rel = float((pp - p0).norm() / p0.norm())
+res.update(losses_peer=out["peer"][0], peer_param_rel=p_first_rel, peer_error=bool(step.opt.peer_error()))
+ok = ok and p_first_rel < 1e-4 and not res["peer_error"] and all(
+    abs(a - b) <= 1e-4 * abs(a) for a, b in zip(out[False][0], out["peer"][0]))
+# every rank must hold the same parameters after the broadcast
+chk = pp.double().sum().reshape(1).clone()
+both = [torch.zeros_like(chk) for _ in range(2)]
+dist.all_gather(both, chk)
+res["peer_params_identical"] = bool(both[0].item() == both[1].item())
+ok = ok and res["peer_params_identical"]
 res["ok"] = bool(ok)
 if rank == 0:
     print(json.dumps(res), flush=True)
