@@ -48,7 +48,9 @@ match_cost_kernel(const float* __restrict__ cls_pred, const float* __restrict__ 
     const float4 gb = reinterpret_cast<const float4*>(gt_bboxes)[g0 + g];  // x1 y1 x2 y2 (pixels)
     const int label = (int)gt_labels[g0 + g];
     // FocalLossCost, match_cost.py:93-99 (alpha .25, gamma 2, eps 1e-12)
-    const float x = cl[label];
+    // a label outside [0, C) would read out of bounds: its cost becomes NaN, the solver reports status 1 for the
+    // problem and HungarianAssigner.check_status() raises what scipy raises on invalid entries
+    const float x = (label >= 0 && label < C) ? cl[label] : __int_as_float(0x7fc00000);
     const float s = 1.0f / (1.0f + expf(-x));
     const float neg = (-logf((1.0f - s) + 1e-12f)) * 0.75f * (s * s);
     const float pos = (-logf(s + 1e-12f)) * 0.25f * ((1.0f - s) * (1.0f - s));

@@ -457,6 +457,17 @@ class FusedSupervisedTrainStep:
             raise RuntimeError("FusedSupervisedTrainStep: exchange='peer' needs NVLink multicast (NVLS) on this node")
         _cache_student_bn_folds(model)
 
+    def check(self):
+        """Off-the-hot-path health check (synchronises; call it at the logging interval): raises what the reference's
+        host-side matcher would have raised inside the step -- scipy's ValueError on NaN / infeasible cost matrices
+        (hungarian_assigner.py:136; an out-of-range label also shows up as an invalid entry) -- and reports a peer
+        that never arrived at the fused gradient exchange."""
+        assigner = getattr(getattr(self.model, "bbox_head", None), "assigner", None)
+        if assigner is not None and hasattr(assigner, "check_status"):
+            assigner.check_status()
+        if self.opt.peer_exchange and self.opt.peer_error():
+            raise RuntimeError("fused gradient exchange: a rank did not arrive within the wait bound")
+
     def _pack(self, grads, params=None):
         """grads (one per parameter, None for unused ones) -> the flat gradient buffer"""
         views = [p.grad for p in (self.opt.params if params is None else params)]
