@@ -394,6 +394,8 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     clocks = sampler.stop() if sampler else None
+    if hasattr(step, "check"):
+        step.check()      # matcher status of the last step, and (N > 1) that no rank timed out in the fused exchange
 
     # ---- per-kernel timing for the roofline: CUDA events around every MSDA launch.  Events recorded inside a
     # captured graph cannot be queried, so the same step runs eagerly for this part -----------------------
@@ -567,7 +569,7 @@ def run_msda(args):
     dom = results["msda_bwd_enc_f32"]
     traffic, traffic_src = _committed_traffic("msda_bwd_micro_enc")
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline and not five:
+    if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         t = cpu_reference_msda_time(2, 1, threads)
         sec = sum(t) / len(t)
@@ -681,7 +683,7 @@ def run_ssod(args):
         return
     h = phases["Hungarian"]
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline and not five:
+    if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         t = cpu_reference_ssod_step_time(1, 0, threads)
         cpu_baseline = dict(value=5 / t[0], unit=UNIT, cores=threads, kind="port",

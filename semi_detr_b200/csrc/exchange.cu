@@ -45,7 +45,7 @@ constexpr int kAcc = kEpoch + 6;            // local: double accumulator of the 
 constexpr int kSmallBase = 128;             // small all-reduce slots: [kSmallBase + slot * 64 ...]
 constexpr int kSmallSlots = 4;
 constexpr int kCtrlWords = kSmallBase + kSmallSlots * 128;
-constexpr long long kSpinLimit = 6000000000LL;   // ~3 s at 1.9 GHz
+constexpr long long kSpinLimit = 120000000000LL;   // ~60 s at 1.9 GHz: ranks may be seconds apart (first-step autotuning)
 
 struct Peers {
   unsigned* ctrl[kMaxWorld];
