@@ -63,7 +63,7 @@ def test_sass_is_sm100a_only(libpath):
 def test_validated_kernels_are_unchanged(libpath):
     """Kernels whose parity and timing were measured on a B200 must still compile to the same SASS: work done without a
     GPU (new template parameters, shared headers, new opt-in variants) may add kernels but not alter validated ones
-    (tools/sass_fingerprint.py, profiles/sass_validated_r1.json; hashes are per nvcc version)."""
+    (tools/sass_fingerprint.py, profiles/sass_validated_r2.json; hashes are per nvcc version)."""
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_fingerprint.py")], capture_output=True,
                        text=True, timeout=600)

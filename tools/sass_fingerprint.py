@@ -1,5 +1,5 @@
 """Guard for kernels that were validated on hardware: a hash of each kernel's SASS (instruction text without addresses
-and encodings) is kept in profiles/sass_validated_r1.json; `--check` (default) reports validated kernels whose SASS is no
+and encodings) is kept in profiles/sass_validated_r2.json; `--check` (default) reports validated kernels whose SASS is no
 longer produced by the current build.
 
     python tools/sass_fingerprint.py            # check the built objects against the committed fingerprints
@@ -22,7 +22,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJDIR = os.path.join(ROOT, "semi_detr_b200", "lib", "obj")
-OUT = os.path.join(ROOT, "profiles", "sass_validated_r1.json")
+OUT = os.path.join(ROOT, "profiles", "sass_validated_r2.json")
 # Objects whose kernels ptxas has been seen to compile differently from identical source (register pairs, swapped
 # neighbours); the digest below absorbs what was observed, but a mismatch there is reported, not fatal.
 LENIENT = {"gemm_tf32.o", "umma_rate.o"}
