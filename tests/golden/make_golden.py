@@ -763,6 +763,80 @@ def make_ssod_wiring():
     print("ssod_wiring_golden.npz: teacher order", list(out["teacher_names"]), "kept", [len(b) for b in rec["boxes"]])
 
 
+def make_ssod_decode():
+    """The reference's own teacher decode for pseudo labels: ``DINODETRSSODHead._get_bboxes_single`` with
+    ``for_pseudo_label=True`` (dino_detr_ssod_head.py:1331-1395; method body compiled from the file) calling the real
+    mmdet ``multiclass_nms`` (thirdparty/mmdetection/mmdet/core/post_processing/bbox_nms.py:8-95, loaded from the file)
+    and the real ``bbox_cxcywh_to_xyxy``.  The one piece that is not under /root/reference is mmcv-full 1.3.16's compiled
+    ``mmcv.ops.nms`` (README.md:30): ``batched_nms`` is restated below from mmcv's published python (ops/nms.py:
+    class-aware offset trick, then -- because the reference passes split_thr=-1 -- the per-class loop with the
+    descending-score re-sort) on ``torchvision.ops.nms``, which implements the same greedy IoU > threshold suppression
+    with offset 0.  Inputs: peaked / overlapping predictions so that NMS, the 0.01 threshold and max_per_img all bite."""
+    import types
+    import torchvision
+    R._install_mmcv_stub()
+    for pk in ("mmcv.ops", "mmdet", "mmdet.core", "mmdet.core.bbox", "mmdet.core.bbox.iou_calculators",
+               "mmdet.core.post_processing"):
+        R._pkg(pk)
+
+    def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):        # mmcv/ops/nms.py (1.3.16), restated
+        nms_cfg_ = dict(nms_cfg)
+        assert not class_agnostic and nms_cfg_.pop("type", "nms") == "nms"
+        max_coordinate = boxes.max()
+        offsets = idxs.to(boxes) * (max_coordinate + torch.tensor(1).to(boxes))
+        boxes_for_nms = boxes + offsets[:, None]
+        split_thr = nms_cfg_.pop("split_thr", 10000)
+        thr = nms_cfg_["iou_threshold"]
+        if boxes_for_nms.shape[0] < split_thr:
+            keep = torchvision.ops.nms(boxes_for_nms, scores, thr)
+            boxes, scores = boxes[keep], scores[keep]
+        else:
+            total_mask = scores.new_zeros(scores.size(), dtype=torch.bool)
+            for cid in torch.unique(idxs):
+                mask = (idxs == cid).nonzero(as_tuple=False).view(-1)
+                k = torchvision.ops.nms(boxes_for_nms[mask], scores[mask], thr)
+                total_mask[mask[k]] = True
+            keep = total_mask.nonzero(as_tuple=False).view(-1)
+            keep = keep[scores[keep].argsort(descending=True)]
+            boxes, scores = boxes[keep], scores[keep]
+        return torch.cat([boxes, scores[:, None]], -1), keep
+
+    nms_mod = types.ModuleType("mmcv.ops.nms")
+    nms_mod.batched_nms = batched_nms
+    sys.modules["mmcv.ops.nms"] = nms_mod
+    sys.modules["mmcv.ops"].nms = nms_mod
+    R.load_hungarian()                      # iou2d_calculator (bbox_nms.py imports bbox_overlaps) and transforms, as for the assigner
+    tr = sys.modules["mmdet.core.bbox.transforms"]
+    bn = R._load("mmdet.core.post_processing.bbox_nms", R.MMDET + "/core/post_processing/bbox_nms.py")
+    fn = R.load_methods(R.REF + "/detr_od/models/dense_heads/dino_detr_ssod_head.py", "DINODETRSSODHead",
+                        ["_get_bboxes_single"],
+                        dict(torch=torch, multiclass_nms=bn.multiclass_nms,
+                             bbox_cxcywh_to_xyxy=tr.bbox_cxcywh_to_xyxy))["_get_bboxes_single"]
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    cases = [(900, 80, 300, (800, 1333, 3), 40), (300, 80, 100, (640, 480, 3), 12), (50, 80, 300, (200, 300, 3), 0)]
+    for ci, (Q, C, max_per_img, img_shape, n_obj) in enumerate(cases):
+        me = types.SimpleNamespace(test_cfg=dict(max_per_img=max_per_img), num_query=Q, num_classes=C, in_warm_up=False,
+                                   loss_cls2=types.SimpleNamespace(use_sigmoid=True))
+        logits = torch.randn(Q, C, generator=g) * 1.2 - 6.5                  # most (query, class) pairs below 0.01
+        boxes = torch.rand(Q, 4, generator=g) * torch.tensor([0.8, 0.8, 0.3, 0.3]) + torch.tensor([0.1, 0.1, 0.02, 0.02])
+        for o in range(n_obj):                                                # clusters of near-duplicate detections
+            ctr = torch.rand(4, generator=g) * torch.tensor([0.7, 0.7, 0.3, 0.3]) + torch.tensor([0.15, 0.15, 0.05, 0.05])
+            members = torch.randperm(Q, generator=g)[:int(torch.randint(2, 9, (1,), generator=g))]
+            cls = int(torch.randint(0, C, (1,), generator=g))
+            boxes[members] = ctr + torch.randn(len(members), 4, generator=g) * 0.01
+            logits[members, cls] = torch.randn(len(members), generator=g) * 1.5 + 1.0
+            if o % 5 == 0:                                                    # a second class on the same boxes
+                logits[members, (cls + 3) % C] = torch.randn(len(members), generator=g) - 1.0
+        boxes = boxes.clamp(0.001, 0.999)
+        det, lab = fn(me, logits.clone(), boxes.clone(), img_shape, None, rescale=False, for_pseudo_label=True)
+        out[f"c{ci}/logits"], out[f"c{ci}/boxes"] = logits.numpy(), boxes.numpy()
+        out[f"c{ci}/img_shape"], out[f"c{ci}/max_per_img"] = np.asarray(img_shape), np.asarray(max_per_img)
+        out[f"c{ci}/det_bboxes"], out[f"c{ci}/det_labels"] = det.numpy(), lab.numpy()
+        print(f"ssod_decode case {ci}: {int((logits.sigmoid() > 0.01).sum())} candidates -> {len(lab)} detections")
+    np.savez_compressed(os.path.join(HERE, "ssod_decode_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -782,3 +856,4 @@ if __name__ == "__main__":
     make_backbone()
     make_dino_ssod_head_forward()
     make_ssod_wiring()
+    make_ssod_decode()

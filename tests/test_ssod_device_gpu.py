@@ -136,3 +136,21 @@ def test_teacher_student_step_reads_back_only_what_decides_shapes():
     assert torch.isfinite(sum(v for k, v in losses.items() if "loss" in k))
     assert c.n.get("nonzero", 0) == 0, c.n.get("nonzero")
     assert c.n.get("_local_scalar_dense", 0) + c.n.get("item", 0) <= 8, {k: v for k, v in c.n.items() if "scalar" in k or k == "item"}
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_teacher_decode_on_the_device_matches_the_reference_head(ci):
+    """The device decode (box arithmetic of `_decode_last_layer` + `sdb_pseudo_label_nms_f32`) against detections
+    produced by the reference's OWN `_get_bboxes_single` + mmdet `multiclass_nms` (tests/golden/ssod_decode_golden.npz):
+    labels and order identical, scores bit-equal, boxes to 1e-4 px."""
+    import sys
+    sys.path.insert(0, HERE)
+    from test_dino_reference_golden import _decode_case
+    from semi_detr_b200.ssod import device_ops
+    scores, xyxy, max_per_img, want_det, want_lab = _decode_case(ci, "cuda")
+    ob, os_, ol, cnt, _ = device_ops.pseudo_label_nms(scores, xyxy, 0.01, 0.6, max_per_img, False)
+    n = int(cnt[0])
+    assert n == len(want_lab)
+    assert np.array_equal(ol[0, :n].cpu().numpy(), want_lab)
+    np.testing.assert_allclose(os_[0, :n].cpu().numpy(), want_det[:, 4], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(ob[0, :n].cpu().numpy(), want_det[:, :4], rtol=1e-6, atol=1e-4)
