@@ -374,3 +374,15 @@ def fake_teacher_detections(img_metas):
         out.append((torch.cat([xy, xy + torch.rand(n, 2, generator=g) * 40 + 2, torch.rand(n, 1, generator=g) ** 2], 1),
                     torch.randint(0, 80, (n,), generator=g)))
     return out
+
+
+def roi_inputs(seed=97, H=384, W=512, n=32):
+    """Four feature levels (strides 8..64) of one 384 x 512 image pair and n RoIs (batch index, x1, y1, x2, y2) whose
+    scales spread over the FPN level mapping (finest_scale 56: < 112 px -> level 0, < 224 -> 1, < 448 -> 2)."""
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(2, 256, -(-H // s), -(-W // s), generator=g) for s in (8, 16, 32, 64)]
+    xy = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.3, H * 0.3])
+    wh = torch.exp(torch.rand(n, 1, generator=g) * 4.7 + 1.2) * torch.exp((torch.rand(n, 2, generator=g) - 0.5) * 0.6)   # ~3 .. 365 px
+    boxes = torch.cat([xy, torch.minimum(xy + wh, torch.tensor([W - 1.0, H - 1.0]))], 1)
+    rois = torch.cat([torch.randint(0, 2, (n, 1), generator=g).float(), boxes], 1)
+    return feats, rois

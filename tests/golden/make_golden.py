@@ -837,6 +837,69 @@ def make_ssod_decode():
     np.savez_compressed(os.path.join(HERE, "ssod_decode_golden.npz"), **out)
 
 
+def make_ssod_roi_projector():
+    """Content of the consistency queries (dino_detr_ssod.py:592-607): the real mmdet ``SingleRoIExtractor``
+    (roi_heads/roi_extractors/single_level_roi_extractor.py + base_roi_extractor.py, loaded from the files, built with
+    the reference's config dino_detr_ssod.py:97-100) followed by the reference's own ``Projector`` class
+    (dino_detr_ssod.py:33-72, class body compiled from the file), by-name deterministic weights, BatchNorm in training
+    mode as in the train step.  Outside /root/reference: mmcv-full 1.3.16's compiled ``mmcv.ops.RoIAlign`` -- restated as
+    a module over ``torchvision.ops.roi_align`` with mmcv's defaults for this call (pool_mode 'avg', aligned=True)."""
+    import ast
+    import types
+    import torchvision
+    import dino_fixture as F
+    R._install_mmcv_stub()
+    for pk in ("mmcv.ops", "mmdet", "mmdet.models", "mmdet.models.roi_heads", "mmdet.models.roi_heads.roi_extractors"):
+        R._pkg(pk)
+
+    class RoIAlign(torch.nn.Module):                  # mmcv/ops/roi_align.py (1.3.16) restated on torchvision's op
+        def __init__(self, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode="avg", aligned=True):
+            super().__init__()
+            assert pool_mode == "avg"
+            self.output_size = torch.nn.modules.utils._pair(output_size)
+            self.spatial_scale, self.sampling_ratio, self.aligned = float(spatial_scale), int(sampling_ratio), aligned
+
+        def forward(self, feat, rois):
+            return torchvision.ops.roi_align(feat, rois, self.output_size, self.spatial_scale, self.sampling_ratio,
+                                             self.aligned)
+    sys.modules["mmcv.ops"].RoIAlign = RoIAlign
+    sys.modules["mmcv"].ops = sys.modules["mmcv.ops"]
+    runner = sys.modules["mmcv.runner"]
+
+    class BaseModule(torch.nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+    runner.BaseModule = BaseModule
+    runner.force_fp32 = lambda *a, **k: (lambda f: f)
+    builder = types.ModuleType("mmdet.models.builder")
+    builder.ROI_EXTRACTORS = R._Registry("roi_extractor")
+    sys.modules["mmdet.models.builder"] = builder
+    sys.modules["mmdet.models"].builder = builder
+    d = R.MMDET + "/models/roi_heads/roi_extractors"
+    R._load("mmdet.models.roi_heads.roi_extractors.base_roi_extractor", d + "/base_roi_extractor.py")
+    sl = R._load("mmdet.models.roi_heads.roi_extractors.single_level_roi_extractor", d + "/single_level_roi_extractor.py")
+    extractor = sl.SingleRoIExtractor(roi_layer=dict(type="RoIAlign", output_size=7, sampling_ratio=0), out_channels=256,
+                                      featmap_strides=[8, 16, 32, 64])
+    path = R.REF + "/detr_ssod/models/dino_detr_ssod.py"
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Projector")
+    ns = dict(nn=torch.nn, torch=torch)
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, "exec"), ns)
+    proj = ns["Projector"]()
+    F.fill_by_name(proj)
+    proj.train()
+    feats, rois = F.roi_inputs()               # seeded; the test regenerates them instead of shipping 6 MB of noise
+    pooled = extractor(feats, rois)
+    lvls = extractor.map_roi_levels(rois, 4)
+    emb = proj(pooled)
+    out = dict(rois=rois.numpy(), pooled_every_8th_channel=pooled.detach().numpy()[:, ::8], levels=lvls.numpy(),
+               embed=emb.detach().numpy(), feat_checksum=np.array([float(f.double().sum()) for f in feats]),
+               names=np.array([k for k, _ in proj.state_dict().items()]))
+    np.savez_compressed(os.path.join(HERE, "ssod_roi_projector_golden.npz"), **out)
+    print("ssod_roi_projector_golden.npz: levels", np.bincount(lvls.numpy(), minlength=4).tolist(),
+          "embed mean", float(emb.detach().mean()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -857,3 +920,4 @@ if __name__ == "__main__":
     make_dino_ssod_head_forward()
     make_ssod_wiring()
     make_ssod_decode()
+    make_ssod_roi_projector()
