@@ -386,3 +386,17 @@ def roi_inputs(seed=97, H=384, W=512, n=32):
     boxes = torch.cat([xy, torch.minimum(xy + wh, torch.tensor([W - 1.0, H - 1.0]))], 1)
     rois = torch.cat([torch.randint(0, 2, (n, 1), generator=g).float(), boxes], 1)
     return feats, rois
+
+
+def ssod_forward_train_inputs(seed=83):
+    """An interleaved teacher-student batch as the SemiDataset collate would deliver it: 2 labelled images and 2 (weak,
+    strong) pairs in mixed order; tiny images, per-sample ground truth lists."""
+    g = torch.Generator().manual_seed(seed)
+    tags = ["unsup_teacher", "sup", "unsup_student", "unsup_student", "sup", "unsup_teacher"]
+    names = ["u1.jpg", "s0.jpg", "u0.jpg", "u1.jpg", "s1.jpg", "u0.jpg"]
+    img = torch.randn(len(tags), 3, 8, 12, generator=g)
+    metas = [dict(tag=t, filename=n, img_shape=(8, 12, 3), scale_factor=1.0) for t, n in zip(tags, names)]
+    counts = [0, 3, 2, 1, 4, 2]
+    gt_bboxes = [torch.rand(c, 4, generator=g) * 8 for c in counts]
+    gt_labels = [torch.randint(0, 80, (c,), generator=g) for c in counts]
+    return dict(img=img, img_metas=metas, gt_bboxes=gt_bboxes, gt_labels=gt_labels)

@@ -900,6 +900,71 @@ def make_ssod_roi_projector():
           "embed mean", float(emb.detach().mean()))
 
 
+def make_ssod_forward_train():
+    """The reference's own ``DinoDetrSSOD.forward_train`` (dino_detr_ssod.py:112-152; method body compiled from the file,
+    minus its first statement -- ``super().forward_train(...)``, a call into MultiSteamDetector that needs the class
+    cell) with the real ``dict_split`` / ``dict_select`` / ``weighted_loss`` of detr_ssod/utils/structure_utils.py
+    (loaded from the file; ``collections.Mapping`` aliased for python >= 3.10, mmdet's BitmapMasks stubbed).  The student
+    and ``foward_unsup_train`` are recorders: what each receives from an interleaved batch, and the loss dict that
+    comes back (prefixes, the 4.0 weight on keys containing 'loss')."""
+    import ast
+    import collections
+    import collections.abc
+    import types
+    collections.Mapping, collections.Sequence = collections.abc.Mapping, collections.abc.Sequence
+    for pk in ("mmdet", "mmdet.core", "mmdet.core.mask"):
+        R._pkg(pk)
+    st = types.ModuleType("mmdet.core.mask.structures")
+    st.BitmapMasks = type("BitmapMasks", (), {})
+    sys.modules["mmdet.core.mask.structures"] = st
+    su = R._load("detr_ssod_ref.utils.structure_utils", R.REF + "/detr_ssod/utils/structure_utils.py") \
+        if "detr_ssod_ref.utils" in sys.modules else None
+    if su is None:
+        for pk in ("detr_ssod_ref", "detr_ssod_ref.utils"):
+            R._pkg(pk)
+        su = R._load("detr_ssod_ref.utils.structure_utils", R.REF + "/detr_ssod/utils/structure_utils.py")
+    path = R.REF + "/detr_ssod/models/dino_detr_ssod.py"
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DinoDetrSSOD")
+    node = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "forward_train")
+    assert isinstance(node.body[0], ast.Expr) and "super" in ast.unparse(node.body[0])
+    node.body = node.body[1:]
+    ns = dict(torch=torch, dict_split=su.dict_split, weighted_loss=su.weighted_loss, log_every_n=lambda *a, **k: None)
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    import dino_fixture as F
+    data = F.ssod_forward_train_inputs()
+    rec = {}
+
+    def student_forward_train(img, img_metas, gt_bboxes, gt_labels, curr_step=None, **kw):
+        rec["sup"] = dict(img=img, names=[m["filename"] for m in img_metas], gt_bboxes=gt_bboxes, gt_labels=gt_labels,
+                          curr_step=curr_step, extra=sorted(kw))
+        return dict(loss_cls=torch.tensor(1.5), loss_bbox=torch.tensor(0.25), pos_num=torch.tensor(3.0))
+
+    def foward_unsup_train(teacher_data, student_data):
+        rec["teacher"], rec["student"] = teacher_data, student_data
+        return dict(loss_cls=torch.tensor(2.0), **{"d0.loss_iou": torch.tensor(0.5)}, consis_count=torch.tensor(7.0))
+    me = types.SimpleNamespace(student=types.SimpleNamespace(forward_train=student_forward_train),
+                               foward_unsup_train=foward_unsup_train, curr_step=1234, unsup_weight=4.0)
+    loss = ns["forward_train"](me, data["img"], data["img_metas"], gt_bboxes=data["gt_bboxes"],
+                               gt_labels=data["gt_labels"])
+    out = {"loss_keys": np.array(sorted(loss)), "loss_vals": np.array([float(loss[k]) for k in sorted(loss)]),
+           "sup/img": rec["sup"]["img"].numpy(), "sup/names": np.array(rec["sup"]["names"]),
+           "sup/curr_step": np.asarray(rec["sup"]["curr_step"]), "sup/extra": np.array(rec["sup"]["extra"], dtype=str)}
+    for i, (b, l) in enumerate(zip(rec["sup"]["gt_bboxes"], rec["sup"]["gt_labels"])):
+        out[f"sup/gt_bboxes{i}"], out[f"sup/gt_labels{i}"] = b.numpy(), l.numpy()
+    for side in ("teacher", "student"):
+        d = rec[side]
+        out[f"{side}/keys"] = np.array(sorted(d))
+        out[f"{side}/img"] = d["img"].numpy()
+        out[f"{side}/names"] = np.array([m["filename"] for m in d["img_metas"]])
+        out[f"{side}/tags"] = np.array([m["tag"] for m in d["img_metas"]])
+        for i, (b, l) in enumerate(zip(d["gt_bboxes"], d["gt_labels"])):
+            out[f"{side}/gt_bboxes{i}"], out[f"{side}/gt_labels{i}"] = b.numpy(), l.numpy()
+    np.savez_compressed(os.path.join(HERE, "ssod_forward_train_golden.npz"), **out)
+    print("ssod_forward_train_golden.npz:", dict(zip(out["loss_keys"].tolist(), out["loss_vals"].tolist())),
+          "sup", out["sup/names"].tolist(), "teacher", out["teacher/names"].tolist(), "student", out["student/names"].tolist())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_msda()
@@ -921,3 +986,4 @@ if __name__ == "__main__":
     make_ssod_wiring()
     make_ssod_decode()
     make_ssod_roi_projector()
+    make_ssod_forward_train()
