@@ -218,8 +218,9 @@ def test_relu_backward_colsum(rows, cols):
 
 
 def test_ffn_layer_uses_fused_relu_backward(monkeypatch):
-    """FFN linear1 + ReLU under the default policy: forward on the tcgen05 kernel (ReLU in the epilogue), backward =
-    one fused ReLU-backward + bias-gradient pass, library products; same numbers as nn.Linear + relu."""
+    """FFN linear1 + ReLU under the default policy: forward = the library GEMM with the ReLU in its epilogue (cuBLASLt is
+    twice as fast as our kernel at this shape, tools/time_linear1.py), backward = ONE fused ReLU-backward + bias-gradient
+    pass of this library + library products; same numbers as nn.Linear + relu."""
     from semi_detr_b200 import _lib
     from semi_detr_b200.layers.linear import Linear
     prev = torch.backends.cuda.matmul.allow_tf32
@@ -233,7 +234,7 @@ def test_ffn_layer_uses_fused_relu_backward(monkeypatch):
         before = dict(_lib.LAUNCHES)
         y = lin(x, relu=True)
         y.backward(gy)
-        assert _lib.LAUNCHES["gemm_tf32"] - before["gemm_tf32"] == 1
+        assert _lib.LAUNCHES["gemm_tf32"] == before["gemm_tf32"]
         assert _lib.LAUNCHES["relu_backward_colsum"] - before["relu_backward_colsum"] == 1
         assert _lib.LAUNCHES["colsum"] == before["colsum"]
         xr = x.detach().clone().requires_grad_(True)

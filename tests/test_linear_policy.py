@@ -17,7 +17,8 @@ def test_product_plan_policies(monkeypatch, tf32_on):
     monkeypatch.setenv("SDB_LINEAR", "auto")
     assert product_plan(256, 256, False) == (False, False, True)      # split-K grad-weight (+ bias gradient) only
     assert product_plan(256, 256, True) == (True, False, True)        # value_proj: the mask rides in the epilogue
-    assert product_plan(256, 2048, True) == (True, False, False)      # FFN linear1: ReLU rides in the epilogue
+    assert product_plan(256, 2048, True, has_mask=False) == (False, False, False)   # FFN linear1: ReLU is a library epilogue too;
+    #                                                     the layer keeps its fused ReLU-backward + bias-gradient pass
     assert product_plan(2048, 256, False) is None                     # FFN linear2: library
     monkeypatch.setenv("SDB_LINEAR", "tcgen05")
     assert product_plan(256, 384, False) == (True, True, True)

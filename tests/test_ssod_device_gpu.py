@@ -142,7 +142,7 @@ def test_teacher_student_step_reads_back_only_what_decides_shapes():
 def test_teacher_decode_on_the_device_matches_the_reference_head(ci):
     """The device decode (box arithmetic of `_decode_last_layer` + `sdb_pseudo_label_nms_f32`) against detections
     produced by the reference's OWN `_get_bboxes_single` + mmdet `multiclass_nms` (tests/golden/ssod_decode_golden.npz):
-    labels and order identical, scores bit-equal, boxes to 1e-4 px."""
+    labels and order identical, scores to 2 ulp (the sigmoid runs on the device), boxes to 1e-4 px."""
     import sys
     sys.path.insert(0, HERE)
     from test_dino_reference_golden import _decode_case
@@ -152,5 +152,5 @@ def test_teacher_decode_on_the_device_matches_the_reference_head(ci):
     n = int(cnt[0])
     assert n == len(want_lab)
     assert np.array_equal(ol[0, :n].cpu().numpy(), want_lab)
-    np.testing.assert_allclose(os_[0, :n].cpu().numpy(), want_det[:, 4], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(os_[0, :n].cpu().numpy(), want_det[:, 4], rtol=0, atol=2.4e-7)   # sigmoid on the device: <= 2 ulp
     np.testing.assert_allclose(ob[0, :n].cpu().numpy(), want_det[:, :4], rtol=1e-6, atol=1e-4)
