@@ -469,6 +469,9 @@ def run_ours(args):
                        "f32 (tf32 tensor-core matmul/conv; MSDA, matching and losses in f32)"), data="synthetic",
                 config=dict(workload=SUP5_WORKLOAD if five else WORKLOAD, global_batch=PER_GPU_BATCH * world, parallelism=f"dp{world}",
                             execution=graph_note,
+                            padding=("no image of the synthetic batch is padded (all 800x1333): the all-False padding mask "
+                                     "of the MSDA value projections is skipped" if os.environ.get("SDB_SKIP_EMPTY_MASK", "1") != "0"
+                                     else "padding mask applied although all-False (SDB_SKIP_EMPTY_MASK=0)"),
                             exchange=(None if world == 1 else
                                       ("gradient sum + clip + AdamW + parameter broadcast fused over NVLink multicast "
                                        "(sdb_dp_adamw_exchange_f32)" if getattr(step, "exchange", "") == "peer" else

@@ -13,6 +13,7 @@ Host-side differences that do not change numerics:
 """
 import copy
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -24,6 +25,7 @@ from ..msda import MSDeformAttn
 from ..registry import TRANSFORMER
 from ..layers import LayerNorm, Linear
 from ..layers.attention import attention_enabled, fused_self_attention
+from ..layers.linear import linear
 
 
 def inverse_sigmoid(x, eps=1e-5):
@@ -223,9 +225,9 @@ class DINOTransformerDecoderLayer(nn.Module):
             # in place from the shared projection's output, no (N*H, T, T) tensor exists
             if attn_mask is not None and attn_mask_t is None:
                 attn_mask_t = attn_mask.t().contiguous()
-            out = fused_self_attention(F.linear(qk, w[:2 * C], b[:2 * C]), F.linear(value, w[2 * C:], b[2 * C:]),
+            out = fused_self_attention(linear(qk, w[:2 * C], b[:2 * C]), linear(value, w[2 * C:], b[2 * C:]),
                                        attn_mask, attn_mask_t, H)
-            return F.linear(out, mha.out_proj.weight, mha.out_proj.bias)
+            return linear(out, mha.out_proj.weight, mha.out_proj.bias)
         q, k = F.linear(qk, w[:2 * C], b[:2 * C]).split(C, -1)
         v = F.linear(value, w[2 * C:], b[2 * C:])
         q = (q * (float(d) ** -0.5)).reshape(T, N * H, d).transpose(0, 1)
@@ -408,7 +410,14 @@ class DINOTransformer(nn.Module):
         level_start_index = device_const(src_flat.device, "level_start", skey,
                                          lambda: torch.as_tensor(starts, dtype=torch.long))
 
-        memory = self.encoder(src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, mask_flat,
+        # A batch in which no image is padded (every img_shape equals the batch shape -- known on the host from the
+        # metas) has an all-False padding mask: the MSDA value projections then skip the mask in both directions
+        # (ms_deform_attn.py:96-97 would fill nothing).  Same numbers; SDB_SKIP_EMPTY_MASK=0 keeps the masked path.
+        msda_mask = mask_flat
+        if (geometry_key is not None and os.environ.get("SDB_SKIP_EMPTY_MASK", "1") != "0"
+                and all(tuple(hw) == (geometry_key[0], geometry_key[1]) for hw in geometry_key[2])):
+            msda_mask = None
+        memory = self.encoder(src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, msda_mask,
                               shapes_list, reference_points=enc_refs)
 
         # two-stage query selection (transformer.py:1314-1346; gen_encoder_output_proposals with its mask-only part
@@ -431,7 +440,7 @@ class DINOTransformer(nn.Module):
         else:
             refpoint_embed, tgt = refpoint_sel, tgt_sel
 
-        hs, references = self.decoder(tgt.transpose(0, 1), memory, attn_mask, mask_flat,
+        hs, references = self.decoder(tgt.transpose(0, 1), memory, attn_mask, msda_mask,
                                       refpoint_embed.transpose(0, 1), level_start_index, spatial_shapes,
                                       valid_ratios, fc_reg)
         hs_enc = tgt_undetach.unsqueeze(0)

@@ -112,6 +112,15 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb
 
 
+def linear(x, weight, bias):
+    """``F.linear`` for layers that are not ``Linear`` modules (the in / out projections of nn.MultiheadAttention): on the
+    device the bias gradient comes from this library's column-sum kernel instead of a generic reduction."""
+    if (x.is_cuda and x.dtype == torch.float32 and bias is not None and weight.shape[0] % 4 == 0
+            and x.numel() >= (1 << 16) and torch.is_grad_enabled() and not torch.is_autocast_enabled()):
+        return _LinearFn.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
 class _TensorCoreLinearFn(torch.autograd.Function):
     """y = [mask rows](relu)(x W^T + b); ``plan`` says which of the three products run on sdb_gemm_tf32."""
 
