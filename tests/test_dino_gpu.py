@@ -43,10 +43,28 @@ def fp32_products():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-@pytest.mark.parametrize("scales", [4, 5])
+def _pad_second_image(data, h, w):
+    """Make image 1 a smaller image padded into the batch canvas (zeros outside h x w, boxes clipped into it): the
+    padding masks of the transformer become non-trivial."""
+    data["img"][1, :, h:, :] = 0
+    data["img"][1, :, :, w:] = 0
+    data["img_metas"][1]["img_shape"] = (h, w, 3)
+    b = data["gt_bboxes"][1]
+    b[:, 0::2] = b[:, 0::2].clamp(0, w - 1)
+    b[:, 1::2] = b[:, 1::2].clamp(0, h - 1)
+    keep = (b[:, 2] - b[:, 0] > 2) & (b[:, 3] - b[:, 1] > 2)
+    data["gt_bboxes"][1], data["gt_labels"][1] = b[keep], data["gt_labels"][1][keep]
+    return data
+
+
+@pytest.mark.parametrize("scales", [4, 5, "4-padded"])
 def test_train_step_matches_cpu_reference_path(cpu_noise, fp32_products, scales):
     """scales=4: configs/dino_detr/dino_detr_r50_8x2_12e_coco.py; scales=5: BASELINE config 4 (5 feature levels,
-    L*P = 20 sampling points per head)."""
+    L*P = 20 sampling points per head); "4-padded": the second image is smaller than the batch canvas, so the padding
+    masks (value_proj row mask and its gradient, valid ratios, proposal masking) are exercised -- an unpadded batch
+    skips the all-False mask."""
+    padded = scales == "4-padded"
+    scales = 4 if padded else scales
     from semi_detr_b200 import dino  # noqa: F401
     from semi_detr_b200.registry import DETECTORS
     from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch, dino_r50_5scale
@@ -61,6 +79,8 @@ def test_train_step_matches_cpu_reference_path(cpu_noise, fp32_products, scales)
                 p.add_(torch.randn_like(p) * 0.37)
     gpu_model = copy.deepcopy(cpu_model).cuda().train()
     data = coco_like_batch(2, 288, 352, seed=5) if scales == 4 else coco_like_batch(2, 224, 256, seed=6)
+    if padded:
+        data = _pad_second_image(data, 240, 300)
     gdata = dict(img=data["img"].cuda(), img_metas=[dict(m) for m in data["img_metas"]],
                  gt_bboxes=[b.cuda() for b in data["gt_bboxes"]], gt_labels=[l.cuda() for l in data["gt_labels"]])
     cpu_noise()
@@ -235,3 +255,29 @@ def test_five_scale_bf16_autocast_step_stays_close_to_the_fp32_reference_path(cp
     cos = dot / (gg ** 0.5 * cc ** 0.5)
     print(f"[bf16 5-scale step] loss {float(loss):.4f} vs {float(ref['loss']):.4f}, gradient cosine {cos:.3f}")
     assert cos >= 0.7
+
+
+def test_skipping_the_empty_padding_mask_changes_nothing(cpu_noise, fp32_products, monkeypatch):
+    """An unpadded batch skips the all-False MSDA padding mask (dino/transformer.py); with fp32 library products both
+    routes run the same kernels on the same numbers: identical losses, gradients equal up to the order of the MSDA
+    backward's fp32 reductions."""
+    from semi_detr_b200 import dino  # noqa: F401
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import DINO_R50_4SCALE, coco_like_batch
+    torch.manual_seed(0)
+    cfg = copy.deepcopy(DINO_R50_4SCALE)
+    cfg["bbox_head"]["transformer"] = dict(type="DINOTransformer", num_encoder_layers=2, num_decoder_layers=2)
+    model = DETECTORS.build(cfg).cuda().train()
+    data = coco_like_batch(2, 224, 288, seed=9, device="cuda")
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SDB_SKIP_EMPTY_MASK", flag)
+        model.zero_grad()
+        cpu_noise()
+        out = model.train_step(dict(data, img_metas=[dict(m) for m in data["img_metas"]]))
+        out["loss"].backward()
+        res[flag] = (float(out["loss"]), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert res["0"][0] == res["1"][0]
+    for n, g in res["0"][1].items():
+        d = float((g - res["1"][1][n]).norm() / (g.norm() + 1e-12))
+        assert d < 1e-4, (n, d)
