@@ -633,7 +633,11 @@ def run_ssod(args):
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
-    fused = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, world_size=world)
+    # lr = 0: every kernel of the step runs on the same volume of data, but the student, the EMA teacher and therefore
+    # the number of pseudo boxes -- which decides tensor shapes and step time downstream -- stay what they are at step 0
+    # instead of drifting with a few steps of training on noise; without it the step time of consecutive runs differs
+    # by 2x (profiles/bench_r2_ssod_drift.txt)
+    fused = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, world_size=world, lr=0.0)
     host = ssod_batch(1, 4, IMG_H, IMG_W, seed=rank)
     host["img"] = host["img"].pin_memory()
     h2d = host["img"].numel() * 4 + sum(x.numel() * 4 for x in host["gt_bboxes"]) + \
@@ -697,6 +701,9 @@ def run_ssod(args):
                 dtype="f32 (tf32 tensor-core matmul/conv; MSDA, matching and losses in f32)", data="synthetic",
                 config=dict(workload=SSOD_WORKLOAD, global_batch=5 * world, parallelism=f"dp{world}",
                             execution="eager", phase="Hungarian (curr_step = 60000); warm-up phase under `phases`",
+                            state="learning rate 0 during the measurement: weights, teacher and pseudo-label counts stay "
+                                  "at their initial state (all kernels run; shapes downstream of the pseudo labels are "
+                                  "data dependent)",
                             l2="per-step working set exceeds the 126 MB L2"),
                 clocks=clocks,
                 e2e=dict(value=h["e2e_images_per_s"], unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,

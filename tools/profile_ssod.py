@@ -10,7 +10,7 @@ torch.backends.cudnn.allow_tf32 = True
 torch.manual_seed(0)
 model = DETECTORS.build(ssod_model_cfg()).cuda().train()
 model.curr_step = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
-data = ssod_batch(1, 4, 800, 1333, seed=0, device="cuda")
+data = ssod_batch(1, 4, 800, 1333, seed=int(os.environ.get("SSOD_SEED", "0")), device="cuda")
 for _ in range(2):
     losses = model(**data); loss, _ = model._parse_losses(losses); loss.backward()
 torch.cuda.synchronize()
