@@ -638,7 +638,7 @@ def run_ssod(args):
     # instead of drifting with a few steps of training on noise; without it the step time of consecutive runs differs
     # by 2x (profiles/bench_r2_ssod_drift.txt)
     fused = FusedSSODTrainStep(model, momentum=0.999, warm_up=0, world_size=world, lr=0.0)
-    host = ssod_batch(1, 4, IMG_H, IMG_W, seed=rank)
+    host = ssod_batch(1, 4, IMG_H, IMG_W, seed=rank + int(os.environ.get("SDB_BENCH_SEED", "0")))
     host["img"] = host["img"].pin_memory()
     h2d = host["img"].numel() * 4 + sum(x.numel() * 4 for x in host["gt_bboxes"]) + \
         sum(x.numel() * 8 for x in host["gt_labels"])

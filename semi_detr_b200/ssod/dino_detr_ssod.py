@@ -36,6 +36,34 @@ from .bbox_utils import Transform2D
 from . import device_ops
 
 
+class _ConvHeuristicAlgo(torch.autograd.Function):
+    """3 x 3 / stride 1 / pad 1 convolution without bias whose cuDNN algorithms -- forward AND both gradients, which run
+    later inside the autograd engine -- come from cuDNN's heuristics even when ``cudnn.benchmark`` is on.  For inputs whose
+    batch size changes every step (the RoIs of the pseudo boxes): autotuning each new size costs hundreds of ms and
+    ends with the autotuner emptying the caching allocator (measured: 0.4 - 2.2 s steps, tools/ssod_steps.py)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False):
+            return F.conv2d(x, w, None, 1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False):
+            gx, gw, _ = torch.ops.aten.convolution_backward(
+                g.contiguous(), x, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
+                (ctx.needs_input_grad[0], ctx.needs_input_grad[1], False))
+        return gx, gw
+
+
+def _conv3x3(conv, x):
+    if x.is_cuda and torch.backends.cudnn.benchmark:
+        return _ConvHeuristicAlgo.apply(x, conv.weight)
+    return conv(x)
+
+
 class Projector(nn.Module):
     """RoI feature (256, 7, 7) -> query content (256): conv-BN-ReLU x2, FC 12544->1024, BN, ReLU, FC 1024->256,
     ReLU (dino_detr_ssod.py:33-72; same parameter names)."""
@@ -56,8 +84,11 @@ class Projector(nn.Module):
         self.fc_relu2 = nn.ReLU()
 
     def forward(self, x):
-        x = self.ac1(self.bn1(self.conv1(x)))
-        x = self.ac2(self.bn2(self.conv2(x)))
+        # The number of RoIs follows the number of pseudo boxes and changes from step to step: under
+        # cudnn.benchmark every new batch size would be autotuned (hundreds of ms, and the autotuner empties the
+        # caching allocator afterwards), so these two convolutions take cuDNN's heuristic choice (_ConvHeuristicAlgo).
+        x = self.ac1(self.bn1(_conv3x3(self.conv1, x)))
+        x = self.ac2(self.bn2(_conv3x3(self.conv2, x)))
         x = self.fc_relu1(self.bn(self.fc1(self.flatten(x))))
         return self.fc_relu2(self.fc2(x))
 
