@@ -649,7 +649,7 @@ def run_ssod(args):
                     gt_labels=[x.to(device, non_blocking=True) for x in host["gt_labels"]])
 
     resident = to_device()
-XX
+    warm = max(args.warmup, 8)      # the first steps of a phase also pay cuDNN's autotuning for its tensor shapes
     phases = {}
     sampler = None
     for phase, it0 in (("warm-up (O2M assigner, consistency loss on)", 0), ("Hungarian", 60000)):
