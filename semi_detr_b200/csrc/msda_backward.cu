@@ -336,10 +336,10 @@ static int msda_backward(cudaStream_t st, const T* grad_out, const T* value, con
     if (v != 9 && fast_ok) {
       // default: the tile-combining kernel for encoder self-attention (one reduction line per touched pixel and tile
       // instead of one per sampled corner), the 8-lane kernel for everything else (profiles/msda_bwd_variants_r2.txt)
-      if ((v == 0 || (v >= 20 && v <= 23)) && Lq == S && L <= 8 && Lq > 0)
+      if ((v == 0 || (v >= 20 && v <= 26)) && Lq == S && L <= 8 && Lq > 0)
         return msda_backward_tile(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value, grad_loc,
                                   grad_attn, nullptr);
-      if (v == 0 || (v >= 20 && v <= 23)) v = 5;   // spill-free 115-register build
+      if (v == 0 || (v >= 20 && v <= 26)) v = 5;   // spill-free 115-register build
       switch (v) {
         case 1: return launch_bwd_d32<128, 4, 8, 6>(SDB_BWD_ARGS);
         case 2: return launch_bwd_d32<256, 4, 8, 3>(SDB_BWD_ARGS);
@@ -399,7 +399,7 @@ extern "C" int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* gra
               attn_logits && grad_offsets && grad_attn_logits, "msda_fused_backward: null pointer");
 #define SDB_FBWD_ARGS st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, batch, S, M, L, \
                       Lq, P, grad_value, grad_offsets, grad_attn_logits, reference_points, ref_dim
-  if ((g_bwd_variant == 0 || (g_bwd_variant >= 20 && g_bwd_variant <= 23)) && Lq == S && ref_dim == 2)
+  if ((g_bwd_variant == 0 || (g_bwd_variant >= 20 && g_bwd_variant <= 26)) && Lq == S && ref_dim == 2)
     return msda_backward_tile(st, grad_out, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
                               batch, S, L, grad_value, grad_offsets, grad_attn_logits, reference_points);
   switch (g_bwd_variant) {     // sdb_msda_set_variant: register budget / occupancy trade-off (tools/microbench.py)

@@ -35,7 +35,7 @@
 
 namespace sdb {
 
-extern int g_bwd_variant;   // msda_backward.cu (sdb_msda_set_variant): 20 = no look-ahead prefetch, 21 / 22 / 23 = 2 / 3 / 4 tasks
+extern int g_bwd_variant;   // msda_backward.cu (sdb_msda_set_variant): 20 = no look-ahead prefetch, 21 / 22 / 23 = 2 / 3 / 4 tasks, 24 / 25 / 26 = windows for 1 / 2 / 0 finer levels
 
 namespace {
 
@@ -49,6 +49,7 @@ constexpr int kMaxBuckets = kTableInts - 8;
 constexpr int kVisitCap = 8192;   // visit slots (padded)
 constexpr int kMaxWinLevels = 8;
 constexpr unsigned kAllLanes = 0xffffffffu;
+constexpr int kDefaultFinerLevels = 1;     // a tile also windows the next finer level when it fits (435 -> 419 us); variant 26: none
 constexpr int kDefaultPrefetchAhead = 2;   // tasks of look-ahead for the L1 prefetch of value lines (447 -> 435 us; 0 = off)
 
 struct Windows {
@@ -129,7 +130,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ attn, int batch, int S, int L,
                      float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn,
-                     const float* __restrict__ ref, int prefetch_ahead) {
+                     const float* __restrict__ ref, int prefetch_ahead, int finer_levels) {
   constexpr int M = 8, P = 4;
   constexpr int px_stride = M * 32;
   constexpr int kLv = kSlots / P;                        // level slots per query
@@ -201,7 +202,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
         const int wh = wy1 - wy0 + 1, ww = wx1 - wx0 + 1;
         // windows only where the tile's footprint is at most its own size (own level and coarser): finer levels
         // spread 64 queries over >= 256 pixels -- little to combine -- and take the direct path
-        const bool use = l >= cur.lvl && l < kMaxWinLevels && ww <= 32 && acc + wh * ww <= kMaxBuckets;
+        const bool use = l >= cur.lvl - finer_levels && l < kMaxWinLevels && ww <= 32 && acc + wh * ww <= kMaxBuckets;
         win.y0[l] = wy0;
         win.x0[l] = wx0;
         win.h[l] = use ? wh : 0;
@@ -570,8 +571,9 @@ int launch_tile(cudaStream_t st, const float* grad_out, const float* value, cons
   if (grid < 1) grid = 1;
   const int v = g_bwd_variant;
   const int ahead = v == 20 ? 0 : (v == 21 ? 2 : (v == 22 ? 3 : (v == 23 ? 4 : kDefaultPrefetchAhead)));
+  const int finer = v == 24 ? 1 : (v == 25 ? 2 : (v == 26 ? 0 : kDefaultFinerLevels));   // windows also for levels finer than the tile's own
   kern<<<(unsigned)grid, kTT, smem, st>>>(grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value, grad_loc,
-                                          grad_attn, ref, ahead);
+                                          grad_attn, ref, ahead, finer);
   SDB_LAUNCH_CHECK("msda_bwd_tile_kernel");
   return SDB_OK;
 }

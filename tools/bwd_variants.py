@@ -34,7 +34,7 @@ for name, Lq, refdim in (("enc", S, 2), ("dec", 1092, 4)):
     # 15 / 16 = 8 x 8 pixel tiles with 256 threads, 1 / 2 points in flight
     # 0 / 20 = default: tile-combining kernel for the encoder shape (msda_backward_tile.cu), 8-lane kernel otherwise
     variants = (0, 5, 6, 3, 2, 7, 8, 10, 11, 12, 15, 16) if "--all" in sys.argv else \
-        ((0, 20, 21, 22, 23) if "--tile" in sys.argv else (0, 5, 7, 12))
+        ((0, 20, 24, 25) if "--tile" in sys.argv else (0, 5, 7, 12))
     for variant in variants:
         _lib.lib().sdb_msda_set_variant(0, variant)
         ts = []
