@@ -370,7 +370,10 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
     // distinct pixel's value line is fetched while the current task is processed.
     if (!all_direct) {
       const int n_tasks = n_slots / kT;
-      const int per = (n_tasks + kTT / 4 - 1) / (kTT / 4);
+      // tasks per group, rounded up to an odd number: the 8 groups of a warp read their 16-byte visit words at a stride
+      // of 16 * per bytes, which touches 8 different bank groups exactly when per is odd (an even per put the
+      // visit-word loads at 2.9 wavefronts per instruction instead of 1)
+      const int per = ((n_tasks + kTT / 4 - 1) / (kTT / 4)) | 1;
       int i = (tid >> 2) * per;
       const int i_end = min(i + per, n_tasks);
       const unsigned res_s = (unsigned)__cvta_generic_to_shared(res);
