@@ -124,6 +124,51 @@ class SupervisedTrainStep:
         return loss.detach(), log_vars
 
 
+class GraphedNoGrad:
+    """Replay a no-grad, static-shape section of an otherwise eager step from a CUDA graph.
+
+    The teacher-student step cannot be captured as a whole (the number of pseudo boxes decides tensor shapes), but its
+    two inference passes can: the teacher's backbone + transformer + decode + NMS / filter on the weak views, and the
+    student's no-grad head pass on the strong views are ~3 000 launches with shapes fixed by the batch geometry.  After
+    ``warmup`` eager calls per key (cuDNN autotuning, per-geometry constant caches) the section is captured once over
+    copies of its tensor inputs; later calls copy the inputs in, replay, and hand out the same output tensors -- valid
+    until the next replay, i.e. for the rest of the step.  Weights are read in place (the EMA teacher is updated between
+    replays on the same storage).  Any failure to capture switches the key back to eager execution for good.
+    ``SDB_SSOD_GRAPHS=0`` disables it."""
+
+    def __init__(self, fn, warmup=2):
+        self.fn, self.warmup, self.cache = fn, warmup, {}
+
+    def __call__(self, key, tensors, *args):
+        on = (os.environ.get("SDB_SSOD_GRAPHS", "1") != "0" and all(t.is_cuda for t in tensors)
+              and not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing())
+        if not on:
+            return self.fn(*tensors, *args)
+        key = (key, tuple((tuple(t.shape), t.dtype, t.stride()) for t in tensors))
+        st = self.cache.setdefault(key, {"calls": 0})
+        if st.get("eager") or st["calls"] < self.warmup:
+            st["calls"] += 1
+            return self.fn(*tensors, *args)
+        if "graph" not in st:
+            try:
+                static_in = [t.detach().clone() for t in tensors]
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self.fn(*static_in, *args)
+                st.update(graph=graph, inputs=static_in, out=out)      # capturing does not execute: replayed below
+            except Exception as e:   # a synchronising op inside the section: stay eager, loudly
+                print(f"GraphedNoGrad: capture failed ({type(e).__name__}: {str(e)[:160]}); section stays eager",
+                      file=sys.stderr)
+                torch.cuda.synchronize()
+                st["eager"] = True
+                return self.fn(*tensors, *args)
+        for dst, src in zip(st["inputs"], tensors):
+            dst.copy_(src)
+        st["graph"].replay()
+        return st["out"]
+
+
 class GraphedTrainStep:
     """The same step captured once into a CUDA graph over static input buffers and replayed.
 

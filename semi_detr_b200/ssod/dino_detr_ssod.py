@@ -235,19 +235,25 @@ class DinoDetrSSOD(nn.Module):
     def extract_teacher_info(self, img, img_metas):
         """Teacher pseudo labels (:893-951): class-wise NMS detections, keep score >= mean + std and w, h > 0."""
         info = dict(img=img, img_metas=img_metas)
-        feat = self.teacher.extract_feat(img)
-        info["backbone_feature"] = feat
         head = self.teacher.bbox_head
         det_bboxes, det_labels, det_scores = [], [], []
         if hasattr(head, "pseudo_label_detections"):
-            # decode + class-wise NMS + mean/std filter for the whole batch in one launch; the per-image counts decide
-            # tensor shapes from here on: ONE device->host read
-            boxes, scores, labels, counts = head.pseudo_label_detections(feat, img_metas, curr_step=self.curr_step)
+            # backbone + transformer + decode + class-wise NMS + mean/std filter for the whole batch: shapes depend on
+            # the batch geometry only, so the section replays from a CUDA graph (engine.GraphedNoGrad); the per-image
+            # counts decide tensor shapes from here on: ONE device->host read
+            key = ("teacher", tuple((tuple(m["img_shape"]), tuple(m.get("batch_input_shape", ()))) for m in img_metas),
+                   bool(self.curr_step < head.warm_up_step) if self.curr_step is not None else None)
+            if self.curr_step is not None:
+                head.in_warm_up = self.curr_step < head.warm_up_step     # host state the replayed section would not set
+            feat, boxes, scores, labels, counts = self._graphed_teacher()(key, [img], img_metas, self.curr_step)
+            info["backbone_feature"] = feat
             for i, n in enumerate(counts.tolist()):
                 det_bboxes.append(boxes[i, :n])
                 det_labels.append(labels[i, :n])
                 det_scores.append(scores[i, :n])
         else:   # any head that only offers the reference's list interface
+            feat = self.teacher.extract_feat(img)
+            info["backbone_feature"] = feat
             proposals = head.simple_test_bboxes(feat, img_metas, rescale=False, curr_step=self.curr_step,
                                                 for_pseudo_label=True)
             for boxes, labels in proposals:
@@ -264,13 +270,33 @@ class DinoDetrSSOD(nn.Module):
                                                     device=img.device) for m in img_metas]
         return info
 
+    def _graphed_teacher(self):
+        g = getattr(self, "_teacher_graphs", None)
+        if g is None:
+            from ..engine import GraphedNoGrad
+            g = GraphedNoGrad(self._teacher_pass)
+            object.__setattr__(self, "_teacher_graphs", g)
+        return g
+
+    def _teacher_pass(self, x, metas, curr_step):
+        head = self.teacher.bbox_head
+        f = self.teacher.extract_feat(x)
+        return (tuple(f),) + tuple(head.pseudo_label_detections(f, metas, curr_step=curr_step))
+
     def extract_student_info(self, img, img_metas, **kwargs):
         """:813-830 -- student features (with grad) and its no-grad predictions on the strong view."""
         info = dict(img=img, img_metas=img_metas)
         feat = self.student.extract_feat(img)
         info["backbone_feature"] = feat
         with torch.no_grad():
-            info["outs"] = self.student.bbox_head.forward(feat, img_metas)
+            # the student's own predictions on the strong view (no gradient, shapes fixed by the geometry): graph replay
+            g = getattr(self, "_student_graphs", None)
+            if g is None:
+                from ..engine import GraphedNoGrad
+                g = GraphedNoGrad(lambda *a: self.student.bbox_head.forward(tuple(a[:-1]), a[-1]))
+                object.__setattr__(self, "_student_graphs", g)
+            key = ("student", tuple((tuple(m["img_shape"]), tuple(m.get("batch_input_shape", ()))) for m in img_metas))
+            info["outs"] = g(key, [f.detach() for f in feat], img_metas)
         info["transform_matrix"] = [torch.as_tensor(np.asarray(m["transform_matrix"]), dtype=torch.float32,
                                                     device=img.device) for m in img_metas]
         return info

@@ -151,3 +151,52 @@ def test_fused_ssod_engine_keeps_the_hook_semantics():
                 assert torch.equal(s, s_prev[n]), n
         assert moved > 100
     assert all(not p.requires_grad for p in model.teacher.parameters())
+
+
+def test_graphed_inference_sections_give_the_eager_pseudo_labels(monkeypatch):
+    """The teacher pass (backbone + transformer + decode + NMS / filter) and the student's no-grad head pass replay from
+    CUDA graphs after two eager calls (engine.GraphedNoGrad).  Same kernels on the same numbers: from the third call on,
+    the graphed teacher must hand out the detections the eager teacher produces, also after its weights were changed in
+    place between two replays (what the EMA update does every step)."""
+    from semi_detr_b200 import dino, ssod  # noqa: F401
+    from semi_detr_b200.registry import DETECTORS
+    from semi_detr_b200.synthetic import ssod_batch, ssod_model_cfg
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)
+        cfg = ssod_model_cfg()
+        cfg["model"]["bbox_head"]["transformer"] = dict(type="DINOTransformer", num_encoder_layers=1, num_decoder_layers=2)
+        model = DETECTORS.build(cfg).cuda().train()
+        model.curr_step = 70000
+        data = ssod_batch(1, 2, 256, 320, seed=3, device="cuda")
+        tags = [m["tag"] for m in data["img_metas"]]
+        idx = [i for i, t in enumerate(tags) if t == "unsup_teacher"]
+        img = data["img"][idx]
+        metas = [dict(data["img_metas"][i], batch_input_shape=tuple(img.shape[-2:])) for i in idx]
+
+        def detections():
+            info = model.extract_teacher_info(img, [dict(m) for m in metas])
+            return [torch.cat([b, s[:, None], l[:, None].float()], 1).clone()
+                    for b, s, l in zip(info["det_bboxes"], info["det_scores"], info["det_labels"])]
+
+        def check(tag):
+            monkeypatch.setenv("SDB_SSOD_GRAPHS", "1")
+            got = detections()
+            monkeypatch.setenv("SDB_SSOD_GRAPHS", "0")
+            want = detections()
+            assert [g.shape for g in got] == [w.shape for w in want], tag
+            for g, w in zip(got, want):
+                assert torch.equal(g[:, 5], w[:, 5]) and torch.allclose(g[:, :5], w[:, :5], rtol=1e-5, atol=1e-5), tag
+        monkeypatch.setenv("SDB_SSOD_GRAPHS", "1")
+        detections()
+        detections()                                   # two eager warm-up calls
+        check("first replay")
+        assert any("graph" in st for st in model._teacher_graphs.cache.values()), "the teacher pass was not captured"
+        with torch.no_grad():                          # in-place weight change, as the EMA blend does
+            for p in model.teacher.bbox_head.fc_cls.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        check("after an in-place weight update")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
