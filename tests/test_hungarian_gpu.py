@@ -116,3 +116,20 @@ def test_batched_step_matches_oracle():
         wi, wl = H.hungarian_assign(bbox[p], cls[p], gtb[i], gtl[i], h, w)
         assert np.array_equal(gi[p].cpu().numpy(), wi.numpy()), p
         assert np.array_equal(lb[p].cpu().numpy(), wl.numpy()), p
+
+
+def test_out_of_range_label_is_reported_like_an_invalid_cost():
+    """A ground-truth label outside [0, num_classes) would index the class scores out of bounds: the cost kernel turns
+    it into a NaN entry instead, the solver flags the problem, and `check_status()` raises what scipy raises for a cost
+    matrix with invalid entries (hungarian_assigner.py:136); `FusedSupervisedTrainStep.check()` calls it off the hot
+    path."""
+    g = torch.Generator().manual_seed(0)
+    bbox = (torch.rand(50, 4, generator=g) * 0.5 + 0.1).cuda()
+    cls = torch.randn(50, 80, generator=g).cuda()
+    gtb = torch.tensor([[10., 10., 60., 90.], [100., 50., 400., 300.]]).cuda()
+    a = _assigner()
+    a.assign(bbox, cls, gtb, torch.tensor([3, 17]).cuda(), dict(img_shape=(800, 1333, 3)))
+    a.check_status()                                   # in-range labels: fine
+    a.assign(bbox, cls, gtb, torch.tensor([3, 80]).cuda(), dict(img_shape=(800, 1333, 3)))
+    with pytest.raises(ValueError, match="invalid numeric entries"):
+        a.check_status()
