@@ -23,6 +23,9 @@ namespace sdb {
 extern int g_bwd_variant;
 
 // encoder self-attention (num_query == spatial_size): tile-combined grad_value (msda_backward_tile.cu), the default
+int msda_backward_tile_bf16(cudaStream_t st, const __nv_bfloat16* grad_out, const __nv_bfloat16* value,
+                            const int64_t* shapes, const int64_t* lsi, const float* loc, const float* attn, int batch,
+                            int S, int L, float* grad_value, float* grad_loc, float* grad_attn);
 int msda_backward_tile(cudaStream_t st, const float* grad_out, const float* value, const int64_t* shapes,
                        const int64_t* lsi, const float* loc, const float* attn, int batch, int S, int L,
                        float* grad_value, float* grad_loc, float* grad_attn, const float* ref);
@@ -446,6 +449,12 @@ extern "C" int sdb_msda_backward_bf16(sdb_stream_t stream, const uint16_t* grad_
                 reinterpret_cast<uintptr_t>(grad_value) | reinterpret_cast<uintptr_t>(grad_sampling_loc) |
                 reinterpret_cast<uintptr_t>(grad_attn_weight)) & 15) == 0,
               "msda_backward_bf16: value/grad_out must be 8-byte aligned, the fp32 tensors 16-byte aligned");
+  // encoder self-attention: the tile-combining kernel (msda_backward_tile.cu), as for fp32
+  if ((g_bwd_variant == 0 || (g_bwd_variant >= 20 && g_bwd_variant <= 26)) && Lq == S && L <= 8)
+    return msda_backward_tile_bf16(st, reinterpret_cast<const __nv_bfloat16*>(grad_out),
+                                   reinterpret_cast<const __nv_bfloat16*>(value), spatial_shapes, level_start_index,
+                                   sampling_loc, attn_weight, batch, S, L, grad_value, grad_sampling_loc,
+                                   grad_attn_weight);
   return launch_bwd_d32<128, 4, 8, 4, false, __nv_bfloat16>(
       st, reinterpret_cast<const __nv_bfloat16*>(grad_out), reinterpret_cast<const __nv_bfloat16*>(value),
       spatial_shapes, level_start_index, sampling_loc, attn_weight, batch, S, M, L, Lq, P, grad_value,

@@ -103,7 +103,8 @@ __device__ __forceinline__ float group4_sum(float v) {
   v += __shfl_xor_sync(kAllLanes, v, 2, 4);
   return v + __shfl_xor_sync(kAllLanes, v, 1, 4);
 }
-// Shared-memory layout (dynamic).  kSlots = point slots per (query, head): 16 (L <= 4) or 32 (L <= 8).
+// Shared-memory layout (dynamic).  kSlots = point slots per (query, head): 16 (L <= 4), 20 (L = 5: two CTAs still fit
+// an SM, which the 32-slot layout does not allow) or 32 (L <= 8).
 template <int kSlots>
 struct TileSmem {
   // point e lives at slot e + (e >> 3): a thread's 4 records are 64 contiguous bytes and the extra 16 bytes per 8
@@ -124,9 +125,11 @@ struct TileSmem {
 
 // kFused: `loc` / `attn` are the RAW sampling offsets / attention logits, `ref` the (N, Lq, L, 2) reference points and
 // the outputs are the gradients of the raw tensors (ms_deform_attn.py:98-105 differentiated here).
-template <int kSlots, bool kFused>
+// V: storage type of `grad_out` and `value` (float, or __nv_bfloat16 widened to fp32 in registers: BASELINE.json
+// configs[3]); locations, weights, every accumulation and all three gradients are fp32 either way.
+template <int kSlots, bool kFused, typename V = float>
 __global__ void __launch_bounds__(kTT, 2)
-msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict__ value,
+msda_bwd_tile_kernel(const V* __restrict__ grad_out, const V* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ attn, int batch, int S, int L,
                      float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn,
@@ -134,7 +137,9 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
   constexpr int M = 8, P = 4;
   constexpr int px_stride = M * 32;
   constexpr int kLv = kSlots / P;                        // level slots per query
-  constexpr int kQLPasses = kTQ * kLv / kTT;             // (query, level) pairs per thread: 1 or 2
+  constexpr int kQLPasses = (kTQ * kLv + kTT - 1) / kTT;   // (query, level) pairs per thread: 1 or 2
+  constexpr bool kExact = kTQ * kLv % kTT == 0;          // otherwise the last pass has threads without a pair
+  static_assert(!kFused || (kLv & (kLv - 1)) == 0, "the fused prologue reduces over kLv adjacent lanes");
   using SM = TileSmem<kSlots>;
   constexpr int kNullRes = SM::kPointSlots * 4;          // the null visit: a zero coefficient slot ...
   constexpr unsigned kNullVisit = (unsigned)(kNullRes * 4) | ((unsigned)(kTQ * 128) << 16);   // ... and the zero grad_out row
@@ -182,9 +187,9 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
       const int q = cur.query(ql, Lq);
       float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
       if (q >= 0) {
-        const float* gp = grad_out + (((long long)n * Lq + q) * M + m) * 32 + 8 * j;
-        g0 = ld_stream_f4(reinterpret_cast<const float4*>(gp));
-        g1 = ld_stream_f4(reinterpret_cast<const float4*>(gp + 4));
+        const V* gp = grad_out + (((long long)n * Lq + q) * M + m) * 32 + 8 * j;
+        g0 = Chan4<V>::stream_in(gp);
+        g1 = Chan4<V>::stream_in(gp + 4);
       }
       *reinterpret_cast<float4*>(gtile + ql * 32 + 8 * j) = g0;
       *reinterpret_cast<float4*>(gtile + ql * 32 + 8 * j + 4) = g1;
@@ -219,9 +224,10 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
 #pragma unroll
     for (int ps = 0; ps < kQLPasses; ++ps) {
       const int u = tid + ps * kTT;
-      const int ql = u / kLv, lv = u % kLv;
+      const bool live = kExact || u < kTQ * kLv;        // a thread without a pair aliases pair 0 and writes nothing
+      const int ql = live ? u / kLv : 0, lv = live ? u % kLv : 0;
       const int q = cur.query(ql, Lq);
-      const bool on = q >= 0 && lv < L;
+      const bool on = live && q >= 0 && lv < L;
       const int lvl = min(lv, L - 1);
       const long long nq = (long long)n * Lq + (q >= 0 ? q : 0);
       const long long pair = nq * M + m;
@@ -291,10 +297,12 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
           }
         }
         const int offm = ((lt.start[lvl] + t.h0 * W + t.w0) * px_stride) | mask;
-        rec[slot(e)] = make_float4(__int_as_float(offm), t.lh, t.lw, a);
-        *reinterpret_cast<float4*>(res + 4 * slot(e)) =
-            make_float4((mask & 1) ? hh * hw * a : 0.f, (mask & 2) ? hh * t.lw * a : 0.f,
-                        (mask & 4) ? t.lh * hw * a : 0.f, (mask & 8) ? t.lh * t.lw * a : 0.f);
+        if (live) {
+          rec[slot(e)] = make_float4(__int_as_float(offm), t.lh, t.lw, a);
+          *reinterpret_cast<float4*>(res + 4 * slot(e)) =
+              make_float4((mask & 1) ? hh * hw * a : 0.f, (mask & 2) ? hh * t.lw * a : 0.f,
+                          (mask & 4) ? t.lh * hw * a : 0.f, (mask & 8) ? t.lh * t.lw * a : 0.f);
+        }
       }
     }
     __syncthreads();
@@ -333,7 +341,8 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
 #pragma unroll
       for (int ps = 0; ps < kQLPasses; ++ps) {
         const int u = tid + ps * kTT;
-        const int ql = u / kLv, lv = u % kLv;
+        const bool live = kExact || u < kTQ * kLv;      // (dead threads hold no visits: every vkey is 0xffff)
+        const int ql = live ? u / kLv : 0, lv = live ? u % kLv : 0;
         const int lvl = min(lv, L - 1);
         const int ww = win.w[lvl], wbase = win.base[lvl], magic = win.magic[lvl];
         const int pix0 = lt.start[lvl] + win.y0[lvl] * lt.W[lvl] + win.x0[lvl], Wl = lt.W[lvl];
@@ -359,7 +368,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
     // halves (banks 0-15 / 16-31) of their grad_out rows: no shared-memory bank conflicts whatever the rows.
     const int j = tid & 3;
     const int c0 = 4 * j + 16 * ((lane >> 2) & 1), c1 = 4 * j + 16 * (1 - ((lane >> 2) & 1));
-    const float* vimg = value + img;
+    const V* vimg = value + img;
     float* gvimg = grad_value + img;
 
     // ---- D: tasks (pixel, <= kT visits) in contiguous runs, one run per 4 lanes ------------------------------------
@@ -386,9 +395,9 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
       int nxt_pix = i < i_end ? lds_i(pix_s + 4u * (unsigned)i) : -1;
       float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
       if (nxt_pix >= 0) {
-        const float* pv = vimg + (long long)nxt_pix * px_stride;
-        n0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
-        n1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
+        const V* pv = vimg + (long long)nxt_pix * px_stride;
+        n0 = Chan4<V>::gather(pv + c0);
+        n1 = Chan4<V>::gather(pv + c1);
       }
       f32x2 w[4] = {0ull, 0ull, 0ull, 0ull};               // value line of cur_pix: channels c0..c0+3, c1..c1+3
       f32x2 acc[4] = {0ull, 0ull, 0ull, 0ull};             // grad_value line of cur_pix
@@ -424,9 +433,9 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
           cur_pix = pix;
         }
         if (nxt_pix >= 0 && nxt_pix != pix) {
-          const float* pv = vimg + (long long)nxt_pix * px_stride;
-          n0 = __ldg(reinterpret_cast<const float4*>(pv + c0));
-          n1 = __ldg(reinterpret_cast<const float4*>(pv + c1));
+          const V* pv = vimg + (long long)nxt_pix * px_stride;
+          n0 = Chan4<V>::gather(pv + c0);
+          n1 = Chan4<V>::gather(pv + c1);
         }
         const unsigned cur_codes[kT] = {codes.x, codes.y, codes.z, codes.w};
         float d[kT];
@@ -477,7 +486,7 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
         const int lvl = (e % kSlots) / P;
         const int ws = lt.wstr[lvl];
         const int off = offm & ~31;
-        const float* pv = vimg + off;
+        const V* pv = vimg + off;
         float* pg = gvimg + off;
         const float4 g0 = *reinterpret_cast<const float4*>(gtile + ql * 32 + c0);
         const float4 g1 = *reinterpret_cast<const float4*>(gtile + ql * 32 + c1);
@@ -488,8 +497,8 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
           d[r] = 0.f;
           if (offm & (1 << r)) {
             const int o = (r & 1) * px_stride + (r >> 1) * ws;
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(pv + o + c0));
-            const float4 x1 = __ldg(reinterpret_cast<const float4*>(pv + o + c1));
+            const float4 x0 = Chan4<V>::gather(pv + o + c0);
+            const float4 x1 = Chan4<V>::gather(pv + o + c1);
             const float c = r == 0 ? C.x : (r == 1 ? C.y : (r == 2 ? C.z : C.w));
             red_add_f4(pg + o + c0, make_float4(c * g0.x, c * g0.y, c * g0.z, c * g0.w));
             red_add_f4(pg + o + c1, make_float4(c * g1.x, c * g1.y, c * g1.z, c * g1.w));
@@ -508,9 +517,10 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
 #pragma unroll
     for (int ps = 0; ps < kQLPasses; ++ps) {
       const int u = tid + ps * kTT;
-      const int ql = u / kLv, lv = u % kLv;
+      const bool live = kExact || u < kTQ * kLv;
+      const int ql = live ? u / kLv : 0, lv = live ? u % kLv : 0;
       const int q = cur.query(ql, Lq);
-      const bool on = q >= 0 && lv < L;
+      const bool on = live && q >= 0 && lv < L;
       const int lvl = min(lv, L - 1);
       const long long pair = ((long long)n * Lq + (q >= 0 ? q : 0)) * M + m;
       const float Wf = (float)lt.W[lvl], Hf = (float)lt.H[lvl];
@@ -552,11 +562,11 @@ msda_bwd_tile_kernel(const float* __restrict__ grad_out, const float* __restrict
   }
 }
 
-template <int kSlots, bool kFused>
-int launch_tile(cudaStream_t st, const float* grad_out, const float* value, const int64_t* shapes, const int64_t* lsi,
+template <int kSlots, bool kFused, typename V = float>
+int launch_tile(cudaStream_t st, const V* grad_out, const V* value, const int64_t* shapes, const int64_t* lsi,
                 const float* loc, const float* attn, int batch, int S, int L, float* grad_value, float* grad_loc,
                 float* grad_attn, const float* ref) {
-  auto kern = msda_bwd_tile_kernel<kSlots, kFused>;
+  auto kern = msda_bwd_tile_kernel<kSlots, kFused, V>;
   constexpr int smem = TileSmem<kSlots>::kTotal;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
@@ -596,8 +606,26 @@ int msda_backward_tile(cudaStream_t st, const float* grad_out, const float* valu
   if (L <= 4)
     return launch_tile<16, false>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value, grad_loc,
                                   grad_attn, nullptr);
+  if (L == 5)
+    return launch_tile<20, false>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value, grad_loc,
+                                  grad_attn, nullptr);
   return launch_tile<32, false>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value, grad_loc,
                                 grad_attn, nullptr);
+}
+
+// bf16 storage of grad_out / value (the unfused form: locations and weights given): BASELINE.json configs[3], where the
+// 5-level encoder backward is a fifth of the step
+int msda_backward_tile_bf16(cudaStream_t st, const __nv_bfloat16* grad_out, const __nv_bfloat16* value,
+                            const int64_t* shapes, const int64_t* lsi, const float* loc, const float* attn, int batch,
+                            int S, int L, float* grad_value, float* grad_loc, float* grad_attn) {
+  if (L <= 4)
+    return launch_tile<16, false, __nv_bfloat16>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value,
+                                                 grad_loc, grad_attn, nullptr);
+  if (L == 5)
+    return launch_tile<20, false, __nv_bfloat16>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value,
+                                                 grad_loc, grad_attn, nullptr);
+  return launch_tile<32, false, __nv_bfloat16>(st, grad_out, value, shapes, lsi, loc, attn, batch, S, L, grad_value,
+                                               grad_loc, grad_attn, nullptr);
 }
 
 }  // namespace sdb
