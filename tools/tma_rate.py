@@ -1,7 +1,6 @@
 """TMA feed rate per SM on B200 (debug microbenchmark sdb_debug_tma_rate): how fast K-major fp32 tiles arrive in shared
 memory for different box heights, boxes per stage and ring depths, with nothing consuming them -- the question the GEMM
-traces raise (docs/ROUND2_NOTES.md).  NOT YET RUN ON HARDWARE (written after the round's GPU
-budget was spent): first thing to run next round."""
+traces raise (docs/ROUND2_NOTES.md).  Results: profiles/tma_rate_r2.txt."""
 import os
 import sys
 
