@@ -263,6 +263,11 @@ int sdb_colsum_f32(sdb_stream_t stream, const float* x, int64_t rows, int cols, 
  * Same shape / alignment requirements as sdb_colsum_f32; g must not alias the inputs. */
 int sdb_relu_backward_colsum_f32(sdb_stream_t stream, const float* dy, const float* y, int64_t rows, int cols,
                                  float* g, float* colsum);
+/* The same two passes on bf16 storage (bit patterns as uint16_t; 8-byte aligned, cols % 4 == 0) with fp32 sums: the
+ * bias gradients of the linears under the bf16 autocast step of BASELINE.json configs[3]. */
+int sdb_colsum_bf16(sdb_stream_t stream, const uint16_t* x, int64_t rows, int cols, float* out);
+int sdb_relu_backward_colsum_bf16(sdb_stream_t stream, const uint16_t* dy, const uint16_t* y, int64_t rows, int cols,
+                                  uint16_t* g, float* colsum);
 
 /* ------------------------------------------------------------------------------------------
  * Decoder self-attention core (the softmax(q k^T / sqrt(d) + mask) v inside nn.MultiheadAttention as the DINO decoder

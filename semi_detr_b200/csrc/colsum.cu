@@ -15,8 +15,11 @@ namespace sdb {
 constexpr int kCsThreads = 256;          // 32 column-lanes (x float4 = 128 columns) x 8 row-lanes
 constexpr int kCsCols = 128;
 
+// V: storage type of the matrix (float, or __nv_bfloat16 widened in registers: the bf16 autocast step of BASELINE.json
+// configs[3]); sums and the output are fp32 either way.
+template <typename V>
 __global__ void __launch_bounds__(kCsThreads)
-colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* __restrict__ out) {
+colsum_kernel(const V* __restrict__ x, long long rows, int cols, float* __restrict__ out) {
   __shared__ float4 s_part[8][32];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * kCsCols + 4 * cl;
@@ -24,7 +27,7 @@ colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* __re
   if (col < cols) {
     const long long stride = (long long)gridDim.y * 8;
     for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += stride) {
-      const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(x + r * cols + col));
+      const float4 v = Chan4<V>::stream_in(x + r * cols + col);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
@@ -46,9 +49,10 @@ colsum_kernel(const float* __restrict__ x, long long rows, int cols, float* __re
 // ReLU backward fused with the column sums: g[r, c] = (y[r, c] > 0 ? dy[r, c] : 0) is written once and its column
 // sums (the bias gradient of the linear layer before the ReLU) accumulate in the same pass -- 12 B per element
 // instead of 12 (threshold_backward) + 4 (a separate column-sum pass over g).
+template <typename V>
 __global__ void __launch_bounds__(kCsThreads)
-relu_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long rows, int cols,
-                       float* __restrict__ g, float* __restrict__ out) {
+relu_bwd_colsum_kernel(const V* __restrict__ dy, const V* __restrict__ y, long long rows, int cols,
+                       V* __restrict__ g, float* __restrict__ out) {
   __shared__ float4 s_part[8][32];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * kCsCols + 4 * cl;
@@ -56,11 +60,11 @@ relu_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y
   if (col < cols) {
     const long long stride = (long long)gridDim.y * 8;
     for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += stride) {
-      const float4 d = ld_stream_f4(reinterpret_cast<const float4*>(dy + r * cols + col));
-      const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(y + r * cols + col));
+      const float4 d = Chan4<V>::stream_in(dy + r * cols + col);
+      const float4 a = Chan4<V>::stream_in(y + r * cols + col);
       const float4 v = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f,
                                    a.w > 0.f ? d.w : 0.f);
-      *reinterpret_cast<float4*>(g + r * cols + col) = v;
+      Chan4<V>::stream_out(g + r * cols + col, v);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
@@ -81,16 +85,19 @@ relu_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y
 
 }  // namespace sdb
 
-extern "C" int sdb_relu_backward_colsum_f32(sdb_stream_t stream, const float* dy, const float* y, int64_t rows, int cols,
-                                            float* g, float* colsum) {
-  using namespace sdb;
-  SDB_REQUIRE(rows >= 0 && cols > 0, "relu_backward_colsum: bad sizes rows=%lld cols=%d", (long long)rows, cols);
-  SDB_REQUIRE(colsum != nullptr, "relu_backward_colsum: null output");
-  SDB_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)cols, (cudaStream_t)stream));
+namespace sdb {
+
+template <typename V>
+int relu_backward_colsum(cudaStream_t st, const V* dy, const V* y, long long rows, int cols, V* g, float* colsum,
+                         const char* what) {
+  SDB_REQUIRE(rows >= 0 && cols > 0, "%s: bad sizes rows=%lld cols=%d", what, rows, cols);
+  SDB_REQUIRE(colsum != nullptr, "%s: null output", what);
+  SDB_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)cols, st));
   if (rows == 0) return SDB_OK;
-  SDB_REQUIRE(dy && y && g, "relu_backward_colsum: null pointer");
-  if (cols % 4 != 0 || ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(g)) & 15) != 0) {
-    set_error("relu_backward_colsum: cols=%d must be a multiple of 4 and the tensors 16-byte aligned", cols);
+  SDB_REQUIRE(dy && y && g, "%s: null pointer", what);
+  if (cols % 4 != 0 || ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(g)) &
+                        Chan4<V>::kAlignMask) != 0) {
+    set_error("%s: cols=%d must be a multiple of 4 and the tensors aligned to 4 elements", what, cols);
     return SDB_ERR_UNSUPPORTED;
   }
   const int strips = (cols + kCsCols - 1) / kCsCols;
@@ -99,21 +106,20 @@ extern "C" int sdb_relu_backward_colsum_f32(sdb_stream_t stream, const float* dy
   if (row_ctas > max_useful) row_ctas = max_useful;
   if (row_ctas < 1) row_ctas = 1;
   if (row_ctas > 65535) row_ctas = 65535;
-  relu_bwd_colsum_kernel<<<dim3(strips, (unsigned)row_ctas), kCsThreads, 0, (cudaStream_t)stream>>>(dy, y, rows, cols, g,
-                                                                                                 colsum);
+  relu_bwd_colsum_kernel<V><<<dim3(strips, (unsigned)row_ctas), kCsThreads, 0, st>>>(dy, y, rows, cols, g, colsum);
   SDB_LAUNCH_CHECK("relu_bwd_colsum_kernel");
   return SDB_OK;
 }
 
-extern "C" int sdb_colsum_f32(sdb_stream_t stream, const float* x, int64_t rows, int cols, float* out) {
-  using namespace sdb;
-  SDB_REQUIRE(rows >= 0 && cols > 0, "colsum: bad sizes rows=%lld cols=%d", (long long)rows, cols);
-  SDB_REQUIRE(out != nullptr, "colsum: null output");
-  SDB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, (cudaStream_t)stream));
+template <typename V>
+int colsum(cudaStream_t st, const V* x, long long rows, int cols, float* out, const char* what) {
+  SDB_REQUIRE(rows >= 0 && cols > 0, "%s: bad sizes rows=%lld cols=%d", what, rows, cols);
+  SDB_REQUIRE(out != nullptr, "%s: null output", what);
+  SDB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st));
   if (rows == 0) return SDB_OK;
-  SDB_REQUIRE(x != nullptr, "colsum: null input");
-  if (cols % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {
-    set_error("colsum: cols=%d must be a multiple of 4 and x 16-byte aligned", cols);
+  SDB_REQUIRE(x != nullptr, "%s: null input", what);
+  if (cols % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & Chan4<V>::kAlignMask) != 0) {
+    set_error("%s: cols=%d must be a multiple of 4 and x aligned to 4 elements", what, cols);
     return SDB_ERR_UNSUPPORTED;
   }
   const int strips = (cols + kCsCols - 1) / kCsCols;
@@ -122,7 +128,30 @@ extern "C" int sdb_colsum_f32(sdb_stream_t stream, const float* x, int64_t rows,
   if (row_ctas > max_useful) row_ctas = max_useful;
   if (row_ctas < 1) row_ctas = 1;
   if (row_ctas > 65535) row_ctas = 65535;
-  colsum_kernel<<<dim3(strips, (unsigned)row_ctas), kCsThreads, 0, (cudaStream_t)stream>>>(x, rows, cols, out);
+  colsum_kernel<V><<<dim3(strips, (unsigned)row_ctas), kCsThreads, 0, st>>>(x, rows, cols, out);
   SDB_LAUNCH_CHECK("colsum_kernel");
   return SDB_OK;
+}
+
+}  // namespace sdb
+
+extern "C" int sdb_relu_backward_colsum_f32(sdb_stream_t stream, const float* dy, const float* y, int64_t rows, int cols,
+                                            float* g, float* colsum) {
+  return sdb::relu_backward_colsum<float>((cudaStream_t)stream, dy, y, rows, cols, g, colsum, "relu_backward_colsum");
+}
+
+extern "C" int sdb_colsum_f32(sdb_stream_t stream, const float* x, int64_t rows, int cols, float* out) {
+  return sdb::colsum<float>((cudaStream_t)stream, x, rows, cols, out, "colsum");
+}
+
+extern "C" int sdb_relu_backward_colsum_bf16(sdb_stream_t stream, const uint16_t* dy, const uint16_t* y, int64_t rows,
+                                             int cols, uint16_t* g, float* colsum) {
+  return sdb::relu_backward_colsum<__nv_bfloat16>((cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                  reinterpret_cast<const __nv_bfloat16*>(y), rows, cols,
+                                                  reinterpret_cast<__nv_bfloat16*>(g), colsum, "relu_backward_colsum_bf16");
+}
+
+extern "C" int sdb_colsum_bf16(sdb_stream_t stream, const uint16_t* x, int64_t rows, int cols, float* out) {
+  return sdb::colsum<__nv_bfloat16>((cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, out,
+                                    "colsum_bf16");
 }

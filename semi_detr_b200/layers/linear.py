@@ -112,6 +112,69 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb
 
 
+def _colsum_bf16(x2d):
+    rows, cols = x2d.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().sdb_colsum_bf16(_lib.current_stream(x2d.device), x2d.data_ptr(), rows, cols, out.data_ptr())
+    _lib.check(rc, "colsum_bf16")
+    _lib.LAUNCHES["colsum"] += 1
+    return out
+
+
+def _relu_backward_colsum_bf16(dy2d, y2d):
+    rows, cols = y2d.shape
+    g = torch.empty_like(y2d)
+    out = torch.empty(cols, dtype=torch.float32, device=y2d.device)
+    with torch.cuda.device(y2d.device):
+        rc = _lib.lib().sdb_relu_backward_colsum_bf16(_lib.current_stream(y2d.device), dy2d.data_ptr(), y2d.data_ptr(),
+                                                      rows, cols, g.data_ptr(), out.data_ptr())
+    _lib.check(rc, "relu_backward_colsum_bf16")
+    _lib.LAUNCHES["relu_backward_colsum"] += 1
+    return g, out
+
+
+class _AutocastLinearFn(torch.autograd.Function):
+    """The layer under ``torch.autocast(bfloat16)`` (BASELINE.json configs[3]): library bf16 GEMMs (ReLU in the library
+    epilogue), and the bias gradient -- with the ReLU backward of FFN linear1 in the same pass -- on this library's bf16
+    column-sum kernels with fp32 sums.  Plain autocast leaves those to a generic bf16 reduction plus a separate
+    threshold pass: 9.9 of the 75 ms of the 5-scale step (profiles/step_profile_r2_sup5.txt)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        with torch.autocast("cuda", enabled=False):
+            xb = x.reshape(-1, x.shape[-1]).to(torch.bfloat16)
+            if not xb.is_contiguous():
+                xb = xb.contiguous()
+            wb, bb = weight.to(torch.bfloat16), bias.to(torch.bfloat16)
+            if relu and hasattr(torch, "_addmm_activation"):
+                y = torch._addmm_activation(bb, xb, wb.t(), use_gelu=False)
+            else:
+                y = torch.addmm(bb, xb, wb.t())
+                if relu:
+                    y = y.relu_()
+        ctx.save_for_backward(xb, wb, y if relu else None)
+        ctx.relu, ctx.x_shape, ctx.x_dtype = relu, x.shape, x.dtype
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, wb, y = ctx.saved_tensors
+        with torch.autocast("cuda", enabled=False):
+            g2 = g.reshape(-1, g.shape[-1])
+            if g2.dtype != torch.bfloat16:
+                g2 = g2.to(torch.bfloat16)
+            if not g2.is_contiguous():
+                g2 = g2.contiguous()
+            if ctx.relu:
+                g2, gb = _relu_backward_colsum_bf16(g2, y)
+            else:
+                gb = _colsum_bf16(g2) if ctx.needs_input_grad[2] else None
+            gx = (g2 @ wb).view(ctx.x_shape).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+            gw = (g2.t() @ xb).float() if ctx.needs_input_grad[1] else None
+        return gx, gw, gb, None
+
+
 def linear(x, weight, bias):
     """``F.linear`` for layers that are not ``Linear`` modules (the in / out projections of nn.MultiheadAttention): on the
     device the bias gradient comes from this library's column-sum kernel instead of a generic reduction."""
@@ -191,6 +254,10 @@ class Linear(nn.Linear):
         forward product runs on the tcgen05 kernel."""
         # bf16 autocast (BASELINE.json configs[3]): the product is a library bf16 GEMM managed by torch.autocast -- the
         # hand-written GEMM of this package is TF32 on fp32 storage
+        if (torch.is_autocast_enabled() and x.is_cuda and row_mask is None and self.bias is not None
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16 and self.out_features % 4 == 0
+                and x.numel() // self.in_features >= MIN_ROWS and torch.is_grad_enabled()):
+            return _AutocastLinearFn.apply(x, self.weight, self.bias, relu)
         plan = None if torch.is_autocast_enabled() else self._plan(x, relu or row_mask is not None, row_mask is not None)
         if plan is not None:
             return _TensorCoreLinearFn.apply(x, self.weight, self.bias, relu, row_mask, plan)

@@ -283,3 +283,51 @@ print("ok")
     env = dict(os.environ, SDB_GEMM_2CTA="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("rows,cols", [(178046, 256), (5000, 2048), (1024, 384), (9, 4)])
+def test_bf16_column_sum_kernels(rows, cols):
+    """sdb_colsum_bf16 / sdb_relu_backward_colsum_bf16: bf16 storage, fp32 sums.  The masked gradient is a copy of bf16
+    inputs (bit-equal); the sums against float64 sums of the same bf16 values."""
+    from semi_detr_b200.layers.linear import _colsum_bf16, _relu_backward_colsum_bf16
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    dy = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.relu(torch.randn(rows, cols, device="cuda", generator=g)).to(torch.bfloat16)
+    s = _colsum_bf16(dy)
+    ref = dy.double().sum(0)
+    assert s.dtype == torch.float32
+    assert float((s.double() - ref).abs().max()) <= 2e-5 * float(dy.double().abs().sum(0).max()) + 1e-6
+    got, gb = _relu_backward_colsum_bf16(dy, y)
+    want = torch.where(y > 0, dy, torch.zeros_like(dy))
+    assert torch.equal(got, want)
+    ref = want.double().sum(0)
+    assert float((gb.double() - ref).abs().max()) <= 2e-5 * float(want.double().abs().sum(0).max()) + 1e-6
+
+
+def test_autocast_linear_matches_plain_autocast():
+    """`Linear` under bf16 autocast (library bf16 GEMMs + this library's bf16 bias-gradient / ReLU-backward pass) against
+    torch's own autocast of the same layer: same bf16 products, so outputs are equal and gradients agree to bf16
+    rounding of the bias-gradient sum (ours is summed in fp32)."""
+    from semi_detr_b200 import _lib
+    from semi_detr_b200.layers.linear import Linear
+    torch.manual_seed(4)
+    for relu in (False, True):
+        lin = Linear(256, 512).cuda()
+        x = torch.randn(3, 700, 256, device="cuda", requires_grad=True)
+        gy = torch.randn(3, 700, 512, device="cuda")
+        before = _lib.LAUNCHES["colsum"] + _lib.LAUNCHES["relu_backward_colsum"]
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = lin(x, relu=relu)
+        y.backward(gy.to(y.dtype))
+        assert _lib.LAUNCHES["colsum"] + _lib.LAUNCHES["relu_backward_colsum"] == before + 1
+        got = y.detach().float(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()
+        x2 = x.detach().clone().requires_grad_(True)
+        w2, b2 = lin.weight.detach().clone().requires_grad_(True), lin.bias.detach().clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y2 = torch.nn.functional.linear(x2, w2, b2)
+            if relu:
+                y2 = torch.relu(y2)
+        y2.backward(gy.to(y2.dtype))
+        assert y.dtype == torch.bfloat16 and torch.equal(got[0], y2.detach().float())
+        for a, b, tol in ((got[1], x2.grad, 1e-2), (got[2], w2.grad, 1e-2), (got[3], b2.grad, 2e-2)):
+            assert a.dtype == b.dtype and float((a - b).abs().max()) <= tol * float(b.abs().max())

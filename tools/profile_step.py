@@ -21,8 +21,13 @@ torch.backends.cuda.matmul.allow_tf32 = True
 torch.backends.cudnn.allow_tf32 = True
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
-model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE)).cuda().train()
-step = FusedSupervisedTrainStep(model, world_size=WORLD)
+FIVE = os.environ.get("SDB_PROFILE_WORKLOAD", "sup") == "sup5"     # configs[3]: 5-scale model under bf16 autocast
+if FIVE:
+    from semi_detr_b200.synthetic import dino_r50_5scale
+    model = DETECTORS.build(dino_r50_5scale()).cuda().train()
+else:
+    model = DETECTORS.build(copy.deepcopy(DINO_R50_4SCALE)).cuda().train()
+step = FusedSupervisedTrainStep(model, world_size=WORLD, autocast=torch.bfloat16 if FIVE else None)
 data = coco_like_batch(2, 800, 1333, seed=0, device="cuda")
 for _ in range(5):
     step(data)
