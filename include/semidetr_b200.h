@@ -131,6 +131,27 @@ int sdb_msda_fused_backward_f32(sdb_stream_t stream, const float* grad_out, cons
                                 int channels, int num_levels, int num_query, int num_point, float* grad_value,
                                 float* grad_offsets, float* grad_attn_logits);
 
+/* The same prologue as a standalone pass for shapes the fused kernels do not take (levels x points > 16, e.g. the
+ * 5-level model): softmax over the head's L*P logits and the location arithmetic of ms_deform_attn.py:98-112 in one
+ * launch, fp32 `sampling_loc` (batch, num_query, num_heads, num_levels, num_point, 2) and `attn_weight` out; the backward
+ * maps grad_sampling_loc / grad_attn_weight to the gradients of the raw offsets / logits (bf16 variants: raw tensors as
+ * bf16 bit patterns).  `spatial_shapes_host`: HOST array of (H, W) per level.  num_point must be 4, levels <= 8. */
+int sdb_msda_prologue_forward_f32(sdb_stream_t stream, const float* offsets, const float* logits, const float* ref,
+                                  int ref_dim, const int64_t* spatial_shapes_host, int batch, int num_query,
+                                  int num_heads, int num_levels, int num_point, float* sampling_loc, float* attn_weight);
+int sdb_msda_prologue_forward_bf16(sdb_stream_t stream, const uint16_t* offsets, const uint16_t* logits, const float* ref,
+                                   int ref_dim, const int64_t* spatial_shapes_host, int batch, int num_query,
+                                   int num_heads, int num_levels, int num_point, float* sampling_loc,
+                                   float* attn_weight);
+int sdb_msda_prologue_backward_f32(sdb_stream_t stream, const float* grad_loc, const float* grad_attn,
+                                   const float* attn_weight, const float* ref, int ref_dim,
+                                   const int64_t* spatial_shapes_host, int batch, int num_query, int num_heads,
+                                   int num_levels, int num_point, float* grad_offsets, float* grad_logits);
+int sdb_msda_prologue_backward_bf16(sdb_stream_t stream, const float* grad_loc, const float* grad_attn,
+                                    const float* attn_weight, const float* ref, int ref_dim,
+                                    const int64_t* spatial_shapes_host, int batch, int num_query, int num_heads,
+                                    int num_levels, int num_point, uint16_t* grad_offsets, uint16_t* grad_logits);
+
 /* TMA-staged forward for encoder self-attention (num_query == spatial_size, channels 32, heads 8, points 4,
  * levels <= 4): per (image, head, 8x8 query tile) one bulk tensor copy per level stages that head's value box in
  * shared memory behind an mbarrier; out-of-box samples use global loads.  Same results as sdb_msda_forward_f32 /

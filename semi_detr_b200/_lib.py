@@ -28,6 +28,10 @@ SIGNATURES = {
     "sdb_msda_forward_tma_f32": [c_void_p, c_int] + [c_void_p] * 6 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p],
     "sdb_msda_fused_forward_f32": [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p],
     "sdb_msda_fused_backward_f32": [c_void_p] * 6 + [c_int] + [c_void_p] * 2 + [c_int] * 7 + [c_void_p] * 3,
+    "sdb_msda_prologue_forward_f32": [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 5 + [c_void_p] * 2,
+    "sdb_msda_prologue_forward_bf16": [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 5 + [c_void_p] * 2,
+    "sdb_msda_prologue_backward_f32": [c_void_p] * 5 + [c_int, c_void_p] + [c_int] * 5 + [c_void_p] * 2,
+    "sdb_msda_prologue_backward_bf16": [c_void_p] * 5 + [c_int, c_void_p] + [c_int] * 5 + [c_void_p] * 2,
     "sdb_match_cost_f32": [c_void_p] * 9 + [c_int] * 3 + [c_float] * 3 + [c_void_p] * 2,
     "sdb_lsap_solve_f32": [c_void_p] * 6 + [c_int] * 3 + [c_void_p] * 3,
     "sdb_hungarian_assign_f32": [c_void_p] * 9 + [c_int] * 4 + [c_float] * 3 + [c_void_p] * 5,
@@ -91,7 +95,8 @@ def debug_lib():
 LAUNCHES = {"msda_forward": 0, "msda_backward": 0, "msda_fused_forward": 0, "msda_fused_backward": 0, "msda_forward_tma": 0, "match_cost": 0, "lsap_solve": 0, "ema_update": 0,
             "layernorm_forward": 0, "layernorm_backward": 0, "adamw_ema_step": 0, "colsum": 0, "gemm_tf32": 0, "relu_backward_colsum": 0, "detr_loss_forward": 0, "detr_loss_backward": 0, "pseudo_label_nms": 0,
             "gmm_threshold": 0, "msda_forward_bf16": 0, "msda_backward_bf16": 0,
-            "mha_forward": 0, "mha_backward": 0, "dp_adamw_exchange": 0, "dp_small_allreduce": 0}
+            "mha_forward": 0, "mha_backward": 0, "dp_adamw_exchange": 0, "dp_small_allreduce": 0,
+            "msda_prologue_forward": 0, "msda_prologue_backward": 0}
 
 
 class EmaChunk(ctypes.Structure):

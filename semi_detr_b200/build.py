@@ -22,7 +22,7 @@ EXTRA = {
     # the matching cost must round like torch's separately-rounded elementwise kernels
     "hungarian.cu": ["-fmad=false"],
 }
-SOURCES = ["abi.cu", "msda_forward.cu", "msda_forward_tma.cu", "msda_backward.cu", "msda_backward_tile.cu", "hungarian.cu", "ema.cu", "layernorm.cu", "optimizer.cu", "colsum.cu", "detr_loss.cu", "ssod.cu", "attention.cu", "exchange.cu", "gemm_tf32.cu"]
+SOURCES = ["abi.cu", "msda_forward.cu", "msda_forward_tma.cu", "msda_backward.cu", "msda_backward_tile.cu", "msda_prologue.cu", "hungarian.cu", "ema.cu", "layernorm.cu", "optimizer.cu", "colsum.cu", "detr_loss.cu", "ssod.cu", "attention.cu", "exchange.cu", "gemm_tf32.cu"]
 # instrumentation library (include/semidetr_b200_debug.h): microbenchmarks + the GEMM with %globaltimer stamps
 DEBUG_LIB = os.path.join(LIBDIR, "libsemidetr_b200_debug.so")
 DEBUG_SOURCES = [("abi.cu", []), ("umma_rate.cu", []), ("gemm_tf32.cu", ["-DSDB_GEMM_TRACE=1"])]

@@ -9,6 +9,8 @@ that name (``sys.modules['MultiScaleDeformableAttention'] = this module``, see
 ``semi_detr_b200.install_as_reference_extension``) lets the reference's own ``MSDeformAttnFunction``
 run on it unchanged.
 """
+import ctypes
+
 import torch
 
 from .. import _lib
@@ -261,3 +263,47 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
     _lib.check(rc, "ms_deform_attn_fused_backward")
     _lib.LAUNCHES["msda_fused_backward"] += 1
     return [grad_value, grad_off, grad_logits]
+
+
+# ---- standalone prologue (levels x points > 16: the fused kernels do not apply) ---------------------------------------
+
+def prologue_supported(sampling_offsets, reference_points, n_levels, n_points):
+    return (sampling_offsets.is_cuda and sampling_offsets.dtype in (torch.float32, _BF16) and n_points == 4
+            and n_levels <= 8 and n_levels * n_points <= 32 and reference_points.shape[-1] in (2, 4))
+
+
+def _shapes_array(shapes_host):
+    flat = [int(v) for hw in shapes_host for v in hw]
+    return (ctypes.c_int64 * len(flat))(*flat)
+
+
+def msda_prologue_forward(sampling_offsets, attn_logits, reference_points, shapes_host):
+    """-> (sampling_locations fp32 (N, Lq, M, L, P, 2), attention_weights fp32 (N, Lq, M, L, P))"""
+    n, q, m, l, p, _ = sampling_offsets.shape
+    off, lg = sampling_offsets.contiguous(), attn_logits.to(sampling_offsets.dtype).contiguous()
+    ref = reference_points.float().contiguous()
+    loc = torch.empty((n, q, m, l, p, 2), dtype=torch.float32, device=off.device)
+    attn = torch.empty((n, q, m, l, p), dtype=torch.float32, device=off.device)
+    fn = _lib.lib().sdb_msda_prologue_forward_bf16 if off.dtype == _BF16 else _lib.lib().sdb_msda_prologue_forward_f32
+    with torch.cuda.device(off.device):
+        rc = fn(_lib.current_stream(off.device), off.data_ptr(), lg.data_ptr(), ref.data_ptr(), ref.shape[-1],
+                _shapes_array(shapes_host), n, q, m, l, p, loc.data_ptr(), attn.data_ptr())
+    _lib.check(rc, "msda_prologue_forward")
+    _lib.LAUNCHES["msda_prologue_forward"] += 1
+    return loc, attn
+
+
+def msda_prologue_backward(grad_loc, grad_attn, attn, reference_points, shapes_host, raw_dtype):
+    """-> (grad_sampling_offsets, grad_attn_logits) in ``raw_dtype``"""
+    n, q, m, l, p, _ = grad_loc.shape
+    ref = reference_points.float().contiguous()
+    g_off = torch.empty((n, q, m, l, p, 2), dtype=raw_dtype, device=grad_loc.device)
+    g_lg = torch.empty((n, q, m, l * p), dtype=raw_dtype, device=grad_loc.device)
+    fn = _lib.lib().sdb_msda_prologue_backward_bf16 if raw_dtype == _BF16 else _lib.lib().sdb_msda_prologue_backward_f32
+    with torch.cuda.device(grad_loc.device):
+        rc = fn(_lib.current_stream(grad_loc.device), grad_loc.float().data_ptr() if grad_loc.dtype != torch.float32
+                else grad_loc.data_ptr(), grad_attn.data_ptr(), attn.data_ptr(), ref.data_ptr(), ref.shape[-1],
+                _shapes_array(shapes_host), n, q, m, l, p, g_off.data_ptr(), g_lg.data_ptr())
+    _lib.check(rc, "msda_prologue_backward")
+    _lib.LAUNCHES["msda_prologue_backward"] += 1
+    return g_off, g_lg

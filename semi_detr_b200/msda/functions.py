@@ -60,3 +60,28 @@ class MSDeformAttnFusedFunction(Function):
         grad_value, grad_off, grad_logits = MSDA.ms_deform_attn_fused_backward(
             value, shapes, level_start, ref, offsets, logits, grad_output.contiguous())
         return grad_value, None, None, None, grad_off, grad_logits
+
+
+class MSDAPrologueFunction(Function):
+    """softmax + sampling-location arithmetic of the module (ms_deform_attn.py:98-112) as one kernel each way
+    (``sdb_msda_prologue_forward/backward_{f32,bf16}``), for shapes the fused MSDA kernels do not take (levels x points >
+    16): raw ``sampling_offsets`` (N, Lq, M, L, P, 2) and ``attention_logits`` (N, Lq, M, L*P) in fp32 or bf16 ->
+    fp32 ``sampling_locations`` and ``attention_weights`` (N, Lq, M, L, P).  ``shapes_host``: tuple of (H, W) per level.
+    No gradient to the reference points (DINO detaches them)."""
+
+    @staticmethod
+    def forward(ctx, sampling_offsets, attention_logits, reference_points, shapes_host):
+        loc, attn = MSDA.msda_prologue_forward(sampling_offsets, attention_logits, reference_points, shapes_host)
+        ctx.save_for_backward(attn, reference_points)
+        ctx.shapes_host, ctx.raw_dtype = shapes_host, sampling_offsets.dtype
+        return loc, attn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loc, grad_attn):
+        attn, ref = ctx.saved_tensors
+        if ctx.needs_input_grad[2]:
+            raise RuntimeError("MSDAPrologueFunction: reference_points must not require grad")
+        g_off, g_logit = MSDA.msda_prologue_backward(grad_loc.contiguous(), grad_attn.contiguous(), attn, ref,
+                                                     ctx.shapes_host, ctx.raw_dtype)
+        return g_off, g_logit, None, None

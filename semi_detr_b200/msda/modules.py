@@ -17,7 +17,7 @@ from torch import nn
 
 from . import MultiScaleDeformableAttention as MSDA
 from ..layers import Linear
-from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from .functions import MSDAPrologueFunction, MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
 def _is_power_of_2(n):
@@ -66,9 +66,11 @@ class MSDeformAttn(nn.Module):
     def _check_len(self, spatial_shapes, len_in):
         key = (spatial_shapes.data_ptr(), spatial_shapes._version, len_in)
         if self._checked_shapes != key:
-            total = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())
+            host = tuple(tuple(int(v) for v in hw) for hw in spatial_shapes.tolist())   # one read per geometry
+            total = sum(h * w for h, w in host)
             assert total == len_in, f"sum(H*W)={total} does not match input length {len_in}"
             self._checked_shapes = key
+            self._shapes_host = host
             self._checked_shapes_ref = spatial_shapes      # keeps the address from being reused while cached
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
@@ -93,6 +95,14 @@ class MSDeformAttn(nn.Module):
                 and MSDA.fused_supported(value, reference_points, L, P)):
             out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                   reference_points.contiguous(), offsets, logits)
+            return self.output_proj(out)
+        if (self.fused_prologue and value.is_cuda and not reference_points.requires_grad
+                and MSDA.prologue_supported(offsets, reference_points, L, P)):
+            # levels x points > 16 (the 5-level model): softmax + location arithmetic as one kernel each way, fp32
+            # locations / weights for the MSDA kernels (bf16 `value` keeps its storage)
+            locations, weights = MSDAPrologueFunction.apply(offsets, logits, reference_points, self._shapes_host)
+            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, locations, weights,
+                                             self.im2col_step)
             return self.output_proj(out)
         weights = F.softmax(logits, -1).view(N, Lq, M, L, P)
         ref = reference_points[:, :, None, :, None, :]

@@ -130,3 +130,39 @@ def test_tma_fused_forward_matches_fused_l1_kernel():
         MSDA.USE_TMA = False
     want = MSDA.ms_deform_attn_fused_forward(value, shapes, start, ref, off, logits)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_standalone_prologue_matches_the_module_arithmetic(ref_dim, dtype):
+    """`MSDAPrologueFunction` (5 levels x 4 points: the fused MSDA kernels do not apply) against the module's own tensor
+    arithmetic (ms_deform_attn.py:98-112) in float32 on the same -- for bf16, already rounded -- raw tensors: locations
+    and softmax weights to 1e-6, and the gradients of the raw offsets / logits to fp32 (bf16: one bf16 ulp) accuracy."""
+    from semi_detr_b200.msda.functions import MSDAPrologueFunction
+    levels = [(40, 52), (20, 26), (10, 13), (5, 7), (3, 4)]
+    N, Lq, M, L, P = 2, 333, 8, 5, 4
+    g = torch.Generator(device="cuda").manual_seed(ref_dim)
+    off = (torch.randn(N, Lq, M, L, P, 2, device="cuda", generator=g) * 3).to(dtype)
+    lg = torch.randn(N, Lq, M, L * P, device="cuda", generator=g).to(dtype)
+    ref = torch.rand(N, Lq, L, ref_dim, device="cuda", generator=g) * 0.8 + 0.1
+    gl = torch.randn(N, Lq, M, L, P, 2, device="cuda", generator=g)
+    ga = torch.randn(N, Lq, M, L, P, device="cuda", generator=g)
+    o1, l1 = off.clone().requires_grad_(True), lg.clone().requires_grad_(True)
+    loc, w = MSDAPrologueFunction.apply(o1, l1, ref, tuple(levels))
+    (loc * gl).sum().backward(retain_graph=True)
+    (w * ga).sum().backward()
+    o2, l2 = off.float().clone().requires_grad_(True), lg.float().clone().requires_grad_(True)
+    w2 = torch.softmax(l2, -1).view(N, Lq, M, L, P)
+    r = ref[:, :, None, :, None, :]
+    if ref_dim == 2:
+        wh = torch.tensor([[wd, ht] for ht, wd in levels], dtype=torch.float32, device="cuda")
+        loc2 = r + o2 / wh[None, None, None, :, None, :]
+    else:
+        loc2 = r[..., :2] + o2 / P * r[..., 2:] * 0.5
+    ((loc2 * gl).sum() + (w2 * ga).sum()).backward()
+    assert loc.dtype == torch.float32 and w.dtype == torch.float32
+    assert float((loc - loc2).abs().max()) < 2e-6 and float((w - w2).abs().max()) < 1e-6
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert o1.grad.dtype == dtype and l1.grad.dtype == dtype
+    assert float((o1.grad.float() - o2.grad).abs().max()) <= tol * float(o2.grad.abs().max())
+    assert float((l1.grad.float() - l2.grad).abs().max()) <= tol * float(l2.grad.abs().max()) + 1e-6
