@@ -301,15 +301,20 @@ int sdb_relu_backward_colsum_bf16(sdb_stream_t stream, const uint16_t* dy, const
  *   forward : out (T, B, H*D) contiguous, lse (B*H, T) = log-sum-exp of every score row (saved for the backward)
  *   backward: dq / dk / dv through the same kind of strided views; needs the transposed mask too (`mask_add_t`, (T, T),
  *             row = key; NULL iff mask_add is NULL) and a (B*H, T) float scratch `delta`.
+ * `tile_flags` (optional, may be NULL): one byte per 64 x 64 tile of the mask, (ceil(T/64), ceil(T/64)) row = query block;
+ * bit 0 = the tile holds a non-zero mask value, bit 1 = every element of the tile is -inf.  Fully masked tiles are
+ * skipped and unmasked tiles never read the mask (the denoising mask is block-structured, dn_components.py:97-113).
  * The four products are TF32 tensor-core contractions with fp32 accumulation (the rounding of torch's TF32 matmul
  * mode, which is when the host layer uses this path); softmax statistics and all sums are fp32.
  * ------------------------------------------------------------------------------------------ */
 int sdb_mha_forward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int64_t q_bat, const float* k,
                         int64_t k_tok, int64_t k_bat, const float* v, int64_t v_tok, int64_t v_bat,
-                        const float* mask_add, int T, int B, int H, int D, float scale, float* out, float* lse);
+                        const float* mask_add, const unsigned char* tile_flags, int T, int B, int H, int D, float scale,
+                        float* out, float* lse);
 int sdb_mha_backward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int64_t q_bat, const float* k,
                          int64_t k_tok, int64_t k_bat, const float* v, int64_t v_tok, int64_t v_bat,
-                         const float* mask_add, const float* mask_add_t, const float* out, const float* dout,
+                         const float* mask_add, const float* mask_add_t, const unsigned char* tile_flags,
+                         const float* out, const float* dout,
                          const float* lse, int T, int B, int H, int D, float scale, float* dq, int64_t dq_tok,
                          int64_t dq_bat, float* dk, int64_t dk_tok, int64_t dk_bat, float* dv, int64_t dv_tok,
                          int64_t dv_bat, float* delta);

@@ -42,9 +42,9 @@ SIGNATURES = {
     "sdb_detr_loss_backward_f32": [c_void_p] * 11 + [c_int] * 3 + [c_float] * 3 + [c_void_p] * 2,
     "sdb_pseudo_label_nms_f32": [c_void_p] * 4 + [c_int] * 4 + [c_float] * 2 + [c_int] * 2 + [c_void_p] * 5,
     "sdb_gmm_threshold_f32": [c_void_p] * 3 + [c_int] * 2 + [c_float, c_int, c_double, c_void_p],
-    "sdb_mha_forward_f32": [c_void_p] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p] + [c_int] * 4 +
+    "sdb_mha_forward_f32": [c_void_p] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p] * 2 + [c_int] * 4 +
                            [c_float, c_void_p, c_void_p],
-    "sdb_mha_backward_f32": [c_void_p] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p] * 5 + [c_int] * 4 +
+    "sdb_mha_backward_f32": [c_void_p] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p] * 6 + [c_int] * 4 +
                             [c_float] + [c_void_p, ctypes.c_int64, ctypes.c_int64] * 3 + [c_void_p],
     "sdb_dp_ctrl_bytes": [],
     "sdb_dp_error_word_offset": [],

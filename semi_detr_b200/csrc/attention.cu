@@ -109,8 +109,8 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // ---- forward ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kAttThreads)
-mha_fwd_kernel(View q, View k, View v, const float* __restrict__ mask, int T, int H, float scale, float* __restrict__ out,
-               float* __restrict__ lse) {
+mha_fwd_kernel(View q, View k, View v, const float* __restrict__ mask, const unsigned char* __restrict__ flags, int T,
+               int H, float scale, float* __restrict__ out, float* __restrict__ lse) {
   __shared__ __align__(16) uint32_t Ks[kTile * kLd];
   __shared__ __align__(16) uint32_t Vs[kTile * kLd];
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
@@ -128,7 +128,14 @@ mha_fwd_kernel(View q, View k, View v, const float* __restrict__ mask, int T, in
   const float* mrow0 = mask ? mask + (long long)min(row0, T - 1) * T : nullptr;
   const float* mrow1 = mask ? mask + (long long)min(row1, T - 1) * T : nullptr;
 
+  const int nb = (T + kTile - 1) / kTile;
   for (int c0 = 0; c0 < T; c0 += kTile) {
+    // tile flags (bit 0: some element of the tile carries a mask value, bit 1: every element is -inf): a fully masked
+    // tile contributes nothing and is skipped, an unmasked one does not touch the mask tensor
+    const int f = flags ? flags[blockIdx.x * nb + c0 / kTile] : 1;
+    if (f & 2) continue;
+    const float* mr0 = (f & 1) ? mrow0 : nullptr;
+    const float* mr1 = (f & 1) ? mrow1 : nullptr;
     __syncthreads();
     load_tile(Ks, kb, k.tok, c0, T, 1.f);
     load_tile(Vs, vb, v.tok, c0, T, 1.f);
@@ -142,8 +149,8 @@ mha_fwd_kernel(View q, View k, View v, const float* __restrict__ mask, int T, in
       for (int e = 0; e < 2; ++e) {
         const int col = c0 + 8 * nt + 2 * t + e;
         const bool in = col < T;
-        const float a0 = in ? (mask ? mrow0[col] : 0.f) : -INFINITY;
-        const float a1 = in ? (mask ? mrow1[col] : 0.f) : -INFINITY;
+        const float a0 = in ? (mr0 ? mr0[col] : 0.f) : -INFINITY;
+        const float a1 = in ? (mr1 ? mr1[col] : 0.f) : -INFINITY;
         s[nt][e] = (s[nt][e] + a0) * kLog2e;
         s[nt][2 + e] = (s[nt][2 + e] + a1) * kLog2e;
         mx0 = fmaxf(mx0, s[nt][e]);
@@ -198,7 +205,8 @@ mha_fwd_kernel(View q, View k, View v, const float* __restrict__ mask, int T, in
 
 // ---- backward, query side: delta = rowsum(dout * out), dq = scale * (p o (dp - delta)) k -----------------------------
 __global__ void __launch_bounds__(kAttThreads)
-mha_bwd_dq_kernel(View q, View k, View v, const float* __restrict__ mask, const float* __restrict__ out,
+mha_bwd_dq_kernel(View q, View k, View v, const float* __restrict__ mask, const unsigned char* __restrict__ flags,
+                  const float* __restrict__ out,
                   const float* __restrict__ dout, const float* __restrict__ lse, int T, int H, float scale, View dq,
                   float* __restrict__ delta) {
   __shared__ __align__(16) uint32_t Ks[kTile * kLd];
@@ -241,7 +249,12 @@ mha_bwd_dq_kernel(View q, View k, View v, const float* __restrict__ mask, const 
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 
+  const int nb = (T + kTile - 1) / kTile;
   for (int c0 = 0; c0 < T; c0 += kTile) {
+    const int f = flags ? flags[blockIdx.x * nb + c0 / kTile] : 1;
+    if (f & 2) continue;                       // p = 0 everywhere in the tile: no contribution to dq
+    const float* mr0 = (f & 1) ? mrow0 : nullptr;
+    const float* mr1 = (f & 1) ? mrow1 : nullptr;
     __syncthreads();
     load_tile(Ks, kb, k.tok, c0, T, 1.f);
     load_tile(Vs, vb, v.tok, c0, T, 1.f);
@@ -255,8 +268,8 @@ mha_bwd_dq_kernel(View q, View k, View v, const float* __restrict__ mask, const 
       for (int e = 0; e < 2; ++e) {
         const int col = c0 + 8 * nt + 2 * t + e;
         const bool in = col < T;
-        const float a0 = in ? (mask ? mrow0[col] : 0.f) : -INFINITY;
-        const float a1 = in ? (mask ? mrow1[col] : 0.f) : -INFINITY;
+        const float a0 = in ? (mr0 ? mr0[col] : 0.f) : -INFINITY;
+        const float a1 = in ? (mr1 ? mr1[col] : 0.f) : -INFINITY;
         const float p0 = exp2f((s[nt][e] + a0) * kLog2e - e0);
         const float p1 = exp2f((s[nt][2 + e] + a1) * kLog2e - e1);
         s[nt][e] = p0 * (dp[nt][e] - d0);
@@ -278,7 +291,8 @@ mha_bwd_dq_kernel(View q, View k, View v, const float* __restrict__ mask, const 
 
 // ---- backward, key side: everything transposed (rows = keys, columns = queries): dv = p^T dout, dk = ds^T (scale q) ----
 __global__ void __launch_bounds__(kAttThreads)
-mha_bwd_dkv_kernel(View q, View k, View v, const float* __restrict__ mask_t, const float* __restrict__ dout,
+mha_bwd_dkv_kernel(View q, View k, View v, const float* __restrict__ mask_t, const unsigned char* __restrict__ flags,
+                   const float* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, int T, int H, float scale, View dk,
                    View dv) {
   __shared__ __align__(16) uint32_t Qs[kTile * kLd];
@@ -304,7 +318,12 @@ mha_bwd_dkv_kernel(View q, View k, View v, const float* __restrict__ mask_t, con
     av[nt][0] = av[nt][1] = av[nt][2] = av[nt][3] = 0.f;
   }
 
+  const int nb = (T + kTile - 1) / kTile;
   for (int c0 = 0; c0 < T; c0 += kTile) {   // query tiles
+    const int f = flags ? flags[(c0 / kTile) * nb + blockIdx.x] : 1;     // flags are (query block, key block)
+    if (f & 2) continue;
+    const float* mr0 = (f & 1) ? mrow0 : nullptr;
+    const float* mr1 = (f & 1) ? mrow1 : nullptr;
     __syncthreads();
     load_tile(Qs, qb, q.tok, c0, T, scale);
     load_tile(Gs, gb, otok, c0, T, 1.f);
@@ -322,8 +341,8 @@ mha_bwd_dkv_kernel(View q, View k, View v, const float* __restrict__ mask_t, con
       for (int e = 0; e < 2; ++e) {
         const int cl = 8 * nt + 2 * t + e, col = c0 + cl;
         const bool in = col < T;
-        const float a0 = in ? (mask_t ? mrow0[col] : 0.f) : -INFINITY;
-        const float a1 = in ? (mask_t ? mrow1[col] : 0.f) : -INFINITY;
+        const float a0 = in ? (mr0 ? mr0[col] : 0.f) : -INFINITY;
+        const float a1 = in ? (mr1 ? mr1[col] : 0.f) : -INFINITY;
         s[nt][e] = exp2f((s[nt][e] + a0) * kLog2e - Ls[cl]);
         s[nt][2 + e] = exp2f((s[nt][2 + e] + a1) * kLog2e - Ls[cl]);
       }
@@ -365,7 +384,8 @@ extern "C" {
 
 int sdb_mha_forward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int64_t q_bat, const float* k,
                         int64_t k_tok, int64_t k_bat, const float* v, int64_t v_tok, int64_t v_bat,
-                        const float* mask_add, int T, int B, int H, int D, float scale, float* out, float* lse) {
+                        const float* mask_add, const unsigned char* tile_flags, int T, int B, int H, int D, float scale,
+                        float* out, float* lse) {
   using namespace sdb;
   SDB_REQUIRE(q && k && v && out && lse, "sdb_mha_forward_f32: null pointer");
   SDB_REQUIRE(T > 0 && B > 0 && H > 0 && (long long)B * H <= 65535, "sdb_mha_forward_f32: bad sizes T=%d B=%d H=%d", T, B, H);
@@ -378,14 +398,15 @@ int sdb_mha_forward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int6
   const dim3 grid((T + kTile - 1) / kTile, B * H);
   mha_fwd_kernel<<<grid, kAttThreads, 0, (cudaStream_t)stream>>>(
       View{const_cast<float*>(q), q_tok, q_bat}, View{const_cast<float*>(k), k_tok, k_bat},
-      View{const_cast<float*>(v), v_tok, v_bat}, mask_add, T, H, scale, out, lse);
+      View{const_cast<float*>(v), v_tok, v_bat}, mask_add, mask_add ? tile_flags : nullptr, T, H, scale, out, lse);
   SDB_LAUNCH_CHECK("mha_fwd_kernel");
   return SDB_OK;
 }
 
 int sdb_mha_backward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int64_t q_bat, const float* k,
                          int64_t k_tok, int64_t k_bat, const float* v, int64_t v_tok, int64_t v_bat,
-                         const float* mask_add, const float* mask_add_t, const float* out, const float* dout,
+                         const float* mask_add, const float* mask_add_t, const unsigned char* tile_flags,
+                         const float* out, const float* dout,
                          const float* lse, int T, int B, int H, int D, float scale, float* dq, int64_t dq_tok,
                          int64_t dq_bat, float* dk, int64_t dk_tok, int64_t dk_bat, float* dv, int64_t dv_tok,
                          int64_t dv_bat, float* delta) {
@@ -405,10 +426,11 @@ int sdb_mha_backward_f32(sdb_stream_t stream, const float* q, int64_t q_tok, int
   const dim3 grid((T + kTile - 1) / kTile, B * H);
   const View Q{const_cast<float*>(q), q_tok, q_bat}, K{const_cast<float*>(k), k_tok, k_bat},
       V{const_cast<float*>(v), v_tok, v_bat};
-  mha_bwd_dq_kernel<<<grid, kAttThreads, 0, (cudaStream_t)stream>>>(Q, K, V, mask_add, out, dout, lse, T, H, scale,
+  const unsigned char* fl = mask_add ? tile_flags : nullptr;
+  mha_bwd_dq_kernel<<<grid, kAttThreads, 0, (cudaStream_t)stream>>>(Q, K, V, mask_add, fl, out, dout, lse, T, H, scale,
                                                                     View{dq, dq_tok, dq_bat}, delta);
   SDB_LAUNCH_CHECK("mha_bwd_dq_kernel");
-  mha_bwd_dkv_kernel<<<grid, kAttThreads, 0, (cudaStream_t)stream>>>(Q, K, V, mask_add_t, dout, lse, delta, T, H, scale,
+  mha_bwd_dkv_kernel<<<grid, kAttThreads, 0, (cudaStream_t)stream>>>(Q, K, V, mask_add_t, fl, dout, lse, delta, T, H, scale,
                                                                      View{dk, dk_tok, dk_bat}, View{dv, dv_tok, dv_bat});
   SDB_LAUNCH_CHECK("mha_bwd_dkv_kernel");
   return SDB_OK;
