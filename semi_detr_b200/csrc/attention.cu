@@ -48,17 +48,33 @@ __device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], uint
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// 64 rows x 32 channels of one (image, head), rows r0.. of the operand, into shared memory as TF32 words (x scale);
-// rows past T are zero
-__device__ __forceinline__ void load_tile(uint32_t* s, const float* base, long long tok, int r0, int T, float scale) {
+// 64 rows x 32 channels of one (image, head), rows r0.. of the operand, go into shared memory as TF32 words (x scale;
+// rows past T are zero) in two steps, so that the global loads of tile i + 1 are in flight while tile i is computed on:
+// fetch = this thread's 4 x 16 bytes into registers, stash = scale, round to TF32, store to shared memory.
+__device__ __forceinline__ void fetch_tile(float4 (&r)[4], const float* base, long long tok, int r0, int T) {
 #pragma unroll
-  for (int i = threadIdx.x; i < kTile * 8; i += kAttThreads) {
-    const int r = i >> 3, c4 = i & 7;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < T) x = __ldg(reinterpret_cast<const float4*>(base + (long long)(r0 + r) * tok + 4 * c4));
-    *reinterpret_cast<uint4*>(s + r * kLd + 4 * c4) =
-        make_uint4(to_tf32(x.x * scale), to_tf32(x.y * scale), to_tf32(x.z * scale), to_tf32(x.w * scale));
+  for (int u = 0; u < 4; ++u) {
+    const int i = threadIdx.x + u * kAttThreads;
+    const int row = i >> 3, c4 = i & 7;
+    r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + row < T) r[u] = __ldg(reinterpret_cast<const float4*>(base + (long long)(r0 + row) * tok + 4 * c4));
   }
+}
+__device__ __forceinline__ void stash_tile(uint32_t* s, const float4 (&r)[4], float scale) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = threadIdx.x + u * kAttThreads;
+    const int row = i >> 3, c4 = i & 7;
+    *reinterpret_cast<uint4*>(s + row * kLd + 4 * c4) =
+        make_uint4(to_tf32(r[u].x * scale), to_tf32(r[u].y * scale), to_tf32(r[u].z * scale), to_tf32(r[u].w * scale));
+  }
+}
+// first tile at or after c0 that is not fully masked (T when there is none)
+__device__ __forceinline__ int next_live_tile(const unsigned char* flags, int row_block, int nb, int c0, int T,
+                                              bool transposed) {
+  if (flags)
+    while (c0 < T && (flags[transposed ? (c0 / kTile) * nb + row_block : row_block * nb + c0 / kTile] & 2)) c0 += kTile;
+  return c0;
 }
 
 // A fragments (16 rows x 32 channels, 4 k-steps) of the warp's own rows, straight from global memory
@@ -129,17 +145,27 @@ mha_fwd_kernel(View q, View k, View v, const float* __restrict__ mask, const uns
   const float* mrow1 = mask ? mask + (long long)min(row1, T - 1) * T : nullptr;
 
   const int nb = (T + kTile - 1) / kTile;
-  for (int c0 = 0; c0 < T; c0 += kTile) {
-    // tile flags (bit 0: some element of the tile carries a mask value, bit 1: every element is -inf): a fully masked
-    // tile contributes nothing and is skipped, an unmasked one does not touch the mask tensor
+  // tile flags (bit 0: some element of the tile carries a mask value, bit 1: every element is -inf): a fully masked
+  // tile contributes nothing and is skipped, an unmasked one does not touch the mask tensor
+  float4 kreg[4], vreg[4];
+  int c0 = next_live_tile(flags, blockIdx.x, nb, 0, T, false);
+  if (c0 < T) {
+    fetch_tile(kreg, kb, k.tok, c0, T);
+    fetch_tile(vreg, vb, v.tok, c0, T);
+  }
+  for (; c0 < T;) {
     const int f = flags ? flags[blockIdx.x * nb + c0 / kTile] : 1;
-    if (f & 2) continue;
     const float* mr0 = (f & 1) ? mrow0 : nullptr;
     const float* mr1 = (f & 1) ? mrow1 : nullptr;
     __syncthreads();
-    load_tile(Ks, kb, k.tok, c0, T, 1.f);
-    load_tile(Vs, vb, v.tok, c0, T, 1.f);
+    stash_tile(Ks, kreg, 1.f);
+    stash_tile(Vs, vreg, 1.f);
     __syncthreads();
+    const int cn = next_live_tile(flags, blockIdx.x, nb, c0 + kTile, T, false);
+    if (cn < T) {                                  // next tile's loads fly under this tile's products
+      fetch_tile(kreg, kb, k.tok, cn, T);
+      fetch_tile(vreg, vb, v.tok, cn, T);
+    }
     float s[8][4];
     mm_nt(s, qa, Ks, g, t);
     float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -184,6 +210,7 @@ mha_fwd_kernel(View q, View k, View v, const float* __restrict__ mask, const uns
       o[nt][3] *= f1;
     }
     mm_pn(o, s, Vs, g, t);
+    c0 = cn;
   }
   l0 = quad_sum(l0);
   l1 = quad_sum(l1);
@@ -250,15 +277,25 @@ mha_bwd_dq_kernel(View q, View k, View v, const float* __restrict__ mask, const 
   for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 
   const int nb = (T + kTile - 1) / kTile;
-  for (int c0 = 0; c0 < T; c0 += kTile) {
+  float4 kreg[4], vreg[4];
+  int c0 = next_live_tile(flags, blockIdx.x, nb, 0, T, false);   // fully masked tiles: p = 0, no contribution to dq
+  if (c0 < T) {
+    fetch_tile(kreg, kb, k.tok, c0, T);
+    fetch_tile(vreg, vb, v.tok, c0, T);
+  }
+  for (; c0 < T;) {
     const int f = flags ? flags[blockIdx.x * nb + c0 / kTile] : 1;
-    if (f & 2) continue;                       // p = 0 everywhere in the tile: no contribution to dq
     const float* mr0 = (f & 1) ? mrow0 : nullptr;
     const float* mr1 = (f & 1) ? mrow1 : nullptr;
     __syncthreads();
-    load_tile(Ks, kb, k.tok, c0, T, 1.f);
-    load_tile(Vs, vb, v.tok, c0, T, 1.f);
+    stash_tile(Ks, kreg, 1.f);
+    stash_tile(Vs, vreg, 1.f);
     __syncthreads();
+    const int cn = next_live_tile(flags, blockIdx.x, nb, c0 + kTile, T, false);
+    if (cn < T) {
+      fetch_tile(kreg, kb, k.tok, cn, T);
+      fetch_tile(vreg, vb, v.tok, cn, T);
+    }
     float s[8][4], dp[8][4];
     mm_nt(s, qa, Ks, g, t);
     mm_nt(dp, ga, Vs, g, t);
@@ -276,6 +313,7 @@ mha_bwd_dq_kernel(View q, View k, View v, const float* __restrict__ mask, const 
         s[nt][2 + e] = p1 * (dp[nt][2 + e] - d1);
       }
     mm_pn(acc, s, Ks, g, t);
+    c0 = cn;
   }
   if (row0 < T) {
     float* p = dq.p + (long long)row0 * dq.tok + b * dq.bat + h * kHd + 2 * t;
@@ -319,20 +357,30 @@ mha_bwd_dkv_kernel(View q, View k, View v, const float* __restrict__ mask_t, con
   }
 
   const int nb = (T + kTile - 1) / kTile;
-  for (int c0 = 0; c0 < T; c0 += kTile) {   // query tiles
-    const int f = flags ? flags[(c0 / kTile) * nb + blockIdx.x] : 1;     // flags are (query block, key block)
-    if (f & 2) continue;
+  float4 qreg[4], greg[4];
+  int c0 = next_live_tile(flags, blockIdx.x, nb, 0, T, true);     // flags are (query block, key block)
+  if (c0 < T) {
+    fetch_tile(qreg, qb, q.tok, c0, T);
+    fetch_tile(greg, gb, otok, c0, T);
+  }
+  for (; c0 < T;) {   // query tiles
+    const int f = flags ? flags[(c0 / kTile) * nb + blockIdx.x] : 1;
     const float* mr0 = (f & 1) ? mrow0 : nullptr;
     const float* mr1 = (f & 1) ? mrow1 : nullptr;
     __syncthreads();
-    load_tile(Qs, qb, q.tok, c0, T, scale);
-    load_tile(Gs, gb, otok, c0, T, 1.f);
+    stash_tile(Qs, qreg, scale);
+    stash_tile(Gs, greg, 1.f);
     if (threadIdx.x < kTile) {
       const int c = c0 + threadIdx.x;
       Ls[threadIdx.x] = c < T ? lse[(long long)bh * T + c] * kLog2e : 0.f;
       Ds[threadIdx.x] = c < T ? delta[(long long)bh * T + c] : 0.f;
     }
     __syncthreads();
+    const int cn = next_live_tile(flags, blockIdx.x, nb, c0 + kTile, T, true);
+    if (cn < T) {
+      fetch_tile(qreg, qb, q.tok, cn, T);
+      fetch_tile(greg, gb, otok, cn, T);
+    }
     float s[8][4], dp[8][4];
     mm_nt(s, ka, Qs, g, t);
 #pragma unroll
@@ -357,6 +405,7 @@ mha_bwd_dkv_kernel(View q, View k, View v, const float* __restrict__ mask_t, con
         s[nt][2 + e] *= dp[nt][2 + e] - d;
       }
     mm_pn(ak, s, Qs, g, t);
+    c0 = cn;
   }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
