@@ -455,6 +455,16 @@ int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const flo
                   int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu, int k_splits,
                   int round_mode, float* a_column_sums);
 
+/* Grad-input product of the linear layer BEHIND a ReLU, carrying that ReLU's backward and the bias gradient of the layer
+ * in front of it in its epilogue (the FFN backward of detr_od/models/utils/transformer.py:626-630 and :878-882,
+ * linear2(dropout(relu(linear1(x)))): autograd runs mm -> threshold_backward -> sum there, three passes over the
+ * (tokens, d_ffn) gradient):
+ *   y[i, j] = (a . op(b))[i, j] * (relu_src[i, j] > 0)          y, relu_src (m, n) row-major
+ *   y_column_sums[j] = sum_i y[i, j]                            optional (n,), overwritten
+ * a / b / round_mode as in sdb_gemm_tf32 (grad x = dy W : (dy, 0, W, 1)); relu_src 16-byte aligned. */
+int sdb_gemm_tf32_relu_grad(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
+                            float* y, int m, int n, int k, const float* relu_src, float* y_column_sums, int round_mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ SIGNATURES = {
     "sdb_colsum_bf16": [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p],
     "sdb_relu_backward_colsum_bf16": [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p],
     "sdb_gemm_tf32": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "sdb_gemm_tf32_relu_grad": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int],
     "sdb_layernorm_bwd_workspace_floats": [],
     "sdb_layernorm_forward_f32": [c_void_p] * 4 + [ctypes.c_int64, c_int, c_float] + [c_void_p] * 3,
     "sdb_add_layernorm_forward_f32": [c_void_p] * 5 + [ctypes.c_int64, c_int, c_float] + [c_void_p] * 5,

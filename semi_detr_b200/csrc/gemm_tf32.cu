@@ -182,7 +182,183 @@ struct GemmArgs {
   float* a_colsum;          // (M,) or null: column sums of an MN-major A are ADDED here (bias gradient)
   const float* bias;        // (N,) or null
   const uint8_t* row_mask;  // (M,) or null; nonzero -> the output row is zero
+  const float* relu_src;    // (M, N) or null: y is zeroed where relu_src <= 0 (ReLU backward in the grad-input epilogue)
+  float* y_colsum;          // (N,) or null: column sums of the finished y are ADDED here (the bias gradient behind it)
 };
+
+// ------------------------------------------------------------------------------------------------------------
+// Epilogue of the 1-CTA kernels (warps 2..5; warp w drains TMEM lanes 32 (w % 4) .. + 31 = 32 output rows).
+// Per 32-column chunk: tcgen05.ld (thread = row) -> bias / ReLU / row mask -> the warp's private 4 KB staging tile
+// (128-byte swizzle, two tiles alternate) -> one TMA store.  kEpHmask adds a second pass over the staged tile in the
+// ACTIVATION's memory layout (lane -> row (lane >> 3) + 4 i, 16-byte chunk lane & 7: four full 128-byte rows per
+// request, where the accumulator's thread-per-row layout would touch 32 lines per request): zero where relu_src <= 0,
+// column sums of what is left (two shuffle steps, one red.v4 per 4 columns).  The accumulator is handed back to the
+// MMA warp as soon as its last chunk is in registers.
+enum { kEpBias = 1, kEpRelu = 2, kEpMask = 4, kEpHmask = 8, kEpGeneric = 16 };
+
+template <int F>
+__device__ __forceinline__ void epilogue_tiles(const GemmArgs& g, const CUtensorMap* tmYw, uint32_t tmem_base,
+                                               uint32_t out_base, uint32_t tfull0, uint32_t tempty0,
+                                               long long num_items, int n_tiles, int warp, int lane) {
+  constexpr bool kGen = (F & kEpGeneric) != 0;
+  constexpr bool kHm = (F & kEpHmask) != 0;
+  constexpr int kChunks = kBN / kOutChunk;
+  const int quarter = warp & 3;
+  const int row = quarter * 32 + lane;
+  const uint32_t wbuf = out_base + (uint32_t)(quarter * 2) * 4096u;     // two 4 KB staging tiles, 1024-byte aligned
+  const uint32_t l7 = (uint32_t)lane & 7u, r0 = (uint32_t)lane >> 3;
+  const uint32_t srow = wbuf + (uint32_t)lane * 128u + (l7 << 4);       // ^ (q << 4): chunk q of this thread's row
+  // second pass: row r0 + 4 i lies at r0 * 128 + i * 512, its chunk l7 at position l7 ^ (r & 7), r & 7 = r0 + 4 (i & 1)
+  const uint32_t off_even = r0 * 128u + ((l7 ^ r0) << 4), off_odd = r0 * 128u + ((l7 ^ (r0 + 4u)) << 4);
+  const bool relu = kGen ? g.relu != 0 : (F & kEpRelu) != 0;
+  int acc = 0, epi_tile = 0;
+  uint32_t acc_phase = 0;
+  bool prev_odd = false;
+  for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const int ks = (int)(item % g.k_splits);
+    const long long tt = item / g.k_splits;
+    const int n0 = (int)(tt % n_tiles) * kBN, m0 = (int)(tt / n_tiles) * kBM;
+    const int nchunks = min(kChunks, (g.N - n0 + kOutChunk - 1) / kOutChunk);
+    const bool use_mask = kGen ? g.row_mask != nullptr : (F & kEpMask) != 0;
+    const bool masked = use_mask && (m0 + row) < g.M && g.row_mask[m0 + row] != 0;
+    const bool add_bias = kGen ? (g.bias != nullptr && ks == 0) : (F & kEpBias) != 0;
+    // activation block of the ReLU-backward epilogue
+    const int rows_live = g.M - (m0 + quarter * 32);
+    const bool h_full = rows_live >= 32 && n0 + kBN <= g.N;
+    const float* hp0 = nullptr;
+    size_t hstep = 0;
+    if (kHm) {
+      hp0 = g.relu_src + (size_t)(m0 + quarter * 32 + (int)r0) * g.N + n0 + 4 * (int)l7;
+      hstep = (size_t)4 * g.N;
+    }
+    float4 h[2][8];
+    auto fetch_h = [&](int c, float4 (&d)[8]) {
+      if (h_full) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = __ldg(reinterpret_cast<const float4*>(hp0 + i * hstep + c * kOutChunk));
+      } else {                                   // ragged edge tile: rows past M / columns past N read as h = 0
+        const int col = n0 + c * kOutChunk + 4 * (int)l7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          d[i] = ((int)r0 + 4 * i < rows_live && col < g.N)
+                     ? __ldg(reinterpret_cast<const float4*>(hp0 + i * hstep + c * kOutChunk))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (kHm) {
+      fetch_h(0, h[0]);                          // does not depend on the product: requested before the wait
+      // chunks are consumed ~1 us apart, less than an HBM round trip under load: ask L2 for the NEXT item's block now
+      // (this thread's row, four 128-byte lines)
+      const long long nxt = item + gridDim.x;
+      if (nxt < num_items) {
+        const long long ntt = nxt / g.k_splits;
+        const int nn0 = (int)(ntt % n_tiles) * kBN, nm = (int)(ntt / n_tiles) * kBM + row;
+        if (nm < g.M) {
+          const float* pr = g.relu_src + (size_t)nm * g.N + nn0;
+#pragma unroll
+          for (int j = 0; j < kBN / 32; ++j)
+            if (nn0 + 32 * j < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + 32 * j));
+        }
+      }
+    }
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 32 + 2 * epi_tile);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBN);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      if (c < nchunks) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(c * kOutChunk), v);
+        if (kHm && c + 1 < nchunks) fetch_h(c + 1, h[(c + 1) & 1]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == nchunks - 1) {                  // the whole accumulator has been read: back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8u * acc);
+        }
+        // this chunk's staging tile was last read by the store issued two chunks ago (after a tile with an odd
+        // number of chunks: by the most recent one)
+        if (lane == 0) {
+          if (c == 0 && prev_odd) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncwarp();
+        const uint32_t tile0 = wbuf + (uint32_t)(c & 1) * 4096u;
+        const uint32_t sb = srow + (uint32_t)(c & 1) * 4096u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (add_bias)                          // warp-uniform address; columns past N are clipped by the store
+            o = __ldg(reinterpret_cast<const float4*>(g.bias + min(n0 + c * kOutChunk + 4 * q, g.N - 4)));
+          o.x += __uint_as_float(v[4 * q + 0]);
+          o.y += __uint_as_float(v[4 * q + 1]);
+          o.z += __uint_as_float(v[4 * q + 2]);
+          o.w += __uint_as_float(v[4 * q + 3]);
+          if (relu) {
+            o.x = fmaxf(o.x, 0.f);
+            o.y = fmaxf(o.y, 0.f);
+            o.z = fmaxf(o.z, 0.f);
+            o.w = fmaxf(o.w, 0.f);
+          }
+          if (masked) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb ^ (uint32_t)(q << 4)), "f"(o.x), "f"(o.y),
+                       "f"(o.z), "f"(o.w)
+                       : "memory");
+        }
+        if (kHm) {
+          __syncwarp();
+          float4 x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                         : "r"(tile0 + ((i & 1) ? off_odd : off_even) + (uint32_t)(i * 512))
+                         : "memory");
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4(&hc)[8] = h[c & 1];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            x[i].x = hc[i].x > 0.f ? x[i].x : 0.f;
+            x[i].y = hc[i].y > 0.f ? x[i].y : 0.f;
+            x[i].z = hc[i].z > 0.f ? x[i].z : 0.f;
+            x[i].w = hc[i].w > 0.f ? x[i].w : 0.f;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile0 + ((i & 1) ? off_odd : off_even) +
+                                                                        (uint32_t)(i * 512)),
+                         "f"(x[i].x), "f"(x[i].y), "f"(x[i].z), "f"(x[i].w)
+                         : "memory");
+            cs.x += x[i].x;
+            cs.y += x[i].y;
+            cs.z += x[i].z;
+            cs.w += x[i].w;
+          }
+          if (g.y_colsum) {                      // rows past M and columns past N staged zeros (zero-filled operands)
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+              cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+              cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
+            const int col = n0 + c * kOutChunk + 4 * lane;
+            if (lane < 8 && col < g.N && rows_live > 0) red_add_f4(g.y_colsum + col, cs);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (kGen && g.k_splits > 1) tma_reduce_add_2d(tmYw, tile0, n0 + c * kOutChunk, m0 + quarter * 32);
+          else tma_store_2d(tmYw, tile0, n0 + c * kOutChunk, m0 + quarter * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    prev_odd = (nchunks & 1) != 0;
+    if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 33 + 2 * epi_tile);
+    ++epi_tile;
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1u;
+  }
+}
 
 // kBRes ("B resident"): for K <= 256 the whole (128 x K) B tile of one n-block -- the weight matrix of the
 // value / offset / attention / output projections -- stays in shared memory for the life of the CTA (128 KB), is
@@ -441,68 +617,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ---------------- epilogue (warps 2..5) ----------------
-    const int quarter = warp & 3;                 // TMEM lanes this warp may read: 32*(warp % 4) .. +31
-    const int row = quarter * 32 + lane;          // accumulator row owned by this thread
-    int acc = 0, obuf = 0, epi_tile = 0;
-    uint32_t acc_phase = 0;
-    for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int ks = (int)(item % g.k_splits);
-      const long long tt = item / g.k_splits;
-      const int n0 = (int)(tt % n_tiles) * kBN, m0 = (int)(tt / n_tiles) * kBM;
-      const bool masked = g.row_mask != nullptr && (m0 + row) < g.M && g.row_mask[m0 + row] != 0;
-      mbar_wait(tfull(acc), acc_phase);
-      if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 32 + 2 * epi_tile);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBN);
-      {
-        // Each warp drains its own 32 accumulator rows: 32x32 sub-tiles through a private double-buffered 4 KB
-        // staging area and its own TMA stores -- no CTA-wide barrier anywhere in the epilogue.
-        const bool add_bias = g.bias != nullptr && ks == 0;
-        const uint32_t wbuf = out_base + (uint32_t)(quarter * 2) * 4096u;
-#pragma unroll 1
-        for (int c = 0; c < kBN / kOutChunk; ++c) {
-          if (n0 + c * kOutChunk >= g.N) break;
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(c * kOutChunk), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          __syncwarp();
-          const uint32_t srow = wbuf + (uint32_t)obuf * 4096u + (uint32_t)lane * 128u;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int col = n0 + c * kOutChunk + 4 * q;
-            if (add_bias && col < g.N) o = __ldg(reinterpret_cast<const float4*>(g.bias + col));   // warp-uniform address
-            float* op = reinterpret_cast<float*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(v[4 * q + e]) + op[e];
-              if (g.relu) x = fmaxf(x, 0.f);
-              op[e] = masked ? 0.f : x;
-            }
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)(((q ^ (lane & 7)) << 4))),
-                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
-                         : "memory");
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            if (g.k_splits > 1)
-              tma_reduce_add_2d(&tmYw, wbuf + (uint32_t)obuf * 4096u, n0 + c * kOutChunk, m0 + quarter * 32);
-            else
-              tma_store_2d(&tmYw, wbuf + (uint32_t)obuf * 4096u, n0 + c * kOutChunk, m0 + quarter * 32);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          obuf ^= 1;
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty(acc));
-      if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 33 + 2 * epi_tile);
-      ++epi_tile;
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
+    // One instantiation per epilogue the step uses, chosen once per kernel: a single warp drains 32 rows, so the
+    // epilogue's rate is its instruction count (ncu source view, docs/ROUND2_NOTES.md section 2) and every runtime
+    // flag tested per element costs all of them.
+    const uint32_t tf0 = tfull(0), te0 = tempty(0);
+    const bool one = g.k_splits == 1;
+    if (one && g.relu_src)
+      epilogue_tiles<kEpHmask>(g, &tmYw, tmem_base, out_base, tf0, te0, num_items, n_tiles, warp, lane);
+    else if (one && !g.bias && !g.relu && !g.row_mask)
+      epilogue_tiles<0>(g, &tmYw, tmem_base, out_base, tf0, te0, num_items, n_tiles, warp, lane);
+    else if (one && g.bias && g.relu && !g.row_mask)
+      epilogue_tiles<kEpBias | kEpRelu>(g, &tmYw, tmem_base, out_base, tf0, te0, num_items, n_tiles, warp, lane);
+    else if (one && g.bias && !g.relu && !g.row_mask)
+      epilogue_tiles<kEpBias>(g, &tmYw, tmem_base, out_base, tf0, te0, num_items, n_tiles, warp, lane);
+    else if (one && g.bias && !g.relu && g.row_mask)
+      epilogue_tiles<kEpBias | kEpMask>(g, &tmYw, tmem_base, out_base, tf0, te0, num_items, n_tiles, warp, lane);
+    else
+      epilogue_tiles<kEpGeneric>(g, &tmYw, tmem_base, out_base, tf0, te0, num_items, n_tiles, warp, lane);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (warp == 2 && lane == 0) stamp(g.trace, 62);
   }
@@ -564,6 +695,8 @@ struct WresArgs {
   const float* b;         // weights
   const float* bias;      // (N,) or null
   const uint8_t* row_mask;  // (M,) or null
+  const float* relu_src;    // (M, N) or null: y is zeroed where relu_src <= 0
+  float* y_colsum;          // (N,) or null: column sums of the finished y are ADDED here
   unsigned long long* trace;
 };
 
@@ -755,10 +888,29 @@ gemm_tf32_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     const float bias = (g.bias != nullptr && feat < g.N) ? __ldg(g.bias + feat) : 0.f;
     const uint32_t wbuf = out_base + (uint32_t)(quarter * kWEpiBufs) * 4096u;
+    // ReLU-backward epilogue: in this kernel's layout (thread = output feature, 32 tokens per chunk) the activation
+    // block is read as it lies in memory -- one full 128-byte row per request -- and the column sum of a feature is a
+    // sum inside its own thread, carried over every tile of the CTA (one n-block per CTA) and added once at the end.
+    const float* hsrc = g.relu_src;
+    const int featc = min(feat, g.N - 1);                 // features past N: zero weights -> y = 0, clipped by the store
+    float colsum = 0.f;
     int acc = 0, epi_tile = 0;
     uint32_t acc_phase = 0;
     for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int m0 = (int)(item / n_tiles) * kBM;
+      const bool m_full = m0 + kBM <= g.M;
+      float hh[2][32];
+      auto fetch_h = [&](int c, float (&d)[32]) {
+        if (m_full) {
+          const float* p = hsrc + (size_t)(m0 + c * 32) * g.N + featc;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) d[e] = __ldg(p + (size_t)e * g.N);
+        } else {                                          // tokens past M: zero activations rows of A -> y = 0
+#pragma unroll
+          for (int e = 0; e < 32; ++e) d[e] = __ldg(hsrc + (size_t)min(m0 + c * 32 + e, g.M - 1) * g.N + featc);
+        }
+      };
+      if (hsrc) fetch_h(0, hh[0]);
       mbar_wait(tfull(acc), acc_phase);
       if (warp == 2 && lane == 0 && epi_tile < 6) stamp(g.trace, 32 + 2 * epi_tile);
       tc_fence_after();
@@ -766,11 +918,12 @@ gemm_tf32_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * kBN);
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < kBM / 32; ++c) {                // 32 tokens per chunk
-        if (m0 + c * 32 >= g.M) break;
+        if (m0 + c * 32 >= g.M) continue;
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
+        if (hsrc && c + 1 < kBM / 32 && m0 + (c + 1) * 32 < g.M) fetch_h(c + 1, hh[(c + 1) & 1]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         uint32_t mask_bits = 0;
         if (g.row_mask != nullptr) {                      // one byte per token, the same for every lane
@@ -783,6 +936,10 @@ gemm_tf32_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           float x = __uint_as_float(v[e]) + bias;
           if (g.relu) x = fmaxf(x, 0.f);
           if ((mask_bits >> e) & 1u) x = 0.f;
+          if (hsrc) {
+            x = hh[c & 1][e] > 0.f ? x : 0.f;
+            colsum += x;
+          }
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbuf + (uint32_t)(e * 128 + lane * 4)), "f"(x) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -799,6 +956,7 @@ gemm_tf32_wres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (g.y_colsum != nullptr && feat < g.N) atomicAdd(g.y_colsum + feat, colsum);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (warp == 2 && lane == 0) stamp(g.trace, 62);
   }
@@ -1177,9 +1335,10 @@ extern "C" int sdb_gemm_tf32_set_trace(unsigned long long* device_buffer) {
 }
 #endif
 
-extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
-                             float* y, int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu,
-                             int k_splits, int round_mode, float* a_column_sums) {
+static int gemm_tf32_impl(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
+                          float* y, int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu,
+                          int k_splits, int round_mode, float* a_column_sums, const float* relu_src,
+                          float* y_column_sums) {
   using namespace sdb;
   SDB_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_tf32: negative size");
   if (m == 0 || n == 0) return SDB_OK;
@@ -1216,6 +1375,8 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
   g.bias = bias;
   g.row_mask = row_mask;
   g.a_colsum = a_column_sums;
+  g.relu_src = relu_src;
+  g.y_colsum = y_column_sums;
   g.trace = g_gemm_trace;
   const long long items = (long long)((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) * g.k_splits;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1227,7 +1388,8 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
     const char* e = getenv("SDB_GEMM_2CTA");
     pair_enabled = (e && strcmp(e, "1") == 0) ? 1 : 0;
   }
-  if (pair_enabled && g.k_splits == 1 && !a_column_sums && sm_count() >= 2) {
+  const bool plain_epilogue = relu_src == nullptr && y_column_sums == nullptr;   // the other variants know no more
+  if (pair_enabled && plain_epilogue && g.k_splits == 1 && !a_column_sums && sm_count() >= 2) {
     const long long pair_items = (long long)((m + 2 * kBM - 1) / (2 * kBM)) * ((n + kPairBN - 1) / kPairBN);
     long long pairs = sm_count() / 2;
     if (pairs > pair_items) pairs = pair_items;
@@ -1250,6 +1412,8 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
     const char* e = getenv("SDB_GEMM_WRES");
     wres_enabled = (e && strcmp(e, "1") == 0) ? 1 : 0;
   }
+  // (its ReLU-backward epilogue reads the activation as 32 single-row requests per chunk: 258 us at the encoder FFN
+  // shape against 201 us on the shared-memory-resident variant, so that product does not come here by default)
   if (wres_enabled && !a_mn_major && g.k_splits == 1 && total_kb <= kResKB && n_tiles <= sm_count() &&
       items >= 2ll * sm_count() && !a_column_sums) {
     CUtensorMap tyn;
@@ -1260,6 +1424,7 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
     w.relu = relu; w.round_a = g.round_a; w.round_b = g.round_b;
     w.b_mn = b_mn_major ? 1 : 0;
     w.b = b; w.bias = bias; w.row_mask = row_mask; w.trace = g_gemm_trace;
+    w.relu_src = relu_src; w.y_colsum = y_column_sums;
     static bool configured = false;
     if (!configured) {
       SDB_CUDA(cudaFuncSetAttribute(gemm_tf32_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemW));
@@ -1282,4 +1447,27 @@ extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major
   }
   if (a_mn_major) return b_mn_major ? launch<true, true, false>(st, ta, tb, tyw, g, items, n_tiles) : launch<true, false, false>(st, ta, tb, tyw, g, items, n_tiles);
   return b_mn_major ? launch<false, true, false>(st, ta, tb, tyw, g, items, n_tiles) : launch<false, false, false>(st, ta, tb, tyw, g, items, n_tiles);
+}
+
+extern "C" int sdb_gemm_tf32(sdb_stream_t stream, const float* a, int a_mn_major, const float* b, int b_mn_major,
+                             float* y, int m, int n, int k, const float* bias, const uint8_t* row_mask, int relu,
+                             int k_splits, int round_mode, float* a_column_sums) {
+  return gemm_tf32_impl(stream, a, a_mn_major, b, b_mn_major, y, m, n, k, bias, row_mask, relu, k_splits, round_mode,
+                        a_column_sums, nullptr, nullptr);
+}
+
+// Grad-input product of the layer BEHIND a ReLU, with that ReLU's backward and the bias gradient of the layer IN FRONT
+// of it in the epilogue: y = (a . op(b)) * (relu_src > 0), y_column_sums[j] = sum_i y[i, j].  In the FFN
+// (transformer.py:626-630, 878-882: linear2(dropout(relu(linear1(x))))) a = d(linear2 output), b = linear2.weight,
+// relu_src = the hidden activation, y = d(linear1 pre-activation), y_column_sums = d(linear1.bias).
+extern "C" int sdb_gemm_tf32_relu_grad(sdb_stream_t stream, const float* a, int a_mn_major, const float* b,
+                                       int b_mn_major, float* y, int m, int n, int k, const float* relu_src,
+                                       float* y_column_sums, int round_mode) {
+  SDB_REQUIRE(relu_src != nullptr, "gemm_tf32_relu_grad: relu_src is null");
+  SDB_REQUIRE(((reinterpret_cast<uintptr_t>(relu_src) | reinterpret_cast<uintptr_t>(y_column_sums)) & 15) == 0,
+              "gemm_tf32_relu_grad: relu_src and y_column_sums must be 16-byte aligned");
+  if (y_column_sums && n > 0)
+    SDB_CUDA(cudaMemsetAsync(y_column_sums, 0, sizeof(float) * (size_t)n, (cudaStream_t)stream));
+  return gemm_tf32_impl(stream, a, a_mn_major, b, b_mn_major, y, m, n, k, nullptr, nullptr, 0, 1, round_mode, nullptr,
+                        relu_src, y_column_sums);
 }

@@ -23,7 +23,7 @@ from torch import nn
 from ..consts import device_const
 from ..msda import MSDeformAttn
 from ..registry import TRANSFORMER
-from ..layers import LayerNorm, Linear
+from ..layers import LayerNorm, Linear, ffn
 from ..layers.attention import attention_enabled, fused_self_attention
 from ..layers.linear import linear
 
@@ -139,6 +139,8 @@ class DINOTransformerEncoderLayer(nn.Module):
         q = query if query is not None else (src if pos is None else src + pos)
         src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, key_padding_mask)
         src = self.norm1.add_norm(src, self.dropout1(src2))
+        if ffn.fused_ok(src, self.linear1, self.linear2, self.norm2, (self.dropout2, self.dropout3)):
+            return ffn.ffn_block(src, self.linear1, self.linear2, self.norm2, next_pos)
         src2 = self.linear2(self.dropout2(self.linear1(src, relu=True)))
         return self.norm2.add_norm(src, self.dropout3(src2), next_pos)
 
@@ -256,6 +258,8 @@ class DINOTransformerDecoderLayer(nn.Module):
                                        memory, spatial_shapes, level_start_index,
                                        memory_key_padding_mask).transpose(0, 1)
                 tgt = self.norm1.add_norm(tgt, self.dropout1(tgt2))
+            elif ffn.fused_ok(tgt, self.linear1, self.linear2, self.norm3, (self.dropout3, self.dropout4)):
+                tgt = ffn.ffn_block(tgt, self.linear1, self.linear2, self.norm3)
             else:
                 tgt2 = self.linear2(self.dropout3(self.linear1(tgt, relu=True)))
                 tgt = self.norm3.add_norm(tgt, self.dropout4(tgt2))

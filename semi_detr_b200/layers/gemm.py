@@ -71,6 +71,34 @@ def linear_grad_input(g2d, weight):
     return gemm_tf32(g2d, 0, weight, 1, m, n, k)
 
 
+def linear_grad_input_relu(g2d, weight, h2d, round_mode=None):
+    """The grad-input product of the layer behind a ReLU with that ReLU's backward in its epilogue:
+    -> ((g2d . weight) * (h2d > 0), its column sums) = (d pre-activation, d bias of the layer in front).
+    g2d (tokens, out), weight (out, in), h2d (tokens, in) = relu output that fed the layer.
+    round_mode (default ``SDB_GEMM_RELU_GRAD_ROUND`` or 2): as in ``gemm_tf32``.  2 = the weights are rounded to the
+    nearest TF32 once per CTA (they are resident), the streamed gradient operand is left to the tensor core's own
+    truncation -- what the library's TF32 GEMM does with both operands -- which takes the per-stage rounding pass over
+    shared memory out of the main loop (181 vs 217 us at the encoder FFN shape, tools/time_ffn_dgrad.py)."""
+    _check(g2d, "g2d")
+    _check(weight, "weight")
+    _check(h2d, "h2d")
+    m, k = g2d.shape
+    n = weight.shape[1]
+    if h2d.shape != (m, n) or weight.shape[0] != k:
+        raise RuntimeError(f"linear_grad_input_relu: shapes {tuple(g2d.shape)} {tuple(weight.shape)} {tuple(h2d.shape)}")
+    if round_mode is None:
+        round_mode = int(os.environ.get("SDB_GEMM_RELU_GRAD_ROUND", "2"))
+    out = torch.empty((m, n), dtype=torch.float32, device=g2d.device)
+    sums = torch.empty(n, dtype=torch.float32, device=g2d.device)
+    with torch.cuda.device(g2d.device):
+        rc = _lib.lib().sdb_gemm_tf32_relu_grad(_lib.current_stream(g2d.device), g2d.data_ptr(), 0, weight.data_ptr(), 1,
+                                                out.data_ptr(), m, n, k, h2d.data_ptr(), sums.data_ptr(),
+                                                int(round_mode))
+    _lib.check(rc, "gemm_tf32_relu_grad")
+    _lib.LAUNCHES["gemm_tf32"] += 1
+    return out, sums
+
+
 def linear_grad_weight(g2d, x2d, with_bias_grad=False):
     """g2d (tokens, out)^T . x2d (tokens, in) -> (out, in); the token axis is split over the SMs.
     with_bias_grad: also return g2d.sum(0), accumulated by the same launch from the tiles of g2d it stages."""

@@ -46,6 +46,40 @@ class _LayerNormFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None
 
 
+def add_layernorm_forward(x2, r2, weight, bias, eps, pos=None):
+    """Raw launch of ``sdb_add_layernorm_forward_f32`` on contiguous operands: -> (y, q or None, mean, rstd) with
+    y = LN(x2 + r2), q = y + pos."""
+    rows = x2.numel() // x2.shape[-1]
+    y = torch.empty_like(x2)
+    q = torch.empty_like(x2) if pos is not None else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        rc = _lib.lib().sdb_add_layernorm_forward_f32(
+            _lib.current_stream(x2.device), x2.data_ptr(), r2.data_ptr(), weight.data_ptr(), bias.data_ptr(), rows,
+            x2.shape[-1], eps, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _lib.ptr(pos), _lib.ptr(q))
+    _lib.check(rc, "add_layernorm_forward")
+    _lib.LAUNCHES["layernorm_forward"] += 1
+    return y, q, mean, rstd
+
+
+def add_layernorm_backward(dy, dq, x, r, weight, mean, rstd):
+    """Raw launch of ``sdb_add_layernorm_backward_f32``: -> (d(x + r), dgamma, dbeta); ``dq`` (gradient of y + pos, or
+    None) is folded into ``dy`` inside the kernel."""
+    rows = x.numel() // x.shape[-1]
+    dx = torch.empty_like(x)
+    dgamma, dbeta = torch.empty_like(weight), torch.empty_like(weight)
+    ws = torch.empty(_lib.lib().sdb_layernorm_bwd_workspace_floats(), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().sdb_add_layernorm_backward_f32(
+            _lib.current_stream(x.device), dy.data_ptr(), _lib.ptr(dq), x.data_ptr(), r.data_ptr(),
+            weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, x.shape[-1], dx.data_ptr(), dgamma.data_ptr(),
+            dbeta.data_ptr(), ws.data_ptr())
+    _lib.check(rc, "add_layernorm_backward")
+    _lib.LAUNCHES["layernorm_backward"] += 2
+    return dx, dgamma, dbeta
+
+
 class _AddLayerNormFn(torch.autograd.Function):
     """y = LN(x + residual) [, q = y + pos] in one pass (``sdb_add_layernorm_forward_f32``); backward hands the same
     d(x + residual) to both addends and folds dq into dy inside the kernel -- no standalone add in either direction."""
@@ -53,18 +87,8 @@ class _AddLayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, eps, pos):
         x2, r2 = x.contiguous(), residual.contiguous()
-        rows = x2.numel() // x2.shape[-1]
-        y = torch.empty_like(x2)
-        q = torch.empty_like(x2) if pos is not None else None
         p2 = pos.contiguous() if pos is not None else None
-        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
-        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            rc = _lib.lib().sdb_add_layernorm_forward_f32(
-                _lib.current_stream(x.device), x2.data_ptr(), r2.data_ptr(), weight.data_ptr(), bias.data_ptr(), rows,
-                x2.shape[-1], eps, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _lib.ptr(p2), _lib.ptr(q))
-        _lib.check(rc, "add_layernorm_forward")
-        _lib.LAUNCHES["layernorm_forward"] += 1
+        y, q, mean, rstd = add_layernorm_forward(x2, r2, weight, bias, eps, p2)
         ctx.save_for_backward(x2, r2, weight, mean, rstd)
         ctx.has_q = q is not None
         return y if q is None else (y, q)
@@ -77,17 +101,7 @@ class _AddLayerNormFn(torch.autograd.Function):
             dy, dq = dq, None
         dy = dy.contiguous()
         dq = dq.contiguous() if dq is not None else None
-        rows = x.numel() // x.shape[-1]
-        dx = torch.empty_like(x)
-        dgamma, dbeta = torch.empty_like(weight), torch.empty_like(weight)
-        ws = torch.empty(_lib.lib().sdb_layernorm_bwd_workspace_floats(), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            rc = _lib.lib().sdb_add_layernorm_backward_f32(
-                _lib.current_stream(x.device), dy.data_ptr(), _lib.ptr(dq), x.data_ptr(), r.data_ptr(),
-                weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, x.shape[-1], dx.data_ptr(), dgamma.data_ptr(),
-                dbeta.data_ptr(), ws.data_ptr())
-        _lib.check(rc, "add_layernorm_backward")
-        _lib.LAUNCHES["layernorm_backward"] += 2
+        dx, dgamma, dbeta = add_layernorm_backward(dy, dq, x, r, weight, mean, rstd)
         return dx, dx, dgamma, dbeta, None, dpos
 
 

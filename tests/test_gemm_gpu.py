@@ -331,3 +331,75 @@ def test_autocast_linear_matches_plain_autocast():
         assert y.dtype == torch.bfloat16 and torch.equal(got[0], y2.detach().float())
         for a, b, tol in ((got[1], x2.grad, 1e-2), (got[2], w2.grad, 1e-2), (got[3], b2.grad, 2e-2)):
             assert a.dtype == b.dtype and float((a - b).abs().max()) <= tol * float(b.abs().max())
+
+
+@pytest.mark.parametrize("m,n,k", [(4446, 2048, 256), (44446, 2048, 256), (2184, 2048, 256), (300, 1000, 256), (4999, 132, 64),
+                                   (129, 36, 256)])
+@pytest.mark.parametrize("round_mode", [3, 2])
+def test_grad_input_with_relu_backward_epilogue(m, n, k, round_mode):
+    """sdb_gemm_tf32_relu_grad: (dy W) * (h > 0) and its column sums -- the resident-weight variant (first two shapes),
+    the streaming variant, ragged row / column tiles.  round_mode 2 leaves the gradient operand to the tensor core's
+    own truncation (what cuBLAS-TF32 does with both operands)."""
+    from semi_detr_b200.layers import gemm as G
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    dy = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    h = torch.relu(torch.randn(m, n, device="cuda", generator=g))
+    y, sums = G.linear_grad_input_relu(dy, w, h, round_mode=round_mode)
+    a = _trunc(dy) if round_mode & 1 else (dy.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref = (a.double() @ _trunc(w).double()) * (h > 0)
+    assert (y[h <= 0] == 0).all()
+    _close(y, ref)
+    # column sums: fp32 atomics over m / 32 partial sums; compared on the scale of the column's absolute sum
+    ref_sums = y.double().sum(0)
+    scale = y.double().abs().sum(0).max().item() + 1e-30
+    assert ((sums.double() - ref_sums).abs().max().item() / scale) < 1e-5
+
+
+def test_ffn_block_matches_layer_by_layer_route(monkeypatch):
+    """layers/ffn.py: the one-node FFN + residual + LayerNorm block against the layer-by-layer modules (the route
+    SDB_FFN_BLOCK=0 takes): outputs identical (same forward kernels), every gradient within TF32 product error."""
+    from semi_detr_b200.layers import LayerNorm, Linear, ffn
+    torch.manual_seed(0)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        l1, l2, ln = Linear(256, 2048).cuda(), Linear(2048, 256).cuda(), LayerNorm(256).cuda()
+        x0 = torch.randn(2, 3000, 256, device="cuda")
+        pos = torch.randn(2, 3000, 256, device="cuda")
+        gy, gq = torch.randn_like(x0), torch.randn_like(x0)
+
+        def run(fused, with_pos):
+            x = x0.clone().requires_grad_(True)
+            p = pos.clone().requires_grad_(True) if with_pos else None
+            for m_ in (l1, l2, ln):
+                m_.zero_grad()
+            drops = (torch.nn.Dropout(0.0), torch.nn.Dropout(0.0))
+            if fused:
+                assert ffn.fused_ok(x, l1, l2, ln, drops)
+                out = ffn.ffn_block(x, l1, l2, ln, p)
+            else:
+                out = ln.add_norm(x, l2(l1(x, relu=True)), p)
+            if with_pos:
+                (out[0] * gy).sum().add((out[1] * gq).sum()).backward()
+                outs = [o.detach() for o in out]
+            else:
+                (out * gy).sum().backward()
+                outs = [out.detach()]
+            grads = [x.grad] + [p_.grad.clone() for m_ in (l1, l2, ln) for p_ in m_.parameters()]
+            if with_pos:
+                grads.append(p.grad)
+            return outs, grads
+
+        for with_pos in (False, True):
+            o_f, g_f = run(True, with_pos)
+            o_r, g_r = run(False, with_pos)
+            for a, b in zip(o_f, o_r):
+                assert torch.equal(a, b)
+            for a, b in zip(g_f, g_r):
+                scale = b.abs().max().item() + 1e-30
+                assert (a - b).abs().max().item() / scale < 2e-3, (a.shape, (a - b).abs().max().item() / scale)
+        monkeypatch.setenv("SDB_FFN_BLOCK", "0")
+        assert not ffn.fused_ok(x0.requires_grad_(True), l1, l2, ln, ())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev

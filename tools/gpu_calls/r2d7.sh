@@ -1,0 +1,5 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gemm_gpu.py -x -q -k "relu_backward_epilogue or ffn_block" 2>&1 | tail -3
+timeout 300 python tools/time_ffn_dgrad.py 2>&1 | tee gpurun_out/r2d7_ffn_dgrad.json | tail -3
