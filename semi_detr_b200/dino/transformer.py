@@ -138,9 +138,11 @@ class DINOTransformerEncoderLayer(nn.Module):
         return ``out + next_pos`` -- both additions then ride in the LayerNorm kernels (``LayerNorm.add_norm``)."""
         q = query if query is not None else (src if pos is None else src + pos)
         src2 = self.self_attn(q, reference_points, src, spatial_shapes, level_start_index, key_padding_mask)
+        if ffn.fused_ok(src, self.norm1, self.linear1, self.linear2, self.norm2,
+                        (self.dropout1, self.dropout2, self.dropout3)):
+            # norm1(src + src2) -> FFN -> norm2 as one autograd node (layers/ffn.py)
+            return ffn.post_attention_block(src, src2, self.norm1, self.linear1, self.linear2, self.norm2, next_pos)
         src = self.norm1.add_norm(src, self.dropout1(src2))
-        if ffn.fused_ok(src, self.linear1, self.linear2, self.norm2, (self.dropout2, self.dropout3)):
-            return ffn.ffn_block(src, self.linear1, self.linear2, self.norm2, next_pos)
         src2 = self.linear2(self.dropout2(self.linear1(src, relu=True)))
         return self.norm2.add_norm(src, self.dropout3(src2), next_pos)
 
@@ -249,7 +251,9 @@ class DINOTransformerDecoderLayer(nn.Module):
     def forward(self, tgt, query_pos, reference_points, memory, memory_key_padding_mask, level_start_index,
                 spatial_shapes, self_attn_mask=None, self_attn_mask_t=None):
         """tgt / query_pos (nq, bs, C); reference_points (nq, bs, L, 4); memory (bs, S, C) batch-first."""
-        for name in self.module_seq:
+        seq, i = self.module_seq, 0
+        while i < len(seq):
+            name = seq[i]
             if name == "sa":
                 tgt2 = self._self_attention(tgt + query_pos, tgt, self_attn_mask, self_attn_mask_t)
                 tgt = self.norm2.add_norm(tgt, self.dropout2(tgt2))
@@ -257,12 +261,18 @@ class DINOTransformerDecoderLayer(nn.Module):
                 tgt2 = self.cross_attn((tgt + query_pos).transpose(0, 1), reference_points.transpose(0, 1).contiguous(),
                                        memory, spatial_shapes, level_start_index,
                                        memory_key_padding_mask).transpose(0, 1)
+                if (i + 1 < len(seq) and seq[i + 1] == "ffn" and
+                        ffn.fused_ok(tgt, self.norm1, self.linear1, self.linear2, self.norm3,
+                                     (self.dropout1, self.dropout3, self.dropout4))):
+                    # norm1(tgt + tgt2) -> FFN -> norm3 as one autograd node (layers/ffn.py)
+                    tgt = ffn.post_attention_block(tgt, tgt2, self.norm1, self.linear1, self.linear2, self.norm3)
+                    i += 2
+                    continue
                 tgt = self.norm1.add_norm(tgt, self.dropout1(tgt2))
-            elif ffn.fused_ok(tgt, self.linear1, self.linear2, self.norm3, (self.dropout3, self.dropout4)):
-                tgt = ffn.ffn_block(tgt, self.linear1, self.linear2, self.norm3)
             else:
                 tgt2 = self.linear2(self.dropout3(self.linear1(tgt, relu=True)))
                 tgt = self.norm3.add_norm(tgt, self.dropout4(tgt2))
+            i += 1
         return tgt
 
 

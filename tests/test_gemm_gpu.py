@@ -356,37 +356,45 @@ def test_grad_input_with_relu_backward_epilogue(m, n, k, round_mode):
     assert ((sums.double() - ref_sums).abs().max().item() / scale) < 1e-5
 
 
-def test_ffn_block_matches_layer_by_layer_route(monkeypatch):
-    """layers/ffn.py: the one-node FFN + residual + LayerNorm block against the layer-by-layer modules (the route
+def test_post_attention_block_matches_layer_by_layer_route(monkeypatch):
+    """layers/ffn.py: norm_a(a + r) -> FFN -> norm_b as one autograd node against the layer-by-layer modules (the route
     SDB_FFN_BLOCK=0 takes): outputs identical (same forward kernels), every gradient within TF32 product error."""
     from semi_detr_b200.layers import LayerNorm, Linear, ffn
     torch.manual_seed(0)
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        l1, l2, ln = Linear(256, 2048).cuda(), Linear(2048, 256).cuda(), LayerNorm(256).cuda()
-        x0 = torch.randn(2, 3000, 256, device="cuda")
+        l1, l2 = Linear(256, 2048).cuda(), Linear(2048, 256).cuda()
+        na, nb = LayerNorm(256).cuda(), LayerNorm(256).cuda()
+        with torch.no_grad():
+            for n_ in (na, nb):
+                n_.weight.add_(torch.randn_like(n_.weight) * 0.1)
+                n_.bias.add_(torch.randn_like(n_.bias) * 0.1)
+        mods = (l1, l2, na, nb)
+        a0 = torch.randn(2, 3000, 256, device="cuda")
+        r0 = torch.randn(2, 3000, 256, device="cuda")
         pos = torch.randn(2, 3000, 256, device="cuda")
-        gy, gq = torch.randn_like(x0), torch.randn_like(x0)
+        gy, gq = torch.randn_like(a0), torch.randn_like(a0)
+        drops = (torch.nn.Dropout(0.0),)
 
         def run(fused, with_pos):
-            x = x0.clone().requires_grad_(True)
+            a, r = a0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
             p = pos.clone().requires_grad_(True) if with_pos else None
-            for m_ in (l1, l2, ln):
+            for m_ in mods:
                 m_.zero_grad()
-            drops = (torch.nn.Dropout(0.0), torch.nn.Dropout(0.0))
             if fused:
-                assert ffn.fused_ok(x, l1, l2, ln, drops)
-                out = ffn.ffn_block(x, l1, l2, ln, p)
+                assert ffn.fused_ok(a, na, l1, l2, nb, drops)
+                out = ffn.post_attention_block(a, r, na, l1, l2, nb, p)
             else:
-                out = ln.add_norm(x, l2(l1(x, relu=True)), p)
+                x = na.add_norm(a, r)
+                out = nb.add_norm(x, l2(l1(x, relu=True)), p)
             if with_pos:
                 (out[0] * gy).sum().add((out[1] * gq).sum()).backward()
                 outs = [o.detach() for o in out]
             else:
                 (out * gy).sum().backward()
                 outs = [out.detach()]
-            grads = [x.grad] + [p_.grad.clone() for m_ in (l1, l2, ln) for p_ in m_.parameters()]
+            grads = [a.grad, r.grad] + [p_.grad.clone() for m_ in mods for p_ in m_.parameters()]
             if with_pos:
                 grads.append(p.grad)
             return outs, grads
@@ -394,12 +402,12 @@ def test_ffn_block_matches_layer_by_layer_route(monkeypatch):
         for with_pos in (False, True):
             o_f, g_f = run(True, with_pos)
             o_r, g_r = run(False, with_pos)
-            for a, b in zip(o_f, o_r):
-                assert torch.equal(a, b)
-            for a, b in zip(g_f, g_r):
-                scale = b.abs().max().item() + 1e-30
-                assert (a - b).abs().max().item() / scale < 2e-3, (a.shape, (a - b).abs().max().item() / scale)
+            for x_, y_ in zip(o_f, o_r):
+                assert torch.equal(x_, y_)
+            for x_, y_ in zip(g_f, g_r):
+                scale = y_.abs().max().item() + 1e-30
+                assert (x_ - y_).abs().max().item() / scale < 2e-3, (x_.shape, (x_ - y_).abs().max().item() / scale)
         monkeypatch.setenv("SDB_FFN_BLOCK", "0")
-        assert not ffn.fused_ok(x0.requires_grad_(True), l1, l2, ln, ())
+        assert not ffn.fused_ok(a0.requires_grad_(True), na, l1, l2, nb, ())
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev

@@ -1,0 +1,16 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+for v in "fold:SDB_FFN_LNFOLD=1" "nofold:SDB_FFN_LNFOLD=0" "noblk:SDB_FFN_BLOCK=0" "fold2:SDB_FFN_LNFOLD=1" "nofold2:SDB_FFN_LNFOLD=0"; do
+  name=${v%%:*}; envs=${v#*:}
+  env $envs timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2d12_sup_$name.json 2> gpurun_out/r2d12_sup_$name.err
+  python - <<P
+import json
+try:
+    d = json.loads(open("gpurun_out/r2d12_sup_$name.json").read().strip().splitlines()[-1])
+    print("$name", d["ms_per_step"], d["e2e"]["last_loss"], d["gpu_launches_per_step"])
+except Exception as e:
+    print("$name failed", e); print(open("gpurun_out/r2d12_sup_$name.err").read()[-1500:])
+P
+done
+nvidia-smi --query-gpu=name,serial,uuid --format=csv | tail -1
