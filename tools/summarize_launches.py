@@ -30,6 +30,28 @@ def main():
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
     ours = sum(v[1] for k, v in agg.items() if k.startswith("sdb::"))
+    if "--categories" in sys.argv:
+        # whose kernels: this library / cuBLAS(Lt) GEMMs / cuDNN convolutions / ATen (elementwise, reductions, copies)
+        def category(k):
+            if "sdb::" in k:
+                return "this library"
+            if "implicit_gemm" in k or "cudnn" in k or "xmma_fprop" in k or "xmma_dgrad" in k or "xmma_wgrad" in k or "conv" in k:
+                return "cuDNN convolutions"
+            if k.startswith("cutlass") or k.startswith("nvjet") or "gemm" in k or "cublas" in k or "splitKreduce" in k:
+                return "cuBLAS"
+            if "at::" in k:
+                return "ATen"
+            return "other"
+        cat = collections.defaultdict(lambda: [0, 0.0])
+        for k, v in agg.items():
+            c = cat[category(k)]
+            c[0] += v[0]
+            c[1] += v[1]
+        print(f"# categories of {path}")
+        for k, v in sorted(cat.items(), key=lambda kv: -kv[1][1]):
+            print(f"{v[1] / 1e3:7.3f} ms {100 * v[1] / tot:5.1f}% {v[0]:6d} launches  {k}")
+        print(f"# {len(body)} launches, {tot / 1e3:.3f} ms of serialised kernel time")
+        return
     print(f"# {path}: {len(body)} launches, {tot / 1e3:.3f} ms of serialised kernel time; sdb:: kernels {ours / 1e3:.3f} ms "
           f"({100 * ours / tot:.1f} %)")
     print(f"# {'total_us':>10} {'share':>7} {'count':>6} {'avg_us':>9}  kernel")
