@@ -106,12 +106,8 @@ def linear_grad_weight(g2d, x2d, with_bias_grad=False):
     n = x2d.shape[1]
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
     splits = max(1, min((k + 31) // 32, (2 * _sm_count(g2d.device)) // tiles))
-    min_kblocks = int(os.environ.get("SDB_GEMM_MIN_KBLOCKS_PER_SPLIT", "0"))
-    if min_kblocks > 1:
-        # EXPERIMENTAL (not yet run on hardware; docs/ROUND2_NOTES.md section 1): never fewer than this many k-blocks
-        # per split -- every split reduce-adds a full 64 KB output tile, which the decoder-sized products (69
-        # k-blocks) currently do once per k-block.  The MN-major kernel has not run with k_splits == 1 yet.
-        splits = max(1, min(splits, ((k + 31) // 32) // min_kblocks))
+    # (a floor on the k-blocks per split -- fewer, longer splits for the decoder-sized products, whose 69 splits each
+    # reduce-add a full 64 KB tile -- was measured: 1.52 / 1.49 / 1.58 / 1.85 ms per step for a floor of 0 / 4 / 8 / 16)
     if not with_bias_grad:
         return gemm_tf32(g2d, 1, x2d, 1, m, n, k, k_splits=splits)
     buf = torch.zeros(m * n + m, dtype=torch.float32, device=g2d.device)      # one fill for both outputs
