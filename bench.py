@@ -299,7 +299,7 @@ def run_ours(args):
     world, rank, local_rank, device = _init_ours()
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("SDB_CUDNN_BENCHMARK", "1") != "0"
 
     five = args.workload == "sup5"
     model = build_model(device, five_scale=five)
