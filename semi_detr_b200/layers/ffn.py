@@ -70,7 +70,7 @@ def fused_ok(a, norm_a, linear1, linear2, norm_b, dropouts):
         return False
     if os.environ.get("SDB_FFN_BLOCK", "1") == "0":            # A/B switch: the layer-by-layer route
         return False
-    if not torch.backends.cuda.matmul.allow_tf32 or policy() == "cublas":
+    if not torch.backends.cuda.matmul.allow_tf32 or policy() != "auto":    # the other policies pin every product's owner
         return False
     if any(d.training and d.p > 0 for d in dropouts):
         return False
