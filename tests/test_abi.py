@@ -86,6 +86,17 @@ def test_argument_errors_without_gpu(libpath):
                                            None, None, None), "msda_backward")
 
 
+def test_relu_grad_gemm_validates_before_any_cuda_call(libpath):
+    """sdb_gemm_tf32_relu_grad: a missing activation pointer and misaligned operands are argument errors (code 1)
+    reported on the CPU box, like every other entry point."""
+    from semi_detr_b200 import _lib
+    l = _lib.lib()
+    rc = l.sdb_gemm_tf32_relu_grad(None, 256, 0, 512, 1, 768, 128, 128, 32, None, None, 2)
+    assert rc == 1 and b"relu_src is null" in l.sdb_last_error()
+    rc = l.sdb_gemm_tf32_relu_grad(None, 256, 0, 512, 1, 768, 128, 128, 32, 1028, None, 2)
+    assert rc == 1 and b"16-byte aligned" in l.sdb_last_error()
+
+
 def test_bf16_entry_points_validate_before_any_cuda_call(libpath):
     """sdb_msda_forward_bf16 / sdb_msda_backward_bf16: size, shape-support, null-pointer and alignment errors are
     reported on the CPU box (codes of include/semidetr_b200.h: 1 = invalid argument, 3 = unsupported)."""
